@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by EXECUTING THE REFERENCE.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the unmodified reference modules (utils.SharedNoiseTable,
+policies.*, learner.FiniteDifferences, dsgd.DSGD, worker.Worker) through the
+test-only `gym` shim in tests/golden/_shim and records inputs + reference
+outputs as small .npz/.json fixtures.  The oracle (oracle/dfd_oracle.py) and the
+CUDA path are then both checked against these files; nothing at test/bench time
+reads /root/reference.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("DFD_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from utils import SharedNoiseTable            # noqa: E402  (reference)
+from policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy  # noqa: E402
+from learner import FiniteDifferences, FDReturn  # noqa: E402
+from dsgd import DSGD                          # noqa: E402
+from worker import Worker                      # noqa: E402
+import torch.nn as nn                          # noqa: E402
+from utils import torch_helpers                # noqa: E402
+
+from oracle import dfd_oracle as O             # noqa: E402  (recipes for synthetic theta only)
+
+torch.set_num_threads(1)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---------------------------------------------------------------- noise tables
+def gen_noise():
+    out = {}
+    for size, P, seed in [(1_000_000, 6092, 123), (200_000, 5197, 124), (25_000_000, 6092, 124),
+                          (25_000_000, 678294, 124)]:
+        t = SharedNoiseTable(size, P, seed)
+        keys = [t.sample()[0] for _ in range(8)]
+        i0 = int(keys[0])
+        out["%d_%d_%d" % (size, P, seed)] = {
+            "size": size, "n_params": P, "seed": seed,
+            "sha256": sha(t._table),
+            "head": [float(x) for x in t._table[:4]],
+            "tail": [float(x) for x in t._table[-2:]],
+            "keys": keys,
+            "norm2_first": float(np.dot(t._table[i0:i0 + P].astype(np.float64), t._table[i0:i0 + P].astype(np.float64))),
+        }
+        del t
+    return out
+
+
+# ---------------------------------------------------------------- worker draws
+class _StubStats(object):
+    mean, std = 0.0, 1.0
+
+    def serialize(self):
+        return []
+
+
+class _StubAgent(object):
+    saved_states = []
+    obs_stats = _StubStats()
+
+    def collect_return(self, **kw):
+        return 1.0, 0.0, 1
+
+
+class _StubStrategy(object):
+    def compute_novelty(self, policy):
+        return 0.0
+
+
+def gen_worker_draws():
+    """Flags (worker stream) and keys (noise stream) of the reference Worker
+    (worker/worker.py:19-38) driven like run_sequential.py:134-147."""
+    torch.manual_seed(124)
+    pol = MujocoPolicy(17, 6, seed=124)
+    table = SharedNoiseTable(1_000_000, pol.num_params, 124)
+    w = Worker(pol, _StubAgent(), table, _StubStrategy(), sigma=0.02, eval_prob=0.1, random_seed=124)
+    w.epoch = 7
+    flags, keys = [], []
+    while len(keys) < 64:
+        for ret in w.collect_returns():
+            flags.append(bool(ret.is_eval))
+            if not ret.is_eval:
+                keys.append(ret.encoded_noise)
+            else:
+                assert ret.encoded_noise == "0"
+    return {"size": 1_000_000, "seed": 124, "eval_prob": 0.1, "batch": 64, "flags": flags, "keys": keys}
+
+
+# ---------------------------------------------------------------- MLP forwards
+def member_outputs(pol, theta, table, idxs, signs, sigma, obs, fwd):
+    thetas, outs = [], []
+    for i, s in zip(idxs, signs):
+        eps = table.decode(str(i))
+        if s < 0:
+            eps = -eps
+        new_flat = theta + sigma * eps                 # worker/worker.py:28
+        pol.set_trainable_flat(new_flat)
+        thetas.append(pol.get_trainable_flat().copy())
+        outs.append(fwd(pol, obs[len(outs)]))
+    pol.set_trainable_flat(theta)
+    return np.stack(thetas), outs
+
+
+def gen_mujoco():
+    torch.manual_seed(124)
+    pol = MujocoPolicy(17, 6, seed=124)
+    theta = pol.get_trainable_flat().copy()
+    table = SharedNoiseTable(1_000_000, pol.num_params, 123)
+    idxs = [int(table.sample()[0]) for _ in range(6)]
+    signs = [1, 1, -1, 1, -1, 1]
+    sigma = 0.02
+    obs = torch.randn(6, 5, 17, generator=torch.Generator().manual_seed(0)).numpy()
+
+    def fwd(p, x):
+        with torch.no_grad():
+            m, s = p.forward(x)
+        return np.concatenate([m.numpy(), s.numpy()], -1)
+
+    thetas, outs = member_outputs(pol, theta, table, idxs, signs, sigma, obs, fwd)
+    np.savez(os.path.join(HERE, "mujoco_c2.npz"), theta=theta, idx=np.array(idxs), sign=np.array(signs, np.int8),
+             sigma=sigma, obs=obs, theta_members=thetas, out=np.stack(outs), table_size=1_000_000, table_seed=123)
+
+
+class _WideMujoco(MujocoPolicy):
+    """Reference MujocoPolicy with the hidden widths of BASELINE config 3
+    (the reference hard-codes 64x64, mujoco.py:33-34)."""
+
+    def _build_model(self):
+        h1 = h2 = 256
+        self.model = nn.Sequential(nn.Linear(self.input_shape, h1), nn.Tanh(), nn.Linear(h1, h2), nn.Tanh(),
+                                   nn.Linear(h2, self.output_shape * 2), torch_helpers.MapContinuousToAction())
+
+
+def gen_humanoid():
+    torch.manual_seed(124)
+    pol = _WideMujoco(376, 17, seed=124)
+    L = O.mujoco_layout(376, 17, 256, 256)
+    assert L.num_params == pol.num_params == 171042
+    theta = O.synthetic_theta(L, 11)
+    table = SharedNoiseTable(1_000_000, pol.num_params, 123)
+    idxs = [int(table.sample()[0]) for _ in range(3)]
+    signs = [1, -1, 1]
+    obs = torch.randn(3, 4, 376, generator=torch.Generator().manual_seed(1)).numpy()
+
+    def fwd(p, x):
+        with torch.no_grad():
+            m, s = p.forward(x)
+        return np.concatenate([m.numpy(), s.numpy()], -1)
+
+    _, outs = member_outputs(pol, theta, table, idxs, signs, 0.02, obs, fwd)
+    np.savez(os.path.join(HERE, "mujoco_c3.npz"), theta_seed=11, idx=np.array(idxs), sign=np.array(signs, np.int8),
+             sigma=0.02, obs=obs, out=np.stack(outs), table_size=1_000_000, table_seed=123)
+
+
+def load_buffers(pol, layout, buffers):
+    sd = pol.state_dict()
+    for e in layout.entries:
+        if e.kind == "buffer":
+            v = torch.from_numpy(buffers[e.offset:e.offset + e.numel].copy()).view(e.shape)
+            sd[e.name] = v.to(sd[e.name].dtype)
+    pol.load_state_dict(sd)
+
+
+def gen_discrete():
+    torch.manual_seed(124)
+    pol = DiscretePolicy(2, 9, seed=124)
+    L = O.discrete_layout(2, 9)
+    assert L.num_params == pol.num_params
+    # refresh running stats the way the drivers do (policy.py:31-34)
+    vbn = torch.rand(64, 2, generator=torch.Generator().manual_seed(5))
+    pol.compute_vbn(vbn)
+    theta = pol.get_trainable_flat().copy()
+    serialized = np.asarray(pol.serialize(), dtype=np.float32)
+    table = SharedNoiseTable(200_000, pol.num_params, 124)
+    idxs = [int(table.sample()[0]) for _ in range(5)]
+    signs = [1, 1, -1, -1, 1]
+    obs = torch.rand(5, 6, 2, generator=torch.Generator().manual_seed(2)).numpy()
+
+    def fwd(p, x):
+        with torch.no_grad():
+            return p.forward(x).numpy()
+
+    thetas, outs = member_outputs(pol, theta, table, idxs, signs, 0.02, obs, fwd)
+    np.savez(os.path.join(HERE, "discrete_c1.npz"), theta=theta, serialized=serialized, idx=np.array(idxs),
+             sign=np.array(signs, np.int8), sigma=0.02, obs=obs, theta_members=thetas, out=np.stack(outs),
+             table_size=200_000, table_seed=124)
+
+
+def gen_atari():
+    torch.manual_seed(124)
+    pol = AtariPolicy((84, 84), 6, seed=124)
+    L = O.atari_layout(6)
+    assert L.num_params == pol.num_params == 678294
+    theta = O.synthetic_theta(L, 21)
+    load_buffers(pol, L, O.synthetic_buffers(L, 22))
+    table = SharedNoiseTable(1_000_000, pol.num_params, 123)
+    idxs = [int(table.sample()[0]) for _ in range(3)]
+    signs = [1, -1, 1]
+    obs = torch.rand(3, 2, 4, 84, 84, generator=torch.Generator().manual_seed(3)).numpy()
+
+    def fwd(p, x):
+        with torch.no_grad():
+            return p.forward(torch.from_numpy(x)).numpy()
+
+    _, outs = member_outputs(pol, theta, table, idxs, signs, 0.02, obs, fwd)
+    np.savez(os.path.join(HERE, "atari_c4.npz"), theta_seed=21, buffer_seed=22, idx=np.array(idxs),
+             sign=np.array(signs, np.int8), sigma=0.02, obs_seed=3, out=np.stack(outs),
+             table_size=1_000_000, table_seed=123)
+
+
+def gen_impala():
+    torch.manual_seed(124)
+    pol = ImpalaPolicy((3, 64, 64), 15, seed=124)
+    L = O.impala_layout(15)
+    assert L.num_params == pol.num_params == 1158709
+    # the reference's own registration order must match the oracle layout
+    names = [k for k, _ in pol.named_parameters()]
+    assert names == [e.name for e in L.entries if e.kind == "param"], "impala layout order"
+    theta = O.synthetic_theta(L, 31)
+    load_buffers(pol, L, O.synthetic_buffers(L, 32))
+    table = SharedNoiseTable(2_000_000, pol.num_params, 123)
+    idxs = [int(table.sample()[0]) for _ in range(2)]
+    signs = [1, -1]
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randint(0, 256, (2, 2, 3, 64, 64), generator=g).float().numpy()
+    rewards = np.array([[0.5, -3.0], [2.0, 0.0]], np.float32)
+    dones = np.array([[False, True], [False, False]])
+    h0 = (0.3 * torch.randn(2, 2, 256, generator=g)).numpy()
+    c0 = (0.3 * torch.randn(2, 2, 256, generator=g)).numpy()
+    probs = np.zeros((2, 2, 15), np.float32)
+    h1 = np.zeros((2, 2, 256), np.float32)
+    c1 = np.zeros((2, 2, 256), np.float32)
+    for m, (i, s) in enumerate(zip(idxs, signs)):
+        eps = table.decode(str(i))
+        if s < 0:
+            eps = -eps
+        pol.set_trainable_flat(theta + 0.02 * eps)
+        for e in range(2):   # each env is one batch-1, T=1 call with its own carried state (impala.py:126,184)
+            pol.model[0].state = (torch.from_numpy(h0[m, e]).view(1, 1, 256).clone(),
+                                  torch.from_numpy(c0[m, e]).view(1, 1, 256).clone())
+            inp = {"frame": torch.from_numpy(frames[m, e]).view(1, 1, 3, 64, 64),
+                   "reward": torch.from_numpy(rewards[m, e:e + 1]).view(1, 1),
+                   "done": torch.from_numpy(dones[m, e:e + 1]).view(1, 1)}
+            with torch.no_grad():
+                p = pol.forward(inp)
+            probs[m, e] = p.view(-1).numpy()
+            h1[m, e] = pol.model[0].state[0].view(-1).numpy()
+            c1[m, e] = pol.model[0].state[1].view(-1).numpy()
+    np.savez(os.path.join(HERE, "impala_c5.npz"), theta_seed=31, buffer_seed=32, idx=np.array(idxs),
+             sign=np.array(signs, np.int8), sigma=0.02, frame_seed=4, reward=rewards, done=dones,
+             probs=probs, h1=h1, c1=c1, table_size=2_000_000, table_seed=123)
+
+
+# ---------------------------------------------------------------- estimator
+class _Omega(object):
+    def __init__(self, omega, lo=0.0, hi=1.0):
+        self.omega, self.min_omega, self.max_omega = omega, lo, hi
+
+
+class SignedTable(SharedNoiseTable):
+    """Test-only antithetic decode: '+i' / '-i' keys."""
+
+    def decode(self, key):
+        key = str(key)
+        if key[0] == "-":
+            return -super().decode(key[1:])
+        return super().decode(key)
+
+
+def mkret(epoch, key, reward):
+    r = FDReturn()
+    r.epoch, r.encoded_noise, r.reward = epoch, key, reward
+    return r
+
+
+def gen_fd_steps():
+    """Unmodified FiniteDifferences.step + DSGD on the C2 policy: 6 current-epoch
+    steps (fd_return mode), then steps whose returns come from older epochs
+    (fd_state mode, H=4 -> H+1 accepted epochs), including too-old and unknown
+    epochs that must be discarded, an all-equal-reward batch (std == 0 branch),
+    a None baseline, an empty batch, and one antithetic step."""
+    import io
+    import contextlib
+    torch.manual_seed(124)
+    pol = MujocoPolicy(17, 6, seed=124)
+    P = pol.num_params
+    table = SignedTable(1_000_000, P, 123)
+    omega = _Omega(0.3)
+    opt = DSGD(pol.parameters(), lr=0.01)
+    H = 4
+    fd = FiniteDifferences(pol, opt, omega, table, noise_std=0.02, batch_size=16, ent_coef=0.0, max_delayed_return=H)
+    rrng = np.random.RandomState(0)
+    erng = np.random.RandomState(1)
+    rec = {"theta0": pol.get_trainable_flat().copy(), "H": H, "sigma": 0.02, "lr": 0.01, "omega": 0.3,
+           "table_size": 1_000_000, "table_seed": 123}
+    n_steps = 14
+    for s in range(n_steps):
+        N = 16
+        keys = [table.sample()[0] for _ in range(N)]
+        rewards = (rrng.randn(N) * 3.0 + 10.0).tolist()
+        baseline = 0.1 * s
+        if s < 6:
+            epochs = [fd.epoch] * N
+        elif s == 9:      # includes too-old, future and negative epochs -> discarded
+            epochs = [fd.epoch - int(k) for k in erng.randint(0, H + 3, size=N)]
+            epochs[3] = fd.epoch + 5
+        elif s == 10:     # std == 0 branch: rewards pass through un-standardised
+            epochs = [fd.epoch - int(k) for k in erng.randint(0, H + 1, size=N)]
+            rewards = [2.5] * N
+        elif s == 11:     # baseline None
+            epochs = [fd.epoch - int(k) for k in erng.randint(0, H + 1, size=N)]
+            baseline = None
+        elif s == 12:     # antithetic pairs, mixed epochs per pair
+            base = keys[:N // 2]
+            keys = ["+" + k for k in base] + ["-" + k for k in base]
+            ep = [fd.epoch - int(k) for k in erng.randint(0, 2, size=N // 2)]
+            epochs = ep + ep
+        else:
+            epochs = [fd.epoch - int(k) for k in erng.randint(0, H + 1, size=N)]
+        batch = [mkret(e, k, r) for e, k, r in zip(epochs, keys, rewards)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step(batch, baseline, 0.0, 0.0)
+        rec["s%d_keys" % s] = np.array(keys)
+        rec["s%d_epochs" % s] = np.array(epochs)
+        rec["s%d_rewards" % s] = np.array(rewards)
+        rec["s%d_baseline" % s] = np.nan if baseline is None else baseline
+        rec["s%d_grad" % s] = fd.gradient_memory.copy()
+        rec["s%d_theta" % s] = pol.get_trainable_flat().copy()
+        rec["s%d_update" % s] = float(upd)
+        rec["s%d_discarded" % s] = fd.discarded_returns
+        rec["s%d_epoch_after" % s] = fd.epoch
+    # empty batch: returns int 0, no update (finite_differences.py:30-31)
+    before = pol.get_trainable_flat().copy()
+    r0 = fd.step([], 0.0, 0.0, 0.0)
+    assert r0 == 0 and np.array_equal(before, pol.get_trainable_flat()) and fd.epoch == n_steps
+    rec["n_steps"] = n_steps
+    np.savez_compressed(os.path.join(HERE, "fd_steps.npz"), **rec)
+
+
+def main():
+    with open(os.path.join(HERE, "noise.json"), "w") as f:
+        json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
+    gen_mujoco()
+    gen_humanoid()
+    gen_discrete()
+    gen_atari()
+    gen_impala()
+    gen_fd_steps()
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
