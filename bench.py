@@ -1,0 +1,567 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json's north_star on synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C3|C1] [--obs-per-member E]
+    python bench.py --impl reference ...        # the CPU restatement of the reference on the host cores
+
+One STEP = one learner epoch over one population batch on each GPU:
+    perturbed forward of all members (theta +/- sigma*eps generated in-kernel from table offsets,
+    E synthetic observations per member) -> synthetic return per member -> dfd_fd_prepare ->
+    dfd_fd_reduce (the eps-weighted gradient reduction) -> [NCCL allreduce of P floats, N > 1] ->
+    dfd_dsgd_step (theta update + theta-history / distance rows).
+metric  = perturbed-policy env-steps/s = members * E * n_gpus / step time (whole job);
+          FD-gradient estimates/s (= steps/s) is reported beside it.
+value   : inputs resident in HBM, fresh noise indices and a different observation buffer every step
+          (table replicas 400 MB and the rotating observation buffers exceed L2; stated in config).
+e2e     : the same step through the reference-facing objects (Worker.evaluate -> FDReturn list ->
+          FiniteDifferences.step) with HOST observations / indices / returns copied in and results
+          copied out every step.
+Weak scaling: every rank evaluates the workload's full per-GPU population (no data-path
+collective in the forward; one parameter-sized allreduce in the estimator).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: kind, n_in, h1, h2, n_act, antithetic pairs per GPU, default E, description
+    "C2": dict(kind="mujoco", n_in=17, h1=64, h2=64, n_act=6, pairs=1024, E=128,
+               desc="C2 HalfCheetah-shaped MLP 17-64-64-6, 1024 antithetic pairs per GPU, fd_return"),
+    "C3": dict(kind="mujoco", n_in=376, h1=256, h2=256, n_act=17, pairs=1024, E=128,
+               desc="C3 Humanoid-shaped MLP 376-256-256-17, 8192 antithetic pairs over 8 GPUs (1024 per GPU), fd_return"),
+    "C1": dict(kind="discrete", n_in=2, h1=64, h2=64, n_act=9, pairs=20, E=128,
+               desc="C1 simple_trap-shaped discrete MLP 2-64-64-9, 20 antithetic pairs, fd_return"),
+}
+TABLE_SIZE = 25_000_000
+TABLE_SEED = 124
+SIGMA = 0.02
+LR = 0.01
+H = 10
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--obs-per-member", type=int, default=0)
+    ap.add_argument("--pairs", type=int, default=0, help="override antithetic pairs per GPU")
+    ap.add_argument("--table-size", type=int, default=TABLE_SIZE)
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-members", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload(args):
+    w = dict(WORKLOADS[args.workload])
+    if args.obs_per_member:
+        w["E"] = args.obs_per_member
+    if args.pairs:
+        w["pairs"] = args.pairs
+    w["members"] = 2 * w["pairs"]
+    w["out_width"] = 2 * w["n_act"] if w["kind"] == "mujoco" else w["n_act"]
+    return w
+
+
+def layer_flops_per_obs(w):
+    return 2 * (w["n_in"] * w["h1"] + w["h1"] * w["h2"] + w["h2"] * w["out_width"])
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port timed on the host cores
+# ----------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _ref_member(m):
+    """One member the way the reference worker evaluates it (worker/worker.py:26-32 +
+    policy.forward), batched over the member's E observations (favourable to the CPU: the
+    reference makes E separate batch-1 calls)."""
+    O, L, theta, table, idx, sign, obs, kind, bufs = (_G[k] for k in ("O", "L", "theta", "table", "idx", "sign", "obs", "kind", "bufs"))
+    th = O.perturb(theta, SIGMA, table[idx[m]:idx[m] + theta.shape[0]], int(sign[m]))
+    if kind == "mujoco":
+        mean, std = O.mujoco_forward(L, th, obs)
+        out = np.concatenate([mean, std], -1)
+    else:
+        out = O.discrete_forward(L, th, bufs, obs)
+    return float(-np.mean((out - _G["target"]) ** 2))
+
+
+def run_reference(args, w, as_baseline=False):
+    import torch
+    from oracle import dfd_oracle as O
+    torch.set_num_threads(1)          # the reference clients run single-threaded (run_client.py:15)
+    cores = len(os.sched_getaffinity(0))
+    P_layout = O.mujoco_layout(w["n_in"], w["n_act"], w["h1"], w["h2"]) if w["kind"] == "mujoco" else \
+        O.discrete_layout(w["n_in"], w["n_act"], w["h1"], w["h2"])
+    P = P_layout.num_params
+    noise = O.NoiseTableOracle(args.table_size, P, TABLE_SEED)
+    theta = O.synthetic_theta(P_layout, 1)
+    bufs = O.synthetic_buffers(P_layout, 2) if P_layout.num_buffer else None
+    M, E = w["members"], w["E"]
+    sample = args.cpu_sample_members or min(M, max(cores * 32, 256))
+    rng = np.random.RandomState(0)
+    obs = rng.randn(E, w["n_in"]).astype(np.float32)
+    _G.update(O=O, L=P_layout, theta=theta, table=noise.table, kind=w["kind"], bufs=bufs, obs=obs,
+              target=np.tanh(rng.randn(w["out_width"])).astype(np.float32) * 0.5)
+    import multiprocessing as mp
+    steps, warm = (args.steps, args.warmup) if not as_baseline else (2, 1)
+    steps = max(1, min(steps, 5))     # each step is already seconds of CPU work
+    warm = max(0, min(warm, 1))
+    times = []
+    for it in range(warm + steps):
+        pairs_idx = np.array([int(noise.sample()[0]) for _ in range(w["pairs"])], dtype=np.int64)
+        idx = np.concatenate([pairs_idx, pairs_idx])
+        sign = np.concatenate([np.ones(w["pairs"]), -np.ones(w["pairs"])]).astype(np.int8)
+        _G.update(idx=idx, sign=sign, theta=theta)
+        members = list(range(0, M, max(1, M // sample)))[:sample]
+        # N single-threaded client processes, like the reference's run_client.py fleet; forked after
+        # _G holds this step's theta / indices so the children see them
+        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+        t0 = time.perf_counter()
+        if pool is not None:
+            rewards_s = pool.map(_ref_member, members, chunksize=max(1, len(members) // (cores * 2)))
+            pool.close()
+        else:
+            rewards_s = [_ref_member(m) for m in members]
+        t_fwd = (time.perf_counter() - t0) * (M / len(members))
+        rewards = rng.randn(M)
+        rewards[:len(rewards_s)] = rewards_s
+        fd = O.FiniteDifferencesOracle(theta, noise, SIGMA, LR, max_delayed_return=H, omega=0.0)
+        batch = [O.Ret(0, ("+%d" if s > 0 else "-%d") % i, float(r)) for i, s, r in zip(idx, sign, rewards)]
+        t1 = time.perf_counter()
+        fd.step(batch, 0.0)
+        t_fd = time.perf_counter() - t1
+        theta = fd.theta
+        if it >= warm:
+            times.append((t_fwd, t_fd))
+    t_fwd = float(np.mean([t[0] for t in times]))
+    t_fd = float(np.mean([t[1] for t in times]))
+    step_s = t_fwd + t_fd
+    value = M * E / step_s
+    sample_txt = ("forward: %d of %d members x %d obs per step on %d processes x 1 torch thread, scaled x%.1f; "
+                  "estimator: full batch of %d returns (FiniteDifferences.step restatement, numpy BLAS threads)"
+                  % (sample, M, E, cores, M / sample, M))
+    return dict(value=value, unit="env-steps/s", cores=cores, kind="port", sample=sample_txt,
+                ms_per_step=step_s * 1e3, fd_estimates_per_s=1.0 / t_fd, forward_s=t_fwd, estimator_s=t_fd)
+
+
+def reference_main(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_reference(args, w)
+    line = {
+        "impl": "reference", "metric": "perturbed-policy env-steps/sec", "value": r["value"], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args, w),
+        "fd_estimates_per_s": r["fd_estimates_per_s"],
+        "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(args, w):
+    return {"workload": w["desc"], "policy": "%s %d-%d-%d-%d" % (w["kind"], w["n_in"], w["h1"], w["h2"], w["out_width"]),
+            "pairs_per_gpu": w["pairs"], "members_per_gpu": w["members"], "obs_per_member": w["E"],
+            "table": "SharedNoiseTable(%d, P, %d)" % (args.table_size, TABLE_SEED), "sigma": SIGMA,
+            "estimator": "fd_return (all returns from the current epoch), antithetic pairs merged per table row",
+            "l2": "fresh noise indices and a different observation buffer each step; table replicas (4x table) and the "
+                  "rotating observation buffers exceed the 126 MB L2; the reduction re-reads rows the forward of the same "
+                  "step touched (L2 reuse by design)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the B200 arm
+# ----------------------------------------------------------------------------------------------
+def b200_main(args, w):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = dist.group.WORLD
+    import __graft_entry__ as G
+    if rank == 0:
+        G.build()
+    if world > 1:
+        dist.barrier()
+    import dfd_starter_b200 as D
+    from dfd_starter_b200 import _lib
+    from dfd_starter_b200.device import get_context, ptr
+    ctx = get_context(local)
+    lib = ctx.lib
+    dev = ctx.device
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+
+    M, E, R = w["members"], w["E"], w["pairs"]
+    torch.manual_seed(TABLE_SEED)
+    cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
+    policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local)
+    P = policy.num_params
+    table = D.SharedNoiseTable(args.table_size, P, TABLE_SEED, device=local)
+    policy.bind_table(table)
+
+    class Omega(object):
+        omega, min_omega, max_omega = 0.0, 0.0, 1.0
+    opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
+    opt.coef = np.sqrt(P)
+    learner = D.FiniteDifferences(policy, opt, Omega(), table, noise_std=SIGMA, batch_size=M, max_delayed_return=H,
+                                  paired=True, process_group=pg)
+
+    CYC = H  # graphs / index sets / observation buffers cycle with the history ring
+    g = torch.Generator().manual_seed(1234 + rank)
+    # every rank draws from its own slice of the index stream (same table on every rank)
+    for _ in range(rank):
+        table.sample_indices(R * CYC)
+    idx_sets = [table.sample_indices(R) for _ in range(CYC)]
+    idx_host = torch.stack([torch.from_numpy(np.concatenate([i, i])) for i in idx_sets]).pin_memory()
+    sign_host = torch.from_numpy(np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)).pin_memory()
+    obs_host = torch.randn(CYC, M, E, w["n_in"], generator=g).pin_memory()
+    idx_d = idx_host.to(dev)
+    sign_d = sign_host.to(dev)
+    obs_d = obs_host.to(dev)
+    target = (torch.tanh(torch.randn(w["out_width"], generator=torch.Generator().manual_seed(7))) * 0.5).to(dev)
+    out_d = torch.empty(M, E, w["out_width"], device=dev)
+    reward_d = torch.empty(M, dtype=torch.float64, device=dev)
+    stats_d = torch.empty(M * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def device_step(k):
+        c = k % CYC
+        policy.forward_members(idx_d[c], sign_d, obs_d[c], SIGMA, out=out_d)
+        _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target), ptr(reward_d),
+                                            ctx.stream))
+        if world > 1:
+            dist.all_gather_into_tensor(stats_d, reward_d, group=pg)
+        learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, stats_d=stats_d)
+
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    # warm-up (fills the history ring so the ring position cycles with period H)
+    n_warm = max(args.warmup, 3, H + 1)
+    for k in range(n_warm):
+        device_step(k)
+    torch.cuda.synchronize()
+    graphs = None
+    if use_graph:
+        try:
+            graphs = []
+            k0 = n_warm
+            for c in range(CYC):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    device_step(k0 + c)
+                graphs.append(gr)
+            torch.cuda.synchronize()
+            n_warm += CYC          # capture advanced the learner's ring bookkeeping by CYC steps
+        except Exception as e:     # plain launches are always available
+            if rank == 0:
+                sys.stderr.write("bench: CUDA-graph capture failed (%s); using plain launches\n" % e)
+            graphs = None
+            torch.cuda.synchronize()
+
+    def run_step(k):
+        if graphs is not None:
+            graphs[k % CYC].replay()
+        else:
+            device_step(k)
+
+    for k in range(3):
+        run_step(n_warm + k)
+    n_warm += 3
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        run_step(n_warm + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = ev0.elapsed_time(ev1)
+    launches_plain = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    # keep the same step running ~1.5 s so nvidia-smi (100 ms period) sees the clocks under this load
+    t_load0 = time.perf_counter()
+    kk = 0
+    while time.perf_counter() - t_load0 < 1.5:
+        for _ in range(50):
+            run_step(n_warm + args.steps + kk)
+            kk += 1
+        torch.cuda.synchronize()
+    t_load1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_load1) if rank == 0 else None
+    n_done = n_warm + args.steps + kk
+
+    # ---------------- per-kernel durations (CUDA events on the launch stream, same inputs, back to back) ----
+    def time_calls(fn, reps):
+        fn(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gr = None
+        if use_graph:
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for r in range(reps):
+                        fn(r)
+                torch.cuda.synchronize()
+            except Exception:
+                gr = None
+        a.record()
+        if gr is not None:
+            gr.replay()
+        else:
+            for r in range(reps):
+                fn(r)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e3   # us per call
+
+    reps = 4 * CYC
+    rows = _lib.DfdFdRows(learner._row_ptr.data_ptr(), learner._row_coef.data_ptr(), learner._rows_cap)
+    minus1 = torch.full((M,), -1, dtype=torch.int32, device=dev)
+    from dfd_starter_b200.device import aligned_ptr
+    # CYC prepared row lists so consecutive reduce launches stream different table rows
+    rowsets = []
+    for c in range(CYC):
+        rp = torch.zeros(R + H, dtype=torch.int64, device=dev)
+        rc = torch.zeros(R + H, dtype=torch.float32, device=dev)
+        rs = _lib.DfdFdRows(rp.data_ptr(), rc.data_ptr(), R + H)
+        _lib.check(lib.dfd_fd_prepare(ctx.handle, table.device_table.ref(), P, ptr(reward_d), ptr(idx_d[c]), ptr(sign_d),
+                                      ptr(minus1), M, 1, 0.0, SIGMA, ptr(learner.dist), learner.Ps, 0, None, 0,
+                                      C.byref(rs), aligned_ptr(learner._prep_scratch), learner._prep_scratch.numel() - 256,
+                                      ctx.stream))
+        rowsets.append((rp, rc, rs))
+    grad_tmp = torch.empty(P, device=dev)
+
+    def k_forward(r):
+        policy.forward_members(idx_d[r % CYC], sign_d, obs_d[r % CYC], SIGMA, out=out_d)
+
+    def k_reduce(r):
+        _lib.check(lib.dfd_fd_reduce(ctx.handle, C.byref(rowsets[r % CYC][2]), R, P, ptr(grad_tmp),
+                                     aligned_ptr(learner._red_scratch), learner._red_scratch.numel() - 256, ctx.stream))
+
+    def k_prepare(r):
+        _lib.check(lib.dfd_fd_prepare(ctx.handle, table.device_table.ref(), P, ptr(reward_d), ptr(idx_d[r % CYC]),
+                                      ptr(sign_d), ptr(minus1), M, 1, 0.0, SIGMA, ptr(learner.dist), learner.Ps, 0, None,
+                                      0, C.byref(rows), aligned_ptr(learner._prep_scratch),
+                                      learner._prep_scratch.numel() - 256, ctx.stream))
+
+    us_forward = time_calls(k_forward, reps)
+    us_reduce = time_calls(k_reduce, reps)
+    us_prepare = time_calls(k_prepare, reps)
+    red_bytes = R * P * 4 + P * 4                       # rows*P*4 + P*4
+    fwd_bytes = R * P * 4 + M * E * w["n_in"] * 4 + M * E * w["out_width"] * 4
+    fwd_flops = M * E * layer_flops_per_obs(w)
+    kernels = {
+        "fd_reduce": {"us": us_reduce, "algorithmic_bytes": red_bytes, "achieved_GBps": red_bytes / us_reduce * 1e-3},
+        "policy_forward": {"us": us_forward, "algorithmic_bytes": fwd_bytes, "flops": fwd_flops,
+                           "achieved_GBps": fwd_bytes / us_forward * 1e-3, "achieved_TFLOPs": fwd_flops / us_forward * 1e-6},
+        "fd_prepare": {"us": us_prepare},
+    }
+    dominant = "policy_forward" if us_forward >= us_reduce else "fd_reduce"
+    dk = kernels[dominant]
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": dk["achieved_GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": dk["us"] / (ms_step * 1e3),
+                "fd_reduce": {"achieved": kernels["fd_reduce"]["achieved_GBps"], "frac": kernels["fd_reduce"]["achieved_GBps"] / hbm_peak,
+                              "us": us_reduce, "algorithmic_bytes": red_bytes}}
+
+    # ---------------- e2e through the reference-facing objects, host buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        class HostObsAgent(object):
+            """obs from pinned host memory every call; returns come back to the host."""
+            saved_states = []
+
+            def collect_returns(self, pol, m_idx, m_sign, sigma):
+                c = self.c
+                o = obs_host[c].to(dev, non_blocking=True)
+                i_d = torch.from_numpy(m_idx).to(dev, non_blocking=True)
+                s_d = torch.from_numpy(m_sign).to(dev, non_blocking=True)
+                pol.forward_members(i_d, s_d, o, sigma, out=out_d)
+                _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target),
+                                                    ptr(reward_d), ctx.stream))
+                rew = reward_d.cpu().numpy()
+                return {"reward": rew, "entropy": np.zeros(M), "timesteps": np.full(M, E), "states": None}
+        agent = HostObsAgent()
+        worker = D.Worker(policy, agent, table, None, sigma=SIGMA, eval_prob=0.0, random_seed=TABLE_SEED)
+        learner._host_policy = True          # mirror theta to the host every step, as the drivers need it
+        learner.policy = type("HostMirror", (), {"set_trainable_flat": staticmethod(lambda f: None)})()
+
+        def e2e_step(k):
+            agent.c = k % CYC
+            worker.epoch = learner.epoch
+            flags = np.zeros(R, dtype=bool)
+            idx = idx_sets[k % CYC]
+            rets = worker.evaluate(flags, idx, antithetic=True)
+            if world > 1:
+                allr = [None] * world
+                dist.all_gather_object(allr, np.array([r.reward for r in rets]))
+                epochs = np.full(M, learner.epoch, np.int64)
+                learner.step_arrays(epochs, np.concatenate([idx, idx]), sign_host.numpy(),
+                                    np.array([r.reward for r in rets]), 0.0, all_rewards=np.concatenate(allr))
+            else:
+                learner.step(rets, 0.0, 0.0, 0.0)
+        for k in range(3):
+            e2e_step(n_done + k)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n_e2e = max(3, min(args.steps, 30))
+        t0 = time.perf_counter()
+        for k in range(n_e2e):
+            e2e_step(n_done + 3 + k)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = obs_host[0].numel() * 4 + M * 8 + M + M * (8 + 8 + 4 + 1)
+        d2h = M * 8 + 4 + P * 4
+        e2e = {"value": M * E * world * n_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e,
+               "api": "Worker.evaluate -> FDReturn list -> FiniteDifferences.step (host observations, host returns, theta mirrored to host)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = M * E * world / (ms_step * 1e-3)
+    line = {
+        "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args, w),
+        "fd_estimates_per_s": 1e3 / ms_step,
+        "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
+        "roofline": roofline, "kernels": kernels, "e2e": e2e,
+        "gpu_launches": int(launches_plain if graphs is None else args.steps * LAUNCHES_PER_STEP),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                   "--obs-per-member", str(E), "--pairs", str(R), "--table-size", str(args.table_size), "--steps", "2",
+                   "--warmup", "1"]
+            outp = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                                  env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            ref = json.loads(outp.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+            line["cpu_baseline"]["fd_estimates_per_s"] = ref.get("fd_estimates_per_s")
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port",
+                                    "sample": "failed: %s" % e}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# forward, synthetic return, fd_coef, fd_reduce, sumsq, dsgd_update  (fd_return mode: no dots pass)
+LAUNCHES_PER_STEP = 6
+
+
+def main():
+    args = parse_args()
+    w = workload(args)
+    if args.impl == "reference":
+        reference_main(args, w)
+    else:
+        b200_main(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+// Shared helpers for the dfd_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/dfd_b200.h"
+
+struct dfd_ctx {
+    int device;
+    int sm_count;
+    int64_t launches;
+};
+
+void dfd_set_error(const char* fmt, ...);
+
+#define DFD_CHECK_ARG(cond, ...)          \
+    do {                                  \
+        if (!(cond)) {                    \
+            dfd_set_error(__VA_ARGS__);   \
+            return 1;                     \
+        }                                 \
+    } while (0)
+
+#define DFD_CUDA(call)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            dfd_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return 2;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+// after a kernel launch: catch launch-configuration errors without synchronising
+#define DFD_LAUNCHED(ctx)                                                                          \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t e__ = cudaPeekAtLastError();                                                   \
+        if (e__ != cudaSuccess) {                                                                  \
+            dfd_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return 3;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+static inline size_t dfd_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// 16-byte streaming load: read-only path, do not allocate in L1 (rows are touched once per kernel)
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// base pointer of table[idx : idx+P] inside the 16-byte aligned replica (idx & 3)
+__device__ __forceinline__ const float* table_row_ptr(const float* replicas, int64_t stride, int64_t idx) {
+    const int64_t s = idx & 3;
+    return replicas + s * stride + (idx - s);
+}
+
+// theta' = theta + sign*sigma*eps, bit-identical to numpy's `flat + sigma*eps`
+// (worker/worker.py:28): product rounded to fp32, then the sum rounded; never an FMA.
+__device__ __forceinline__ float perturb1(float theta, float sigma_signed, float eps) {
+    return __fadd_rn(theta, __fmul_rn(sigma_signed, eps));
+}

@@ -1,0 +1,510 @@
+// The estimator on the device: learner/finite_differences.py:24-114 and
+// dsgd/dynamic_sgd.py:18-39, as three hot calls (see include/dfd_b200.h).
+//
+//   g = sum_i w_i * lambda_i / ||lambda_i||^2,   lambda_i = s_i*sigma*eps_i + d_{e_i}
+//
+// is evaluated as ONE streaming pass  g[p] = sum_r coef_r * row_r[p]  over a row
+// list (table rows + the few theta-history distance rows).  The row norms come
+// from an fp64 prefix sum of squares of the table (two loads per row) plus, for
+// returns from older epochs only, eps_i . d_e dot products (a first pass over
+// just those rows).  The reduction is HBM-bound: rows*P*4 bytes in, P*4 out.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------
+// (1) prepare: dots for delayed rows, then coefficients + row list
+// ---------------------------------------------------------------------------
+static const int DOT_CHUNK = 8192;  // columns per CTA in the dots pass
+static const int DOT_THREADS = 256;
+
+// layout of the prepare scratch (doubles): dot[n_returns] | dd[n_hist]
+extern "C" size_t dfd_fd_prepare_scratch_bytes(int n_returns, int n_hist) {
+    return dfd_align_up((size_t)(n_returns + n_hist) * sizeof(double), 256);
+}
+
+// blockIdx.y < n_returns: dot of table row i with its dist row (skipped when hist_row < 0)
+// blockIdx.y >= n_returns: ||dist row||^2
+__global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __restrict__ replicas, int64_t stride,
+                                                              const int64_t* __restrict__ idx,
+                                                              const int32_t* __restrict__ hist_row, int n_returns,
+                                                              const float* __restrict__ dist, int64_t dist_stride,
+                                                              int64_t P, double* __restrict__ out) {
+    __shared__ double sh[DOT_THREADS / 32];
+    const int r = blockIdx.y;
+    const float* a;
+    const float* b;
+    if (r < n_returns) {
+        const int h = hist_row[r];
+        if (h < 0) return;
+        a = table_row_ptr(replicas, stride, idx[r]);
+        b = dist + (int64_t)h * dist_stride;
+    } else {
+        a = b = dist + (int64_t)(r - n_returns) * dist_stride;
+    }
+    const int64_t c0 = (int64_t)blockIdx.x * DOT_CHUNK;
+    const int64_t c1 = min(c0 + (int64_t)DOT_CHUNK, P);
+    double acc = 0.0;
+    // both bases are 16-byte aligned (replica rows by construction, dist rows because dist_stride % 4 == 0)
+    const int64_t v1 = c0 + ((c1 - c0) & ~(int64_t)3);
+    for (int64_t c = c0 + 4 * threadIdx.x; c < v1; c += 4 * DOT_THREADS) {
+        const float4 x = ldg_stream_f4(a + c);
+        const float4 y = *reinterpret_cast<const float4*>(b + c);
+        float s = x.x * y.x;
+        s = fmaf(x.y, y.y, s);
+        s = fmaf(x.z, y.z, s);
+        s = fmaf(x.w, y.w, s);
+        acc += (double)s;
+    }
+    for (int64_t c = v1 + threadIdx.x; c < c1; c += DOT_THREADS) acc += (double)a[c] * (double)b[c];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < DOT_THREADS / 32; ++i) t += sh[i];
+        atomicAdd(out + r, t);
+    }
+}
+
+__device__ __forceinline__ double block_reduce_d(double v, double* sh, int op /*0 sum,1 min,2 max*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double y = __shfl_xor_sync(0xffffffffu, v, o);
+        v = op == 0 ? v + y : (op == 1 ? fmin(v, y) : fmax(v, y));
+    }
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = sh[0];
+    for (int i = 1; i < nw; ++i) t = op == 0 ? t + sh[i] : (op == 1 ? fmin(t, sh[i]) : fmax(t, sh[i]));
+    return t;
+}
+
+// single CTA.  standardize_arr (utils/math_helpers.py:127-134): population std, identity when std == 0.
+__global__ void __launch_bounds__(1024) fd_coef_kernel(const float* __restrict__ replicas, int64_t stride,
+                                                       const double* __restrict__ prefix, int64_t P,
+                                                       const double* __restrict__ reward,
+                                                       const int64_t* __restrict__ idx,
+                                                       const int8_t* __restrict__ sign,
+                                                       const int32_t* __restrict__ hist_row, int n, int paired,
+                                                       double baseline, float sigma, const float* __restrict__ dist,
+                                                       int64_t dist_stride, int n_hist,
+                                                       const double* __restrict__ stats_reward, int n_stats,
+                                                       const double* __restrict__ dots, const float** row_ptr,
+                                                       float* __restrict__ row_coef) {
+    __shared__ double sh[32];
+    __shared__ double q_hist[128];  // n_hist <= 128
+    const double* sr = stats_reward ? stats_reward : reward;
+    const int ns = stats_reward ? n_stats : n;
+    // finite_differences.py:40  rewards - policy_reward ; :43 standardize
+    double s = 0.0, mn = 1e300, mx = -1e300;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const double x = sr[i] - baseline;
+        s += x;
+        mn = fmin(mn, x);
+        mx = fmax(mx, x);
+    }
+    const double mean = block_reduce_d(s, sh, 0) / (double)ns;
+    mn = block_reduce_d(mn, sh, 1);
+    mx = block_reduce_d(mx, sh, 2);
+    double v = 0.0;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const double d = (sr[i] - baseline) - mean;
+        v += d * d;
+    }
+    double sd = sqrt(block_reduce_d(v, sh, 0) / (double)ns);
+    if (mn == mx) sd = 0.0;  // all rewards equal: numpy's std is exactly 0 and the array passes through
+    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) q_hist[h] = 0.0;
+    __syncthreads();
+
+    const double sig = (double)sigma;
+    const double* dd = dots + n;
+    const int R = paired ? n / 2 : n;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        double c = 0.0;
+        for (int k = 0; k < (paired ? 2 : 1); ++k) {
+            const int i = r + k * R;
+            const double x = reward[i] - baseline;
+            const double w = sd == 0.0 ? x : (x - mean) / sd;
+            const int64_t id = idx[i];
+            const double sg = (double)sign[i];
+            double n2 = sig * sig * (prefix[id + P] - prefix[id]);
+            const int h = hist_row[i];
+            if (h >= 0) n2 += 2.0 * sg * sig * dots[i] + dd[h];
+            const double winv = w / n2;
+            c += winv * sg * sig;
+            if (h >= 0) atomicAdd(&q_hist[h], winv);
+        }
+        row_ptr[r] = table_row_ptr(replicas, stride, idx[r]);
+        row_coef[r] = (float)c;
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) {
+        row_ptr[R + h] = dist + (int64_t)h * dist_stride;
+        row_coef[R + h] = (float)q_hist[h];
+    }
+}
+
+extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward,
+                              const int64_t* idx, const int8_t* sign, const int32_t* hist_row, int n_returns,
+                              int paired, double baseline, float sigma, const float* dist, int64_t dist_stride,
+                              int n_hist, const double* stats_reward, int n_stats, dfd_fd_rows* rows, void* scratch,
+                              size_t scratch_bytes, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && table && reward && idx && sign && hist_row && rows && scratch, "dfd_fd_prepare: NULL argument");
+    DFD_CHECK_ARG(n_returns > 0, "dfd_fd_prepare: empty batch (the host returns 0 before calling, finite_differences.py:30-31)");
+    DFD_CHECK_ARG(!paired || (n_returns % 2) == 0, "dfd_fd_prepare: paired mode needs an even number of returns");
+    DFD_CHECK_ARG(n_hist >= 0 && n_hist <= 128, "dfd_fd_prepare: n_hist %d out of range (0..128)", n_hist);
+    DFD_CHECK_ARG(n_hist == 0 || (dist && dist_stride >= n_params && dist_stride % 4 == 0 && ((uintptr_t)dist & 15) == 0),
+                  "dfd_fd_prepare: dist must be 16-byte aligned with a stride that is a multiple of 4 floats");
+    DFD_CHECK_ARG(n_params > 0 && n_params < table->size, "dfd_fd_prepare: n_params out of range");
+    const int R = paired ? n_returns / 2 : n_returns;
+    DFD_CHECK_ARG(rows->max_rows >= R + n_hist, "dfd_fd_prepare: row list too small (%d < %d)", rows->max_rows, R + n_hist);
+    DFD_CHECK_ARG(scratch_bytes >= dfd_fd_prepare_scratch_bytes(n_returns, n_hist), "dfd_fd_prepare: scratch too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dots = (double*)scratch;
+    if (n_hist > 0) {
+        DFD_CUDA(cudaMemsetAsync(dots, 0, (size_t)(n_returns + n_hist) * sizeof(double), st));
+        dim3 grid((unsigned)((n_params + DOT_CHUNK - 1) / DOT_CHUNK), (unsigned)(n_returns + n_hist));
+        fd_dots_kernel<<<grid, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
+                                                     dist, dist_stride, n_params, dots);
+        DFD_LAUNCHED(ctx);
+    }
+    fd_coef_kernel<<<1, 1024, 0, st>>>(table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx,
+                                       sign, hist_row, n_returns, paired, baseline, sigma, dist, dist_stride, n_hist,
+                                       stats_reward, n_stats, dots, rows->row_ptr, rows->row_coef);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (2) the streaming reduction  g[p] = sum_r coef[r] * row[r][p]
+// ---------------------------------------------------------------------------
+// CTA = RW warps; every warp owns the same 32*4*VPT-column tile and a different
+// slice of the CTA's row range; lanes load 16-byte vectors (rows are 16-byte
+// aligned by the replica construction), U rows in flight per lane.  Warps are
+// combined through shared memory; row-split CTAs of a column tile are combined
+// by the last CTA to finish (fixed order -> run-to-run deterministic).
+static const int RED_WARPS = 8;
+static const int RED_THREADS = RED_WARPS * 32;
+static const int RED_U = 8;
+
+template <int VPT>
+__global__ void __launch_bounds__(RED_THREADS) fd_reduce_kernel(const float* const* __restrict__ row_ptr,
+                                                                const float* __restrict__ row_coef, int n_rows,
+                                                                int64_t P, int rows_per_cta, int n_splits,
+                                                                float* __restrict__ partial, int64_t partial_stride,
+                                                                unsigned* __restrict__ counters,
+                                                                float* __restrict__ grad) {
+    constexpr int TILE = 128 * VPT;
+    __shared__ float4 sm[RED_WARPS][VPT][32];
+    __shared__ unsigned ticket_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * TILE + 4 * lane;
+    const int split = blockIdx.y;
+    const int r_begin = split * rows_per_cta;
+    const int r_end = min(r_begin + rows_per_cta, n_rows);
+
+    float4 acc[VPT];
+    bool active[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+        acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        active[v] = (col0 + 128 * v) < P;
+    }
+
+    // the CTA's rows are split evenly over its warps; each warp walks its slice in batches of 32
+    // (row pointer / coefficient fetched once per batch, one per lane, then broadcast by shuffle)
+    const int rpw = (r_end - r_begin + RED_WARPS - 1) / RED_WARPS;
+    const int w_begin = r_begin + warp * rpw;
+    const int w_end = min(w_begin + rpw, r_end);
+    for (int rb = w_begin; rb < w_end; rb += 32) {
+        const int my = rb + lane;
+        const float* pl = my < w_end ? row_ptr[my] : nullptr;
+        const float cl = my < w_end ? row_coef[my] : 0.f;
+        const int cnt = min(32, w_end - rb);
+        for (int j0 = 0; j0 < cnt; j0 += RED_U) {
+            float4 x[RED_U][VPT];
+            float c[RED_U];
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+                const int j = j0 + u;
+                const float* p = (const float*)__shfl_sync(0xffffffffu, (unsigned long long)pl, j & 31);
+                c[u] = __shfl_sync(0xffffffffu, cl, j & 31);
+                const bool ok = j < cnt;
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    if (ok && active[v])
+                        x[u][v] = ldg_stream_f4(p + col0 + 128 * v);
+                    else
+                        x[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (!ok) c[u] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RED_U; ++u) {
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    acc[v].x = fmaf(c[u], x[u][v].x, acc[v].x);
+                    acc[v].y = fmaf(c[u], x[u][v].y, acc[v].y);
+                    acc[v].z = fmaf(c[u], x[u][v].z, acc[v].z);
+                    acc[v].w = fmaf(c[u], x[u][v].w, acc[v].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) sm[warp][v][lane] = acc[v];
+    __syncthreads();
+    // threads 0..32*VPT-1 combine the warps for one float4 each
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int v_me = threadIdx.x >> 5, l_me = threadIdx.x & 31;
+    const bool combiner = threadIdx.x < 32 * VPT;
+    const int64_t colc = (int64_t)blockIdx.x * TILE + 128 * v_me + 4 * l_me;
+    if (combiner) {
+#pragma unroll
+        for (int w = 0; w < RED_WARPS; ++w) {
+            const float4 t = sm[w][v_me][l_me];
+            tot.x += t.x;
+            tot.y += t.y;
+            tot.z += t.z;
+            tot.w += t.w;
+        }
+    }
+    if (n_splits == 1) {
+        if (combiner && colc < P) {
+            if (colc + 3 < P && (((uintptr_t)grad) & 15) == 0)
+                *reinterpret_cast<float4*>(grad + colc) = tot;
+            else {
+                const float t[4] = {tot.x, tot.y, tot.z, tot.w};
+                for (int k = 0; k < 4 && colc + k < P; ++k) grad[colc + k] = t[k];
+            }
+        }
+        return;
+    }
+    // partial_stride is a multiple of 4 and covers whole tiles, so vector stores are always in range
+    if (combiner) *reinterpret_cast<float4*>(partial + (int64_t)split * partial_stride + colc) = tot;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_s = atomicAdd(counters + blockIdx.x, 1u);
+    __syncthreads();
+    if (ticket_s != (unsigned)(n_splits - 1)) return;
+    __threadfence();
+    if (combiner) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_splits; ++s) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(partial + (int64_t)s * partial_stride + colc));
+            g.x += t.x;
+            g.y += t.y;
+            g.z += t.z;
+            g.w += t.w;
+        }
+        const float t[4] = {g.x, g.y, g.z, g.w};
+        for (int k = 0; k < 4 && colc + k < P; ++k) grad[colc + k] = t[k];
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;  // ready for the next launch
+}
+
+struct RedPlan {
+    int vpt, tiles, splits, rows_per_cta;
+    int64_t partial_stride;
+};
+
+static RedPlan red_plan(int sm_count, int64_t P, int n_rows) {
+    RedPlan p;
+    // wide rows: 256 columns per warp (1 KB contiguous per row per warp); narrow rows: 128
+    p.vpt = (P >= (int64_t)sm_count * 8 * 256) ? 2 : 1;
+    const int tile = 128 * p.vpt;
+    p.tiles = (int)((P + tile - 1) / tile);
+    // aim at ~8 resident CTAs per SM worth of CTAs, but keep >= 32 rows per warp-batch where possible
+    const int target = sm_count * 8;
+    int splits = (target + p.tiles - 1) / p.tiles;
+    const int max_splits = (n_rows + RED_WARPS * 4 - 1) / (RED_WARPS * 4);  // >= 4 rows per warp
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.rows_per_cta = (n_rows + splits - 1) / splits;
+    p.splits = (n_rows + p.rows_per_cta - 1) / p.rows_per_cta;
+    p.partial_stride = (int64_t)p.tiles * tile;
+    return p;
+}
+
+extern "C" size_t dfd_fd_reduce_scratch_bytes(const dfd_ctx* ctx, int64_t n_params, int n_rows) {
+    if (!ctx || n_params <= 0 || n_rows <= 0) return 256;
+    const RedPlan p = red_plan(ctx->sm_count, n_params, n_rows);
+    const size_t counters = dfd_align_up((size_t)p.tiles * sizeof(unsigned), 256);
+    const size_t partial = p.splits > 1 ? (size_t)p.splits * p.partial_stride * sizeof(float) : 0;
+    return counters + dfd_align_up(partial, 256) + 256;
+}
+
+extern "C" int dfd_fd_reduce(dfd_ctx* ctx, const dfd_fd_rows* rows, int n_rows, int64_t n_params, float* grad,
+                             void* scratch, size_t scratch_bytes, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && rows && rows->row_ptr && rows->row_coef && grad && scratch, "dfd_fd_reduce: NULL argument");
+    DFD_CHECK_ARG(n_rows > 0 && n_rows <= rows->max_rows, "dfd_fd_reduce: n_rows %d out of range", n_rows);
+    DFD_CHECK_ARG(n_params > 0, "dfd_fd_reduce: n_params must be positive");
+    DFD_CHECK_ARG(((uintptr_t)scratch & 255) == 0, "dfd_fd_reduce: scratch must be 256-byte aligned");
+    DFD_CHECK_ARG(scratch_bytes >= dfd_fd_reduce_scratch_bytes(ctx, n_params, n_rows), "dfd_fd_reduce: scratch too small");
+    const RedPlan p = red_plan(ctx->sm_count, n_params, n_rows);
+    // the tile counters must be zero on entry; they are self-resetting, the caller zeroes scratch once at allocation
+    unsigned* counters = (unsigned*)scratch;
+    float* partial = (float*)((char*)scratch + dfd_align_up((size_t)p.tiles * sizeof(unsigned), 256));
+    dim3 grid(p.tiles, p.splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.vpt == 2)
+        fd_reduce_kernel<2><<<grid, RED_THREADS, 0, st>>>(rows->row_ptr, rows->row_coef, n_rows, n_params,
+                                                          p.rows_per_cta, p.splits, partial, p.partial_stride,
+                                                          counters, grad);
+    else
+        fd_reduce_kernel<1><<<grid, RED_THREADS, 0, st>>>(rows->row_ptr, rows->row_coef, n_rows, n_params,
+                                                          p.rows_per_cta, p.splits, partial, p.partial_stride,
+                                                          counters, grad);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// (3) DSGD + theta-history / distance rows
+// ---------------------------------------------------------------------------
+static const int DSGD_THREADS = 256;
+static const int DSGD_MAX_CTAS = 592;
+
+extern "C" size_t dfd_dsgd_scratch_bytes(int64_t n_params) {
+    (void)n_params;
+    return dfd_align_up((size_t)(2 * DSGD_MAX_CTAS + 8) * sizeof(double), 256);
+}
+
+__global__ void __launch_bounds__(DSGD_THREADS) sumsq_partial_kernel(const float* __restrict__ g, int64_t P,
+                                                                     double* __restrict__ partial) {
+    __shared__ double sh[DSGD_THREADS / 32];
+    double acc = 0.0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const double x = (double)g[p];
+        acc += x * x;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < DSGD_THREADS / 32; ++i) t += sh[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+// dynamic_sgd.py:27-37: the learner hands grad = -g, DSGD does p -= coef*grad, coef = lr*sqrt(P)*lr_scale/||grad||.
+// theta_new = theta - fl(coef * (-g)) in fp32 like torch; dist rows and the ring slot are refreshed in the same pass.
+__global__ void __launch_bounds__(DSGD_THREADS) dsgd_update_kernel(float* __restrict__ theta,
+                                                                   const float* __restrict__ g, int64_t P, double step,
+                                                                   const double* __restrict__ gnorm_partial,
+                                                                   int n_partial, float* __restrict__ hist,
+                                                                   float* __restrict__ dist, int64_t hist_stride,
+                                                                   int n_hist_valid, int hist_write_row,
+                                                                   double* __restrict__ upd_partial,
+                                                                   unsigned* __restrict__ done_counter,
+                                                                   float* __restrict__ update_size_out) {
+    __shared__ double sh[DSGD_THREADS / 32];
+    __shared__ float coef_s;
+    __shared__ unsigned ticket_s;
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < n_partial; i += 32) t += gnorm_partial[i];
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            const double norm = sqrt(t);
+            // a zero gradient trips `assert norm > 0` in the reference; here the step degenerates to no update
+            coef_s = norm > 0.0 ? (float)(step / norm) : 0.f;
+        }
+    }
+    __syncthreads();
+    const float coef = coef_s;
+    double acc = 0.0;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const float t_old = theta[p];
+        const float t_new = __fsub_rn(t_old, __fmul_rn(coef, -g[p]));
+        theta[p] = t_new;
+        const float d = __fsub_rn(t_old, t_new);
+        acc += (double)d * (double)d;
+        for (int r = 0; r < n_hist_valid; ++r)
+            dist[(int64_t)r * hist_stride + p] = __fsub_rn(hist[(int64_t)r * hist_stride + p], t_new);
+        if (hist_write_row >= 0) hist[(int64_t)hist_write_row * hist_stride + p] = t_new;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < DSGD_THREADS / 32; ++i) t += sh[i];
+        upd_partial[blockIdx.x] = t;
+        __threadfence();
+        ticket_s = atomicAdd(done_counter, 1u);
+    }
+    __syncthreads();
+    if (ticket_s != gridDim.x - 1) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(upd_partial + i);
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            *update_size_out = (float)sqrt(t);
+            *done_counter = 0;
+        }
+    }
+}
+
+extern "C" int dfd_dsgd_step(dfd_ctx* ctx, float* theta, const float* grad, int64_t n_params, double lr, double lr_scale,
+                             float* hist, float* dist, int64_t hist_stride, int n_hist_valid, int hist_write_row,
+                             float* update_size_out, void* scratch, size_t scratch_bytes, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && theta && grad && update_size_out && scratch, "dfd_dsgd_step: NULL argument");
+    DFD_CHECK_ARG(n_params > 0, "dfd_dsgd_step: n_params must be positive");
+    DFD_CHECK_ARG(scratch_bytes >= dfd_dsgd_scratch_bytes(n_params), "dfd_dsgd_step: scratch too small");
+    DFD_CHECK_ARG((n_hist_valid == 0 && hist_write_row < 0) || (hist && dist && hist_stride >= n_params),
+                  "dfd_dsgd_step: history buffers missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    int ctas = (int)((n_params + DSGD_THREADS * 4 - 1) / (DSGD_THREADS * 4));
+    if (ctas > DSGD_MAX_CTAS) ctas = DSGD_MAX_CTAS;
+    if (ctas < 1) ctas = 1;
+    double* gpart = (double*)scratch;
+    double* upart = gpart + DSGD_MAX_CTAS;
+    unsigned* counter = (unsigned*)(upart + DSGD_MAX_CTAS);  // zero on entry (self-resetting)
+    sumsq_partial_kernel<<<ctas, DSGD_THREADS, 0, st>>>(grad, n_params, gpart);
+    DFD_LAUNCHED(ctx);
+    // dynamic_sgd.py:30  coef = lr * sqrt(d) * lr_scale / norm  (python floats = fp64)
+    const double step = lr * sqrt((double)n_params) * lr_scale;
+    dsgd_update_kernel<<<ctas, DSGD_THREADS, 0, st>>>(theta, grad, n_params, step, gpart, ctas, hist, dist, hist_stride,
+                                                      n_hist_valid, hist_write_row, upart, counter, update_size_out);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic return (stand-in for the environment, which is outside this path):
+// reward[m] = -mean_{e,j} (out[m,e,j] - target[j])^2, fp64, one CTA per member
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) synthetic_reward_kernel(const float* __restrict__ out, int per_member, int width,
+                                                               const float* __restrict__ target,
+                                                               double* __restrict__ reward) {
+    __shared__ double sh[8];
+    const float* o = out + (int64_t)blockIdx.x * per_member;
+    double acc = 0.0;
+    for (int t = threadIdx.x; t < per_member; t += 256) {
+        const float d = o[t] - target[t % width];
+        acc += (double)d * (double)d;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += sh[i];
+        reward[blockIdx.x] = -t / (double)per_member;
+    }
+}
+
+extern "C" int dfd_synthetic_reward(dfd_ctx* ctx, const float* out, int n_members, int obs_per_member, int out_width,
+                                    const float* target, double* reward, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && out && target && reward, "dfd_synthetic_reward: NULL argument");
+    if (n_members <= 0) return 0;
+    synthetic_reward_kernel<<<n_members, 256, 0, (cudaStream_t)stream>>>(out, obs_per_member * out_width, out_width,
+                                                                         target, reward);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}

@@ -1,0 +1,295 @@
+"""`FiniteDifferences` with the reference's constructor and `step` contract
+(learner/finite_differences.py:6-114), evaluated on the device.
+
+    learner = FiniteDifferences(policy, gradient_optimizer, omega, noise_source,
+                                noise_std=0.1, batch_size=100, ent_coef=0.0, max_delayed_return=10)
+    update_size = learner.step(batch, policy_reward, policy_novelty, policy_entropy)
+
+`batch` is a list of FDReturn-like objects (fields epoch, encoded_noise, reward).
+Host logic kept here: the epoch acceptance test (:80-85), key parsing, the ring
+bookkeeping of theta-history rows.  Device work (three C-ABI calls, no host
+synchronisation between them): dfd_fd_prepare -> dfd_fd_reduce -> [one NCCL
+allreduce of P floats when the population is sharded] -> dfd_dsgd_step.
+
+`policy` may be one of this package's device policies or any object with the
+reference's `get_trainable_flat/set_trainable_flat/num_params` (e.g. a reference
+`Policy`); in the second case theta is mirrored back to it after every step
+because the drivers serialise it next (run_server.py:192-197).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import get_context, ptr, aligned_ptr
+from .dsgd import is_dsgd
+from .noise_sources import parse_key
+
+
+class _Staging(object):
+    """Pinned host + device staging for one batch: rewards f64 | idx i64 | hist_row i32 | sign i8."""
+
+    def __init__(self, device, cap):
+        self.cap = cap
+        nbytes = cap * (8 + 8 + 4 + 1)
+        self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        o = 0
+        self.views = {}
+        for name, dt, sz in (("reward", torch.float64, 8), ("idx", torch.int64, 8), ("hist_row", torch.int32, 4),
+                             ("sign", torch.int8, 1)):
+            self.views[name] = (self.host[o:o + cap * sz].view(dt), self.dev[o:o + cap * sz].view(dt))
+            o += cap * sz
+
+    def upload(self, n, **arrays):
+        for k, a in arrays.items():
+            self.views[k][0][:n].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        self.dev.copy_(self.host, non_blocking=True)
+        return {k: v[1] for k, v in self.views.items()}
+
+
+class FiniteDifferences(object):
+    def __init__(self, policy, gradient_optimizer, omega, noise_source, noise_std=0.1, batch_size=100, ent_coef=0.0,
+                 max_delayed_return=10, paired=False, process_group=None, device=None, sync_policy=True):
+        self.max_delayed_return = max_delayed_return
+        self.ent_coef = ent_coef
+        self.noise_std = noise_std
+        self.policy = policy
+        self.gradient_optimizer = gradient_optimizer
+        self.noise_source = noise_source
+        self.omega = omega
+        self.paired = paired                    # extension: batch = [R plus-members | R minus-members]
+        self.process_group = process_group      # extension: population sharded over ranks, one allreduce per step
+        self.sync_policy = sync_policy
+        self.using_dsgd = is_dsgd(gradient_optimizer)
+
+        self.ctx = get_context(device if device is not None else getattr(getattr(policy, "ctx", None), "device", None))
+        self.lib = self.ctx.lib
+        dev = self.ctx.device
+        self.table = noise_source.device_table
+        P = int(policy.num_params)
+        self.P = P
+        self.Ps = (P + 3) // 4 * 4              # row stride of history / dist rows (16-byte aligned rows)
+        H = max(int(max_delayed_return), 1)
+        self.H = H
+
+        # theta lives on the device; share the policy's tensor when it has one
+        if hasattr(policy, "theta") and torch.is_tensor(policy.theta) and policy.theta.is_cuda:
+            self.theta = policy.theta
+            self._host_policy = False
+        else:
+            self.theta = torch.from_numpy(np.asarray(policy.get_trainable_flat(), dtype=np.float32).copy()).to(dev)
+            self._host_policy = True
+        self.grad = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.hist = torch.zeros(H, self.Ps, dtype=torch.float32, device=dev)
+        self.dist = torch.zeros(H, self.Ps, dtype=torch.float32, device=dev)
+        self.hist[0, :P].copy_(self.theta)                       # policy_history = [(theta0, 0)]   (:16)
+        self._hist_epoch = [0]                                   # epoch held by each ring row
+        self._dist_epoch = {}                                    # epoch -> dist row (delayed epochs only)
+        self.epoch = 0
+        self.discarded_returns = 0
+        self._update_size = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._update_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._theta_host = torch.zeros(P, dtype=torch.float32).pin_memory()
+        self._stage = None
+        self._rows_cap = 0
+        self._dsgd_scratch = self.ctx.zeros_bytes(self.lib.dfd_dsgd_scratch_bytes(P))
+        self._ensure_capacity(max(int(batch_size), 1))
+
+    # ------------------------------------------------------------------ buffers
+    def _ensure_capacity(self, n):
+        if self._stage is not None and n <= self._stage.cap:
+            return
+        cap = max(n, 16)
+        dev = self.ctx.device
+        self._stage = _Staging(dev, cap)
+        self._rows_cap = cap + self.H
+        self._row_ptr = torch.zeros(self._rows_cap, dtype=torch.int64, device=dev)
+        self._row_coef = torch.zeros(self._rows_cap, dtype=torch.float32, device=dev)
+        self._rows = _lib.DfdFdRows(self._row_ptr.data_ptr(), self._row_coef.data_ptr(), self._rows_cap)
+        self._prep_scratch = self.ctx.zeros_bytes(self.lib.dfd_fd_prepare_scratch_bytes(cap, self.H))
+        self._red_scratch = self.ctx.zeros_bytes(self.lib.dfd_fd_reduce_scratch_bytes(self.ctx.handle, self.P, self._rows_cap))
+        self._red_scratch_rows = self._rows_cap
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def gradient_memory(self):
+        """fp64 copy of the last gradient (finite_differences.py:20,49)."""
+        return self.grad.double().cpu().numpy()
+
+    @property
+    def dist_map(self):
+        """Accepted epochs -> ring row (the reference maps epoch -> theta_e - theta_now)."""
+        m = {e: r for e, r in self._dist_epoch.items()}
+        m[self.epoch] = -1
+        return m
+
+    @property
+    def policy_history(self):
+        return [(self.hist[r, :self.P].cpu().numpy(), e) for r, e in
+                sorted(enumerate(self._hist_epoch), key=lambda t: t[1])]
+
+    # ------------------------------------------------------------------ the step
+    def step(self, batch, policy_reward, policy_novelty=None, policy_entropy=None):
+        epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
+        rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
+        keys = [parse_key(r.encoded_noise) for r in batch]
+        idx = np.fromiter((k[0] for k in keys), dtype=np.int64, count=len(batch))
+        sign = np.fromiter((k[1] for k in keys), dtype=np.int8, count=len(batch))
+        return self.step_arrays(epochs, idx, sign, rewards, policy_reward)
+
+    def step_arrays(self, epochs, idx, sign, rewards, policy_reward, all_rewards=None):
+        """SoA form of `step`: int64 epochs/idx, int8 sign, float64 rewards (host arrays).
+        all_rewards: with a process group, the rewards of ALL ranks' accepted returns (the
+        standardisation is global); gathered here when omitted."""
+        epochs = np.asarray(epochs, dtype=np.int64)
+        n_in = epochs.shape[0]
+        # finite_differences.py:80-85: a return is usable iff its epoch is still in the distance map
+        hist_row = np.full(n_in, -2, dtype=np.int32)
+        hist_row[epochs == self.epoch] = -1
+        for e, r in self._dist_epoch.items():
+            hist_row[epochs == e] = r
+        keep = hist_row > -2
+        n_bad = int(n_in - keep.sum())
+        if n_bad:
+            for e in epochs[~keep]:
+                print("FINITE DIFFERENCE LEARNER RECEIVED RETURN THAT WAS TOO OLD")
+                print("RECEIVED EPOCH:", int(e), "ACCEPTABLE EPOCHS:", self.dist_map.keys())
+            self.discarded_returns += n_bad
+            if self.paired:
+                # keep pairs intact: drop both members of a pair if either is unusable
+                R = n_in // 2
+                pk = keep[:R] & keep[R:2 * R]
+                keep = np.concatenate([pk, pk])
+        if policy_reward is None:
+            policy_reward = 0
+        idx = np.asarray(idx, dtype=np.int64)[keep]
+        sign = np.asarray(sign, dtype=np.int8)[keep]
+        rewards = np.asarray(rewards, dtype=np.float64)[keep]
+        hist_row = hist_row[keep]
+        n = idx.shape[0]
+        pg = self.process_group
+        if pg is None and n == 0:
+            return 0                                             # :30-31, no update, epoch unchanged
+        stats = None
+        if pg is not None:
+            import torch.distributed as dist
+            if all_rewards is None:
+                gathered = [None] * dist.get_world_size(pg)
+                dist.all_gather_object(gathered, rewards, group=pg)
+                all_rewards = np.concatenate(gathered)
+            if all_rewards.shape[0] == 0:
+                return 0
+            stats = torch.from_numpy(np.ascontiguousarray(all_rewards, dtype=np.float64)).to(self.ctx.device)
+
+        self._ensure_capacity(n)
+        st = self.ctx.stream
+        n_hist = len(self._dist_epoch) and (max(self._dist_epoch.values()) + 1)
+        if n > 0:
+            d = self._stage.upload(n, reward=rewards, idx=idx, hist_row=hist_row, sign=sign)
+            paired = 1 if (self.paired and n % 2 == 0) else 0
+            _lib.check(self.lib.dfd_fd_prepare(
+                self.ctx.handle, self.table.ref(), self.P, ptr(d["reward"]), ptr(d["idx"]), ptr(d["sign"]),
+                ptr(d["hist_row"]), n, paired, float(policy_reward), float(self.noise_std), ptr(self.dist), self.Ps,
+                int(n_hist), ptr(stats), 0 if stats is None else int(stats.shape[0]), C.byref(self._rows),
+                aligned_ptr(self._prep_scratch), self._prep_scratch.numel() - 256, st), "dfd_fd_prepare")
+            n_rows = (n // 2 if paired else n) + int(n_hist)
+            _lib.check(self.lib.dfd_fd_reduce(
+                self.ctx.handle, C.byref(self._rows), n_rows, self.P, ptr(self.grad),
+                aligned_ptr(self._red_scratch), self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
+        else:
+            self.grad.zero_()
+        if pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=pg)     # the one parameter-sized exchange
+        return self._apply_update()
+
+    def step_device(self, idx_d, sign_d, reward_d, n, policy_reward=0.0, hist_row_d=None, stats_d=None):
+        """Device-resident SoA step (no host synchronisation, CUDA-graph capturable): the n returns
+        are already in HBM as int64 idx / int8 sign / float64 reward (and optional int32 hist_row;
+        default: all from the current epoch).  DSGD only.  Returns nothing; `last_update_size()`
+        reads the update magnitude back when wanted."""
+        if not self.using_dsgd:
+            raise _lib.DfdError("step_device needs the DSGD optimizer")
+        self._ensure_capacity(n)
+        st = self.ctx.stream
+        if hist_row_d is None:
+            if getattr(self, "_minus1", None) is None or self._minus1.shape[0] < n:
+                self._minus1 = torch.full((max(n, 16),), -1, dtype=torch.int32, device=self.ctx.device)
+            hist_row_d, n_hist = self._minus1, 0
+        else:
+            n_hist = len(self._dist_epoch) and (max(self._dist_epoch.values()) + 1)
+        paired = 1 if (self.paired and n % 2 == 0) else 0
+        _lib.check(self.lib.dfd_fd_prepare(
+            self.ctx.handle, self.table.ref(), self.P, ptr(reward_d), ptr(idx_d), ptr(sign_d), ptr(hist_row_d), n,
+            paired, float(policy_reward), float(self.noise_std), ptr(self.dist), self.Ps, int(n_hist), ptr(stats_d),
+            0 if stats_d is None else int(stats_d.shape[0]), C.byref(self._rows), aligned_ptr(self._prep_scratch),
+            self._prep_scratch.numel() - 256, st), "dfd_fd_prepare")
+        n_rows = (n // 2 if paired else n) + int(n_hist)
+        _lib.check(self.lib.dfd_fd_reduce(
+            self.ctx.handle, C.byref(self._rows), n_rows, self.P, ptr(self.grad), aligned_ptr(self._red_scratch),
+            self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.process_group)
+        self._apply_update(sync=False)
+
+    def last_update_size(self):
+        return float(self._update_size.cpu()[0])
+
+    # ------------------------------------------------------------------ optimizer + history
+    def _ring_write_row(self):
+        if len(self._hist_epoch) < self.H:
+            return len(self._hist_epoch)
+        return int(np.argmin(self._hist_epoch))
+
+    def _apply_update(self, sync=True):
+        st = self.ctx.stream
+        n_valid = len(self._hist_epoch)
+        write_row = self._ring_write_row()
+        if self.using_dsgd:
+            self.gradient_optimizer.adjust_lr(self.omega)                    # :51-52
+            lr, lr_scale = float(self.gradient_optimizer.lr), float(self.gradient_optimizer.lr_scale)
+            _lib.check(self.lib.dfd_dsgd_step(
+                self.ctx.handle, ptr(self.theta), ptr(self.grad), self.P, lr, lr_scale, ptr(self.hist), ptr(self.dist),
+                self.Ps, n_valid, write_row, ptr(self._update_size), aligned_ptr(self._dsgd_scratch),
+                self._dsgd_scratch.numel() - 256, st), "dfd_dsgd_step")
+            if hasattr(self.gradient_optimizer, "steps"):
+                self.gradient_optimizer.steps += 1
+            if not sync:
+                return self._advance_epoch(write_row, None)
+            self._update_host.copy_(self._update_size, non_blocking=True)
+            if self._host_policy and self.sync_policy:
+                self._theta_host.copy_(self.theta, non_blocking=True)
+            torch.cuda.current_stream(self.ctx.device).synchronize()
+            update_size = float(self._update_host[0])
+            if self._host_policy and self.sync_policy:
+                self.policy.set_trainable_flat(self._theta_host.numpy())
+        else:
+            # any other torch optimizer: it owns the update rule and runs where the policy's parameters live
+            # (finite_differences.py:54-57); the device keeps the history / distance rows
+            flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32).copy()
+            self.gradient_optimizer.zero_grad()
+            self.policy.set_grad_from_flat(-self.gradient_memory)
+            self.gradient_optimizer.step()
+            new_flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32)
+            update_size = float(np.linalg.norm(flat - new_flat))
+            self.theta.copy_(torch.from_numpy(new_flat.copy()))
+            zero = torch.zeros_like(self.grad)
+            _lib.check(self.lib.dfd_dsgd_step(
+                self.ctx.handle, ptr(self.theta), ptr(zero), self.P, 0.0, 0.0, ptr(self.hist), ptr(self.dist),
+                self.Ps, n_valid, write_row, ptr(self._update_size), aligned_ptr(self._dsgd_scratch),
+                self._dsgd_scratch.numel() - 256, st), "dfd_dsgd_step")
+        return self._advance_epoch(write_row, update_size)
+
+    def _advance_epoch(self, write_row, update_size):
+        self.epoch += 1                                                      # :60
+        # :66-78 — the distance map is rebuilt from the history BEFORE the new theta is appended, so
+        # H+1 epochs stay acceptable while the ring holds H rows
+        self._dist_epoch = {e: r for r, e in enumerate(self._hist_epoch)}
+        if write_row < len(self._hist_epoch):
+            self._hist_epoch[write_row] = self.epoch
+        else:
+            self._hist_epoch.append(self.epoch)
+        return update_size

@@ -1,0 +1,93 @@
+"""Noise sources with the reference's interface (utils/noise_sources.py).
+
+`SharedNoiseTable(size, n_params, random_seed=123)`: `sample() -> (key, noise)`,
+`decode(key) -> noise` exactly as utils/noise_sources.py:36-51.  The fp32 table
+and every index come from numpy's legacy `RandomState` on the host (bit-exact
+requirement; the same generator first fills the table, then serves the draws),
+and the table is mirrored once per GPU as four 16-byte aligned shifted replicas
+plus an fp64 prefix sum of squares (include/dfd_b200.h, dfd_table)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .device import get_context, ptr, aligned_ptr
+
+
+class SharedNoiseTable(object):
+    def __init__(self, size, n_params, random_seed=123, device=None, upload=None):
+        assert size > n_params, "!ATTEMPTED TO MAKE NOISE TABLE WITH SIZE {} FOR {} PARAMETERS!".format(size, n_params)
+        self._rng = np.random.RandomState(random_seed)
+        self._table = self._rng.randn(size).astype(np.float32)
+        self._n_params = n_params
+        self._max_sample_idx = size - n_params
+        self.size = size
+        self._device = device
+        self._dev = None
+        if upload is None:
+            upload = torch.cuda.is_available()
+        if upload:
+            self.to_device(device)
+
+    # ---- reference interface -------------------------------------------------
+    def sample(self):
+        noise_idx = self._rng.randint(0, self._max_sample_idx)
+        return "{}".format(noise_idx), self._table[noise_idx:noise_idx + self._n_params]
+
+    def decode(self, noise_idx):
+        """Plain decimal keys as in the reference.  '+i' / '-i' keys are the
+        antithetic extension: '-i' decodes to -table[i:i+P]."""
+        i, s = parse_key(noise_idx)
+        v = self._table[i:i + self._n_params]
+        return -v if s < 0 else v
+
+    # ---- batched draws (same stream, same order as repeated sample()) ----------
+    def sample_indices(self, n):
+        """n successive `sample()` index draws as an int64 array."""
+        return np.array([self._rng.randint(0, self._max_sample_idx) for _ in range(n)], dtype=np.int64)
+
+    @property
+    def n_params(self):
+        return self._n_params
+
+    # ---- device mirror -------------------------------------------------------
+    def to_device(self, device=None):
+        if self._dev is not None:
+            return self._dev
+        ctx = get_context(device if device is not None else self._device)
+        lib = ctx.lib
+        size = self.size
+        stride = int(lib.dfd_table_replica_stride(size))
+        with torch.cuda.device(ctx.device):
+            raw = torch.from_numpy(self._table).to(ctx.device)
+            replicas = torch.empty(4 * stride, dtype=torch.float32, device=ctx.device)
+            prefix = torch.empty(size + 1, dtype=torch.float64, device=ctx.device)
+            scratch = ctx.zeros_bytes(lib.dfd_table_scratch_bytes(size))
+            _lib.check(lib.dfd_table_build(ctx.handle, ptr(raw), size, ptr(replicas), stride, ptr(prefix),
+                                           aligned_ptr(scratch), scratch.numel() - 256, ctx.stream), "dfd_table_build")
+            torch.cuda.current_stream(ctx.device).synchronize()
+        del raw, scratch
+        self._dev = DeviceTable(ctx, replicas, stride, prefix, size)
+        return self._dev
+
+    @property
+    def device_table(self):
+        return self.to_device()
+
+
+class DeviceTable(object):
+    def __init__(self, ctx, replicas, stride, prefix, size):
+        self.ctx, self.replicas, self.stride, self.prefix, self.size = ctx, replicas, stride, prefix, size
+        self.c = _lib.DfdTable(replicas.data_ptr(), stride, prefix.data_ptr(), size)
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def parse_key(key):
+    """'123' -> (123, +1); '+123' -> (123, +1); '-123' -> (123, -1)."""
+    k = str(key)
+    if k[0] == "-":
+        return int(k[1:]), -1
+    return int(k), 1

@@ -1,0 +1,365 @@
+"""Policies with the reference's `Policy` interface (policies/policy.py:8-153),
+evaluated by the sm_100a kernels behind the C ABI.
+
+A policy object owns the flat parameter vector theta (device, fp32), the shared
+BatchNorm running statistics (device) and a layout table that maps the flat
+vector to tensors in `parameters()` order.  Besides the
+reference's single-observation methods it has the batched entry point
+
+    forward_members(idx, sign, obs, sigma)  ->  [members, obs_per_member, out_width]
+
+which evaluates member m with theta + sign[m]*sigma*table[idx[m]:idx[m]+P]
+(worker/worker.py:28) without ever materialising the perturbed vector in HBM.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .device import get_context, ptr, aligned_ptr
+
+KIND = {"mujoco": 0, "discrete": 1, "atari": 2, "impala": 3}
+
+
+# ----------------------------------------------------------------------------
+# layouts: (name, shape, is_param) in state_dict order
+# ----------------------------------------------------------------------------
+class Layout(object):
+    def __init__(self):
+        self.entries = []      # dicts: name, shape, numel, param(bool), off (in theta or buffer vec), sd_off
+        self.num_params = self.num_buffers = self.num_state = 0
+
+    def _add(self, name, shape, param=True):
+        n = int(np.prod(shape)) if len(shape) else 1
+        e = dict(name=name, shape=tuple(shape), numel=n, param=param, sd_off=self.num_state,
+                 off=self.num_params if param else self.num_buffers)
+        if param:
+            self.num_params += n
+        else:
+            self.num_buffers += n
+        self.num_state += n
+        self.entries.append(e)
+
+    def dense(self, name, n_out, *in_shape):
+        self._add(name + ".weight", (n_out,) + tuple(in_shape))
+        self._add(name + ".bias", (n_out,))
+
+    def norm(self, name, c):
+        self._add(name + ".weight", (c,))
+        self._add(name + ".bias", (c,))
+        self._add(name + ".running_mean", (c,), False)
+        self._add(name + ".running_var", (c,), False)
+        self._add(name + ".num_batches_tracked", (), False)
+
+    def split_state(self, serialized):
+        s = np.asarray(serialized, dtype=np.float32)
+        if s.shape[0] != self.num_state:
+            raise ValueError("serialized state has %d values, layout needs %d" % (s.shape[0], self.num_state))
+        theta = np.empty(self.num_params, np.float32)
+        buf = np.empty(self.num_buffers, np.float32)
+        for e in self.entries:
+            (theta if e["param"] else buf)[e["off"]:e["off"] + e["numel"]] = s[e["sd_off"]:e["sd_off"] + e["numel"]]
+        return theta, buf
+
+    def join_state(self, theta, buf):
+        s = np.empty(self.num_state, np.float32)
+        for e in self.entries:
+            s[e["sd_off"]:e["sd_off"] + e["numel"]] = (theta if e["param"] else buf)[e["off"]:e["off"] + e["numel"]]
+        return s
+
+
+def build_layout(kind, n_in, n_act, h1=64, h2=64):
+    L = Layout()
+    if kind == "mujoco":          # policies/mujoco.py:32-41
+        L.dense("model.0", h1, n_in)
+        L.dense("model.2", h2, h1)
+        L.dense("model.4", 2 * n_act, h2)
+    elif kind == "discrete":      # policies/discrete.py:34-48
+        L.norm("model.0", n_in)
+        L.dense("model.1", h1, n_in)
+        L.norm("model.3", h1)
+        L.dense("model.4", h2, h1)
+        L.norm("model.6", h2)
+        L.dense("model.7", n_act, h2)
+    elif kind == "atari":         # policies/atari.py:34-51
+        L.dense("model.0", 16, 4, 8, 8)
+        L.norm("model.1", 16)
+        L.dense("model.3", 32, 16, 4, 4)
+        L.norm("model.4", 32)
+        L.dense("model.7", 256, 2592)
+        L.norm("model.8", 256)
+        L.dense("model.10", n_act, 256)
+    elif kind == "impala":        # policies/impala.py:56-126, registration order
+        widths = ((3, 16), (16, 32), (32, 32))
+        for s, (ci, co) in enumerate(widths):
+            L.norm("model.0.feat_convs.%d.0" % s, ci)
+            L.dense("model.0.feat_convs.%d.1" % s, co, ci, 3, 3)
+        for blk in ("resnet1", "resnet2"):
+            for s, (_, c) in enumerate(widths):
+                base = "model.0.%s.%d" % (blk, s)
+                L.norm(base + ".0", c)
+                L.dense(base + ".2", c, c, 3, 3)
+                L.norm(base + ".3", c)
+                L.dense(base + ".5", c, c, 3, 3)
+        L.norm("model.0.fc.0", 2048)
+        L.dense("model.0.fc.1", 256, 2048)
+        L._add("model.0.core.weight_ih_l0", (1024, 257))
+        L._add("model.0.core.weight_hh_l0", (1024, 256))
+        L._add("model.0.core.bias_ih_l0", (1024,))
+        L._add("model.0.core.bias_hh_l0", (1024,))
+        L.norm("model.0.policy.0", 256)
+        L.dense("model.0.policy.1", n_act, 256)
+    else:
+        raise ValueError(kind)
+    return L
+
+
+# ----------------------------------------------------------------------------
+# initial parameters: torch default init drawn in registration order, then the
+# reference's normc re-initialisation of Sequential layers (policy.py:88-115)
+# ----------------------------------------------------------------------------
+def _default_init(layout):
+    """Draw torch's default initialisation for every tensor, consuming the global
+    torch RNG in registration order exactly as constructing the modules would."""
+    theta = np.zeros(layout.num_params, np.float32)
+    buf = np.zeros(layout.num_buffers, np.float32)
+    ents = layout.entries
+    i = 0
+    while i < len(ents):
+        e = ents[i]
+        name = e["name"]
+        if name.endswith("running_mean") or name.endswith("num_batches_tracked"):
+            i += 1
+            continue
+        if name.endswith("running_var"):
+            buf[e["off"]:e["off"] + e["numel"]] = 1.0
+            i += 1
+            continue
+        nxt = ents[i + 2]["name"] if i + 2 < len(ents) else ""
+        if name.endswith(".weight") and nxt.endswith("running_mean"):      # BatchNorm affine
+            theta[e["off"]:e["off"] + e["numel"]] = 1.0
+            i += 2
+            continue
+        if "core.weight_ih" in name:                                        # nn.LSTM: U(-1/sqrt(H), 1/sqrt(H)) x4
+            k = 1.0 / math.sqrt(256)
+            for j in range(4):
+                ee = ents[i + j]
+                t = torch.empty(ee["shape"]).uniform_(-k, k)
+                theta[ee["off"]:ee["off"] + ee["numel"]] = t.numpy().ravel()
+            i += 4
+            continue
+        shape = e["shape"]
+        if len(shape) == 2:
+            m = nn.Linear(shape[1], shape[0])
+        else:
+            m = nn.Conv2d(shape[1], shape[0], kernel_size=(shape[2], shape[3]))
+        b = ents[i + 1]
+        theta[e["off"]:e["off"] + e["numel"]] = m.weight.detach().numpy().ravel()
+        theta[b["off"]:b["off"] + b["numel"]] = m.bias.detach().numpy().ravel()
+        i += 2
+    return theta, buf
+
+
+def _normc(layout, theta, rng):
+    """policy.py:88-115: for every layer of `self.model` that has a weight (Linear,
+    Conv2d AND BatchNorm), w += (normc_sample - w), b += -b; the last such layer uses
+    gain 0.01.  Applied in fp32 with the same two roundings."""
+    groups = []
+    for e in layout.entries:
+        if e["param"] and e["name"].endswith(".weight"):
+            groups.append(e)
+    by_name = {e["name"]: e for e in layout.entries}
+    for n, e in enumerate(groups):
+        std = 0.01 if n == len(groups) - 1 else 1.0
+        out = rng.randn(*e["shape"]).astype(np.float32)
+        out *= std / np.sqrt(np.square(out).sum(axis=0, keepdims=True))
+        w = theta[e["off"]:e["off"] + e["numel"]].reshape(e["shape"])
+        w += (out - w)
+        b = by_name[e["name"][:-6] + "bias"]
+        bv = theta[b["off"]:b["off"] + b["numel"]]
+        bv += -bv
+
+
+def initial_parameters(kind, n_in, n_act, seed=124, h1=64, h2=64):
+    """(theta, buffers) exactly as constructing the reference policy would leave them:
+    torch default init from the global torch RNG, then normc from RandomState(seed)
+    (IMPALA: normc finds no layer with a weight in `self.model`, policy.py:94-100)."""
+    layout = build_layout(kind, n_in, n_act, h1, h2)
+    theta, buf = _default_init(layout)
+    if kind != "impala":
+        _normc(layout, theta, np.random.RandomState(seed))
+    return theta, buf
+
+
+class Policy(object):
+    """Host-side mirror of policies/policy.py:8-153 backed by device state."""
+    kind = None
+
+    def __init__(self, n_inputs, n_actions, seed=124, h1=64, h2=64, device=None, precision=0):
+        self.input_shape = n_inputs
+        self.output_shape = n_actions
+        self.rng = np.random.RandomState(seed)
+        self.h1, self.h2 = h1, h2
+        n_in = int(np.prod(n_inputs)) if self.kind in ("mujoco", "discrete") else 0
+        self.layout = build_layout(self.kind, n_in, int(n_actions), h1, h2)
+        self.num_params = self.layout.num_params
+        self.desc = _lib.DfdPolicyDesc(KIND[self.kind], n_in, h1, h2, int(n_actions), int(precision))
+        self.ctx = get_context(device)
+        lib = self.ctx.lib
+        assert lib.dfd_policy_num_params(C.byref(self.desc)) == self.num_params
+        assert lib.dfd_policy_num_buffers(C.byref(self.desc)) == self.layout.num_buffers
+        self.out_width = int(lib.dfd_policy_out_width(C.byref(self.desc)))
+        theta, buf = initial_parameters(self.kind, n_in, int(n_actions), seed, h1, h2)
+        dev = self.ctx.device
+        self.theta = torch.from_numpy(theta).to(dev)
+        self.buffers = torch.from_numpy(buf).to(dev) if self.layout.num_buffers else None
+        self._one_idx = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._one_sign = torch.zeros(1, dtype=torch.int8, device=dev)
+        self._table = None
+
+    # ---- flat parameter access (policy.py:36-61) -------------------------------
+    def get_trainable_flat(self):
+        return self.theta.cpu().numpy()
+
+    def set_trainable_flat(self, flat):
+        self.theta.copy_(torch.as_tensor(np.asarray(flat), dtype=torch.float32), non_blocking=False)
+
+    def serialize(self):
+        buf = self.buffers.cpu().numpy() if self.buffers is not None else np.zeros(0, np.float32)
+        return self.layout.join_state(self.get_trainable_flat(), buf).tolist()
+
+    def deserialize(self, serialized_state_dict):
+        theta, buf = self.layout.split_state(serialized_state_dict)
+        self.set_trainable_flat(theta)
+        if self.buffers is not None:
+            self.buffers.copy_(torch.from_numpy(buf))
+
+    def set_buffers(self, buf):
+        self.buffers.copy_(torch.as_tensor(np.asarray(buf), dtype=torch.float32))
+
+    def reset(self):
+        pass
+
+    # ---- batched forward ---------------------------------------------------------
+    def bind_table(self, noise_source):
+        """The table whose rows perturb the members (needed even for the unperturbed
+        M=1 wrappers: the kernel signature always carries a table)."""
+        self._table = noise_source.device_table
+        return self
+
+    def forward_members(self, idx, sign, obs, sigma, out=None):
+        """idx int64 [M], sign int8 [M] (0 = unperturbed), obs float32 [M, E, ...] — device tensors."""
+        if self._table is None:
+            raise _lib.DfdError("policy.bind_table(noise_source) must be called before forward_members")
+        M = idx.shape[0]
+        E = obs.shape[1]
+        if out is None:
+            out = torch.empty(M, E, self.out_width, dtype=torch.float32, device=self.ctx.device)
+        obs = obs.contiguous()
+        _lib.check(self.ctx.lib.dfd_policy_forward(
+            self.ctx.handle, C.byref(self.desc), self._table.ref(), ptr(self.theta), ptr(self.buffers), ptr(idx),
+            ptr(sign), M, float(sigma), ptr(obs), E, ptr(out), self.ctx.stream), "dfd_policy_forward")
+        return out
+
+    # ---- reference single-policy wrappers (M = 1, sign = 0) ----------------------
+    def _obs_tensor(self, x):
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32)
+        return x.reshape((1, -1) + self._obs_shape()).to(self.ctx.device)
+
+    def _obs_shape(self):
+        return (int(np.prod(self.input_shape)),)
+
+    def forward(self, x):
+        return self.forward_members(self._one_idx, self._one_sign, self._obs_tensor(x), 0.0)[0]
+
+
+class MujocoPolicy(Policy):
+    """policies/mujoco.py:8-41 (hidden widths are parameters: SURVEY.md G3)."""
+    kind = "mujoco"
+
+    def forward(self, x):
+        y = super().forward(x)
+        a = self.output_shape
+        return y[..., :a], y[..., a:]
+
+    def get_action(self, x, deterministic=False):
+        mean, std = self.forward(x)
+        if deterministic:
+            return mean.flatten().tolist()
+        return torch.normal(mean, std).flatten().tolist()
+
+    def get_entropy(self, x):
+        _, std = self.forward(x)
+        ent = 0.5 + 0.5 * math.log(2 * math.pi) + torch.log(std)
+        return ent.sum(dim=-1).mean().item()
+
+    def get_strategy(self, x):
+        return super().forward(x).cpu().numpy()
+
+
+class DiscretePolicy(Policy):
+    """policies/discrete.py:8-48."""
+    kind = "discrete"
+
+    def get_action(self, x, deterministic=False):
+        probs = self.forward(x)
+        if deterministic:
+            return probs.argmax().item()
+        return torch.multinomial(probs.reshape(-1, probs.shape[-1]), 1).reshape(-1)[0].item()
+
+    def get_entropy(self, x):
+        p = self.forward(x)
+        logp = torch.log(p.clamp_min(torch.finfo(torch.float32).tiny))
+        return (-(p * logp).sum(-1)).mean().item()
+
+    def get_strategy(self, x):
+        return self.forward(x).cpu().numpy()
+
+    def compute_vbn(self, buffer):
+        """policy.py:31-34: a train-mode forward of the UNPERTURBED policy refreshes the
+        shared BN running statistics (momentum 0.1, unbiased variance).  Once per epoch,
+        off the hot path; plain torch ops on the device."""
+        x = torch.as_tensor(np.asarray(buffer), dtype=torch.float32).reshape(-1, int(np.prod(self.input_shape)))
+        x = x.to(self.ctx.device)
+        L = {e["name"]: e for e in self.layout.entries}
+
+        def par(n):
+            e = L[n]
+            return self.theta[e["off"]:e["off"] + e["numel"]].view(e["shape"])
+
+        def bufv(n):
+            e = L[n]
+            return self.buffers[e["off"]:e["off"] + e["numel"]]
+
+        for bn, lin, act in (("model.0", "model.1", True), ("model.3", "model.4", True), ("model.6", "model.7", False)):
+            mean = x.mean(0)
+            var_b = x.var(0, unbiased=False)
+            n = x.shape[0]
+            bufv(bn + ".running_mean").mul_(0.9).add_(0.1 * mean)
+            bufv(bn + ".running_var").mul_(0.9).add_(0.1 * var_b * (n / max(n - 1, 1)))
+            bufv(bn + ".num_batches_tracked").add_(1)
+            x = (x - mean) / torch.sqrt(var_b + 1e-5) * par(bn + ".weight") + par(bn + ".bias")
+            x = torch.nn.functional.linear(x, par(lin + ".weight"), par(lin + ".bias"))
+            if act:
+                x = torch.relu(x)
+
+
+class AtariPolicy(DiscretePolicy):
+    """policies/atari.py:7-51; n_inputs = (84, 84), observations NCHW (E,4,84,84)."""
+    kind = "atari"
+
+    def __init__(self, n_inputs, n_actions, seed=124, device=None, precision=0):
+        super().__init__(n_inputs, n_actions, seed=seed, device=device, precision=precision)
+        self.input_shape = (4, n_inputs[0], n_inputs[1])
+
+    def _obs_shape(self):
+        return (4, 84, 84)
+
+    def compute_vbn(self, buffer):
+        raise NotImplementedError("AtariPolicy.compute_vbn: refresh BN statistics with set_buffers()")
+
+
+POLICY_CLASSES = {"mujoco": MujocoPolicy, "discrete": DiscretePolicy, "atari": AtariPolicy}

@@ -1,0 +1,150 @@
+"""`Worker` with the reference's interface (worker/worker.py:8-57), batched.
+
+The reference evaluates one perturbed member at a time (`flat + sigma*eps` ->
+`set_trainable_flat` -> rollout -> restore).  Here `collect_returns(n)` draws the
+n eval flags and noise indices from the SAME two RandomState streams in the SAME
+order (worker.py:23,27), then evaluates all n members in ONE batched call: the
+perturbation is generated in-kernel from the table offsets and never written to
+HBM.  Rollouts are delegated to a batched agent:
+
+    agent.collect_returns(policy, idx, sign, sigma) -> dict(reward[n], entropy[n], timesteps[n], states)
+
+(`SyntheticAgent` below evaluates synthetic observations; environment stepping
+itself is outside this path)
+"""
+import math
+
+import numpy as np
+import torch
+
+from .fd_return import FDReturn
+
+
+class Worker(object):
+    def __init__(self, policy, agent, noise_source, strategy_handler=None, sigma=0.02, eval_prob=0.1, random_seed=123):
+        self.policy = policy
+        self.agent = agent
+        self.noise_source = noise_source
+        self.strategy_handler = strategy_handler
+        self.sigma = sigma
+        self.epoch = -1
+        self.rng = np.random.RandomState(random_seed)
+        self.eval_prob = eval_prob
+        if hasattr(policy, "bind_table"):
+            policy.bind_table(noise_source)
+
+    def draw(self, n):
+        """n calls' worth of (is_eval, idx): one uniform per call from the worker stream and,
+        for non-eval calls only, one randint from the noise stream (worker.py:23-27)."""
+        flags = np.zeros(n, dtype=bool)
+        idx = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            flags[i] = self.rng.uniform(0, 1) < self.eval_prob
+            if not flags[i]:
+                idx[i] = int(self.noise_source.sample()[0])
+        return flags, idx
+
+    def draw_batch(self, batch_size):
+        """The drivers' loop (run_sequential.py:134-147): keep calling until `batch_size`
+        NON-eval members exist.  Returns flags/idx over all calls made."""
+        flags, idx = [], []
+        n_train = 0
+        while n_train < batch_size:
+            f, i = self.draw(1)
+            flags.append(bool(f[0]))
+            idx.append(int(i[0]))
+            n_train += 0 if f[0] else 1
+        return np.array(flags, dtype=bool), np.array(idx, dtype=np.int64)
+
+    @torch.no_grad()
+    def collect_returns(self, n=1, antithetic=False):
+        flags, idx = self.draw(n)
+        return self.evaluate(flags, idx, antithetic=antithetic)
+
+    @torch.no_grad()
+    def evaluate(self, flags, idx, antithetic=False):
+        """Evaluate the drawn members in one batched launch and wrap them as FDReturns.
+        antithetic=True (extension): every non-eval draw yields a +/- pair
+        with keys '+i' / '-i'; returns are ordered [evals..., plus..., minus...]."""
+        flags = np.asarray(flags, dtype=bool)
+        idx = np.asarray(idx, dtype=np.int64)
+        ev = np.nonzero(flags)[0]
+        tr = np.nonzero(~flags)[0]
+        if antithetic:
+            m_idx = np.concatenate([idx[ev], idx[tr], idx[tr]])
+            m_sign = np.concatenate([np.zeros(len(ev)), np.ones(len(tr)), -np.ones(len(tr))]).astype(np.int8)
+            keys = ["0"] * len(ev) + ["+%d" % i for i in idx[tr]] + ["-%d" % i for i in idx[tr]]
+            is_eval = [True] * len(ev) + [False] * (2 * len(tr))
+        else:
+            m_idx = idx.copy()
+            m_sign = np.where(flags, 0, 1).astype(np.int8)
+            keys = ["0" if f else "%d" % i for f, i in zip(flags, idx)]     # worker.py:34: eval key is "0"
+            is_eval = [bool(f) for f in flags]
+        res = self.agent.collect_returns(self.policy, m_idx, m_sign, self.sigma)
+        rets = []
+        for j in range(len(keys)):
+            ret = FDReturn()
+            ret.is_eval = is_eval[j]
+            ret.timesteps = int(res["timesteps"][j])
+            ret.encoded_noise = keys[j]
+            ret.reward = float(res["reward"][j])
+            ret.novelty = 0
+            ret.entropy = float(res["entropy"][j])
+            ret.epoch = self.epoch
+            ret.obs_stats_update = []
+            if ret.is_eval and res.get("states") is not None:
+                ret.eval_states = res["states"]
+            rets.append(ret)
+        return rets
+
+    def update(self, state):
+        """worker.py:40-43: load the learner's snapshot (flattened state_dict incl. BN buffers)."""
+        self.policy.deserialize(state.policy_params)
+        self.epoch = state.epoch
+
+
+class SyntheticAgent(object):
+    """Evaluates every member on `obs_per_member` synthetic observations (no
+    environment): reward = - mean squared distance of the policy head to a fixed
+    target head, so a learner can be seen to improve.  Observations are resident on
+    the device; `host_obs=True` re-uploads them from pinned host memory each call
+    (the end-to-end path)."""
+
+    def __init__(self, policy, obs_per_member, seed=0, shared_obs=True, host_obs=False, members_hint=1):
+        self.E = int(obs_per_member)
+        g = torch.Generator().manual_seed(seed)
+        shape = policy._obs_shape()
+        self.shape = shape
+        self.shared = shared_obs
+        n_sets = 1 if shared_obs else members_hint
+        self.obs_host = torch.randn((n_sets, self.E) + shape, generator=g).pin_memory() \
+            if torch.cuda.is_available() else torch.randn((n_sets, self.E) + shape, generator=g)
+        self.target = torch.tanh(torch.randn(policy.out_width, generator=g)) * 0.5
+        self.host_obs = host_obs
+        self.obs_dev = None
+        self.saved_states = []
+
+    def _obs(self, policy, M):
+        dev = policy.ctx.device
+        if self.obs_dev is None or self.host_obs:
+            self.obs_dev = self.obs_host.to(dev, non_blocking=True)
+            self.target_dev = self.target.to(dev)
+        if self.obs_dev.shape[0] == M:
+            return self.obs_dev
+        return self.obs_dev[:1].expand((M, self.E) + self.shape).contiguous()
+
+    def collect_returns(self, policy, idx, sign, sigma):
+        dev = policy.ctx.device
+        M = len(idx)
+        idx_d = torch.from_numpy(np.ascontiguousarray(idx)).to(dev)
+        sign_d = torch.from_numpy(np.ascontiguousarray(sign)).to(dev)
+        out = policy.forward_members(idx_d, sign_d, self._obs(policy, M), sigma)
+        err = (out - self.target_dev) ** 2
+        reward = -err.mean(dim=(1, 2))
+        if policy.kind == "mujoco":
+            a = policy.output_shape
+            ent = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(out[..., a:])).sum(-1).mean(-1)
+        else:
+            ent = -(out * torch.log(out.clamp_min(1e-30))).sum(-1).mean(-1)
+        return {"reward": reward.double().cpu().numpy(), "entropy": ent.double().cpu().numpy(),
+                "timesteps": np.full(M, self.E), "states": None}

@@ -1,0 +1,177 @@
+/*
+ * dfd_b200.h — C ABI of the B200-native finite-difference learner hot path.
+ *
+ * The reference (nexus-rl/dfd-starter) is 100 % Python and has no FFI; its
+ * boundary for this path is a set of duck-typed Python objects.
+ * Each entry point below names the reference code it replaces (file:line under
+ * the reference root).  The host-side Python mirror of those objects lives in
+ * dfd_starter_b200/*.py and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C symbols, int status return: 0 = ok, non-zero = error;
+ *     dfd_last_error() returns a thread-local message for the last failure;
+ *   - no C++ exceptions cross the boundary;
+ *   - the CALLER owns every buffer (all pointers are device pointers unless a
+ *     name says `host`); hot calls never allocate and never synchronise;
+ *   - every hot call takes the CUDA stream to launch on (cudaStream_t as void*);
+ *   - one context per device, not re-entrant per context;
+ *   - compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef DFD_B200_H
+#define DFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_ABI_VERSION 1
+
+typedef struct dfd_ctx dfd_ctx;
+typedef void* dfd_stream; /* cudaStream_t */
+
+/* ---- context ----------------------------------------------------------- */
+int dfd_abi_version(void);
+const char* dfd_last_error(void);
+int dfd_ctx_create(int device, dfd_ctx** out);
+int dfd_ctx_destroy(dfd_ctx* ctx);
+int dfd_ctx_sm_count(const dfd_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's
+ * gpu_launches claim is read from here, not guessed) */
+int64_t dfd_ctx_launch_count(const dfd_ctx* ctx);
+
+/* ---- noise table: utils/noise_sources.py:36-51 (SharedNoiseTable) ------- */
+/* The fp32 table itself is produced on the host by numpy's legacy RandomState
+ * (bit-exact requirement) and uploaded once.  On the
+ * device it is kept as FOUR element-shifted replicas so that every slice
+ * table[idx : idx+P] starts 16-byte aligned in replica (idx & 3):
+ *     replica_s[j] = table[j + s],  s = 0..3,  row base = replica_{idx&3} + (idx & ~3)
+ * plus an fp64 inclusive prefix sum of squares (prefix[i] = sum_{j<i} table[j]^2,
+ * size+1 entries) so ||table[idx:idx+P]||^2 is two loads. */
+typedef struct dfd_table {
+    const float* replicas;   /* 4 * replica_stride floats                                   */
+    int64_t replica_stride;  /* floats between replicas; multiple of 32, >= size + 64         */
+    const double* prefix_sq; /* size + 1 doubles                                             */
+    int64_t size;            /* number of table entries                                      */
+} dfd_table;
+
+int64_t dfd_table_replica_stride(int64_t size);
+/* table_dev: `size` floats already on the device.  Fills replicas (4*stride
+ * floats) and prefix_sq (size+1 doubles); scratch needs dfd_table_scratch_bytes(size). */
+size_t dfd_table_scratch_bytes(int64_t size);
+int dfd_table_build(dfd_ctx* ctx, const float* table_dev, int64_t size, float* replicas, int64_t replica_stride,
+                    double* prefix_sq, void* scratch, size_t scratch_bytes, dfd_stream stream);
+
+/* ---- perturbation: worker/worker.py:28  new_flat = flat + sigma * eps ---- */
+/* out[m, :] = theta + sign[m]*sigma*table[idx[m] : idx[m]+P], fp32, product
+ * rounded then sum rounded (no FMA) so the result is bit-identical to numpy.
+ * Materialising members is for parity tests and generic host policies; the
+ * forward kernels below generate the same values in-kernel and never write
+ * them to HBM.  out_stride in floats (>= P). */
+int dfd_perturb_members(dfd_ctx* ctx, const dfd_table* table, const float* theta, int64_t n_params,
+                        const int64_t* idx, const int8_t* sign, int n_members, float sigma, float* out,
+                        int64_t out_stride, dfd_stream stream);
+
+/* ---- policy forwards: policies/policy.py:26-29 + mujoco/discrete/atari/impala */
+enum { DFD_POLICY_MUJOCO = 0, DFD_POLICY_DISCRETE = 1, DFD_POLICY_ATARI = 2, DFD_POLICY_IMPALA = 3 };
+
+typedef struct dfd_policy_desc {
+    int kind;      /* DFD_POLICY_*                                                         */
+    int n_in;      /* MLPs: observation width K                                            */
+    int h1, h2;    /* MLPs: hidden widths (reference: 64, 64; mujoco.py:33-34)             */
+    int n_act;     /* actions A (MuJoCo head emits 2A: mean | std)                         */
+    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tcgen05 tensor cores      */
+} dfd_policy_desc;
+
+int64_t dfd_policy_num_params(const dfd_policy_desc* desc);
+int64_t dfd_policy_num_buffers(const dfd_policy_desc* desc);
+int64_t dfd_policy_out_width(const dfd_policy_desc* desc);
+
+/* Batched member x observation forward (the new surface of SURVEY.md §8b):
+ *   member m uses theta + sign[m]*sigma*table[idx[m]:idx[m]+P] (sign 0 = unperturbed
+ *   eval member, worker.py:23-25,35); obs is [n_members, obs_per_member, obs_width];
+ *   out is [n_members, obs_per_member, out_width]:
+ *     MuJoCo   mean(A) | std(A)            (mujoco.py:35-41, torch_helpers.py:20-25)
+ *     Discrete probs(A)                    (discrete.py:37-48)
+ *     Atari    probs(A), obs NCHW 4x84x84  (atari.py:35-51)
+ *   bn_buffers: BatchNorm running stats in state_dict order (mean, var, num_batches_tracked
+ *   per BN layer), shared by all members; NULL for MuJoCo. */
+int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                       const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
+                       const float* obs, int obs_per_member, float* out, dfd_stream stream);
+
+/* IMPALA CNN+LSTM (impala.py:136-186): E independent single-step environments
+ * per member, each with its own carried (h, c) of 256 floats.
+ * frame [M,E,3,64,64] (0..255), reward [M,E], done [M,E] (uint8),
+ * h_in/c_in/h_out/c_out [M,E,256], probs [M,E,A]. scratch: dfd_impala_scratch_bytes. */
+size_t dfd_impala_scratch_bytes(int n_members, int obs_per_member);
+int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                       const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
+                       const float* frame, const float* reward, const uint8_t* done, const float* h_in,
+                       const float* c_in, int obs_per_member, float* probs, float* h_out, float* c_out,
+                       void* scratch, size_t scratch_bytes, dfd_stream stream);
+
+/* ---- the estimator: learner/finite_differences.py:24-114 ---------------- */
+/* One learner step on the device, in three hot calls.
+ *
+ * (1) dfd_fd_prepare  — finite_differences.py:40-43 (baseline, standardise),
+ *     :87-89,107 (lambda_i = sign_i*sigma*eps_i + d_{e_i}, ||lambda_i||^2).
+ *     Inputs are the ACCEPTED returns only (the host applies the epoch test of
+ *     :82-85): reward[n] (fp64), idx[n], sign[n] (+1/-1), hist_row[n] (-1 = return
+ *     from the current epoch, dist = 0; else row of `dist` [n_hist, dist_stride]
+ *     holding theta_e - theta_now).  For delayed rows the eps_i . d_e dot products
+ *     are computed by this call (a first pass over those rows only).
+ *     If `paired` != 0 the n returns are [R plus-members | R minus-members] of the
+ *     same R table rows and their coefficients are merged so each row is read once.
+ *     If stats_reward != NULL the mean / std are taken over stats_reward[n_stats]
+ *     (multi-GPU: every rank standardises its shard with the statistics of ALL
+ *     ranks' returns); otherwise over reward[n_returns].
+ *     Outputs the row list of step (2): row_ptr[n_rows], row_coef[n_rows] with
+ *     n_rows = (paired ? n_returns/2 : n_returns) + n_hist  (known to the host
+ *     without a synchronisation).
+ * (2) dfd_fd_reduce   — finite_differences.py:49  g = sum_i w_i * lambda_i/||lambda_i||^2
+ *     as ONE streaming pass:  g[p] = sum_r row_coef[r] * row_ptr[r][p].
+ * (3) dfd_dsgd_step   — dsgd/dynamic_sgd.py:18-39 + finite_differences.py:54-78:
+ *     theta += lr*sqrt(P)*lr_scale * g/||g|| (the learner hands -g to DSGD, which
+ *     subtracts), update_size = ||theta_old - theta_new||, then the theta-history
+ *     ring and the dist rows (theta_e - theta_new) are refreshed in place.
+ */
+typedef struct dfd_fd_rows {
+    const float** row_ptr; /* [max_rows] device array of 16-byte aligned row base pointers */
+    float* row_coef;       /* [max_rows]                                                  */
+    int max_rows;
+} dfd_fd_rows;
+
+size_t dfd_fd_prepare_scratch_bytes(int n_returns, int n_hist);
+int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward, const int64_t* idx,
+                   const int8_t* sign, const int32_t* hist_row, int n_returns, int paired, double baseline,
+                   float sigma, const float* dist, int64_t dist_stride, int n_hist, const double* stats_reward,
+                   int n_stats, dfd_fd_rows* rows, void* scratch, size_t scratch_bytes, dfd_stream stream);
+
+size_t dfd_fd_reduce_scratch_bytes(const dfd_ctx* ctx, int64_t n_params, int n_rows);
+int dfd_fd_reduce(dfd_ctx* ctx, const dfd_fd_rows* rows, int n_rows, int64_t n_params, float* grad, void* scratch,
+                  size_t scratch_bytes, dfd_stream stream);
+
+/* hist: [hist_cap, hist_stride] ring of past theta (policy_history), dist: same
+ * shape.  For the n_hist_valid rows that hold data BEFORE this call,
+ * dist[r] = hist[r] - theta_new (finite_differences.py:66-73); then theta_new is
+ * written to ring slot hist_write_row (-1: do not record; :75-78).
+ * update_size_out: one device float.  All scratch buffers of the fd_* / dsgd
+ * calls must be zero-filled once when allocated (their counters self-reset). */
+int dfd_dsgd_step(dfd_ctx* ctx, float* theta, const float* grad, int64_t n_params, double lr, double lr_scale,
+                  float* hist, float* dist, int64_t hist_stride, int n_hist_valid, int hist_write_row,
+                  float* update_size_out, void* scratch, size_t scratch_bytes, dfd_stream stream);
+size_t dfd_dsgd_scratch_bytes(int64_t n_params);
+
+/* ---- synthetic return (bench / tests only) ------------------------------- */
+/* Stand-in for the environment, which is outside this path (worker/agent.py is
+ * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */
+int dfd_synthetic_reward(dfd_ctx* ctx, const float* out, int n_members, int obs_per_member, int out_width,
+                         const float* target, double* reward, dfd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_B200_H */

@@ -1,0 +1,350 @@
+"""GPU parity tests proper (-m gpu): every call goes through the C ABI and is compared
+with the CPU oracle and with the golden fixtures captured from the reference.
+Bars: indices / flags / perturbed fp32 parameters bit-exact; fp32 policy outputs atol 1e-5
+(post-tanh / post-softmax, |y| <= 1); gradient max|g - g_ref| / max|g_ref| <= 1e-5;
+update size rel 1e-5; parameters after the update atol 2e-6."""
+import io
+import contextlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dfd_oracle as O  # noqa: E402  (checker only)
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.fixture(scope="module")
+def D():
+    _need_gpu()
+    import __graft_entry__ as G
+    G.build()
+    import dfd_starter_b200 as D
+    return D
+
+
+@pytest.fixture(scope="module")
+def table1m(D):
+    return D.SharedNoiseTable(1_000_000, 6092, 123, device=0)
+
+
+class HostPolicy(object):
+    """A reference-style host policy: only the flat get/set the learner needs."""
+
+    def __init__(self, theta):
+        self.theta_h = np.array(theta, dtype=np.float32)
+        self.num_params = self.theta_h.shape[0]
+
+    def get_trainable_flat(self):
+        return self.theta_h.copy()
+
+    def set_trainable_flat(self, flat):
+        self.theta_h = np.array(flat, dtype=np.float32)
+
+
+class Omega(object):
+    def __init__(self, w=0.3):
+        self.omega, self.min_omega, self.max_omega = w, 0.0, 1.0
+
+
+def make_learner(D, table, theta, sigma, H=4, lr=0.01, omega=0.3, paired=False, batch=64):
+    opt = D.DSGD([torch.nn.Parameter(torch.zeros(len(theta)))], lr=lr)
+    return D.FiniteDifferences(HostPolicy(theta), opt, Omega(omega), table, noise_std=sigma, batch_size=batch,
+                               max_delayed_return=H, paired=paired)
+
+
+def rel_max(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+# ---------------------------------------------------------------- a1-a3 table
+def test_table_replicas_and_prefix(D, table1m):
+    dt = table1m.device_table
+    t = table1m._table
+    rep = dt.replicas.view(4, dt.stride).cpu().numpy()
+    for s in range(4):
+        assert np.array_equal(rep[s, :t.shape[0] - s], t[s:])
+        assert not rep[s, t.shape[0] - s:].any()
+    pref = dt.prefix.cpu().numpy()
+    ref = np.concatenate([[0.0], np.cumsum(t.astype(np.float64) ** 2)])
+    assert pref[0] == 0.0
+    assert np.max(np.abs(pref - ref) / np.maximum(ref, 1.0)) < 1e-13
+
+
+# ---------------------------------------------------------------- a5 perturbation
+def test_perturbation_bit_exact_golden(D, table1m, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mujoco_c2.npz"))
+    from dfd_starter_b200 import _lib
+    from dfd_starter_b200.device import get_context, ptr
+    ctx = get_context(0)
+    theta = torch.from_numpy(g["theta"]).cuda()
+    idx = torch.from_numpy(g["idx"].astype(np.int64)).cuda()
+    sign = torch.from_numpy(g["sign"].astype(np.int8)).cuda()
+    out = torch.empty(len(g["idx"]), 6092, device="cuda")
+    _lib.check(ctx.lib.dfd_perturb_members(ctx.handle, table1m.device_table.ref(), ptr(theta), 6092, ptr(idx), ptr(sign),
+                                           len(g["idx"]), float(g["sigma"]), ptr(out), 6092, ctx.stream))
+    assert np.array_equal(out.cpu().numpy(), g["theta_members"])
+
+
+@pytest.mark.parametrize("P", [1, 3, 5, 127, 6092, 6093, 30498])
+def test_perturbation_bit_exact_all_alignments(D, table1m, P):
+    from dfd_starter_b200 import _lib
+    from dfd_starter_b200.device import get_context, ptr
+    ctx = get_context(0)
+    rng = np.random.RandomState(P)
+    theta = rng.randn(P).astype(np.float32)
+    idx = np.concatenate([np.arange(8), rng.randint(0, 1_000_000 - P, size=24), [1_000_000 - P - 1, 0]]).astype(np.int64)
+    sign = rng.choice([-1, 0, 1], size=len(idx)).astype(np.int8)
+    out = torch.empty(len(idx), P + 3, device="cuda")        # odd stride: exercises the unaligned path too
+    _lib.check(ctx.lib.dfd_perturb_members(ctx.handle, table1m.device_table.ref(), ptr(torch.from_numpy(theta).cuda()), P,
+                                           ptr(torch.from_numpy(idx).cuda()), ptr(torch.from_numpy(sign).cuda()),
+                                           len(idx), 0.02, ptr(out), P + 3, ctx.stream))
+    got = out.cpu().numpy()[:, :P]
+    for m in range(len(idx)):
+        eps = table1m._table[idx[m]:idx[m] + P]
+        ref = theta if sign[m] == 0 else O.perturb(theta, 0.02, eps, int(sign[m]))
+        assert np.array_equal(got[m], ref), (P, m)
+
+
+# ---------------------------------------------------------------- a7-a8 MLP forwards
+def test_mujoco_forward_golden(D, table1m, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mujoco_c2.npz"))
+    torch.manual_seed(124)
+    pol = D.MujocoPolicy(17, 6, seed=124, device=0).bind_table(table1m)
+    assert np.array_equal(pol.get_trainable_flat(), g["theta"])          # init is bit-identical to the reference
+    idx = torch.from_numpy(g["idx"].astype(np.int64)).cuda()
+    sign = torch.from_numpy(g["sign"].astype(np.int8)).cuda()
+    out = pol.forward_members(idx, sign, torch.from_numpy(g["obs"]).cuda(), float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=1e-5)
+    # E = 1 (the reference call shape) takes the small-tile kernel
+    out1 = pol.forward_members(idx, sign, torch.from_numpy(g["obs"][:, :1]).cuda(), float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out1, g["out"][:, :1], rtol=0, atol=1e-5)
+    # reference single-policy wrappers (M = 1, unperturbed)
+    mean, std = pol.forward(g["obs"][0, 0])
+    om, os_ = O.mujoco_forward(O.mujoco_layout(17, 6), g["theta"], g["obs"][0, :1])
+    np.testing.assert_allclose(mean.cpu().numpy(), om, atol=1e-5)
+    np.testing.assert_allclose(std.cpu().numpy(), os_, atol=1e-5)
+    assert len(pol.get_action(g["obs"][0, 0], deterministic=True)) == 6
+
+
+@pytest.mark.parametrize("E", [1, 3, 16, 37])
+def test_mujoco_forward_vs_oracle_ragged(D, table1m, E):
+    torch.manual_seed(1)
+    pol = D.MujocoPolicy(17, 6, seed=3, device=0).bind_table(table1m)
+    theta = pol.get_trainable_flat()
+    rng = np.random.RandomState(E)
+    M = 9
+    idx = rng.randint(0, 1_000_000 - 6092, size=M).astype(np.int64)
+    sign = rng.choice([-1, 0, 1], size=M).astype(np.int8)
+    obs = rng.randn(M, E, 17).astype(np.float32)
+    out = pol.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(),
+                              0.05).cpu().numpy()
+    L = O.mujoco_layout(17, 6)
+    for m in range(M):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.05, table1m._table[idx[m]:idx[m] + 6092], int(sign[m]))
+        mean, std = O.mujoco_forward(L, th, obs[m])
+        np.testing.assert_allclose(out[m], np.concatenate([mean, std], -1), rtol=0, atol=1e-5)
+
+
+def test_humanoid_width_forward_golden(D, golden_dir):
+    g = np.load(os.path.join(golden_dir, "mujoco_c3.npz"))
+    table = D.SharedNoiseTable(int(g["table_size"]), 171042, int(g["table_seed"]), device=0)
+    pol = D.MujocoPolicy(376, 17, seed=124, h1=256, h2=256, device=0).bind_table(table)
+    assert pol.num_params == 171042
+    pol.set_trainable_flat(O.synthetic_theta(O.mujoco_layout(376, 17, 256, 256), int(g["theta_seed"])))
+    out = pol.forward_members(torch.from_numpy(g["idx"].astype(np.int64)).cuda(),
+                              torch.from_numpy(g["sign"].astype(np.int8)).cuda(), torch.from_numpy(g["obs"]).cuda(),
+                              float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=2e-5)
+
+
+def test_discrete_forward_golden(D, golden_dir):
+    g = np.load(os.path.join(golden_dir, "discrete_c1.npz"))
+    table = D.SharedNoiseTable(int(g["table_size"]), 5197, int(g["table_seed"]), device=0)
+    torch.manual_seed(124)
+    pol = D.DiscretePolicy(2, 9, seed=124, device=0).bind_table(table)
+    pol.deserialize(g["serialized"])                 # flattened state_dict incl. BN running stats (policy.py:51-61)
+    assert np.array_equal(pol.get_trainable_flat(), g["theta"])
+    assert np.array_equal(np.asarray(pol.serialize(), dtype=np.float32), g["serialized"])
+    out = pol.forward_members(torch.from_numpy(g["idx"].astype(np.int64)).cuda(),
+                              torch.from_numpy(g["sign"].astype(np.int8)).cuda(), torch.from_numpy(g["obs"]).cuda(),
+                              float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out.sum(-1), 1.0, atol=1e-5)
+    assert 0 <= pol.get_action(g["obs"][0, 0], deterministic=True) < 9
+
+
+def test_discrete_compute_vbn_matches_reference_stats(D, golden_dir):
+    """compute_vbn on the same seeded buffer the golden generator used must reproduce the
+    reference's refreshed running statistics (policy.py:31-34)."""
+    g = np.load(os.path.join(golden_dir, "discrete_c1.npz"))
+    table = D.SharedNoiseTable(int(g["table_size"]), 5197, int(g["table_seed"]), device=0)
+    torch.manual_seed(124)
+    pol = D.DiscretePolicy(2, 9, seed=124, device=0).bind_table(table)
+    vbn = torch.rand(64, 2, generator=torch.Generator().manual_seed(5))
+    pol.compute_vbn(vbn.numpy())
+    np.testing.assert_allclose(np.asarray(pol.serialize(), dtype=np.float32), g["serialized"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- a13-a19 estimator
+def test_estimator_steps_golden(D, table1m, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fd_steps.npz"))
+    fd = make_learner(D, table1m, g["theta0"], float(g["sigma"]), H=int(g["H"]), lr=float(g["lr"]), omega=float(g["omega"]))
+    for s in range(int(g["n_steps"])):
+        batch = []
+        for e, k, r in zip(g["s%d_epochs" % s], g["s%d_keys" % s], g["s%d_rewards" % s]):
+            ret = D.FDReturn()
+            ret.epoch, ret.encoded_noise, ret.reward = int(e), str(k), float(r)
+            batch.append(ret)
+        b = float(g["s%d_baseline" % s])
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step(batch, None if np.isnan(b) else b, 0.0, 0.0)
+        assert rel_max(fd.gradient_memory, g["s%d_grad" % s]) <= 1e-5, s
+        assert abs(upd - float(g["s%d_update" % s])) <= 1e-5 * float(g["s%d_update" % s]), s
+        assert np.max(np.abs(fd.policy.get_trainable_flat() - g["s%d_theta" % s])) <= 2e-6, s
+        assert fd.discarded_returns == int(g["s%d_discarded" % s]), s
+        assert fd.epoch == int(g["s%d_epoch_after" % s]), s
+    before = fd.policy.get_trainable_flat()
+    assert fd.step([], 0.0, 0.0, 0.0) == 0                    # empty batch: int 0, no update, epoch unchanged
+    assert fd.epoch == int(g["n_steps"]) and np.array_equal(before, fd.policy.get_trainable_flat())
+    assert sorted(fd.dist_map.keys()) == list(range(fd.epoch - int(g["H"]), fd.epoch + 1))   # H+1 accepted epochs
+
+
+def _batch_arrays(table, n, rng, P):
+    idx = rng.randint(0, table.size - P, size=n).astype(np.int64)
+    rewards = rng.randn(n) * 2.0 + 5.0
+    return idx, rewards
+
+
+@pytest.mark.parametrize("P,N", [(6092, 2048), (5197, 40), (1, 7), (5, 3), (130, 1), (30498, 64)])
+def test_fd_return_mode_vs_closed_form(D, table1m, P, N):
+    """One-sided (reference-native) batches incl. C1/C2 sizes and ragged edge shapes."""
+    rng = np.random.RandomState(P + N)
+    table = table1m if P == 6092 else D.SharedNoiseTable(1_000_000, P, 123, device=0)
+    theta = rng.randn(P).astype(np.float32)
+    fd = make_learner(D, table, theta, 0.02, batch=N)
+    idx, rewards = _batch_arrays(table, N, rng, P)
+    if N == 1:
+        rewards[:] = 1.5        # single return: std == 0, weight = reward - baseline
+    upd = fd.step_arrays(np.zeros(N, np.int64), idx, np.ones(N, np.int8), rewards, 0.1)
+    ref = O.fd_gradient_closed_form(table._table, idx, np.ones(N), rewards, 0.02, P, baseline=0.1)
+    assert rel_max(fd.gradient_memory, ref) <= 1e-5
+    expect = 0.01 * np.sqrt(P) * (0.23 + 0.3 * 0.77)
+    assert abs(upd - expect) <= 2e-5 * expect
+
+
+def test_antithetic_pairs_merge_equals_unmerged(D, table1m):
+    """Paired mode reads each table row once; it must equal the same 2R returns fed one by one,
+    and the identity g = sum_j ((R+_j - R-_j)/s) eps_j / (sigma ||eps_j||^2)."""
+    rng = np.random.RandomState(7)
+    P, R = 6092, 1024
+    theta = rng.randn(P).astype(np.float32)
+    idx = rng.randint(0, 1_000_000 - P, size=R).astype(np.int64)
+    rp, rm = rng.randn(R), rng.randn(R)
+    idx2 = np.concatenate([idx, idx])
+    sign2 = np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)
+    rew2 = np.concatenate([rp, rm])
+    a = make_learner(D, table1m, theta, 0.02, paired=True, batch=2 * R)
+    b = make_learner(D, table1m, theta, 0.02, paired=False, batch=2 * R)
+    a.step_arrays(np.zeros(2 * R, np.int64), idx2, sign2, rew2, 0.0)
+    b.step_arrays(np.zeros(2 * R, np.int64), idx2, sign2, rew2, 0.0)
+    assert rel_max(a.gradient_memory, b.gradient_memory) <= 2e-6
+    s = np.std(rew2)
+    ident = np.zeros(P)
+    for j in range(R):
+        eps = table1m._table[idx[j]:idx[j] + P].astype(np.float64)
+        ident += (rp[j] - rm[j]) / s * eps / (0.02 * np.dot(eps, eps))
+    assert rel_max(a.gradient_memory, ident) <= 1e-5
+
+
+def test_batch_order_and_repeat_launch_invariance(D, table1m):
+    rng = np.random.RandomState(11)
+    P, N = 6092, 300
+    theta = rng.randn(P).astype(np.float32)
+    idx, rewards = _batch_arrays(table1m, N, rng, P)
+    perm = rng.permutation(N)
+    a = make_learner(D, table1m, theta, 0.02, batch=N)
+    b = make_learner(D, table1m, theta, 0.02, batch=N)
+    a.step_arrays(np.zeros(N, np.int64), idx, np.ones(N, np.int8), rewards, 0.0)
+    b.step_arrays(np.zeros(N, np.int64), idx[perm], np.ones(N, np.int8), rewards[perm], 0.0)
+    assert rel_max(a.gradient_memory, b.gradient_memory) <= 2e-6
+    g1 = a.gradient_memory
+    # same rows again from the (now current) epoch: scratch counters must have reset themselves
+    a.step_arrays(np.full(N, a.epoch, np.int64), idx, np.ones(N, np.int8), rewards, 0.0)
+    assert rel_max(a.gradient_memory, g1) <= 1e-7
+
+
+def test_fd_state_mode_large_delays(D, table1m):
+    """Delayed returns against the oracle estimator over 12 steps with H = 6 (H+1 accepted epochs)."""
+    rng = np.random.RandomState(5)
+    P, N, H = 6092, 48, 6
+    theta = (rng.randn(P) * 0.1).astype(np.float32)
+    fd = make_learner(D, table1m, theta, 0.05, H=H, lr=0.05, batch=N)
+    ofd = O.FiniteDifferencesOracle(theta, O.NoiseTableOracle(1_000_000, P, 123), 0.05, 0.05, max_delayed_return=H, omega=0.3)
+    for s in range(12):
+        idx, rewards = _batch_arrays(table1m, N, rng, P)
+        epochs = fd.epoch - rng.randint(0, H + 2, size=N)       # some one epoch too old
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step_arrays(epochs, idx, np.ones(N, np.int8), rewards, 0.5)
+        oupd = ofd.step([O.Ret(int(e), str(int(i)), float(r)) for e, i, r in zip(epochs, idx, rewards)], 0.5)
+        assert fd.discarded_returns == ofd.discarded_returns
+        assert rel_max(fd.gradient_memory, ofd.gradient_memory) <= 1e-5, s
+        assert abs(upd - oupd) <= 1e-5 * oupd
+        assert np.max(np.abs(fd.policy.get_trainable_flat() - ofd.theta)) <= 5e-6, s
+
+
+def test_atari_sized_reduction_full_config(D):
+    """BASELINE config 4 size: P = 678 294, 512 antithetic pairs, checked against the fp64 closed form."""
+    P, R = 678294, 512
+    table = D.SharedNoiseTable(25_000_000, P, 124, device=0)
+    rng = np.random.RandomState(0)
+    theta = rng.randn(P).astype(np.float32) * 0.05
+    idx = table.sample_indices(R)
+    assert idx[:3].tolist() == [10700291, 7636593, 9022969]
+    rew = rng.randn(2 * R)
+    fd = make_learner(D, table, theta, 0.02, paired=True, batch=2 * R)
+    fd.step_arrays(np.zeros(2 * R, np.int64), np.concatenate([idx, idx]),
+                   np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8), rew, 0.0)
+    ref = O.fd_gradient_closed_form(table._table, np.concatenate([idx, idx]),
+                                    np.concatenate([np.ones(R), -np.ones(R)]), rew, 0.02, P)
+    assert rel_max(fd.gradient_memory, ref) <= 1e-5
+    cos = np.dot(fd.gradient_memory, ref) / np.linalg.norm(fd.gradient_memory) / np.linalg.norm(ref)
+    assert cos >= 1 - 1e-8
+
+
+def test_worker_batched_collect_and_learning(D, table1m):
+    """Worker.collect_returns(n) -> FDReturns -> learner.step: flags/keys follow the reference streams and
+    the synthetic objective improves."""
+    torch.manual_seed(124)
+    table = D.SharedNoiseTable(1_000_000, 6092, 124, device=0)
+    pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+    agent = D.SyntheticAgent(pol, obs_per_member=8, seed=0)
+    w = D.Worker(pol, agent, table, None, sigma=0.02, eval_prob=0.1, random_seed=124)
+    w.epoch = 0
+    ot = O.NoiseTableOracle(1_000_000, 6092, 124)
+    flags, oidx = O.draw_flags_and_indices(np.random.RandomState(124), ot, 0.1, 64)
+    rets = []
+    while sum(1 for r in rets if not r.is_eval) < 64:
+        rets += w.collect_returns()
+    assert [r.is_eval for r in rets] == flags
+    assert [r.encoded_noise for r in rets if not r.is_eval] == [str(i) for i in oidx]
+    assert all(r.encoded_noise == "0" for r in rets if r.is_eval)
+    opt = D.DSGD([torch.nn.Parameter(torch.zeros(6092))], lr=0.02)
+    fd = D.FiniteDifferences(pol, opt, Omega(1.0), table, noise_std=0.02, batch_size=256, max_delayed_return=4)
+
+    def eval_reward():
+        return w.evaluate(np.array([True]), np.array([0]))[0].reward
+    r0 = eval_reward()
+    for _ in range(30):
+        w.epoch = fd.epoch
+        f, i = w.draw_batch(128)
+        batch = [r for r in w.evaluate(f, i, antithetic=True) if not r.is_eval]
+        fd.step(batch, 0.0, 0.0, 0.0)
+    assert eval_reward() > r0 + 1e-3

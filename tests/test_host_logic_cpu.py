@@ -1,0 +1,107 @@
+"""CPU-only host logic: noise-source interface and streams, worker draws, policy init,
+state_dict layouts, DSGD lr map — all against the golden fixtures captured from the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dfd_starter_b200.noise_sources import SharedNoiseTable, parse_key
+from dfd_starter_b200 import policies as P
+from dfd_starter_b200.dsgd import DSGD, affine_transform, is_dsgd
+from dfd_starter_b200.worker import Worker
+from dfd_starter_b200.fd_return import FDReturn
+
+
+@pytest.fixture(scope="module")
+def noise_json(golden_dir):
+    with open(os.path.join(golden_dir, "noise.json")) as f:
+        return json.load(f)
+
+
+def test_noise_source_interface_matches_reference(noise_json):
+    g = noise_json["tables"]["1000000_6092_123"]
+    t = SharedNoiseTable(g["size"], g["n_params"], g["seed"], upload=False)
+    keys = []
+    for _ in range(8):
+        k, v = t.sample()
+        assert isinstance(k, str) and v.dtype == np.float32 and v.shape == (6092,)
+        assert np.shares_memory(v, t._table)          # a view, like the reference
+        assert np.array_equal(t.decode(k), v)
+        keys.append(k)
+    assert keys == g["keys"]
+    assert np.array_equal(t.decode("-%s" % keys[0]), -t.decode(keys[0]))
+    assert parse_key("+17") == (17, 1) and parse_key("-17") == (17, -1) and parse_key("17") == (17, 1)
+    with pytest.raises(AssertionError):
+        SharedNoiseTable(10, 10, upload=False)
+
+
+def test_sample_indices_is_the_same_stream(noise_json):
+    g = noise_json["tables"]["200000_5197_124"]
+    t = SharedNoiseTable(g["size"], g["n_params"], g["seed"], upload=False)
+    assert [str(i) for i in t.sample_indices(8)] == g["keys"]
+
+
+class _StubPolicy(object):
+    num_params = 6092
+    input_shape = 17
+
+
+def test_worker_draws_match_reference_worker(noise_json):
+    g = noise_json["worker"]
+    t = SharedNoiseTable(g["size"], 6092, g["seed"], upload=False)
+    w = Worker(_StubPolicy(), None, t, None, sigma=0.02, eval_prob=g["eval_prob"], random_seed=g["seed"])
+    flags, idx = w.draw_batch(g["batch"])
+    assert flags.tolist() == g["flags"]
+    assert [str(i) for i in idx[~flags]] == g["keys"]
+
+
+def test_policy_init_bit_identical(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mujoco_c2.npz"))
+    torch.manual_seed(124)
+    th, _ = P.initial_parameters("mujoco", 17, 6, 124)
+    assert np.array_equal(th, g["theta"])
+    g = np.load(os.path.join(golden_dir, "discrete_c1.npz"))
+    torch.manual_seed(124)
+    th, buf = P.initial_parameters("discrete", 2, 9, 124)
+    assert np.array_equal(th, g["theta"])
+    assert buf.shape == (263,)
+
+
+def test_layouts_and_state_dict_roundtrip(golden_dir):
+    assert P.build_layout("mujoco", 17, 6).num_params == 6092
+    assert P.build_layout("mujoco", 376, 17, 256, 256).num_params == 171042
+    assert P.build_layout("atari", 0, 6).num_params == 678294
+    L = P.build_layout("impala", 0, 15)
+    assert (L.num_params, L.num_buffers) == (1158709, 5367)
+    off = {e["name"]: e["off"] for e in L.entries if e["param"]}
+    # SURVEY.md App. B offsets
+    assert off["model.0.fc.1.weight"] == 102438 and off["model.0.core.weight_ih_l0"] == 626982
+    assert off["model.0.policy.1.bias"] == 1158694 and off["model.0.resnet2.0.0.weight"] == 56390
+    g = np.load(os.path.join(golden_dir, "discrete_c1.npz"))
+    Ld = P.build_layout("discrete", 2, 9)
+    theta, buf = Ld.split_state(g["serialized"])
+    assert np.array_equal(theta, g["theta"])
+    assert np.array_equal(Ld.join_state(theta, buf), g["serialized"])
+    with pytest.raises(ValueError):
+        Ld.split_state(g["serialized"][:-1])
+
+
+def test_dsgd_lr_scale_map():
+    class Om(object):
+        omega, min_omega, max_omega = 0.3, 0.0, 1.0
+    opt = DSGD([torch.nn.Parameter(torch.zeros(6092))], lr=0.01)
+    assert is_dsgd(opt) and abs(opt.coef - np.sqrt(6092)) < 1e-12
+    opt.adjust_lr(Om())
+    assert abs(opt.lr_scale - (0.23 + 0.3 * 0.77)) < 1e-12
+    assert affine_transform(1.0, 0.0, 0.0, 0.23, 1.0) == 0.23
+    assert not is_dsgd(torch.optim.SGD([torch.nn.Parameter(torch.zeros(3))], lr=0.1))
+
+
+def test_fd_return_record_roundtrip():
+    r = FDReturn()
+    r.epoch, r.encoded_noise, r.reward = 3, "123", 1.5
+    q = FDReturn()
+    q.deserialize(r.serialize())
+    assert (q.epoch, q.encoded_noise, q.reward, q.is_eval) == (3, "123", 1.5, False)
