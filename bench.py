@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=0, help="override antithetic pairs per GPU")
     ap.add_argument("--table-size", type=int, default=TABLE_SIZE)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"],
+                    help="forward arithmetic: fp32 CUDA cores (exact path) or tf32 tcgen05 tensor cores; "
+                         "auto = tf32 for MuJoCo MLPs with >= 32 observations per member")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-members", type=int, default=0)
@@ -275,7 +278,9 @@ def b200_main(args, w):
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
     cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
-    policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local)
+    use_tc = args.precision == "tf32" or (args.precision == "auto" and w["kind"] == "mujoco" and E >= 32)
+    policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,
+                 precision=1 if use_tc else 0)
     P = policy.num_params
     table = D.SharedNoiseTable(args.table_size, P, TABLE_SEED, device=local)
     policy.bind_table(table)
@@ -525,7 +530,8 @@ def b200_main(args, w):
     line = {
         "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(args, w),
+        "vs_baseline": None, "dtype": "tf32 forward (fp32 accumulate), f32 estimator" if use_tc else "f32",
+        "data": "synthetic", "config": bench_config(args, w),
         "fd_estimates_per_s": 1e3 / ms_step,
         "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
         "roofline": roofline, "kernels": kernels, "e2e": e2e,

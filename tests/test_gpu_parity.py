@@ -73,9 +73,13 @@ def test_table_replicas_and_prefix(D, table1m):
         assert np.array_equal(rep[s, :t.shape[0] - s], t[s:])
         assert not rep[s, t.shape[0] - s:].any()
     pref = dt.prefix.cpu().numpy()
-    ref = np.concatenate([[0.0], np.cumsum(t.astype(np.float64) ** 2)])
+    ref = np.concatenate([[0.0], np.cumsum(t.astype(np.longdouble) ** 2)])      # 80-bit reference
     assert pref[0] == 0.0
-    assert np.max(np.abs(pref - ref) / np.maximum(ref, 1.0)) < 1e-13
+    assert np.max(np.abs(pref - ref) / np.maximum(ref, 1.0)) < 1e-14
+    # what the estimator uses: ||table[i:i+P]||^2 = prefix[i+P] - prefix[i]
+    for i, P in [(0, 6092), (850700, 6092), (3, 1), (999000, 1000), (17, 678294)]:
+        exact = float(np.sum(t[i:i + P].astype(np.longdouble) ** 2))
+        assert abs((pref[i + P] - pref[i]) - exact) <= 1e-11 * exact
 
 
 # ---------------------------------------------------------------- a5 perturbation
@@ -103,8 +107,8 @@ def test_perturbation_bit_exact_all_alignments(D, table1m, P):
     idx = np.concatenate([np.arange(8), rng.randint(0, 1_000_000 - P, size=24), [1_000_000 - P - 1, 0]]).astype(np.int64)
     sign = rng.choice([-1, 0, 1], size=len(idx)).astype(np.int8)
     out = torch.empty(len(idx), P + 3, device="cuda")        # odd stride: exercises the unaligned path too
-    _lib.check(ctx.lib.dfd_perturb_members(ctx.handle, table1m.device_table.ref(), ptr(torch.from_numpy(theta).cuda()), P,
-                                           ptr(torch.from_numpy(idx).cuda()), ptr(torch.from_numpy(sign).cuda()),
+    theta_d, idx_d, sign_d = torch.from_numpy(theta).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda()
+    _lib.check(ctx.lib.dfd_perturb_members(ctx.handle, table1m.device_table.ref(), ptr(theta_d), P, ptr(idx_d), ptr(sign_d),
                                            len(idx), 0.02, ptr(out), P + 3, ctx.stream))
     got = out.cpu().numpy()[:, :P]
     for m in range(len(idx)):
@@ -278,7 +282,7 @@ def test_batch_order_and_repeat_launch_invariance(D, table1m):
     g1 = a.gradient_memory
     # same rows again from the (now current) epoch: scratch counters must have reset themselves
     a.step_arrays(np.full(N, a.epoch, np.int64), idx, np.ones(N, np.int8), rewards, 0.0)
-    assert rel_max(a.gradient_memory, g1) <= 1e-7
+    assert rel_max(a.gradient_memory, g1) <= 1e-6      # one extra (zero-weight) distance row changes the row split
 
 
 def test_fd_state_mode_large_delays(D, table1m):
