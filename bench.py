@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"],
                     help="forward arithmetic: fp32 CUDA cores (exact path) or tf32 tcgen05 tensor cores; "
                          "auto = tf32 for MuJoCo MLPs with >= 32 observations per member")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="for runs under ncu: timed steps only (no clock-load loop, per-kernel timing, e2e or CPU baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-members", type=int, default=0)
@@ -378,6 +380,12 @@ def b200_main(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "ms_per_step": ms_step, "launches": launches_plain}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # keep the same step running ~1.5 s so nvidia-smi (100 ms period) sees the clocks under this load
     t_load0 = time.perf_counter()
     kk = 0

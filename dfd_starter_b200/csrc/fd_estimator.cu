@@ -81,28 +81,55 @@ __device__ __forceinline__ double block_reduce_d(double v, double* sh, int op /*
 }
 
 // single CTA.  standardize_arr (utils/math_helpers.py:127-134): population std, identity when std == 0.
-__global__ void __launch_bounds__(1024) fd_coef_kernel(const float* __restrict__ replicas, int64_t stride,
-                                                       const double* __restrict__ prefix, int64_t P,
-                                                       const double* __restrict__ reward,
-                                                       const int64_t* __restrict__ idx,
-                                                       const int8_t* __restrict__ sign,
-                                                       const int32_t* __restrict__ hist_row, int n, int paired,
-                                                       double baseline, float sigma, const float* __restrict__ dist,
-                                                       int64_t dist_stride, int n_hist,
-                                                       const double* __restrict__ stats_reward, int n_stats,
-                                                       const double* __restrict__ dots, const float** row_ptr,
-                                                       float* __restrict__ row_coef) {
+// Each thread owns up to COEF_PER returns per pass and issues all of their global loads (reward, idx,
+// sign, hist_row, then the two prefix entries) before the block-wide statistics, so the DRAM latencies overlap.
+static const int COEF_THREADS = 1024;
+static const int COEF_PER = 4;
+
+__global__ void __launch_bounds__(COEF_THREADS) fd_coef_kernel(const float* __restrict__ replicas, int64_t stride,
+                                                               const double* __restrict__ prefix, int64_t P,
+                                                               const double* __restrict__ reward,
+                                                               const int64_t* __restrict__ idx,
+                                                               const int8_t* __restrict__ sign,
+                                                               const int32_t* __restrict__ hist_row, int n, int paired,
+                                                               double baseline, float sigma,
+                                                               const float* __restrict__ dist, int64_t dist_stride,
+                                                               int n_hist, const double* __restrict__ stats_reward,
+                                                               int n_stats, const double* __restrict__ dots,
+                                                               const float** row_ptr, float* __restrict__ row_coef) {
     __shared__ double sh[32];
     __shared__ double q_hist[128];  // n_hist <= 128
+    __shared__ double c_pair[COEF_THREADS * COEF_PER];   // per-return coefficient, for the antithetic merge
     const double* sr = stats_reward ? stats_reward : reward;
     const int ns = stats_reward ? n_stats : n;
-    // finite_differences.py:40  rewards - policy_reward ; :43 standardize
+    const double sig = (double)sigma;
+    const double* dd = dots + n;
+    const int R = paired ? n / 2 : n;
+    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) q_hist[h] = 0.0;
+
+    // statistics over the (possibly global) reward vector: finite_differences.py:40,43
     double s = 0.0, mn = 1e300, mx = -1e300;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) {
         const double x = sr[i] - baseline;
         s += x;
         mn = fmin(mn, x);
         mx = fmax(mx, x);
+    }
+    // first batch of this thread's returns: loads in flight while the reductions run
+    double x_[COEF_PER], n2_[COEF_PER], sg_[COEF_PER];
+    int h_[COEF_PER];
+#pragma unroll
+    for (int j = 0; j < COEF_PER; ++j) {
+        const int i = threadIdx.x + j * COEF_THREADS;
+        x_[j] = 0.0; n2_[j] = 1.0; sg_[j] = 0.0; h_[j] = -1;
+        if (i < n) {
+            const int64_t id = idx[i];
+            x_[j] = reward[i] - baseline;
+            sg_[j] = (double)sign[i];
+            h_[j] = hist_row[i];
+            n2_[j] = sig * sig * (prefix[id + P] - prefix[id]);
+            if (h_[j] >= 0) n2_[j] += 2.0 * sg_[j] * sig * dots[i] + dd[h_[j]];
+        }
     }
     const double mean = block_reduce_d(s, sh, 0) / (double)ns;
     mn = block_reduce_d(mn, sh, 1);
@@ -114,29 +141,57 @@ __global__ void __launch_bounds__(1024) fd_coef_kernel(const float* __restrict__
     }
     double sd = sqrt(block_reduce_d(v, sh, 0) / (double)ns);
     if (mn == mx) sd = 0.0;  // all rewards equal: numpy's std is exactly 0 and the array passes through
-    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) q_hist[h] = 0.0;
-    __syncthreads();
 
-    const double sig = (double)sigma;
-    const double* dd = dots + n;
-    const int R = paired ? n / 2 : n;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        double c = 0.0;
-        for (int k = 0; k < (paired ? 2 : 1); ++k) {
-            const int i = r + k * R;
-            const double x = reward[i] - baseline;
-            const double w = sd == 0.0 ? x : (x - mean) / sd;
-            const int64_t id = idx[i];
-            const double sg = (double)sign[i];
-            double n2 = sig * sig * (prefix[id + P] - prefix[id]);
-            const int h = hist_row[i];
-            if (h >= 0) n2 += 2.0 * sg * sig * dots[i] + dd[h];
-            const double winv = w / n2;
-            c += winv * sg * sig;
-            if (h >= 0) atomicAdd(&q_hist[h], winv);
+    for (int base = 0; base < n; base += COEF_THREADS * COEF_PER) {
+        if (base > 0) {   // later batches (n > 4096): plain loads
+#pragma unroll
+            for (int j = 0; j < COEF_PER; ++j) {
+                const int i = base + threadIdx.x + j * COEF_THREADS;
+                x_[j] = 0.0; n2_[j] = 1.0; sg_[j] = 0.0; h_[j] = -1;
+                if (i < n) {
+                    const int64_t id = idx[i];
+                    x_[j] = reward[i] - baseline;
+                    sg_[j] = (double)sign[i];
+                    h_[j] = hist_row[i];
+                    n2_[j] = sig * sig * (prefix[id + P] - prefix[id]);
+                    if (h_[j] >= 0) n2_[j] += 2.0 * sg_[j] * sig * dots[i] + dd[h_[j]];
+                }
+            }
         }
-        row_ptr[r] = table_row_ptr(replicas, stride, idx[r]);
-        row_coef[r] = (float)c;
+#pragma unroll
+        for (int j = 0; j < COEF_PER; ++j) {
+            const int i = base + threadIdx.x + j * COEF_THREADS;
+            if (i < n) {
+                const double w = sd == 0.0 ? x_[j] : (x_[j] - mean) / sd;
+                const double winv = w / n2_[j];
+                const double c = winv * sg_[j] * sig;
+                if (h_[j] >= 0) atomicAdd(&q_hist[h_[j]], winv);
+                if (!paired) {
+                    row_ptr[i] = table_row_ptr(replicas, stride, idx[i]);
+                    row_coef[i] = (float)c;
+                } else if (i < R) {
+                    row_ptr[i] = table_row_ptr(replicas, stride, idx[i]);
+                }
+                c_pair[threadIdx.x + j * COEF_THREADS] = c;
+            }
+        }
+        if (paired) {
+            // plus-member i and minus-member i + R may sit in different batches when n > 4096: accumulate in global
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < COEF_PER; ++j) {
+                const int i = base + threadIdx.x + j * COEF_THREADS;
+                if (i < n) {
+                    const int r = i < R ? i : i - R;
+                    if (n <= COEF_THREADS * COEF_PER) {
+                        if (i < R) row_coef[r] = (float)(c_pair[i] + c_pair[i + R]);
+                    } else {
+                        atomicAdd(row_coef + r, (float)c_pair[threadIdx.x + j * COEF_THREADS]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
     __syncthreads();
     for (int h = threadIdx.x; h < n_hist; h += blockDim.x) {
@@ -169,7 +224,9 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
                                                      dist, dist_stride, n_params, dots);
         DFD_LAUNCHED(ctx);
     }
-    fd_coef_kernel<<<1, 1024, 0, st>>>(table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx,
+    if (paired && n_returns > COEF_THREADS * COEF_PER)   // large paired batches merge through atomics: start from zero
+        DFD_CUDA(cudaMemsetAsync(rows->row_coef, 0, (size_t)R * sizeof(float), st));
+    fd_coef_kernel<<<1, COEF_THREADS, 0, st>>>(table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx,
                                        sign, hist_row, n_returns, paired, baseline, sigma, dist, dist_stride, n_hist,
                                        stats_reward, n_stats, dots, rows->row_ptr, rows->row_coef);
     DFD_LAUNCHED(ctx);
@@ -394,8 +451,8 @@ __global__ void __launch_bounds__(DSGD_THREADS) sumsq_partial_kernel(const float
 __global__ void __launch_bounds__(DSGD_THREADS) dsgd_update_kernel(float* __restrict__ theta,
                                                                    const float* __restrict__ g, int64_t P, double step,
                                                                    const double* __restrict__ gnorm_partial,
-                                                                   int n_partial, float* __restrict__ hist,
-                                                                   float* __restrict__ dist, int64_t hist_stride,
+                                                                   int n_partial, float* hist,
+                                                                   float* dist, int64_t hist_stride,
                                                                    int n_hist_valid, int hist_write_row,
                                                                    double* __restrict__ upd_partial,
                                                                    unsigned* __restrict__ done_counter,
@@ -419,12 +476,20 @@ __global__ void __launch_bounds__(DSGD_THREADS) dsgd_update_kernel(float* __rest
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const float t_old = theta[p];
         const float t_new = __fsub_rn(t_old, __fmul_rn(coef, -g[p]));
-        theta[p] = t_new;
         const float d = __fsub_rn(t_old, t_new);
         acc += (double)d * (double)d;
-        for (int r = 0; r < n_hist_valid; ++r)
-            dist[(int64_t)r * hist_stride + p] = __fsub_rn(hist[(int64_t)r * hist_stride + p], t_new);
-        if (hist_write_row >= 0) hist[(int64_t)hist_write_row * hist_stride + p] = t_new;
+        // history rows: all loads of a batch are issued before its stores (hist is read AND written here)
+        for (int r0 = 0; r0 < n_hist_valid; r0 += 8) {
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                h[j] = (r0 + j < n_hist_valid) ? __ldcg(hist + (int64_t)(r0 + j) * hist_stride + p) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (r0 + j < n_hist_valid) __stcg(dist + (int64_t)(r0 + j) * hist_stride + p, __fsub_rn(h[j], t_new));
+        }
+        theta[p] = t_new;
+        if (hist_write_row >= 0) __stcg(hist + (int64_t)hist_write_row * hist_stride + p, t_new);
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -459,7 +524,7 @@ extern "C" int dfd_dsgd_step(dfd_ctx* ctx, float* theta, const float* grad, int6
     DFD_CHECK_ARG((n_hist_valid == 0 && hist_write_row < 0) || (hist && dist && hist_stride >= n_params),
                   "dfd_dsgd_step: history buffers missing");
     cudaStream_t st = (cudaStream_t)stream;
-    int ctas = (int)((n_params + DSGD_THREADS * 4 - 1) / (DSGD_THREADS * 4));
+    int ctas = (int)((n_params + DSGD_THREADS - 1) / DSGD_THREADS);
     if (ctas > DSGD_MAX_CTAS) ctas = DSGD_MAX_CTAS;
     if (ctas < 1) ctas = 1;
     double* gpart = (double*)scratch;
