@@ -7,7 +7,7 @@ from .dsgd import DSGD
 from .noise_sources import SharedNoiseTable
 from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
-from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, Policy
+from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
 __all__ = ["FDReturn", "FDState", "DSGD", "SharedNoiseTable", "FiniteDifferences", "Worker", "SyntheticAgent",
-           "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "Policy"]
+           "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

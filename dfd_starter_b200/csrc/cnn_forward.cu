@@ -1,20 +1,242 @@
-// Atari / IMPALA perturbed forwards (policies/atari.py:35-51, policies/impala.py:136-186).
+// Atari perturbed forward (policies/atari.py:35-51): Conv(4->16,k8,s4) BN ReLU -> Conv(16->32,k4,s2) BN ReLU
+// -> flatten(C,H,W) -> Linear(2592->256) BN ReLU -> Linear(256->A) -> softmax.  Eval-mode BN with shared
+// running statistics and per-member (perturbed) gamma / beta.  Member m evaluates
+// theta + sign[m]*sigma*table[idx[m]:idx[m]+P] (worker/worker.py:28); the perturbed weights only ever exist in
+// shared memory / registers.  98 % of the parameters are the first Linear (663 552 weights), so at small E the
+// kernel is a stream of that weight block through the SM: HBM-bound on pairs*P*4 bytes.
 #include "common.cuh"
+
+namespace {
+
+constexpr int AT_THREADS = 512;
+constexpr int AT_ET = 4;              // observations per CTA pass (FC1 weights are streamed once per pass)
+constexpr int FRAME = 4 * 84 * 84;    // 28224
+constexpr int A0N = 16 * 20 * 20;     // 6400
+constexpr int A1N = 32 * 9 * 9;       // 2592
+
+// flat parameter offsets and BN buffer offsets (state_dict order)
+constexpr int O_W0 = 0, O_B0 = 4096, O_G1 = 4112, O_BE1 = 4128, O_W3 = 4144, O_B3 = 12336, O_G4 = 12368,
+              O_BE4 = 12400, O_W7 = 12432, O_B7 = 675984, O_G8 = 676240, O_BE8 = 676496, O_W10 = 676752;
+constexpr int BU_M1 = 0, BU_V1 = 16, BU_M4 = 33, BU_V4 = 65, BU_M8 = 98, BU_V8 = 354;
+
+__global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const float* __restrict__ replicas, int64_t stride,
+                                                                      const float* __restrict__ theta,
+                                                                      const float* __restrict__ bnbuf,
+                                                                      const int64_t* __restrict__ idx,
+                                                                      const int8_t* __restrict__ sign, float sigma,
+                                                                      const float* __restrict__ obs, int E, int tiles,
+                                                                      int A, float* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float* frame = sm;                     // 28224; conv3 weights alias it once conv0 is done with the frame
+    float* w0 = frame + FRAME;             // [256 k][16 oc]
+    float* sc0 = w0 + 4096;                // 16 scale | 16 shift (conv bias and BN folded)
+    float* a0 = sc0 + 32;                  // [16][20][20]
+    float* a1 = a0 + A0N;                  // [ET][2592]
+    float* a2 = a1 + AT_ET * A1N;          // [ET][256]
+    float* lg = a2 + AT_ET * 256;          // [ET][32] logits
+    float* w3 = frame;                     // [256 k][32 oc]
+    float* sc3 = frame + 8192;             // 32 scale | 32 shift
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const int e0 = tile * AT_ET;
+    const int ne = min(AT_ET, E - e0);
+    const float sg = sigma * (float)sign[m];
+    const float* row = table_row_ptr(replicas, stride, idx[m]);
+    auto par = [&](int p) { return perturb1(theta[p], sg, row[p]); };
+
+    // conv0 weights -> [k][oc]; bias + BN1 folded into per-channel scale / shift
+    for (int t = tid; t < 4096; t += AT_THREADS) {
+        const int oc = t >> 8, k = t & 255;
+        w0[k * 16 + oc] = par(O_W0 + t);
+    }
+    if (tid < 16) {
+        const float inv = 1.0f / sqrtf(bnbuf[BU_V1 + tid] + 1e-5f);
+        const float s = par(O_G1 + tid) * inv;
+        sc0[tid] = s;
+        sc0[16 + tid] = (par(O_B0 + tid) - bnbuf[BU_M1 + tid]) * s + par(O_BE1 + tid);
+    }
+
+    for (int e = 0; e < ne; ++e) {
+        __syncthreads();   // previous observation is done with frame / w3 / a0
+        const float* fr = obs + ((int64_t)m * E + e0 + e) * FRAME;
+        for (int t = tid; t < FRAME / 4; t += AT_THREADS)
+            reinterpret_cast<float4*>(frame)[t] = ldg_stream_f4(fr + 4 * t);
+        __syncthreads();
+        // ---- conv0: one output pixel x 16 channels per thread (400 threads)
+        if (tid < 400) {
+            const int oy = tid / 20, ox = tid - oy * 20;
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                for (int ky = 0; ky < 8; ++ky) {
+                    const float* xr = frame + c * 7056 + (4 * oy + ky) * 84 + 4 * ox;
+                    const float4 x0 = *reinterpret_cast<const float4*>(xr);
+                    const float4 x1 = *reinterpret_cast<const float4*>(xr + 4);
+                    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    const float* wk = w0 + (c * 64 + ky * 8) * 16;
+#pragma unroll
+                    for (int kx = 0; kx < 8; ++kx) {
+                        const float4* w4 = reinterpret_cast<const float4*>(wk + kx * 16);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 w = w4[q];
+                            acc[4 * q + 0] = fmaf(w.x, xs[kx], acc[4 * q + 0]);
+                            acc[4 * q + 1] = fmaf(w.y, xs[kx], acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(w.z, xs[kx], acc[4 * q + 2]);
+                            acc[4 * q + 3] = fmaf(w.w, xs[kx], acc[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int oc = 0; oc < 16; ++oc) a0[oc * 400 + tid] = fmaxf(fmaf(acc[oc], sc0[oc], sc0[16 + oc]), 0.f);
+        }
+        __syncthreads();
+        // ---- conv3 weights -> [k][oc] over the (now free) frame region; bias + BN4 folded
+        for (int t = tid; t < 8192; t += AT_THREADS) {
+            const int oc = t >> 8, k = t & 255;
+            w3[k * 32 + oc] = par(O_W3 + t);
+        }
+        if (tid < 32) {
+            const float inv = 1.0f / sqrtf(bnbuf[BU_V4 + tid] + 1e-5f);
+            const float s = par(O_G4 + tid) * inv;
+            sc3[tid] = s;
+            sc3[32 + tid] = (par(O_B3 + tid) - bnbuf[BU_M4 + tid]) * s + par(O_BE4 + tid);
+        }
+        __syncthreads();
+        // ---- conv3: one output pixel x 8 channels per thread (81 pixels x 4 channel groups = 324 threads)
+        if (tid < 324) {
+            const int pix = tid % 81, og = tid / 81;
+            const int oy = pix / 9, ox = pix - oy * 9;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            for (int c = 0; c < 16; ++c) {
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) {
+                    const float* xr = a0 + c * 400 + (2 * oy + ky) * 20 + 2 * ox;
+                    const float2 xa = *reinterpret_cast<const float2*>(xr);
+                    const float2 xb = *reinterpret_cast<const float2*>(xr + 2);
+                    const float xs[4] = {xa.x, xa.y, xb.x, xb.y};
+                    const float* wk = w3 + (c * 16 + ky * 4) * 32 + og * 8;
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const float4 wa = *reinterpret_cast<const float4*>(wk + kx * 32);
+                        const float4 wb = *reinterpret_cast<const float4*>(wk + kx * 32 + 4);
+                        acc[0] = fmaf(wa.x, xs[kx], acc[0]);
+                        acc[1] = fmaf(wa.y, xs[kx], acc[1]);
+                        acc[2] = fmaf(wa.z, xs[kx], acc[2]);
+                        acc[3] = fmaf(wa.w, xs[kx], acc[3]);
+                        acc[4] = fmaf(wb.x, xs[kx], acc[4]);
+                        acc[5] = fmaf(wb.y, xs[kx], acc[5]);
+                        acc[6] = fmaf(wb.z, xs[kx], acc[6]);
+                        acc[7] = fmaf(wb.w, xs[kx], acc[7]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int oc = og * 8 + i;
+                a1[e * A1N + oc * 81 + pix] = fmaxf(fmaf(acc[i], sc3[oc], sc3[32 + oc]), 0.f);   // flatten (C,H,W)
+            }
+        }
+    }
+    for (int t = tid; t < (AT_ET - ne) * A1N; t += AT_THREADS) a1[ne * A1N + t] = 0.f;   // ragged tile
+    __syncthreads();
+
+    // ---- Linear 2592 -> 256: each warp streams 16 weight rows (theta + sg*eps, 16-byte vectors), AT_ET
+    //      observations share every weight; then bias + BN8 + ReLU
+    for (int o = warp; o < 256; o += AT_THREADS / 32) {
+        const int64_t base = O_W7 + (int64_t)o * A1N;
+        float acc[AT_ET];
+#pragma unroll
+        for (int e = 0; e < AT_ET; ++e) acc[e] = 0.f;
+        for (int it0 = 0; it0 < 648; it0 += 32 * 4) {
+            float4 tw[4], ew[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = it0 + u * 32 + lane;
+                tw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                ew[u] = tw[u];
+                if (v < 648) {
+                    tw[u] = *reinterpret_cast<const float4*>(theta + base + 4 * v);
+                    ew[u] = ldg_stream_f4(row + base + 4 * v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = it0 + u * 32 + lane;
+                if (v < 648) {
+                    const float4 w = make_float4(perturb1(tw[u].x, sg, ew[u].x), perturb1(tw[u].y, sg, ew[u].y),
+                                                 perturb1(tw[u].z, sg, ew[u].z), perturb1(tw[u].w, sg, ew[u].w));
+#pragma unroll
+                    for (int e = 0; e < AT_ET; ++e) {
+                        const float4 x = *reinterpret_cast<const float4*>(a1 + e * A1N + 4 * v);
+                        acc[e] = fmaf(w.x, x.x, acc[e]);
+                        acc[e] = fmaf(w.y, x.y, acc[e]);
+                        acc[e] = fmaf(w.z, x.z, acc[e]);
+                        acc[e] = fmaf(w.w, x.w, acc[e]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < AT_ET; ++e) acc[e] = warp_sum(acc[e]);
+        if (lane == 0) {
+            const float inv = 1.0f / sqrtf(bnbuf[BU_V8 + o] + 1e-5f);
+            const float s = par(O_G8 + o) * inv;
+            const float sh = (par(O_B7 + o) - bnbuf[BU_M8 + o]) * s + par(O_BE8 + o);
+#pragma unroll
+            for (int e = 0; e < AT_ET; ++e) a2[e * 256 + o] = fmaxf(fmaf(acc[e], s, sh), 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- Linear 256 -> A (warp per action), softmax per observation
+    for (int a = warp; a < A; a += AT_THREADS / 32) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = par(O_W10 + a * 256 + lane + 32 * j);
+        const float b = par(O_W10 + A * 256 + a);
+        for (int e = 0; e < ne; ++e) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(w[j], a2[e * 256 + lane + 32 * j], s);
+            s = warp_sum(s);
+            if (lane == 0) lg[e * 32 + a] = s + b;
+        }
+    }
+    __syncthreads();
+    if (tid < ne) {
+        const float* l = lg + tid * 32;
+        float mx = -INFINITY;
+        for (int a = 0; a < A; ++a) mx = fmaxf(mx, l[a]);
+        float s = 0.f;
+        for (int a = 0; a < A; ++a) s += expf(l[a] - mx);
+        const float inv = 1.0f / s;
+        float* o = out + ((int64_t)m * E + e0 + tid) * A;
+        for (int a = 0; a < A; ++a) o[a] = expf(l[a] - mx) * inv;
+    }
+}
+
+}  // namespace
 
 int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                            const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
                            const float* obs, int obs_per_member, float* out, cudaStream_t st) {
-    dfd_set_error("dfd_policy_forward: the Atari forward is not built yet");
-    return 4;
-}
-
-extern "C" size_t dfd_impala_scratch_bytes(int n_members, int obs_per_member) { return 256; }
-
-extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
-                                  const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members,
-                                  float sigma, const float* frame, const float* reward, const uint8_t* done,
-                                  const float* h_in, const float* c_in, int obs_per_member, float* probs, float* h_out,
-                                  float* c_out, void* scratch, size_t scratch_bytes, dfd_stream stream) {
-    dfd_set_error("dfd_impala_forward: not built yet");
-    return 4;
+    DFD_CHECK_ARG(bn_buffers, "dfd_policy_forward: Atari needs bn_buffers");
+    DFD_CHECK_ARG(desc->n_act >= 1 && desc->n_act <= 32, "dfd_policy_forward: Atari n_act %d out of range (1..32)", desc->n_act);
+    DFD_CHECK_ARG((((uintptr_t)obs) & 15) == 0 && (((uintptr_t)theta) & 15) == 0,
+                  "dfd_policy_forward: Atari obs / theta must be 16-byte aligned");
+    DFD_CHECK_ARG(dfd_policy_num_params(desc) < table->size, "dfd_policy_forward: num_params >= table size");
+    const int tiles = (obs_per_member + AT_ET - 1) / AT_ET;
+    DFD_CHECK_ARG((int64_t)n_members * tiles < 2147483647LL, "dfd_policy_forward: grid too large");
+    const size_t smem = (size_t)(FRAME + 4096 + 32 + A0N + AT_ET * A1N + AT_ET * 256 + AT_ET * 32) * sizeof(float);
+    DFD_CUDA(cudaFuncSetAttribute(atari_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atari_forward_kernel<<<n_members * tiles, AT_THREADS, smem, st>>>(table->replicas, table->replica_stride, theta,
+                                                                      bn_buffers, idx, sign, sigma, obs, obs_per_member,
+                                                                      tiles, desc->n_act, out);
+    DFD_LAUNCHED(ctx);
+    return 0;
 }

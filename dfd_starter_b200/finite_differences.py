@@ -176,9 +176,8 @@ class FiniteDifferences(object):
         if pg is not None:
             import torch.distributed as dist
             if all_rewards is None:
-                gathered = [None] * dist.get_world_size(pg)
-                dist.all_gather_object(gathered, rewards, group=pg)
-                all_rewards = np.concatenate(gathered)
+                from .dist import all_gather_rewards
+                all_rewards = all_gather_rewards(rewards, pg)
             if all_rewards.shape[0] == 0:
                 return 0
             stats = torch.from_numpy(np.ascontiguousarray(all_rewards, dtype=np.float64)).to(self.ctx.device)

@@ -362,4 +362,58 @@ class AtariPolicy(DiscretePolicy):
         raise NotImplementedError("AtariPolicy.compute_vbn: refresh BN statistics with set_buffers()")
 
 
-POLICY_CLASSES = {"mujoco": MujocoPolicy, "discrete": DiscretePolicy, "atari": AtariPolicy}
+class ImpalaPolicy(DiscretePolicy):
+    """policies/impala.py:8-186: IMPALA ResNet trunk + FC + LSTM(257->256) + softmax head.
+    n_inputs = (3, 64, 64).  The carried LSTM state lives on the device, one (h, c) pair of 256
+    floats per (member, environment); `reset()` zeroes the M = 1 wrapper state (impala.py:29-30)."""
+    kind = "impala"
+
+    def __init__(self, n_inputs, n_actions, seed=124, device=None, precision=0):
+        super().__init__(n_inputs, n_actions, seed=seed, device=device, precision=precision)
+        self.input_shape = tuple(n_inputs)
+        self.state = None
+        self.reset()
+
+    def _obs_shape(self):
+        return (3, 64, 64)
+
+    def reset(self):
+        dev = self.ctx.device
+        self.state = (torch.zeros(1, 1, 256, device=dev), torch.zeros(1, 1, 256, device=dev))
+
+    def forward_members_impala(self, idx, sign, frame, reward, done, h, c, sigma):
+        """idx/sign [M]; frame [M,E,3,64,64] float 0..255; reward [M,E] float; done [M,E] bool/uint8;
+        h, c [M,E,256].  Returns probs [M,E,A], h', c' — E independent environments per member."""
+        if self._table is None:
+            raise _lib.DfdError("policy.bind_table(noise_source) must be called before forward_members_impala")
+        M, E = frame.shape[0], frame.shape[1]
+        dev = self.ctx.device
+        frame = frame.contiguous().float()
+        reward = reward.contiguous().float()
+        done8 = done.contiguous().to(torch.uint8)
+        h, c = h.contiguous(), c.contiguous()
+        probs = torch.empty(M, E, self.out_width, device=dev)
+        h1, c1 = torch.empty_like(h), torch.empty_like(c)
+        _lib.check(self.ctx.lib.dfd_impala_forward(
+            self.ctx.handle, C.byref(self.desc), self._table.ref(), ptr(self.theta), ptr(self.buffers), ptr(idx),
+            ptr(sign), M, float(sigma), ptr(frame), ptr(reward), ptr(done8), ptr(h), ptr(c), E, ptr(probs), ptr(h1),
+            ptr(c1), None, 0, self.ctx.stream), "dfd_impala_forward")
+        return probs, h1, c1
+
+    def forward(self, x):
+        """Reference call shape: dict(frame (1,1,3,64,64) 0..255, reward (1,1), done (1,1)); one step of the
+        carried state (impala.py:136-186)."""
+        dev = self.ctx.device
+        frame = torch.as_tensor(x["frame"]).float().reshape(1, 1, 3, 64, 64).to(dev)
+        reward = torch.as_tensor(x["reward"]).float().reshape(1, 1).to(dev)
+        done = torch.as_tensor(x["done"]).reshape(1, 1).to(dev)
+        probs, h1, c1 = self.forward_members_impala(self._one_idx, self._one_sign, frame, reward, done,
+                                                    self.state[0], self.state[1], 0.0)
+        self.state = (h1, c1)
+        return probs[0]
+
+    def compute_vbn(self, buffer):
+        raise NotImplementedError("ImpalaPolicy.compute_vbn: refresh BN statistics with set_buffers()")
+
+
+POLICY_CLASSES = {"mujoco": MujocoPolicy, "discrete": DiscretePolicy, "atari": AtariPolicy, "impala": ImpalaPolicy}

@@ -513,3 +513,19 @@ def fd_gradient_closed_form(table, idx, sign, rewards, sigma, n_params, baseline
         lam = lam.astype(np.float64)
         g += w[i] * lam / np.dot(lam, lam)
     return g
+
+
+def fd_partial_gradient(table, idx, sign, rewards, all_rewards, sigma, n_params, baseline=0.0):
+    """A rank's share of the estimator when the population is sharded: weights are standardised with
+    the mean / std of ALL ranks' rewards, the sum runs over this rank's rows only.  Summing the partial
+    gradients over ranks gives `fd_gradient_closed_form` of the whole batch (linearity of :49)."""
+    allr = np.asarray(all_rewards, dtype=np.float64) - baseline
+    m, s = allr.mean(), allr.std()
+    x = np.asarray(rewards, dtype=np.float64) - baseline
+    w = x if s == 0 else (x - m) / s
+    g = np.zeros(n_params)
+    sig32 = np.float32(sigma)
+    for i in range(len(idx)):
+        lam = (table[idx[i]:idx[i] + n_params] * sig32 * np.float32(sign[i])).astype(np.float64)
+        g += w[i] * lam / np.dot(lam, lam)
+    return g

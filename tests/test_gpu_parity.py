@@ -352,3 +352,78 @@ def test_worker_batched_collect_and_learning(D, table1m):
         batch = [r for r in w.evaluate(f, i, antithetic=True) if not r.is_eval]
         fd.step(batch, 0.0, 0.0, 0.0)
     assert eval_reward() > r0 + 1e-3
+
+
+# ---------------------------------------------------------------- a9 Atari CNN
+def test_atari_forward_golden(D, golden_dir):
+    """policies/atari.py:35-51 against the reference's own outputs (synthetic seeded theta / BN stats)."""
+    g = np.load(os.path.join(golden_dir, "atari_c4.npz"))
+    L = O.atari_layout(6)
+    table = D.SharedNoiseTable(int(g["table_size"]), L.num_params, int(g["table_seed"]), device=0)
+    pol = D.AtariPolicy((84, 84), 6, seed=124, device=0).bind_table(table)
+    assert pol.num_params == 678294 and pol.input_shape == (4, 84, 84)
+    pol.set_trainable_flat(O.synthetic_theta(L, int(g["theta_seed"])))
+    pol.set_buffers(O.synthetic_buffers(L, int(g["buffer_seed"])))
+    obs = torch.rand(3, 2, 4, 84, 84, generator=torch.Generator().manual_seed(int(g["obs_seed"])))
+    out = pol.forward_members(torch.from_numpy(g["idx"].astype(np.int64)).cuda(),
+                              torch.from_numpy(g["sign"].astype(np.int8)).cuda(), obs.cuda(), float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out.sum(-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("E", [1, 5])
+def test_atari_forward_vs_oracle_ragged(D, E):
+    L = O.atari_layout(6)
+    table = D.SharedNoiseTable(1_000_000, L.num_params, 123, device=0)
+    pol = D.AtariPolicy((84, 84), 6, seed=124, device=0).bind_table(table)
+    theta, buf = O.synthetic_theta(L, 41), O.synthetic_buffers(L, 42)
+    pol.set_trainable_flat(theta)
+    pol.set_buffers(buf)
+    rng = np.random.RandomState(E)
+    M = 3
+    idx = rng.randint(0, 1_000_000 - L.num_params, size=M).astype(np.int64)
+    sign = np.array([1, -1, 0], dtype=np.int8)
+    obs = rng.rand(M, E, 4, 84, 84).astype(np.float32)
+    out = pol.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(),
+                              0.02).cpu().numpy()
+    for m in range(M):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + L.num_params], int(sign[m]))
+        np.testing.assert_allclose(out[m], O.atari_forward(L, th, buf, obs[m]), rtol=0, atol=1e-5)
+    # reference single-policy wrapper: NCHW tensor in, action index out
+    assert 0 <= pol.get_action(obs[0, 0], deterministic=True) < 6
+
+
+# ---------------------------------------------------------------- a10 IMPALA CNN + LSTM
+def test_impala_forward_golden(D, golden_dir):
+    """policies/impala.py:136-186 against the reference's own outputs: probs and the carried (h, c),
+    non-zero incoming state, one `done` environment, clamped rewards."""
+    g = np.load(os.path.join(golden_dir, "impala_c5.npz"))
+    L = O.impala_layout(15)
+    table = D.SharedNoiseTable(int(g["table_size"]), L.num_params, int(g["table_seed"]), device=0)
+    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0).bind_table(table)
+    assert pol.num_params == 1158709
+    pol.set_trainable_flat(O.synthetic_theta(L, int(g["theta_seed"])))
+    pol.set_buffers(O.synthetic_buffers(L, int(g["buffer_seed"])))
+    gen = torch.Generator().manual_seed(int(g["frame_seed"]))
+    frames = torch.randint(0, 256, (2, 2, 3, 64, 64), generator=gen).float()
+    h0 = 0.3 * torch.randn(2, 2, 256, generator=gen)
+    c0 = 0.3 * torch.randn(2, 2, 256, generator=gen)
+    probs, h1, c1 = pol.forward_members_impala(
+        torch.from_numpy(g["idx"].astype(np.int64)).cuda(), torch.from_numpy(g["sign"].astype(np.int8)).cuda(),
+        frames.cuda(), torch.from_numpy(g["reward"]).cuda(), torch.from_numpy(g["done"]).cuda(), h0.cuda(), c0.cuda(),
+        float(g["sigma"]))
+    np.testing.assert_allclose(probs.cpu().numpy(), g["probs"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(h1.cpu().numpy(), g["h1"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(c1.cpu().numpy(), g["c1"], rtol=0, atol=2e-5)
+    # the M = 1 wrapper carries its state across calls and reset() zeroes it
+    pol.reset()
+    inp = {"frame": frames[0, 0].view(1, 1, 3, 64, 64), "reward": torch.zeros(1, 1), "done": torch.zeros(1, 1, dtype=torch.bool)}
+    p1 = pol.forward(inp).cpu().numpy()
+    p2 = pol.forward(inp).cpu().numpy()
+    ref1, rh, rc = O.impala_forward(L, pol.get_trainable_flat(), pol.buffers.cpu().numpy(), frames[0, 0].numpy()[None],
+                                    np.zeros(1, np.float32), np.zeros(1, bool), np.zeros((1, 256), np.float32),
+                                    np.zeros((1, 256), np.float32))
+    ref2, _, _ = O.impala_forward(L, pol.get_trainable_flat(), pol.buffers.cpu().numpy(), frames[0, 0].numpy()[None],
+                                  np.zeros(1, np.float32), np.zeros(1, bool), rh, rc)
+    np.testing.assert_allclose(p1, ref1, atol=1e-5)
+    np.testing.assert_allclose(p2, ref2, atol=1e-5)
