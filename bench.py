@@ -38,6 +38,11 @@ WORKLOADS = {
                desc="C2 HalfCheetah-shaped MLP 17-64-64-6, 1024 antithetic pairs per GPU, fd_return"),
     "C3": dict(kind="mujoco", n_in=376, h1=256, h2=256, n_act=17, pairs=1024, E=128,
                desc="C3 Humanoid-shaped MLP 376-256-256-17, 8192 antithetic pairs over 8 GPUs (1024 per GPU), fd_return"),
+    "C4": dict(kind="atari", n_in=4 * 84 * 84, h1=0, h2=0, n_act=6, pairs=512, E=1,
+               desc="C4 Atari 2-conv CNN policy (84x84x4 frames), 512 antithetic pairs, fd_return"),
+    "C5": dict(kind="impala", n_in=3 * 64 * 64, h1=0, h2=0, n_act=15, pairs=256, E=1,
+               desc="C5 IMPALA-CNN + LSTM policy (64x64x3 frames), 2048 antithetic pairs over 8 GPUs (256 per GPU), "
+                    "fd_state estimator (returns from the last 10 epochs)"),
     "C1": dict(kind="discrete", n_in=2, h1=64, h2=64, n_act=9, pairs=20, E=128,
                desc="C1 simple_trap-shaped discrete MLP 2-64-64-9, 20 antithetic pairs, fd_return"),
 }
@@ -82,6 +87,10 @@ def workload(args):
 
 
 def layer_flops_per_obs(w):
+    if w["kind"] == "atari":
+        return 5934080
+    if w["kind"] == "impala":
+        return 62268928
     return 2 * (w["n_in"] * w["h1"] + w["h1"] * w["h2"] + w["h2"] * w["out_width"])
 
 
@@ -100,8 +109,14 @@ def _ref_member(m):
     if kind == "mujoco":
         mean, std = O.mujoco_forward(L, th, obs)
         out = np.concatenate([mean, std], -1)
-    else:
+    elif kind == "discrete":
         out = O.discrete_forward(L, th, bufs, obs)
+    elif kind == "atari":
+        out = O.atari_forward(L, th, bufs, obs.reshape(-1, 4, 84, 84))
+    else:
+        n = obs.shape[0]
+        out, _, _ = O.impala_forward(L, th, bufs, obs.reshape(-1, 3, 64, 64) * 255.0, np.zeros(n, np.float32),
+                                     np.zeros(n, bool), np.zeros((n, 256), np.float32), np.zeros((n, 256), np.float32))
     return float(-np.mean((out - _G["target"]) ** 2))
 
 
@@ -110,8 +125,9 @@ def run_reference(args, w, as_baseline=False):
     from oracle import dfd_oracle as O
     torch.set_num_threads(1)          # the reference clients run single-threaded (run_client.py:15)
     cores = len(os.sched_getaffinity(0))
-    P_layout = O.mujoco_layout(w["n_in"], w["n_act"], w["h1"], w["h2"]) if w["kind"] == "mujoco" else \
-        O.discrete_layout(w["n_in"], w["n_act"], w["h1"], w["h2"])
+    P_layout = {"mujoco": lambda: O.mujoco_layout(w["n_in"], w["n_act"], w["h1"], w["h2"]),
+                "discrete": lambda: O.discrete_layout(w["n_in"], w["n_act"], w["h1"], w["h2"]),
+                "atari": lambda: O.atari_layout(w["n_act"]), "impala": lambda: O.impala_layout(w["n_act"])}[w["kind"]]()
     P = P_layout.num_params
     noise = O.NoiseTableOracle(args.table_size, P, TABLE_SEED)
     theta = O.synthetic_theta(P_layout, 1)
@@ -119,7 +135,7 @@ def run_reference(args, w, as_baseline=False):
     M, E = w["members"], w["E"]
     sample = args.cpu_sample_members or min(M, max(cores * 32, 256))
     rng = np.random.RandomState(0)
-    obs = rng.randn(E, w["n_in"]).astype(np.float32)
+    obs = (rng.rand(E, w["n_in"]) if w["kind"] in ("atari", "impala") else rng.randn(E, w["n_in"])).astype(np.float32)
     _G.update(O=O, L=P_layout, theta=theta, table=noise.table, kind=w["kind"], bufs=bufs, obs=obs,
               target=np.tanh(rng.randn(w["out_width"])).astype(np.float32) * 0.5)
     import multiprocessing as mp
@@ -145,11 +161,14 @@ def run_reference(args, w, as_baseline=False):
         t_fwd = (time.perf_counter() - t0) * (M / len(members))
         rewards = rng.randn(M)
         rewards[:len(rewards_s)] = rewards_s
+        # the estimator restatement on a bounded number of returns (its cost is linear in returns x P)
+        n_fd = min(M, max(64, int(2.0e8 // P) // 2 * 2))
+        sel = np.concatenate([np.arange(n_fd // 2), w["pairs"] + np.arange(n_fd // 2)])
         fd = O.FiniteDifferencesOracle(theta, noise, SIGMA, LR, max_delayed_return=H, omega=0.0)
-        batch = [O.Ret(0, ("+%d" if s > 0 else "-%d") % i, float(r)) for i, s, r in zip(idx, sign, rewards)]
+        batch = [O.Ret(0, ("+%d" if s > 0 else "-%d") % i, float(r)) for i, s, r in zip(idx[sel], sign[sel], rewards[sel])]
         t1 = time.perf_counter()
         fd.step(batch, 0.0)
-        t_fd = time.perf_counter() - t1
+        t_fd = (time.perf_counter() - t1) * (M / n_fd)
         theta = fd.theta
         if it >= warm:
             times.append((t_fwd, t_fd))
@@ -158,8 +177,8 @@ def run_reference(args, w, as_baseline=False):
     step_s = t_fwd + t_fd
     value = M * E / step_s
     sample_txt = ("forward: %d of %d members x %d obs per step on %d processes x 1 torch thread, scaled x%.1f; "
-                  "estimator: full batch of %d returns (FiniteDifferences.step restatement, numpy BLAS threads)"
-                  % (sample, M, E, cores, M / sample, M))
+                  "estimator: %d of %d returns (FiniteDifferences.step restatement, numpy BLAS threads), scaled linearly"
+                  % (sample, M, E, cores, M / sample, n_fd, M))
     return dict(value=value, unit="env-steps/s", cores=cores, kind="port", sample=sample_txt,
                 ms_per_step=step_s * 1e3, fd_estimates_per_s=1.0 / t_fd, forward_s=t_fwd, estimator_s=t_fd)
 
@@ -184,10 +203,12 @@ def reference_main(args, w):
 
 
 def bench_config(args, w):
+    fd_mode = "fd_state (returns spread over the last %d epochs: theta-history distance rows + dot pass)" % H \
+        if w["kind"] == "impala" else "fd_return (all returns from the current epoch)"
     return {"workload": w["desc"], "policy": "%s %d-%d-%d-%d" % (w["kind"], w["n_in"], w["h1"], w["h2"], w["out_width"]),
             "pairs_per_gpu": w["pairs"], "members_per_gpu": w["members"], "obs_per_member": w["E"],
             "table": "SharedNoiseTable(%d, P, %d)" % (args.table_size, TABLE_SEED), "sigma": SIGMA,
-            "estimator": "fd_return (all returns from the current epoch), antithetic pairs merged per table row",
+            "estimator": fd_mode + ", antithetic pairs merged per table row",
             "l2": "fresh noise indices and a different observation buffer each step; table replicas (4x table) and the "
                   "rotating observation buffers exceed the 126 MB L2; the reduction re-reads rows the forward of the same "
                   "step touched (L2 reuse by design)"}
@@ -279,10 +300,19 @@ def b200_main(args, w):
 
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
-    cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
-    use_tc = args.precision == "tf32" or (args.precision == "auto" and w["kind"] == "mujoco" and E >= 32)
-    policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,
-                 precision=1 if use_tc else 0)
+    use_tc = w["kind"] == "mujoco" and (args.precision == "tf32" or (args.precision == "auto" and E >= 32))
+    if w["kind"] in ("mujoco", "discrete"):
+        cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
+        policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,
+                     precision=1 if use_tc else 0)
+        obs_shape = (w["n_in"],)
+    elif w["kind"] == "atari":
+        policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local)
+        obs_shape = (4, 84, 84)
+    else:
+        policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local)
+        obs_shape = (3, 64, 64)
+    is_impala = w["kind"] == "impala"
     P = policy.num_params
     table = D.SharedNoiseTable(args.table_size, P, TABLE_SEED, device=local)
     policy.bind_table(table)
@@ -302,7 +332,14 @@ def b200_main(args, w):
     idx_sets = [table.sample_indices(R) for _ in range(CYC)]
     idx_host = torch.stack([torch.from_numpy(np.concatenate([i, i])) for i in idx_sets]).pin_memory()
     sign_host = torch.from_numpy(np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)).pin_memory()
-    obs_host = torch.randn(CYC, M, E, w["n_in"], generator=g).pin_memory()
+    n_obs_buf = CYC if M * E * w["n_in"] * 4 * CYC < (8 << 30) else 3
+    if w["kind"] in ("atari", "impala"):
+        obs_host = torch.rand((n_obs_buf, M, E) + obs_shape, generator=g)
+        if is_impala:
+            obs_host = (obs_host * 255.0).floor()
+        obs_host = obs_host.pin_memory()
+    else:
+        obs_host = torch.randn((n_obs_buf, M, E) + obs_shape, generator=g).pin_memory()
     idx_d = idx_host.to(dev)
     sign_d = sign_host.to(dev)
     obs_d = obs_host.to(dev)
@@ -310,15 +347,33 @@ def b200_main(args, w):
     out_d = torch.empty(M, E, w["out_width"], device=dev)
     reward_d = torch.empty(M, dtype=torch.float64, device=dev)
     stats_d = torch.empty(M * world, dtype=torch.float64, device=dev) if world > 1 else None
+    hist_row_d = None
+    if is_impala:
+        zero_r = torch.zeros(M, E, device=dev)
+        zero_done = torch.zeros(M, E, dtype=torch.uint8, device=dev)
+        h_d = torch.zeros(M, E, 256, device=dev)
+        c_d = torch.zeros(M, E, 256, device=dev)
+        h1_d, c1_d = torch.empty_like(h_d), torch.empty_like(c_d)
+        # fd_state mode: returns spread over the current epoch (-1) and the H history rows
+        hist_row_d = torch.randint(-1, H, (M,), generator=g).to(torch.int32).to(dev)
+
+    def forward_only(c):
+        if is_impala:
+            _lib.check(lib.dfd_impala_forward(ctx.handle, C.byref(policy.desc), table.device_table.ref(), ptr(policy.theta),
+                                              ptr(policy.buffers), ptr(idx_d[c]), ptr(sign_d), M, SIGMA,
+                                              ptr(obs_d[c % n_obs_buf]), ptr(zero_r), ptr(zero_done), ptr(h_d), ptr(c_d), E,
+                                              ptr(out_d), ptr(h1_d), ptr(c1_d), None, 0, ctx.stream))
+        else:
+            policy.forward_members(idx_d[c], sign_d, obs_d[c % n_obs_buf], SIGMA, out=out_d)
 
     def device_step(k):
         c = k % CYC
-        policy.forward_members(idx_d[c], sign_d, obs_d[c], SIGMA, out=out_d)
+        forward_only(c)
         _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target), ptr(reward_d),
                                             ctx.stream))
         if world > 1:
             dist.all_gather_into_tensor(stats_d, reward_d, group=pg)
-        learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, stats_d=stats_d)
+        learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, hist_row_d=hist_row_d, stats_d=stats_d)
 
     use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
     # warm-up (fills the history ring so the ring position cycles with period H)
@@ -441,7 +496,7 @@ def b200_main(args, w):
     grad_tmp = torch.empty(P, device=dev)
 
     def k_forward(r):
-        policy.forward_members(idx_d[r % CYC], sign_d, obs_d[r % CYC], SIGMA, out=out_d)
+        forward_only(r % CYC)
 
     def k_reduce(r):
         _lib.check(lib.dfd_fd_reduce(ctx.handle, C.byref(rowsets[r % CYC][2]), R, P, ptr(grad_tmp),
@@ -482,10 +537,16 @@ def b200_main(args, w):
 
             def collect_returns(self, pol, m_idx, m_sign, sigma):
                 c = self.c
-                o = obs_host[c].to(dev, non_blocking=True)
+                o = obs_host[c % n_obs_buf].to(dev, non_blocking=True)
                 i_d = torch.from_numpy(m_idx).to(dev, non_blocking=True)
                 s_d = torch.from_numpy(m_sign).to(dev, non_blocking=True)
-                pol.forward_members(i_d, s_d, o, sigma, out=out_d)
+                if is_impala:
+                    _lib.check(lib.dfd_impala_forward(ctx.handle, C.byref(pol.desc), table.device_table.ref(), ptr(pol.theta),
+                                                      ptr(pol.buffers), ptr(i_d), ptr(s_d), M, sigma, ptr(o), ptr(zero_r),
+                                                      ptr(zero_done), ptr(h_d), ptr(c_d), E, ptr(out_d), ptr(h1_d),
+                                                      ptr(c1_d), None, 0, ctx.stream))
+                else:
+                    pol.forward_members(i_d, s_d, o, sigma, out=out_d)
                 _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target),
                                                     ptr(reward_d), ctx.stream))
                 rew = reward_d.cpu().numpy()
@@ -501,10 +562,13 @@ def b200_main(args, w):
             flags = np.zeros(R, dtype=bool)
             idx = idx_sets[k % CYC]
             rets = worker.evaluate(flags, idx, antithetic=True)
+            if is_impala:       # fd_state mode: spread the returns' epochs over the accepted window
+                for j, r in enumerate(rets):
+                    r.epoch = learner.epoch - (j % (H + 1))
             if world > 1:
                 allr = [None] * world
                 dist.all_gather_object(allr, np.array([r.reward for r in rets]))
-                epochs = np.full(M, learner.epoch, np.int64)
+                epochs = np.array([r.epoch for r in rets], dtype=np.int64)
                 learner.step_arrays(epochs, np.concatenate([idx, idx]), sign_host.numpy(),
                                     np.array([r.reward for r in rets]), 0.0, all_rewards=np.concatenate(allr))
             else:

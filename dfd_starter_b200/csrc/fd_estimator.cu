@@ -9,6 +9,7 @@
 // returns from older epochs only, eps_i . d_e dot products (a first pass over
 // just those rows).  The reduction is HBM-bound: rows*P*4 bytes in, P*4 out.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------
 // (1) prepare: dots for delayed rows, then coefficients + row list
@@ -372,8 +373,10 @@ static RedPlan red_plan(int sm_count, int64_t P, int n_rows) {
     p.vpt = (P >= (int64_t)sm_count * 8 * 256) ? 2 : 1;
     const int tile = 128 * p.vpt;
     p.tiles = (int)((P + tile - 1) / tile);
-    // aim at ~8 resident CTAs per SM worth of CTAs, but keep >= 32 rows per warp-batch where possible
-    const int target = sm_count * 8;
+    // one full wave of resident CTAs (3 per SM at 69 registers): a second, ragged wave costs a whole CTA lifetime
+    // (measured on B200: 25 MB launches are fastest in a single wave, larger ones with ~8 CTAs per SM queued)
+    static const char* tgt = getenv("DFD_RED_TARGET");
+    const int target = sm_count * (tgt ? atoi(tgt) : (p.tiles < sm_count ? 3 : 8));
     int splits = (target + p.tiles - 1) / p.tiles;
     const int max_splits = (n_rows + RED_WARPS * 4 - 1) / (RED_WARPS * 4);  // >= 4 rows per warp
     if (splits > max_splits) splits = max_splits;
@@ -384,12 +387,29 @@ static RedPlan red_plan(int sm_count, int64_t P, int n_rows) {
     return p;
 }
 
+size_t dfd_tma_scratch_bytes(int sm_count, int64_t P, int n_rows);
+int dfd_fd_reduce_tma(dfd_ctx* ctx, const dfd_fd_rows* rows, int n_rows, int64_t P, float* grad, void* scratch,
+                      cudaStream_t st);
+
+// which implementation streams the rows: 1 = TMA bulk copies into a shared-memory ring (fd_reduce_tma.cu),
+// 0 = register-staged 16-byte loads (below).  DFD_REDUCE_MODE=ldg|tma overrides for experiments.
+static int reduce_mode(int64_t P, int n_rows) {
+    static const char* e = getenv("DFD_REDUCE_MODE");
+    if (e && e[0] == 'l') return 0;
+    if (e && e[0] == 't') return 1;
+    (void)n_rows;
+    static const char* mp = getenv("DFD_TMA_MIN_P");
+    return P >= (mp ? atoll(mp) : 16384) ? 1 : 0;   // measured on B200: the register-staged kernel wins below ~16 K columns
+}
+
 extern "C" size_t dfd_fd_reduce_scratch_bytes(const dfd_ctx* ctx, int64_t n_params, int n_rows) {
     if (!ctx || n_params <= 0 || n_rows <= 0) return 256;
     const RedPlan p = red_plan(ctx->sm_count, n_params, n_rows);
     const size_t counters = dfd_align_up((size_t)p.tiles * sizeof(unsigned), 256);
     const size_t partial = p.splits > 1 ? (size_t)p.splits * p.partial_stride * sizeof(float) : 0;
-    return counters + dfd_align_up(partial, 256) + 256;
+    const size_t a = counters + dfd_align_up(partial, 256) + 256;
+    const size_t b = dfd_tma_scratch_bytes(ctx->sm_count, n_params, n_rows);
+    return a > b ? a : b;   // either implementation may be chosen at launch
 }
 
 extern "C" int dfd_fd_reduce(dfd_ctx* ctx, const dfd_fd_rows* rows, int n_rows, int64_t n_params, float* grad,
@@ -399,6 +419,8 @@ extern "C" int dfd_fd_reduce(dfd_ctx* ctx, const dfd_fd_rows* rows, int n_rows, 
     DFD_CHECK_ARG(n_params > 0, "dfd_fd_reduce: n_params must be positive");
     DFD_CHECK_ARG(((uintptr_t)scratch & 255) == 0, "dfd_fd_reduce: scratch must be 256-byte aligned");
     DFD_CHECK_ARG(scratch_bytes >= dfd_fd_reduce_scratch_bytes(ctx, n_params, n_rows), "dfd_fd_reduce: scratch too small");
+    if (reduce_mode(n_params, n_rows) == 1)
+        return dfd_fd_reduce_tma(ctx, rows, n_rows, n_params, grad, scratch, (cudaStream_t)stream);
     const RedPlan p = red_plan(ctx->sm_count, n_params, n_rows);
     // the tile counters must be zero on entry; they are self-resetting, the caller zeroes scratch once at allocation
     unsigned* counters = (unsigned*)scratch;

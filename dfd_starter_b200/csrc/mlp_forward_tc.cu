@@ -63,6 +63,30 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         : "memory");
 }
 
+// Warp-uniform variants: the whole warp executes the call (descriptors stay in uniform registers, the
+// issue loop carries no divergence), one elected lane issues.
+__device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -384,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) mlp_forward_tc_kernel(TcLayout 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
                 __syncthreads();
                 TC_STAMP(3 + 4 * l);
-                if (tid == 0) {
+                if (warp == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     // layer 0, streamed: the A chunk is [128 x kc] on its own; otherwise A is a full [128 x Kp] tile
                     const int a_kc = (l == 0 && !resident) ? kc : Kp;
@@ -392,11 +416,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) mlp_forward_tc_kernel(TcLayout 
                     const uint32_t b_base = smem_u32(Wbuf + (resident ? wofs[l] : 0));
                     const uint64_t adesc = make_desc(a_base, 128, (uint32_t)a_kc * 32u);
                     const uint64_t bdesc = make_desc(b_base, 128, (uint32_t)kc * 32u);
-                    umma_tf32(d_tmem, adesc, bdesc, idesc, kdone > 0 ? 1u : 0u);
+                    umma_tf32_elect(d_tmem, adesc, bdesc, idesc, kdone > 0 ? 1u : 0u);
 #pragma unroll 4
                     for (int j = 1; j < kc / 8; ++j)
-                        umma_tf32(d_tmem, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, 1u);
-                    umma_commit(bar);
+                        umma_tf32_elect(d_tmem, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, 1u);
+                    umma_commit_elect(bar);
+                    __syncwarp();
                 }
                 TC_STAMP(4 + 4 * l);
                 if (warp == 0) mbar_wait(bar, phase);   // one warp polls; the rest sleep at the barrier
