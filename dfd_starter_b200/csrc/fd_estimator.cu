@@ -17,9 +17,9 @@
 static const int DOT_CHUNK = 8192;  // columns per CTA in the dots pass
 static const int DOT_THREADS = 256;
 
-// layout of the prepare scratch (doubles): dot[n_returns] | dd[n_hist]
+// layout of the prepare scratch (doubles): dot[n_returns] | dd[n_hist] | q_hist[n_hist] | counter
 extern "C" size_t dfd_fd_prepare_scratch_bytes(int n_returns, int n_hist) {
-    return dfd_align_up((size_t)(n_returns + n_hist) * sizeof(double), 256);
+    return dfd_align_up((size_t)(n_returns + 2 * n_hist + 2) * sizeof(double), 256);
 }
 
 // blockIdx.y < n_returns: dot of table row i with its dist row (skipped when hist_row < 0)
@@ -81,11 +81,12 @@ __device__ __forceinline__ double block_reduce_d(double v, double* sh, int op /*
     return t;
 }
 
-// single CTA.  standardize_arr (utils/math_helpers.py:127-134): population std, identity when std == 0.
-// Each thread owns up to COEF_PER returns per pass and issues all of their global loads (reward, idx,
-// sign, hist_row, then the two prefix entries) before the block-wide statistics, so the DRAM latencies overlap.
-static const int COEF_THREADS = 1024;
-static const int COEF_PER = 4;
+// Coefficients + row list.  One thread per table ROW (both members of an antithetic pair), a few CTAs; every
+// CTA recomputes the batch statistics itself (N doubles from L2) so there is no grid-wide dependency:
+//   standardize_arr (utils/math_helpers.py:127-134): population std, identity when std == 0;
+//   ||lambda||^2 = sigma^2 (S[i+P]-S[i]) [+ 2 s sigma (eps.d) + ||d||^2 for returns from older epochs].
+// The two dependent global round trips (rewards -> statistics, idx -> prefix entries) run concurrently.
+static const int COEF_THREADS = 256;
 
 __global__ void __launch_bounds__(COEF_THREADS) fd_coef_kernel(const float* __restrict__ replicas, int64_t stride,
                                                                const double* __restrict__ prefix, int64_t P,
@@ -97,108 +98,84 @@ __global__ void __launch_bounds__(COEF_THREADS) fd_coef_kernel(const float* __re
                                                                const float* __restrict__ dist, int64_t dist_stride,
                                                                int n_hist, const double* __restrict__ stats_reward,
                                                                int n_stats, const double* __restrict__ dots,
+                                                               double* __restrict__ q_hist, unsigned* __restrict__ counter,
                                                                const float** row_ptr, float* __restrict__ row_coef) {
     __shared__ double sh[32];
-    __shared__ double q_hist[128];  // n_hist <= 128
-    __shared__ double c_pair[COEF_THREADS * COEF_PER];   // per-return coefficient, for the antithetic merge
+    __shared__ unsigned ticket_s;
     const double* sr = stats_reward ? stats_reward : reward;
     const int ns = stats_reward ? n_stats : n;
     const double sig = (double)sigma;
     const double* dd = dots + n;
     const int R = paired ? n / 2 : n;
-    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) q_hist[h] = 0.0;
+    const int r = blockIdx.x * COEF_THREADS + threadIdx.x;
 
-    // statistics over the (possibly global) reward vector: finite_differences.py:40,43
+    // this thread's row: issue its loads first, they fly while the statistics are reduced
+    double x_[2] = {0.0, 0.0}, n2_[2] = {1.0, 1.0}, sg_[2] = {0.0, 0.0};
+    int h_[2] = {-1, -1};
+    int64_t id0 = 0;
+    const int nk = paired ? 2 : 1;
+    if (r < R) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k < nk) {
+                const int i = r + k * R;
+                const int64_t id = idx[i];
+                if (k == 0) id0 = id;
+                x_[k] = reward[i] - baseline;
+                sg_[k] = (double)sign[i];
+                h_[k] = hist_row[i];
+                n2_[k] = sig * sig * (prefix[id + P] - prefix[id]);
+                if (h_[k] >= 0) n2_[k] += 2.0 * sg_[k] * sig * dots[i] + dd[h_[k]];
+            }
+        }
+    }
+    // finite_differences.py:40  rewards - policy_reward ; :43 standardize
     double s = 0.0, mn = 1e300, mx = -1e300;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ns; i += COEF_THREADS) {
         const double x = sr[i] - baseline;
         s += x;
         mn = fmin(mn, x);
         mx = fmax(mx, x);
     }
-    // first batch of this thread's returns: loads in flight while the reductions run
-    double x_[COEF_PER], n2_[COEF_PER], sg_[COEF_PER];
-    int h_[COEF_PER];
-#pragma unroll
-    for (int j = 0; j < COEF_PER; ++j) {
-        const int i = threadIdx.x + j * COEF_THREADS;
-        x_[j] = 0.0; n2_[j] = 1.0; sg_[j] = 0.0; h_[j] = -1;
-        if (i < n) {
-            const int64_t id = idx[i];
-            x_[j] = reward[i] - baseline;
-            sg_[j] = (double)sign[i];
-            h_[j] = hist_row[i];
-            n2_[j] = sig * sig * (prefix[id + P] - prefix[id]);
-            if (h_[j] >= 0) n2_[j] += 2.0 * sg_[j] * sig * dots[i] + dd[h_[j]];
-        }
-    }
     const double mean = block_reduce_d(s, sh, 0) / (double)ns;
     mn = block_reduce_d(mn, sh, 1);
     mx = block_reduce_d(mx, sh, 2);
     double v = 0.0;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ns; i += COEF_THREADS) {
         const double d = (sr[i] - baseline) - mean;
         v += d * d;
     }
     double sd = sqrt(block_reduce_d(v, sh, 0) / (double)ns);
     if (mn == mx) sd = 0.0;  // all rewards equal: numpy's std is exactly 0 and the array passes through
+    const double inv_sd = sd == 0.0 ? 1.0 : 1.0 / sd;
 
-    for (int base = 0; base < n; base += COEF_THREADS * COEF_PER) {
-        if (base > 0) {   // later batches (n > 4096): plain loads
+    if (r < R) {
+        float c = 0.f;
 #pragma unroll
-            for (int j = 0; j < COEF_PER; ++j) {
-                const int i = base + threadIdx.x + j * COEF_THREADS;
-                x_[j] = 0.0; n2_[j] = 1.0; sg_[j] = 0.0; h_[j] = -1;
-                if (i < n) {
-                    const int64_t id = idx[i];
-                    x_[j] = reward[i] - baseline;
-                    sg_[j] = (double)sign[i];
-                    h_[j] = hist_row[i];
-                    n2_[j] = sig * sig * (prefix[id + P] - prefix[id]);
-                    if (h_[j] >= 0) n2_[j] += 2.0 * sg_[j] * sig * dots[i] + dd[h_[j]];
-                }
+        for (int k = 0; k < 2; ++k) {
+            if (k < nk) {
+                const double w = sd == 0.0 ? x_[k] : (x_[k] - mean) * inv_sd;
+                const double winv = w / n2_[k];
+                c += (float)(winv * sg_[k] * sig);
+                if (h_[k] >= 0) atomicAdd(q_hist + h_[k], winv);
             }
         }
-#pragma unroll
-        for (int j = 0; j < COEF_PER; ++j) {
-            const int i = base + threadIdx.x + j * COEF_THREADS;
-            if (i < n) {
-                const double w = sd == 0.0 ? x_[j] : (x_[j] - mean) / sd;
-                const double winv = w / n2_[j];
-                const double c = winv * sg_[j] * sig;
-                if (h_[j] >= 0) atomicAdd(&q_hist[h_[j]], winv);
-                if (!paired) {
-                    row_ptr[i] = table_row_ptr(replicas, stride, idx[i]);
-                    row_coef[i] = (float)c;
-                } else if (i < R) {
-                    row_ptr[i] = table_row_ptr(replicas, stride, idx[i]);
-                }
-                c_pair[threadIdx.x + j * COEF_THREADS] = c;
-            }
-        }
-        if (paired) {
-            // plus-member i and minus-member i + R may sit in different batches when n > 4096: accumulate in global
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < COEF_PER; ++j) {
-                const int i = base + threadIdx.x + j * COEF_THREADS;
-                if (i < n) {
-                    const int r = i < R ? i : i - R;
-                    if (n <= COEF_THREADS * COEF_PER) {
-                        if (i < R) row_coef[r] = (float)(c_pair[i] + c_pair[i + R]);
-                    } else {
-                        atomicAdd(row_coef + r, (float)c_pair[threadIdx.x + j * COEF_THREADS]);
-                    }
-                }
-            }
-            __syncthreads();
-        }
+        row_ptr[r] = table_row_ptr(replicas, stride, id0);
+        row_coef[r] = c;
     }
+    if (n_hist == 0) return;
+    // the last CTA to finish turns the per-epoch sums into the distance rows' coefficients
+    __threadfence();
     __syncthreads();
-    for (int h = threadIdx.x; h < n_hist; h += blockDim.x) {
+    if (threadIdx.x == 0) ticket_s = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (ticket_s != gridDim.x - 1) return;
+    __threadfence();
+    for (int h = threadIdx.x; h < n_hist; h += COEF_THREADS) {
         row_ptr[R + h] = dist + (int64_t)h * dist_stride;
-        row_coef[R + h] = (float)q_hist[h];
+        row_coef[R + h] = (float)__ldcg(q_hist + h);
     }
+    if (threadIdx.x == 0) *counter = 0;
 }
 
 extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward,
@@ -218,18 +195,19 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
     DFD_CHECK_ARG(scratch_bytes >= dfd_fd_prepare_scratch_bytes(n_returns, n_hist), "dfd_fd_prepare: scratch too small");
     cudaStream_t st = (cudaStream_t)stream;
     double* dots = (double*)scratch;
+    double* q_hist = dots + n_returns + n_hist;
+    unsigned* counter = (unsigned*)((double*)scratch + (dfd_fd_prepare_scratch_bytes(n_returns, n_hist) / sizeof(double) - 1));
     if (n_hist > 0) {
-        DFD_CUDA(cudaMemsetAsync(dots, 0, (size_t)(n_returns + n_hist) * sizeof(double), st));
+        DFD_CUDA(cudaMemsetAsync(dots, 0, (size_t)(n_returns + 2 * n_hist) * sizeof(double), st));
         dim3 grid((unsigned)((n_params + DOT_CHUNK - 1) / DOT_CHUNK), (unsigned)(n_returns + n_hist));
         fd_dots_kernel<<<grid, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
                                                      dist, dist_stride, n_params, dots);
         DFD_LAUNCHED(ctx);
     }
-    if (paired && n_returns > COEF_THREADS * COEF_PER)   // large paired batches merge through atomics: start from zero
-        DFD_CUDA(cudaMemsetAsync(rows->row_coef, 0, (size_t)R * sizeof(float), st));
-    fd_coef_kernel<<<1, COEF_THREADS, 0, st>>>(table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx,
-                                       sign, hist_row, n_returns, paired, baseline, sigma, dist, dist_stride, n_hist,
-                                       stats_reward, n_stats, dots, rows->row_ptr, rows->row_coef);
+    fd_coef_kernel<<<(R + COEF_THREADS - 1) / COEF_THREADS, COEF_THREADS, 0, st>>>(
+        table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx, sign, hist_row, n_returns, paired,
+        baseline, sigma, dist, dist_stride, n_hist, stats_reward, n_stats, dots, q_hist, counter, rows->row_ptr,
+        rows->row_coef);
     DFD_LAUNCHED(ctx);
     return 0;
 }
@@ -571,13 +549,26 @@ __global__ void __launch_bounds__(256) synthetic_reward_kernel(const float* __re
                                                                double* __restrict__ reward) {
     __shared__ double sh[8];
     const float* o = out + (int64_t)blockIdx.x * per_member;
-    double acc = 0.0;
-    for (int t = threadIdx.x; t < per_member; t += 256) {
-        const float d = o[t] - target[t % width];
-        acc += (double)d * (double)d;
+    float acc = 0.f;
+    if ((((uintptr_t)o) & 15) == 0 && (width & 3) == 0) {
+        for (int t = threadIdx.x; t < (per_member >> 2); t += 256) {
+            const float4 v = ldg_stream_f4(o + 4 * t);
+            const int j = (4 * t) % width;
+            const float d0 = v.x - target[j], d1 = v.y - target[j + 1], d2 = v.z - target[j + 2], d3 = v.w - target[j + 3];
+            acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        for (int t = (per_member & ~3) + threadIdx.x; t < per_member; t += 256) {
+            const float d = o[t] - target[t % width];
+            acc += d * d;
+        }
+    } else {
+        for (int t = threadIdx.x; t < per_member; t += 256) {
+            const float d = o[t] - target[t % width];
+            acc += d * d;
+        }
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    double a = warp_sum((double)acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.0;
