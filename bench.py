@@ -64,9 +64,11 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=0, help="override antithetic pairs per GPU")
     ap.add_argument("--table-size", type=int, default=TABLE_SIZE)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32"],
-                    help="forward arithmetic: fp32 CUDA cores (exact path) or tf32 tcgen05 tensor cores; "
-                         "auto = tf32 for MuJoCo MLPs with >= 32 observations per member")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32", "tf32a"],
+                    help="forward arithmetic: fp32 CUDA cores (exact path, atol 1e-5), tf32 = tcgen05 tensor cores with "
+                         "tf32 operands / fp32 accumulate / ~1e-6 tanh (max-abs 2e-3 vs fp32), tf32a = the same with the "
+                         "single-instruction tanh.approx.f32 (2^-11 relative; max-abs 4e-3 vs fp32); "
+                         "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, fp32 otherwise")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: timed steps only (no clock-load loop, per-kernel timing, e2e or CPU baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -300,11 +302,12 @@ def b200_main(args, w):
 
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
-    use_tc = w["kind"] == "mujoco" and (args.precision == "tf32" or (args.precision == "auto" and E >= 32))
+    use_tc = w["kind"] == "mujoco" and (args.precision in ("tf32", "tf32a") or (args.precision == "auto" and E >= 32))
+    tc_level = 1 if args.precision == "tf32" else 2
     if w["kind"] in ("mujoco", "discrete"):
         cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
         policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,
-                     precision=1 if use_tc else 0)
+                     precision=tc_level if use_tc else 0)
         obs_shape = (w["n_in"],)
     elif w["kind"] == "atari":
         policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local)
@@ -375,7 +378,9 @@ def b200_main(args, w):
             dist.all_gather_into_tensor(stats_d, reward_d, group=pg)
         learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, hist_row_d=hist_row_d, stats_d=stats_d)
 
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    # NCCL collectives issued through torch.distributed are stream-ordered and graph-capturable, so the
+    # sharded step replays as one graph too (plain launches remain the fallback if capture fails)
+    use_graph = args.graph in ("on", "auto")
     # warm-up (fills the history ring so the ring position cycles with period H)
     n_warm = max(args.warmup, 3, H + 1)
     for k in range(n_warm):
@@ -602,7 +607,8 @@ def b200_main(args, w):
     line = {
         "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32 forward (fp32 accumulate), f32 estimator" if use_tc else "f32",
+        "vs_baseline": None, "dtype": ("tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"))
+        if use_tc else "f32",
         "data": "synthetic", "config": bench_config(args, w),
         "fd_estimates_per_s": 1e3 / ms_step,
         "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",

@@ -82,7 +82,8 @@ typedef struct dfd_policy_desc {
     int n_in;      /* MLPs: observation width K                                            */
     int h1, h2;    /* MLPs: hidden widths (reference: 64, 64; mujoco.py:33-34)             */
     int n_act;     /* actions A (MuJoCo head emits 2A: mean | std)                         */
-    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tcgen05 tensor cores      */
+    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tcgen05 tensor cores,
+                      2 = tf32 tcgen05 + single-instruction tanh.approx (2^-11 relative)      */
 } dfd_policy_desc;
 
 int64_t dfd_policy_num_params(const dfd_policy_desc* desc);

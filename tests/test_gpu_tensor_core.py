@@ -23,10 +23,10 @@ def D():
     return D
 
 
-def _check(D, n_in, h, n_act, E, M, seed, atol):
+def _check(D, n_in, h, n_act, E, M, seed, atol, precision=1):
     L = O.mujoco_layout(n_in, n_act, h, h)
     table = D.SharedNoiseTable(1_000_000, L.num_params, 123, device=0)
-    pol = D.MujocoPolicy(n_in, n_act, seed=seed, h1=h, h2=h, device=0, precision=1).bind_table(table)
+    pol = D.MujocoPolicy(n_in, n_act, seed=seed, h1=h, h2=h, device=0, precision=precision).bind_table(table)
     exact = D.MujocoPolicy(n_in, n_act, seed=seed, h1=h, h2=h, device=0, precision=0).bind_table(table)
     theta = O.synthetic_theta(L, seed)
     pol.set_trainable_flat(theta)
@@ -52,6 +52,23 @@ def _check(D, n_in, h, n_act, E, M, seed, atol):
 @pytest.mark.parametrize("E", [128, 1, 37, 200])
 def test_halfcheetah_shape_tf32(D, E):
     _check(D, 17, 64, 6, E, M=24, seed=3, atol=2e-3)
+
+
+@pytest.mark.parametrize("E", [128, 1, 37, 200, 300])
+def test_halfcheetah_shape_tf32_tanh_approx(D, E):
+    """precision=2: tf32 operands + tanh.approx.f32 (2^-11 relative per activation); stated tolerance
+    max-abs 4e-3, mean-abs 3e-4 (checked inside _check)."""
+    _check(D, 17, 64, 6, E, M=300, seed=4, atol=4e-3, precision=2)
+
+
+def test_halfcheetah_shape_tf32_many_members(D):
+    """more members than persistent CTAs x pipeline stages: every ring slot is reused several times"""
+    _check(D, 17, 64, 6, 128, M=1500, seed=6, atol=2e-3, precision=1)
+
+
+@pytest.mark.parametrize("shape", [(8, 3), (31, 16), (12, 5)])
+def test_small_net_other_shapes_tf32(D, shape):
+    _check(D, shape[0], 64, shape[1], 128, M=200, seed=8, atol=2e-3, precision=1)
 
 
 @pytest.mark.parametrize("E", [128, 16])
