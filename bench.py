@@ -71,6 +71,8 @@ def parse_args():
                          "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, fp32 otherwise")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: timed steps only (no clock-load loop, per-kernel timing, e2e or CPU baseline)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange as one NVLink peer-memory kernel (default) or NCCL collectives")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-members", type=int, default=0)
@@ -324,8 +326,14 @@ def b200_main(args, w):
         omega, min_omega, max_omega = 0.0, 0.0, 1.0
     opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
     opt.coef = np.sqrt(P)
+    # sharded population: fd_return workloads exchange through ONE peer-memory kernel per step (dist.PeerExchange);
+    # fd_state (IMPALA, delayed returns) keeps the rewards all-gather + NCCL all_reduce
+    xchg = None
+    if world > 1 and not is_impala and args.exchange == "peer":
+        from dfd_starter_b200.dist import PeerExchange
+        xchg = PeerExchange(ctx, P, pg)
     learner = D.FiniteDifferences(policy, opt, Omega(), table, noise_std=SIGMA, batch_size=M, max_delayed_return=H,
-                                  paired=True, process_group=pg)
+                                  paired=True, process_group=pg, peer_exchange=xchg)
 
     CYC = H  # graphs / index sets / observation buffers cycle with the history ring
     g = torch.Generator().manual_seed(1234 + rank)
@@ -374,9 +382,10 @@ def b200_main(args, w):
         forward_only(c)
         _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target), ptr(reward_d),
                                             ctx.stream))
-        if world > 1:
+        if world > 1 and xchg is None:
             dist.all_gather_into_tensor(stats_d, reward_d, group=pg)
-        learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, hist_row_d=hist_row_d, stats_d=stats_d)
+        learner.step_device(idx_d[c], sign_d, reward_d, M, 0.0, hist_row_d=hist_row_d,
+                            stats_d=stats_d if xchg is None else None)
 
     # NCCL collectives issued through torch.distributed are stream-ordered and graph-capturable, so the
     # sharded step replays as one graph too (plain launches remain the fallback if capture fails)
@@ -443,8 +452,7 @@ def b200_main(args, w):
     if args.profile_mode:
         if rank == 0:
             print(json.dumps({"profile_mode": True, "ms_per_step": ms_step, "launches": launches_plain}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     # keep the same step running ~1.5 s so nvidia-smi (100 ms period) sees the clocks under this load
     t_load0 = time.perf_counter()
@@ -568,14 +576,13 @@ def b200_main(args, w):
             idx = idx_sets[k % CYC]
             rets = worker.evaluate(flags, idx, antithetic=True)
             if is_impala:       # fd_state mode: spread the returns' epochs over the accepted window
-                for j, r in enumerate(rets):
-                    r.epoch = learner.epoch - (j % (H + 1))
-            if world > 1:
+                rets.epoch[:] = learner.epoch - (np.arange(len(rets)) % (H + 1))
+            if world > 1 and xchg is not None:
+                learner.step(rets, 0.0, 0.0, 0.0)           # the exchange kernel carries the statistics
+            elif world > 1:
                 allr = [None] * world
-                dist.all_gather_object(allr, np.array([r.reward for r in rets]))
-                epochs = np.array([r.epoch for r in rets], dtype=np.int64)
-                learner.step_arrays(epochs, np.concatenate([idx, idx]), sign_host.numpy(),
-                                    np.array([r.reward for r in rets]), 0.0, all_rewards=np.concatenate(allr))
+                dist.all_gather_object(allr, rets.reward)
+                learner.step_arrays(rets.epoch, rets.idx, rets.sign, rets.reward, 0.0, all_rewards=np.concatenate(allr))
             else:
                 learner.step(rets, 0.0, 0.0, 0.0)
         for k in range(3):
@@ -597,11 +604,10 @@ def b200_main(args, w):
         d2h = M * 8 + 4 + P * 4
         e2e = {"value": M * E * world * n_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e,
-               "api": "Worker.evaluate -> FDReturn list -> FiniteDifferences.step (host observations, host returns, theta mirrored to host)"}
+               "api": "Worker.evaluate -> ReturnBatch (sequence of FDReturn) -> FiniteDifferences.step (host observations, host returns, theta mirrored to host)"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     value = M * E * world / (ms_step * 1e-3)
     line = {
@@ -630,8 +636,21 @@ def b200_main(args, w):
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port",
                                     "sample": "failed: %s" % e}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world):
+    """N > 1: leave together and skip communicator / IPC teardown - destroying an NCCL communicator while
+    captured graphs that reference it are alive can block, and the driver only needs the JSON line."""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    os._exit(0)
 
 
 # forward, synthetic return, fd_coef, fd_reduce, sumsq, dsgd_update  (fd_return mode: no dots pass)

@@ -1,7 +1,7 @@
 """dfd_starter_b200 — B200-native finite-difference learner hot path with the
 reference's (nexus-rl/dfd-starter) object interface.  Importing the package needs
 neither the shared library nor a GPU; using it needs both (no CPU fallback)."""
-from .fd_return import FDReturn
+from .fd_return import FDReturn, ReturnBatch
 from .fd_state import FDState
 from .dsgd import DSGD
 from .noise_sources import SharedNoiseTable
@@ -9,5 +9,5 @@ from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
 from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
-__all__ = ["FDReturn", "FDState", "DSGD", "SharedNoiseTable", "FiniteDifferences", "Worker", "SyntheticAgent",
+__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "FiniteDifferences", "Worker", "SyntheticAgent",
            "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

@@ -16,6 +16,8 @@ SYMBOLS = [
     "dfd_perturb_members", "dfd_policy_num_params", "dfd_policy_num_buffers", "dfd_policy_out_width",
     "dfd_policy_forward", "dfd_impala_scratch_bytes", "dfd_impala_forward", "dfd_fd_prepare_scratch_bytes",
     "dfd_fd_prepare", "dfd_fd_reduce_scratch_bytes", "dfd_fd_reduce", "dfd_dsgd_step", "dfd_dsgd_scratch_bytes", "dfd_synthetic_reward",
+    "dfd_fd_prepare_partial", "dfd_xchg_mailbox_bytes", "dfd_xchg_mailbox_create", "dfd_xchg_mailbox_open",
+    "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
 ]
 
 
@@ -78,6 +80,13 @@ def load():
     proto("dfd_dsgd_scratch_bytes", sz, [i64])
     proto("dfd_dsgd_step", i32, [vp, vp, vp, i64, f64, f64, vp, vp, i64, i32, i32, vp, vp, sz, vp])
     proto("dfd_synthetic_reward", i32, [vp, vp, i32, i32, i32, vp, vp, vp])
+    proto("dfd_fd_prepare_partial", i32, [vp, P(DfdTable), i64, vp, vp, vp, vp, i32, f64, f32, P(DfdFdRows), vp, vp, sz, vp])
+    proto("dfd_xchg_mailbox_bytes", sz, [i64, i32])
+    proto("dfd_xchg_mailbox_create", i32, [vp, sz, P(vp), C.c_char_p])
+    proto("dfd_xchg_mailbox_open", i32, [vp, C.c_char_p, P(vp)])
+    proto("dfd_xchg_mailbox_close", i32, [vp, vp])
+    proto("dfd_xchg_mailbox_destroy", i32, [vp, vp])
+    proto("dfd_xchg_allreduce", i32, [vp, vp, i32, i32, i64, vp, vp, vp, vp])
     _lib = L
     return L
 

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(COEF_THREADS) fd_coef_kernel(const float* __re
                                                                int n_hist, const double* __restrict__ stats_reward,
                                                                int n_stats, const double* __restrict__ dots,
                                                                double* __restrict__ q_hist, unsigned* __restrict__ counter,
-                                                               const float** row_ptr, float* __restrict__ row_coef) {
+                                                               const float** row_ptr, float* __restrict__ row_coef,
+                                                               double* __restrict__ stats_out) {
     __shared__ double sh[32];
     __shared__ unsigned ticket_s;
     const double* sr = stats_reward ? stats_reward : reward;
@@ -140,14 +141,33 @@ __global__ void __launch_bounds__(COEF_THREADS) fd_coef_kernel(const float* __re
     const double mean = block_reduce_d(s, sh, 0) / (double)ns;
     mn = block_reduce_d(mn, sh, 1);
     mx = block_reduce_d(mx, sh, 2);
-    double v = 0.0;
+    const double sum_x = mean * (double)ns;
+    double v = 0.0, v2 = 0.0;
     for (int i = threadIdx.x; i < ns; i += COEF_THREADS) {
-        const double d = (sr[i] - baseline) - mean;
+        const double x = sr[i] - baseline;
+        const double d = x - mean;
         v += d * d;
+        v2 += x * x;
     }
     double sd = sqrt(block_reduce_d(v, sh, 0) / (double)ns);
     if (mn == mx) sd = 0.0;  // all rewards equal: numpy's std is exactly 0 and the array passes through
-    const double inv_sd = sd == 0.0 ? 1.0 : 1.0 / sd;
+    double inv_sd = sd == 0.0 ? 1.0 : 1.0 / sd;
+    // sharded population (dfd_fd_prepare_partial): this rank's statistics are published for the exchange step
+    // and the coefficients stay un-standardised - in paired form the mean cancels and 1/std is applied after
+    // the gradients of all ranks have been summed
+    const bool deferred = stats_out != nullptr;
+    if (deferred) {
+        v2 = block_reduce_d(v2, sh, 0);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            stats_out[0] = sum_x;
+            stats_out[1] = v2;
+            stats_out[2] = (double)ns;
+            stats_out[3] = mn;
+            stats_out[4] = mx;
+        }
+        sd = 0.0;          // w = x below
+        inv_sd = 1.0;
+    }
 
     if (r < R) {
         float c = 0.f;
@@ -207,7 +227,28 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
     fd_coef_kernel<<<(R + COEF_THREADS - 1) / COEF_THREADS, COEF_THREADS, 0, st>>>(
         table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx, sign, hist_row, n_returns, paired,
         baseline, sigma, dist, dist_stride, n_hist, stats_reward, n_stats, dots, q_hist, counter, rows->row_ptr,
-        rows->row_coef);
+        rows->row_coef, nullptr);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+extern "C" int dfd_fd_prepare_partial(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward,
+                                      const int64_t* idx, const int8_t* sign, const int32_t* hist_row, int n_returns,
+                                      double baseline, float sigma, dfd_fd_rows* rows, double* stats_out, void* scratch,
+                                      size_t scratch_bytes, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && table && reward && idx && sign && hist_row && rows && stats_out && scratch,
+                  "dfd_fd_prepare_partial: NULL argument");
+    DFD_CHECK_ARG(n_returns > 0 && (n_returns % 2) == 0, "dfd_fd_prepare_partial: needs a non-empty batch of antithetic pairs");
+    DFD_CHECK_ARG(n_params > 0 && n_params < table->size, "dfd_fd_prepare_partial: n_params out of range");
+    const int R = n_returns / 2;
+    DFD_CHECK_ARG(rows->max_rows >= R, "dfd_fd_prepare_partial: row list too small (%d < %d)", rows->max_rows, R);
+    DFD_CHECK_ARG(scratch_bytes >= dfd_fd_prepare_scratch_bytes(n_returns, 0), "dfd_fd_prepare_partial: scratch too small");
+    double* dots = (double*)scratch;
+    double* q_hist = dots + n_returns;
+    unsigned* counter = (unsigned*)((double*)scratch + (dfd_fd_prepare_scratch_bytes(n_returns, 0) / sizeof(double) - 1));
+    fd_coef_kernel<<<(R + COEF_THREADS - 1) / COEF_THREADS, COEF_THREADS, 0, (cudaStream_t)stream>>>(
+        table->replicas, table->replica_stride, table->prefix_sq, n_params, reward, idx, sign, hist_row, n_returns, 1,
+        baseline, sigma, nullptr, 0, 0, nullptr, 0, dots, q_hist, counter, rows->row_ptr, rows->row_coef, stats_out);
     DFD_LAUNCHED(ctx);
     return 0;
 }

@@ -1,0 +1,196 @@
+// The one exchange step of the sharded learner: each GPU holds the partial gradient of its
+// slice of the population; every rank needs the sum, scaled by 1 / std of ALL ranks' rewards
+// (learner/finite_differences.py:43,49 over the whole batch).
+//
+// One process per GPU; every rank owns a MAILBOX in its HBM that all peers map through CUDA IPC.  ONE kernel
+// per step and rank does the whole exchange over NVLink / NVSwitch peer stores - no NCCL call on this path:
+//   1. push: the rank's partial gradient (P floats) and its reward statistics (sum, sum of squares, count,
+//      min, max - 5 doubles) are written with 16-byte stores straight into slot [parity][rank] of EVERY
+//      peer's mailbox (and its own);
+//   2. publish: after a grid-wide arrival count the last CTA release-stores the step number into
+//      flags[parity][rank] of every peer (system scope);
+//   3. combine: every CTA acquire-polls its own flags until all ranks have published this step, then sums the
+//      world slots IN RANK ORDER (bitwise identical result on every rank, run-to-run deterministic), applies
+//      1 / std and writes the gradient the optimizer consumes.
+// Slots and flags are double-buffered by step parity: a rank can run at most one step ahead of the slowest
+// peer (it cannot publish step k+1 before it has combined step k), so parity k+2 never overwrites data a
+// peer still reads.  The step counter lives in the mailbox, so the launch is CUDA-graph replayable.
+#include "common.cuh"
+#include <string.h>
+
+namespace {
+
+constexpr int XCHG_THREADS = 256;
+constexpr int XCHG_MAX_WORLD = 16;
+constexpr size_t XCHG_HDR = 256;                       // bar_ctr (u32) | step_ctr (u64 at +8)
+constexpr size_t XCHG_FLAGS = 2 * XCHG_MAX_WORLD * 8;  // u64 flags[2][16]
+
+__host__ __device__ inline size_t xchg_slot_bytes(int64_t P) { return (size_t)((P + 3) / 4 * 4) * 4 + 256; }
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* const* __restrict__ mailboxes, int rank,
+                                                                      int world, int64_t P,
+                                                                      const float* __restrict__ grad_partial,
+                                                                      const double* __restrict__ stats5,
+                                                                      float* __restrict__ grad_out) {
+    __shared__ unsigned ticket_s;
+    __shared__ double inv_sd_s;
+    char* const mine = mailboxes[rank];
+    unsigned* bar_ctr = reinterpret_cast<unsigned*>(mine);
+    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(mine + 8);
+    // every CTA reads the step before anyone can advance it (the advance happens after all CTAs arrived below)
+    const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(step_ctr);
+    const int par = (int)(step & 1ull);
+    const size_t slot = xchg_slot_bytes(P);
+    const int64_t n4 = (P + 3) / 4;
+    const size_t my_slot_off = XCHG_HDR + XCHG_FLAGS + ((size_t)par * world + rank) * slot;
+
+    // ---- 1. push ----------------------------------------------------------------------------------------
+    for (int64_t i = (int64_t)blockIdx.x * XCHG_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * XCHG_THREADS) {
+        float4 v;
+        if (4 * i + 3 < P) {
+            v = *reinterpret_cast<const float4*>(grad_partial + 4 * i);
+        } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < 4 && 4 * i + k < P; ++k) t[k] = grad_partial[4 * i + k];
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        for (int w = 0; w < world; ++w) {
+            const int dst = (rank + w) % world;    // spread the peers over time: rank r starts at its own mailbox
+            *reinterpret_cast<float4*>(mailboxes[dst] + my_slot_off + 16 * (size_t)i) = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 5) {
+        const double s = stats5[threadIdx.x];
+        for (int w = 0; w < world; ++w)
+            *reinterpret_cast<double*>(mailboxes[w] + my_slot_off + 16 * (size_t)n4 + 8 * threadIdx.x) = s;
+    }
+    // ---- 2. publish --------------------------------------------------------------------------------------
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket_s = atomicAdd(bar_ctr, 1u);
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {
+        __threadfence_system();
+        if (threadIdx.x < world) {
+            unsigned long long* f = reinterpret_cast<unsigned long long*>(mailboxes[threadIdx.x] + XCHG_HDR) +
+                                    par * XCHG_MAX_WORLD + rank;
+            st_release_sys(f, step + 1ull);
+        }
+        if (threadIdx.x == 0) {
+            *bar_ctr = 0u;
+            *step_ctr = step + 1ull;
+        }
+    }
+    // ---- 3. combine --------------------------------------------------------------------------------------
+    if (threadIdx.x < world) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCHG_HDR) + par * XCHG_MAX_WORLD +
+                                      threadIdx.x;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < step + 1ull) {
+            if (++spins > (1u << 24)) __trap();    // a missing peer must fault, not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const size_t slots0 = XCHG_HDR + XCHG_FLAGS + (size_t)par * world * slot;
+    if (threadIdx.x == 0) {
+        // standardize_arr over the whole population (utils/math_helpers.py:127-134): population std,
+        // identity when all rewards are equal
+        double s = 0.0, ss = 0.0, n = 0.0, mn = 1e300, mx = -1e300;
+        for (int w = 0; w < world; ++w) {
+            const double* st = reinterpret_cast<const double*>(mine + slots0 + (size_t)w * slot + 16 * (size_t)n4);
+            const double nw = __ldcg(st + 2);
+            if (nw > 0.0) {
+                s += __ldcg(st + 0);
+                ss += __ldcg(st + 1);
+                n += nw;
+                mn = fmin(mn, __ldcg(st + 3));
+                mx = fmax(mx, __ldcg(st + 4));
+            }
+        }
+        double inv = 1.0;
+        if (n > 0.0 && mn != mx) {
+            const double mean = s / n;
+            const double var = fmax(ss / n - mean * mean, 0.0);
+            if (var > 0.0) inv = 1.0 / sqrt(var);
+        }
+        inv_sd_s = inv;
+    }
+    __syncthreads();
+    const float inv_sd = (float)inv_sd_s;
+    for (int64_t i = (int64_t)blockIdx.x * XCHG_THREADS + threadIdx.x; i < n4; i += (int64_t)gridDim.x * XCHG_THREADS) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < world; ++w) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + slots0 + (size_t)w * slot + 16 * (size_t)i));
+            g.x += t.x;
+            g.y += t.y;
+            g.z += t.z;
+            g.w += t.w;
+        }
+        const float t[4] = {g.x * inv_sd, g.y * inv_sd, g.z * inv_sd, g.w * inv_sd};
+        for (int k = 0; k < 4 && 4 * i + k < P; ++k) grad_out[4 * i + k] = t[k];
+    }
+}
+
+}  // namespace
+
+extern "C" size_t dfd_xchg_mailbox_bytes(int64_t n_params, int world) {
+    if (n_params <= 0 || world <= 0 || world > XCHG_MAX_WORLD) return 0;
+    return XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params);
+}
+
+extern "C" int dfd_xchg_mailbox_create(dfd_ctx* ctx, size_t bytes, void** mailbox, unsigned char* ipc_handle64) {
+    DFD_CHECK_ARG(ctx && mailbox && ipc_handle64 && bytes > 0, "dfd_xchg_mailbox_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* p = nullptr;
+    DFD_CUDA(cudaMalloc(&p, bytes));   // its own allocation: IPC handles cover whole cudaMalloc blocks
+    DFD_CUDA(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    DFD_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(ipc_handle64, &h, 64);
+    *mailbox = p;
+    return 0;
+}
+
+extern "C" int dfd_xchg_mailbox_open(dfd_ctx* ctx, const unsigned char* ipc_handle64, void** peer_mailbox) {
+    DFD_CHECK_ARG(ctx && ipc_handle64 && peer_mailbox, "dfd_xchg_mailbox_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    DFD_CUDA(cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int dfd_xchg_mailbox_close(dfd_ctx* ctx, void* peer_mailbox) {
+    DFD_CHECK_ARG(ctx && peer_mailbox, "dfd_xchg_mailbox_close: bad argument");
+    DFD_CUDA(cudaIpcCloseMemHandle(peer_mailbox));
+    return 0;
+}
+
+extern "C" int dfd_xchg_mailbox_destroy(dfd_ctx* ctx, void* mailbox) {
+    DFD_CHECK_ARG(ctx && mailbox, "dfd_xchg_mailbox_destroy: bad argument");
+    DFD_CUDA(cudaFree(mailbox));
+    return 0;
+}
+
+extern "C" int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params,
+                                  const float* grad_partial, const double* stats5, float* grad_out, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && mailboxes && grad_partial && stats5 && grad_out, "dfd_xchg_allreduce: NULL argument");
+    DFD_CHECK_ARG(world >= 1 && world <= XCHG_MAX_WORLD && rank >= 0 && rank < world, "dfd_xchg_allreduce: rank %d / world %d", rank, world);
+    DFD_CHECK_ARG(n_params > 0 && (((uintptr_t)grad_partial) & 15) == 0, "dfd_xchg_allreduce: grad_partial must be 16-byte aligned");
+    const int64_t n4 = (n_params + 3) / 4;
+    int grid = (int)((n4 + XCHG_THREADS - 1) / XCHG_THREADS);
+    if (grid > ctx->sm_count) grid = ctx->sm_count;   // all CTAs co-resident: the in-kernel arrival count cannot deadlock
+    xchg_allreduce_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params,
+                                                                           grad_partial, stats5, grad_out);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}

@@ -31,3 +31,57 @@ def all_gather_rewards(local_rewards, group=None):
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
     return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)]) if mx else np.zeros(0)
+
+
+class PeerExchange(object):
+    """The sharded learner's one exchange step over NVLink peer memory (csrc/xchg_allreduce.cu).
+
+    Every rank creates a mailbox in its own HBM, the 64-byte CUDA IPC handles travel through the process
+    group once (all_gather_object), every rank maps its peers' mailboxes, and from then on
+    `allreduce(grad_partial, stats5, grad_out)` is ONE kernel launch per step and rank: push to all peers,
+    publish, wait, sum in rank order, scale by 1/std of all ranks' rewards.  No NCCL call on the step."""
+
+    def __init__(self, ctx, n_params, group=None):
+        import ctypes as C
+        from . import _lib
+        self.ctx, self.lib, self.group = ctx, ctx.lib, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.P = int(n_params)
+        nbytes = int(self.lib.dfd_xchg_mailbox_bytes(self.P, self.world))
+        if nbytes == 0:
+            raise _lib.DfdError("PeerExchange: world size %d not supported (1..16)" % self.world)
+        mine = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.dfd_xchg_mailbox_create(ctx.handle, nbytes, C.byref(mine), handle), "dfd_xchg_mailbox_create")
+        self._mine = mine.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._peers = []
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self._mine)
+                continue
+            p = C.c_void_p()
+            _lib.check(self.lib.dfd_xchg_mailbox_open(ctx.handle, C.create_string_buffer(h, 64), C.byref(p)),
+                       "dfd_xchg_mailbox_open (rank %d)" % r)
+            self._peers.append(p.value)
+            ptrs.append(p.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64).to(ctx.device)     # device array of world pointers
+        torch.cuda.synchronize(ctx.device)
+        dist.barrier(group=group)               # every mailbox is zero-filled and mapped before the first step
+
+    def allreduce(self, grad_partial, stats5, grad_out):
+        from . import _lib
+        from .device import ptr
+        _lib.check(self.lib.dfd_xchg_allreduce(self.ctx.handle, ptr(self.table), self.rank, self.world, self.P,
+                                               ptr(grad_partial), ptr(stats5), ptr(grad_out), self.ctx.stream),
+                   "dfd_xchg_allreduce")
+
+    def close(self):
+        for p in self._peers:
+            self.lib.dfd_xchg_mailbox_close(self.ctx.handle, p)
+        self._peers = []
+        if self._mine:
+            self.lib.dfd_xchg_mailbox_destroy(self.ctx.handle, self._mine)
+            self._mine = None

@@ -51,7 +51,8 @@ class _Staging(object):
 
 class FiniteDifferences(object):
     def __init__(self, policy, gradient_optimizer, omega, noise_source, noise_std=0.1, batch_size=100, ent_coef=0.0,
-                 max_delayed_return=10, paired=False, process_group=None, device=None, sync_policy=True):
+                 max_delayed_return=10, paired=False, process_group=None, device=None, sync_policy=True,
+                 peer_exchange=None):
         self.max_delayed_return = max_delayed_return
         self.ent_coef = ent_coef
         self.noise_std = noise_std
@@ -61,6 +62,9 @@ class FiniteDifferences(object):
         self.omega = omega
         self.paired = paired                    # extension: batch = [R plus-members | R minus-members]
         self.process_group = process_group      # extension: population sharded over ranks, one allreduce per step
+        # dist.PeerExchange: the exchange runs as one peer-memory kernel instead of NCCL calls whenever the batch
+        # is antithetic pairs of the current epoch (otherwise: rewards all-gather + NCCL all_reduce)
+        self.peer_exchange = peer_exchange
         self.sync_policy = sync_policy
         self.using_dsgd = is_dsgd(gradient_optimizer)
 
@@ -82,6 +86,8 @@ class FiniteDifferences(object):
             self.theta = torch.from_numpy(np.asarray(policy.get_trainable_flat(), dtype=np.float32).copy()).to(dev)
             self._host_policy = True
         self.grad = torch.zeros(P, dtype=torch.float32, device=dev)
+        self._grad_partial = torch.zeros((P + 3) // 4 * 4, dtype=torch.float32, device=dev)
+        self._stats5 = torch.zeros(8, dtype=torch.float64, device=dev)
         self.hist = torch.zeros(H, self.Ps, dtype=torch.float32, device=dev)
         self.dist = torch.zeros(H, self.Ps, dtype=torch.float32, device=dev)
         self.hist[0, :P].copy_(self.theta)                       # policy_history = [(theta0, 0)]   (:16)
@@ -132,6 +138,9 @@ class FiniteDifferences(object):
 
     # ------------------------------------------------------------------ the step
     def step(self, batch, policy_reward, policy_novelty=None, policy_entropy=None):
+        soa = getattr(batch, "soa", None)
+        if soa is not None:                      # untouched ReturnBatch from the batched Worker: arrays as they are
+            return self.step_arrays(soa[0], soa[1], soa[2], soa[3], policy_reward)
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
         keys = [parse_key(r.encoded_noise) for r in batch]
@@ -173,6 +182,21 @@ class FiniteDifferences(object):
         if pg is None and n == 0:
             return 0                                             # :30-31, no update, epoch unchanged
         stats = None
+        if pg is not None and self.peer_exchange is not None:
+            # the mode is fixed per learner (every rank must take the same path every step): a learner built
+            # with a PeerExchange only accepts what the one-kernel exchange can express
+            if not (self.paired and n % 2 == 0 and bool((hist_row == -1).all())):
+                raise _lib.DfdError("a learner with peer_exchange takes antithetic pairs of the current epoch only "
+                                    "(fd_return mode); build it without peer_exchange for delayed returns")
+            if n == 0:                           # this shard is empty this step: still take part in the exchange
+                self._grad_partial.zero_()
+                self._stats5.zero_()
+                self.peer_exchange.allreduce(self._grad_partial, self._stats5, self.grad)
+            else:
+                self._ensure_capacity(n)
+                d = self._stage.upload(n, reward=rewards, idx=idx, hist_row=hist_row, sign=sign)
+                self._fused_exchange(d["idx"], d["sign"], d["reward"], d["hist_row"], n, policy_reward)
+            return self._apply_update()
         if pg is not None:
             import torch.distributed as dist
             if all_rewards is None:
@@ -204,6 +228,18 @@ class FiniteDifferences(object):
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=pg)     # the one parameter-sized exchange
         return self._apply_update()
 
+    def _fused_exchange(self, idx_d, sign_d, reward_d, hist_row_d, n, policy_reward):
+        """prepare (standardisation deferred) -> reduce -> ONE peer-memory exchange kernel -> self.grad."""
+        st = self.ctx.stream
+        _lib.check(self.lib.dfd_fd_prepare_partial(
+            self.ctx.handle, self.table.ref(), self.P, ptr(reward_d), ptr(idx_d), ptr(sign_d), ptr(hist_row_d), n,
+            float(policy_reward), float(self.noise_std), C.byref(self._rows), ptr(self._stats5),
+            aligned_ptr(self._prep_scratch), self._prep_scratch.numel() - 256, st), "dfd_fd_prepare_partial")
+        _lib.check(self.lib.dfd_fd_reduce(
+            self.ctx.handle, C.byref(self._rows), n // 2, self.P, ptr(self._grad_partial), aligned_ptr(self._red_scratch),
+            self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
+        self.peer_exchange.allreduce(self._grad_partial, self._stats5, self.grad)
+
     def step_device(self, idx_d, sign_d, reward_d, n, policy_reward=0.0, hist_row_d=None, stats_d=None):
         """Device-resident SoA step (no host synchronisation, CUDA-graph capturable): the n returns
         are already in HBM as int64 idx / int8 sign / float64 reward (and optional int32 hist_row;
@@ -220,6 +256,12 @@ class FiniteDifferences(object):
         else:
             n_hist = len(self._dist_epoch) and (max(self._dist_epoch.values()) + 1)
         paired = 1 if (self.paired and n % 2 == 0) else 0
+        if self.process_group is not None and self.peer_exchange is not None:
+            if not (paired and n_hist == 0 and stats_d is None):
+                raise _lib.DfdError("a learner with peer_exchange takes antithetic pairs of the current epoch only")
+            self._fused_exchange(idx_d, sign_d, reward_d, hist_row_d, n, policy_reward)
+            self._apply_update(sync=False)
+            return
         _lib.check(self.lib.dfd_fd_prepare(
             self.ctx.handle, self.table.ref(), self.P, ptr(reward_d), ptr(idx_d), ptr(sign_d), ptr(hist_row_d), n,
             paired, float(policy_reward), float(self.noise_std), ptr(self.dist), self.Ps, int(n_hist), ptr(stats_d),

@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from .fd_return import FDReturn
+from .fd_return import FDReturn, ReturnBatch  # noqa: F401
 
 
 class Worker(object):
@@ -73,29 +73,16 @@ class Worker(object):
         if antithetic:
             m_idx = np.concatenate([idx[ev], idx[tr], idx[tr]])
             m_sign = np.concatenate([np.zeros(len(ev)), np.ones(len(tr)), -np.ones(len(tr))]).astype(np.int8)
-            keys = ["0"] * len(ev) + ["+%d" % i for i in idx[tr]] + ["-%d" % i for i in idx[tr]]
-            is_eval = [True] * len(ev) + [False] * (2 * len(tr))
+            is_eval = np.concatenate([np.ones(len(ev), bool), np.zeros(2 * len(tr), bool)])
         else:
             m_idx = idx.copy()
             m_sign = np.where(flags, 0, 1).astype(np.int8)
-            keys = ["0" if f else "%d" % i for f, i in zip(flags, idx)]     # worker.py:34: eval key is "0"
-            is_eval = [bool(f) for f in flags]
+            is_eval = flags.copy()                                           # worker.py:34: eval key is "0"
         res = self.agent.collect_returns(self.policy, m_idx, m_sign, self.sigma)
-        rets = []
-        for j in range(len(keys)):
-            ret = FDReturn()
-            ret.is_eval = is_eval[j]
-            ret.timesteps = int(res["timesteps"][j])
-            ret.encoded_noise = keys[j]
-            ret.reward = float(res["reward"][j])
-            ret.novelty = 0
-            ret.entropy = float(res["entropy"][j])
-            ret.epoch = self.epoch
-            ret.obs_stats_update = []
-            if ret.is_eval and res.get("states") is not None:
-                ret.eval_states = res["states"]
-            rets.append(ret)
-        return rets
+        # records are built lazily (ReturnBatch): the learner consumes the arrays, any other caller
+        # still sees a sequence of FDReturn objects
+        return ReturnBatch(self.epoch, m_idx, m_sign, res["reward"], res["entropy"], res["timesteps"], is_eval,
+                           states=res.get("states"))
 
     def update(self, state):
         """worker.py:40-43: load the learner's snapshot (flattened state_dict incl. BN buffers)."""

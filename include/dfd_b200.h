@@ -166,6 +166,34 @@ int dfd_dsgd_step(dfd_ctx* ctx, float* theta, const float* grad, int64_t n_param
                   float* update_size_out, void* scratch, size_t scratch_bytes, dfd_stream stream);
 size_t dfd_dsgd_scratch_bytes(int64_t n_params);
 
+/* ---- population sharded over GPUs: the one exchange step --------------------------
+ * One process per GPU.  Every rank evaluates its slice of the antithetic pairs and runs
+ *   dfd_fd_prepare_partial -> dfd_fd_reduce -> dfd_xchg_allreduce -> dfd_dsgd_step.
+ * dfd_fd_prepare_partial: dfd_fd_prepare for current-epoch antithetic pairs with the standardisation of
+ *   finite_differences.py:43 DEFERRED: coefficients are (R+ - R-) * sigma / ||sigma*eps||^2 (the mean cancels
+ *   inside a pair, 1/std is common to all rows) and this rank's (sum x, sum x^2, n, min, max) of
+ *   x = reward - baseline are written to stats_out[5] (device doubles).  hist_row must be all -1.
+ * dfd_xchg_allreduce: ONE kernel pushes the partial gradient and the statistics into every peer's mailbox
+ *   over NVLink (peer stores into CUDA-IPC mapped memory), waits for all peers, sums the world partials in
+ *   rank order (bitwise identical on every rank), applies 1/std(all rewards) (identity when all rewards are
+ *   equal, utils/math_helpers.py:131-133) and writes grad_out.  No host synchronisation, CUDA-graph
+ *   replayable; every rank must call it the same number of times.
+ * Mailboxes: each rank creates one (dfd_xchg_mailbox_create, zero-filled, returns the 64-byte CUDA IPC
+ *   handle), the handles are exchanged by the host (torch.distributed all_gather_object in dist.py), every
+ *   rank opens its peers' (dfd_xchg_mailbox_open) and passes a DEVICE array of world pointers with entry r =
+ *   rank r's mailbox as mapped in this process (entry `rank` = its own). */
+int dfd_fd_prepare_partial(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward,
+                           const int64_t* idx, const int8_t* sign, const int32_t* hist_row, int n_returns,
+                           double baseline, float sigma, dfd_fd_rows* rows, double* stats_out, void* scratch,
+                           size_t scratch_bytes, dfd_stream stream);
+size_t dfd_xchg_mailbox_bytes(int64_t n_params, int world);
+int dfd_xchg_mailbox_create(dfd_ctx* ctx, size_t bytes, void** mailbox, unsigned char* ipc_handle64);
+int dfd_xchg_mailbox_open(dfd_ctx* ctx, const unsigned char* ipc_handle64, void** peer_mailbox);
+int dfd_xchg_mailbox_close(dfd_ctx* ctx, void* peer_mailbox);
+int dfd_xchg_mailbox_destroy(dfd_ctx* ctx, void* mailbox);
+int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params,
+                       const float* grad_partial, const double* stats5, float* grad_out, dfd_stream stream);
+
 /* ---- synthetic return (bench / tests only) ------------------------------- */
 /* Stand-in for the environment, which is outside this path (worker/agent.py is
  * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */

@@ -105,3 +105,23 @@ def test_fd_return_record_roundtrip():
     q = FDReturn()
     q.deserialize(r.serialize())
     assert (q.epoch, q.encoded_noise, q.reward, q.is_eval) == (3, "123", 1.5, False)
+
+
+def test_return_batch_is_a_sequence_of_fdreturns_and_keeps_the_arrays():
+    """ReturnBatch: lazily built FDReturn records (reference fields, learner/fd_return.py:5-23) over the
+    SoA arrays; the SoA view disappears once a record object has been handed out."""
+    from dfd_starter_b200.fd_return import ReturnBatch, FDReturn
+    idx = np.array([0, 11, 22, 11, 22], dtype=np.int64)
+    sign = np.array([0, 1, 1, -1, -1], dtype=np.int8)
+    rb = ReturnBatch(7, idx, sign, np.arange(5) * 0.5, np.zeros(5), np.full(5, 3), sign == 0)
+    assert len(rb) == 5 and rb.soa is not None
+    e, i, s, r = rb.soa
+    assert e.tolist() == [7] * 5 and i.tolist() == idx.tolist() and s.tolist() == sign.tolist()
+    assert [rb.key(j) for j in range(5)] == ["0", "+11", "+22", "-11", "-22"]
+    recs = list(rb)
+    assert rb.soa is None                       # records may now be edited by the caller
+    assert all(isinstance(x, FDReturn) for x in recs)
+    assert recs[0].is_eval and recs[0].encoded_noise == "0" and recs[3].encoded_noise == "-11"
+    assert recs[2].reward == 1.0 and recs[2].epoch == 7 and recs[2].timesteps == 3
+    one_sided = ReturnBatch(0, idx[1:3], np.ones(2, np.int8), np.zeros(2), np.zeros(2), np.ones(2), np.zeros(2, bool))
+    assert [one_sided.key(j) for j in range(2)] == ["11", "22"]
