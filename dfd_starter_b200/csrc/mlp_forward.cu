@@ -199,6 +199,10 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
                             const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
                             int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
 
+int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                                const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
+                                int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
+
 extern "C" int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table,
                                   const float* theta, const float* bn_buffers, const int64_t* idx, const int8_t* sign,
                                   int n_members, float sigma, const float* obs, int obs_per_member, float* out,
@@ -217,10 +221,14 @@ extern "C" int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     const MlpLayout L = make_layout(desc);
     DFD_CHECK_ARG(L.P < table->size, "dfd_policy_forward: num_params %lld >= table size", (long long)L.P);
     if (desc->precision >= 1 && desc->kind == DFD_POLICY_MUJOCO) {
-        // 64x64 nets: warp-specialised pipelined kernel; other shapes: the generic tcgen05 kernel
+        // 64x64 nets: warp-specialised resident-weight kernel; wide nets: warp-specialised streaming kernel;
+        // anything else: the generic tcgen05 kernel
         const int rc = dfd_mlp_forward_ws_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member, out,
                                                desc->precision == 2 ? 1 : 0, st);
         if (rc >= 0) return rc;
+        const int rs = dfd_mlp_forward_stream_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member,
+                                                   out, desc->precision == 2 ? 1 : 0, st);
+        if (rs >= 0) return rs;
         return dfd_mlp_forward_tc_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member, out, st);
     }
     int maxdim = L.K;

@@ -1,0 +1,468 @@
+// Warp-specialised STREAMING per-member MLP forward for the wide MuJoCo nets (hidden widths 64..256, e.g. the
+// Humanoid-shaped 376-256-256-17 of BASELINE config 3; policies/mujoco.py:35-41, perturbation worker/worker.py:28).
+// A member's weights (171 042 floats) do not fit on chip, so they stream through a shared-memory ring in K chunks:
+//
+//   builder warps (8)  two teams of four warps alternate chunks, so the global loads of two chunks are always in
+//                      flight (the chunk is small on purpose: shared memory stays under 100 KB and the rest of the
+//                      SM's 228 KB is L1, whose capacity bounds how many load bytes can be outstanding);
+//                      theta and eps(member) straight from global memory, theta + s*sigma*eps with the reference's
+//                      two roundings, tf32, stored as the UMMA K-major canonical B operand chunk [N x 16]; for layer 0
+//                      also the observation chunk [128 x 16] (A);
+//   MMA warp (1 lane)  tcgen05.mma kind::tf32, M = 128 observations, N = layer width, 2 instructions per chunk;
+//                      layer 0 takes A from shared memory, layers 1 and 2 take A from TENSOR MEMORY;
+//   epilogue warps (4) TMEM accumulator -> + perturbed bias -> tanh -> tf32 -> the same TMEM columns (the next
+//                      layer's A operand), 32 columns at a time, each batch published on its own mbarrier so the next
+//                      layer's MMAs start on the first 32 activations while the rest are still being computed.
+// TMEM: region R1 (columns 0-255) = layer-0 accumulator / layer-1 A operand / head accumulator,
+//       region R2 (columns 256-511) = layer-1 accumulator / layer-2 A operand.
+// The builders run ahead of the MMA warp by the depth of the ring, across layer and member boundaries.
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int ST_KC = 16;                 // K columns per chunk
+constexpr int ST_TEAMS = 2;               // builder teams: team t builds chunks t, t+2, ... so two chunks' loads are in flight
+constexpr int ST_TEAM_WARPS = 4;
+constexpr int ST_NS = 4;                  // ring stages (max; the launcher may use fewer to leave L1 for in-flight loads)
+constexpr int ST_NBUILD = 256;
+constexpr int ST_NEPI = 128;               // 4 warps, one per TMEM lane quarter (and per SM sub-partition: the SFU is per sub-partition)
+constexpr int ST_THREADS = ST_NBUILD + ST_NEPI + 32;
+constexpr int ST_WCHUNK = 256 * ST_KC;    // floats
+constexpr int ST_ACHUNK = 128 * ST_KC;
+constexpr int ST_STAGE = ST_WCHUNK + ST_ACHUNK;
+
+struct StParams {
+    int K0, N1, N2, nout, N3, A;
+    int w_off[3], b_off[3], kin[3], nreal[3], npad[3], nchunk[3];
+    int E, tiles, n_work, pair_order, prefetch, ns;
+    int64_t P;
+    float sigma;
+};
+
+// work item -> (member, tile).  pair_order: consecutive work items are the two members of an antithetic pair
+// ([plus | minus] batches: members j and j + M/2 share their table row), so the CTAs b and b+1 stream the same eps
+// row at the same time and HBM serves it once.
+__device__ __forceinline__ void st_item(const StParams& p, int work, int& m, int& tile) {
+    const int mm = p.tiles == 1 ? work : work / p.tiles;
+    tile = work - mm * p.tiles;
+    const int M = p.n_work / p.tiles;
+    m = p.pair_order ? ((mm & 1) ? (M >> 1) + (mm >> 1) : (mm >> 1)) : mm;
+}
+
+__device__ __forceinline__ float st_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+template <bool APPROX>
+__device__ __forceinline__ float st_tanh(float x) {
+    if (APPROX) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    } else {
+        return tanh_fast(x);
+    }
+}
+
+__device__ int st_spin_mode;   // experiment switch: 1 = plain try_wait loop, 0 = try_wait with a suspend-time hint
+__device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    if (st_spin_mode) {
+        do {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+            if (!ok && ++spins > (1u << 26)) __trap();
+        } while (!ok);
+        return;
+    }
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(200000u)
+            : "memory");
+        if (!ok && ++spins > (1u << 22)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void st_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void st_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void st_tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// barrier slots
+enum { SB_FULL = 0, SB_EMPTY = 4, SB_DFULL = 8, SB_HREADY = 11 /* [2 layers][8 chunks] */, SB_R1FREE = 27, SB_BFULL = 28, SB_BEMPTY = 30, SB_COUNT = 32 };
+
+template <bool APPROX>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, int64_t stride, const float* __restrict__ theta,
+                          const int64_t* __restrict__ idx, const int8_t* __restrict__ sign, const float* __restrict__ obs,
+                          float* __restrict__ out, long long* __restrict__ prof) {
+#define ST_TL(cond, slot) do { if (prof && (cond) && u == 3) prof[(size_t)blockIdx.x * 32 + (slot)] = clock64(); } while (0)
+    extern __shared__ __align__(128) float smem[];   // [NS stages: W chunk | A chunk][2 x 3 x 256 bias]
+    __shared__ __align__(8) uint64_t bars[SB_COUNT];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n_my = ((int)blockIdx.x < p.n_work) ? (p.n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    const uint32_t smem0 = smem_u32(smem);
+    float* bias_s = smem + p.ns * ST_STAGE;
+#define ST_BAR(i) (bar0 + 8u * (uint32_t)(i))
+
+    if (tid == 0) {
+        for (int s = 0; s < ST_NS; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ST_BAR(SB_FULL + s)), "r"(ST_TEAM_WARPS));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ST_BAR(SB_EMPTY + s)));
+        }
+        for (int l = 0; l < 3; ++l) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ST_BAR(SB_DFULL + l)));
+        for (int j = 0; j < 16; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(ST_BAR(SB_HREADY + j)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ST_BAR(SB_R1FREE)), "r"(ST_NEPI / 32));
+        for (int b = 0; b < 2; ++b) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ST_BAR(SB_BFULL + b)), "r"(ST_NBUILD / 32));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ST_BAR(SB_BEMPTY + b)), "r"(ST_NEPI / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t tR1 = tmem, tR2 = tmem + 256u;
+
+    if (warp < ST_NBUILD / 32) {
+        // =============================== builders ===============================================
+        // lane -> (row-in-group i = lane & 7, k-quad j = lane >> 3): a warp reads 8 rows x 64 contiguous bytes
+        // (full 32-byte sectors) and every quarter-warp stores 128 contiguous bytes (conflict-free)
+        const int li = lane & 7, lj = lane >> 3;
+        const int team = warp / ST_TEAM_WARPS, tw = warp % ST_TEAM_WARPS;
+        int g = 0;           // running chunk number over layers and members: stage = g % ns, team = g % ST_TEAMS
+        for (int u = 0; u < n_my; ++u) {
+            const int work = (int)blockIdx.x + u * (int)gridDim.x;
+            int m, tile;
+            st_item(p, work, m, tile);
+            const int e0i = tile * 128, ne = min(128, p.E - e0i);
+            const float sg = p.sigma * (float)sign[m];
+            const float* row = table_row_ptr(replicas, stride, idx[m]);
+            const float* ob = obs + ((int64_t)m * p.E + e0i) * p.K0;
+            if ((p.prefetch & 1) && tid == 0 && u + 1 < n_my) {      // next member's eps row and observation tile -> L2
+                int nm, nt;
+                st_item(p, work + (int)gridDim.x, nm, nt);
+                l2_prefetch(table_row_ptr(replicas, stride, idx[nm]), (size_t)p.P * 4);
+                l2_prefetch(obs + ((int64_t)nm * p.E + nt * 128) * p.K0, (size_t)min(128, p.E - nt * 128) * p.K0 * 4);
+            }
+            // perturbed biases of the three layers into bias buffer (u & 1)
+            {
+                const int bb = u & 1;
+                st_wait(ST_BAR(SB_BEMPTY + bb), (uint32_t)((u >> 1) & 1) ^ 1u);
+                float* bs = bias_s + bb * 768;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    float v = 0.f;
+                    if (tid < p.nreal[l]) {
+                        const int q = p.b_off[l] + tid;
+                        v = perturb1(theta[q], sg, row[q]);
+                    }
+                    bs[l * 256 + tid] = v;
+                }
+                __syncwarp();
+                if (lane == 0) st_arrive(ST_BAR(SB_BFULL + bb));
+            }
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {      // unrolled: every p.xxx[l] is a compile-time constant-bank read
+                const int kin = p.kin[l], nreal = p.nreal[l], nrg = p.npad[l] >> 3, nchunk = p.nchunk[l];
+                const float* th_l = theta + p.w_off[l];
+                const float* ep_l = row + p.w_off[l];
+#pragma unroll 1
+                for (int c = 0; c < nchunk; ++c, ++g) {
+                    if (g % ST_TEAMS != team) continue;
+                    const int s = g % p.ns;
+                    st_wait(ST_BAR(SB_EMPTY + s), (uint32_t)((g / p.ns) & 1) ^ 1u);
+                    const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
+                    const uint32_t Ad = Wd + 4u * ST_WCHUNK;
+                    const int k0 = c * ST_KC, k = k0 + lj * 4;
+                    // W chunk [N x 16]: one warp item = one row group (8 rows x 4 k-quads); ALL of a thread's loads
+                    // of the chunk are issued before the first use
+                    constexpr int NI = 32 / ST_TEAM_WARPS;       // row groups per warp (N <= 256)
+                    float4 a[NI], e[NI], o4[16 / ST_TEAM_WARPS];
+#pragma unroll
+                    for (int h = 0; h < NI; ++h) {
+                        const int rg = tw + h * ST_TEAM_WARPS;
+                        const int n = rg * 8 + li;
+                        a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        e[h] = a[h];
+                        if (rg < nrg && n < nreal && k < kin) {      // kin % 4 == 0: whole quads only
+                            const int q = n * kin + k;
+                            if (!(p.prefetch & 2)) a[h] = *reinterpret_cast<const float4*>(th_l + q);
+                            if (!(p.prefetch & 4)) e[h] = ldg_stream_f4(ep_l + q);
+                        }
+                    }
+                    if (l == 0) {     // observation chunk [128 x 16]: 16 row groups
+#pragma unroll
+                        for (int h = 0; h < 16 / ST_TEAM_WARPS; ++h) {
+                            const int r = (tw + h * ST_TEAM_WARPS) * 8 + li;
+                            o4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r < ne && k < p.K0 && !(p.prefetch & 8)) o4[h] = ldg_stream_f4(ob + (int64_t)r * p.K0 + k);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < NI; ++h) {
+                        const int rg = tw + h * ST_TEAM_WARPS;
+                        if (rg < nrg) {
+                            const uint32_t d = Wd + 4u * (uint32_t)(rg * (ST_KC * 8) + lj * 32 + li * 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
+                                         "f"(st_tf32(perturb1(a[h].x, sg, e[h].x))), "f"(st_tf32(perturb1(a[h].y, sg, e[h].y))),
+                                         "f"(st_tf32(perturb1(a[h].z, sg, e[h].z))), "f"(st_tf32(perturb1(a[h].w, sg, e[h].w)))
+                                         : "memory");
+                        }
+                    }
+                    if (l == 0) {
+#pragma unroll
+                        for (int h = 0; h < 16 / ST_TEAM_WARPS; ++h) {
+                            const int rg = tw + h * ST_TEAM_WARPS;
+                            const uint32_t d = Ad + 4u * (uint32_t)(rg * (ST_KC * 8) + lj * 32 + li * 4);
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d), "f"(st_tf32(o4[h].x)),
+                                         "f"(st_tf32(o4[h].y)), "f"(st_tf32(o4[h].z)), "f"(st_tf32(o4[h].w))
+                                         : "memory");
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) st_arrive(ST_BAR(SB_FULL + s));
+                }
+            }
+        }
+    } else if (warp < (ST_NBUILD + ST_NEPI) / 32) {
+        // =============================== epilogue warps =========================================
+        const int q = (warp - ST_NBUILD / 32) & 3;
+        const int gt = q * 32 + lane;                 // observation row of this thread
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        uint32_t pd[3] = {0, 0, 0};
+        for (int u = 0; u < n_my; ++u) {
+            const int work = (int)blockIdx.x + u * (int)gridDim.x;
+            int m, tile;
+            st_item(p, work, m, tile);
+            const int e0i = tile * 128, ne = min(128, p.E - e0i);
+            const int bb = u & 1;
+            const float* bs = bias_s + bb * 768;
+            st_wait(ST_BAR(SB_BFULL + bb), (uint32_t)((u >> 1) & 1));
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                const uint32_t treg = l == 0 ? tR1 : tR2;
+                const int N = p.npad[l];
+                ST_TL(gt == 0, 8 + 2 * l);
+                st_wait(ST_BAR(SB_DFULL + l), pd[l]); pd[l] ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                ST_TL(gt == 0, 9 + 2 * l);
+#pragma unroll 1
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    uint32_t r[32];
+                    st_tmem_ld32(treg + lane_sel + (uint32_t)c0, r);
+                    const float4* b4 = reinterpret_cast<const float4*>(bs + l * 256 + c0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = b4[i];
+                        r[4 * i + 0] = __float_as_uint(st_tf32(st_tanh<APPROX>(__uint_as_float(r[4 * i + 0]) + b.x)));
+                        r[4 * i + 1] = __float_as_uint(st_tf32(st_tanh<APPROX>(__uint_as_float(r[4 * i + 1]) + b.y)));
+                        r[4 * i + 2] = __float_as_uint(st_tf32(st_tanh<APPROX>(__uint_as_float(r[4 * i + 2]) + b.z)));
+                        r[4 * i + 3] = __float_as_uint(st_tf32(st_tanh<APPROX>(__uint_as_float(r[4 * i + 3]) + b.w)));
+                    }
+                    st_tmem_st32(treg + lane_sel + (uint32_t)c0, r);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) st_arrive(ST_BAR(SB_HREADY + l * 8 + (c0 >> 5)));   // these 32 activations are an A chunk now
+                }
+            }
+            // head: accumulator in R1 columns [0, N3)
+            ST_TL(gt == 0, 12);
+            st_wait(ST_BAR(SB_DFULL + 2), pd[2]); pd[2] ^= 1u;
+            ST_TL(gt == 0, 13);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+                float* o = out + ((int64_t)m * p.E + e0i + gt) * p.nout;
+#pragma unroll 1
+                for (int c = 0; c < p.N3; c += 16) {
+                    float v[16];
+                    tmem_ld16(tR1 + lane_sel + (uint32_t)c, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float y = st_tanh<APPROX>(v[i] + bs[512 + c + i]);
+                        v[i] = c + i < p.A ? y : 0.55f + 0.45f * y;   // MapContinuousToAction
+                    }
+                    if (gt < ne) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c + i < p.nout) o[c + i] = v[i];
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            ST_TL(gt == 0, 14);
+            if (lane == 0) {
+                st_arrive(ST_BAR(SB_R1FREE));
+                st_arrive(ST_BAR(SB_BEMPTY + bb));
+            }
+        }
+    } else {
+        // =============================== MMA issue warp =========================================
+        int g = 0;
+        uint32_t ph = 0, pr1 = 0;
+        for (int u = 0; u < n_my; ++u) {
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const uint32_t idesc = make_idesc_tf32(p.npad[l]);
+                const uint32_t d_tmem = l == 1 ? tR2 : tR1;
+                const uint32_t a_tmem = l == 1 ? tR1 : tR2;
+                ST_TL(lane == 0, 2 * l);
+                if (l == 0 && u > 0) { st_wait(ST_BAR(SB_R1FREE), pr1); pr1 ^= 1u; }   // head of the previous member read out
+                ST_TL(lane == 0 && l == 0, 6);
+#pragma unroll 1
+                for (int c = 0; c < p.nchunk[l]; ++c, ++g) {
+                    const int s = g % p.ns;
+                    if (l > 0 && (c * ST_KC) % 32 == 0)
+                        st_wait(ST_BAR(SB_HREADY + (l - 1) * 8 + (c * ST_KC) / 32), ph);   // these activations are in TMEM
+                    st_wait(ST_BAR(SB_FULL + s), (uint32_t)((g / p.ns) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
+                    const uint64_t bdesc = make_desc(Wd, 128, ST_KC * 32u);
+                    if (l == 0) {
+                        const uint64_t adesc = make_desc(Wd + 4u * ST_WCHUNK, 128, ST_KC * 32u);
+#pragma unroll
+                        for (int j = 0; j < ST_KC / 8; ++j)
+                            umma_tf32_elect(d_tmem, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (c | j) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < ST_KC / 8; ++j)
+                            st_umma_ts(d_tmem, a_tmem + (uint32_t)(c * ST_KC + j * 8), bdesc + (uint64_t)(j * 16), idesc, (c | j) ? 1u : 0u);
+                    }
+                    umma_commit_elect(ST_BAR(SB_EMPTY + s));
+                    if (c == p.nchunk[l] - 1) umma_commit_elect(ST_BAR(SB_DFULL + l));
+                    __syncwarp();
+                }
+                ST_TL(lane == 0, 2 * l + 1);
+            }
+            ph ^= 1u;          // every activation barrier completes once per member
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+#undef ST_BAR
+#undef ST_TL
+}
+
+}  // namespace
+
+// returns -1 when the shape is not served by this kernel (the caller falls back to the generic tcgen05 kernel)
+int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                                const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
+                                int obs_per_member, float* out, int approx_tanh, cudaStream_t st) {
+    const int K0 = desc->n_in, N1 = desc->h1, N2 = desc->h2, nout = 2 * desc->n_act;
+    if (getenv("DFD_TC_NO_STREAM")) return -1;
+    // whole 16-byte quads along K in every layer, hidden widths in whole 64-column halves, head within one MMA
+    if (K0 % 4 || N1 % 64 || N2 % 64 || N1 > 256 || N2 > 256 || N1 < 64 || N2 < 64 || nout > 64) return -1;
+    if ((((uintptr_t)theta) & 15) || (((uintptr_t)obs) & 15)) return -1;
+    StParams p = {};
+    p.K0 = K0; p.N1 = N1; p.N2 = N2; p.nout = nout; p.A = desc->n_act;
+    p.N3 = (nout + 15) / 16 * 16;
+    const int in_[3] = {K0, N1, N2}, outr[3] = {N1, N2, nout}, outp[3] = {N1, N2, p.N3};
+    int off = 0;
+    for (int l = 0; l < 3; ++l) {
+        p.w_off[l] = off; off += in_[l] * outr[l];
+        p.b_off[l] = off; off += outr[l];
+        p.kin[l] = in_[l];
+        p.nreal[l] = outr[l];
+        p.npad[l] = outp[l];
+        p.nchunk[l] = (in_[l] + ST_KC - 1) / ST_KC;
+        if (p.w_off[l] % 4) return -1;
+    }
+    p.P = off;
+    p.E = obs_per_member;
+    p.tiles = (obs_per_member + 127) / 128;
+    DFD_CHECK_ARG((int64_t)n_members * p.tiles < 2147483647LL, "tcgen05 MLP path: too many work items");
+    p.n_work = n_members * p.tiles;
+    p.sigma = sigma;
+    p.pair_order = (n_members % 2 == 0 && !getenv("DFD_ST_NOPAIR")) ? 1 : 0;
+    p.prefetch = getenv("DFD_ST_NOPF") ? 0 : 1;
+    if (getenv("DFD_ST_DBG")) p.prefetch |= atoi(getenv("DFD_ST_DBG"));   // experiments: 2 no theta, 4 no eps, 8 no obs loads
+    // 4 x 24 KB + biases: shared memory stays near 100 KB so ~96 KB of the SM's 228 KB remain L1 - measured on B200:
+    // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
+    p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : ST_NS;
+    if (p.ns < 2 || p.ns > ST_NS) p.ns = ST_NS;
+    const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768) * sizeof(float);
+    int grid = ctx->sm_count;
+    if (grid > p.n_work) grid = p.n_work;
+    {
+        const int sm = getenv("DFD_ST_SPIN") ? 1 : 0;
+        cudaMemcpyToSymbolAsync(st_spin_mode, &sm, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+    }
+    long long* prof = nullptr;
+    if (getenv("DFD_ST_PROF")) { cudaMalloc(&prof, (size_t)grid * 32 * 8); cudaMemset(prof, 0, (size_t)grid * 32 * 8); }
+    if (approx_tanh) {
+        DFD_CUDA(cudaFuncSetAttribute(mlp_forward_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_forward_stream_kernel<true><<<grid, ST_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+    } else {
+        DFD_CUDA(cudaFuncSetAttribute(mlp_forward_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_forward_stream_kernel<false><<<grid, ST_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+    }
+    DFD_LAUNCHED(ctx);
+    if (prof) {
+        cudaStreamSynchronize(st);
+        static long long h[32];
+        cudaMemcpy(h, prof + 32 * 7, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        fprintf(stderr, "[stream timeline] CTA 7 unit 3 (cycles from L0 start): MMA: L0 start %lld (r1free seen %lld) issued %lld | L1 start %lld issued %lld | L2 start %lld issued %lld || EPI: wait0 %lld got %lld | wait1 %lld got %lld | wait2 %lld got %lld | end %lld\n", h[0]-t0, h[6]-t0, h[1]-t0, h[2]-t0, h[3]-t0, h[4]-t0, h[5]-t0, h[8]-t0, h[9]-t0, h[10]-t0, h[11]-t0, h[12]-t0, h[13]-t0, h[14]-t0);
+        cudaFree(prof);
+    }
+    return 0;
+}
