@@ -46,6 +46,10 @@ WORKLOADS = {
     "C1": dict(kind="discrete", n_in=2, h1=64, h2=64, n_act=9, pairs=20, E=128,
                desc="C1 simple_trap-shaped discrete MLP 2-64-64-9, 20 antithetic pairs, fd_return"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+# `ncu --set full` capture of this workload (profiles/r01/SUMMARY.md); None where no capture exists
+NCU_TRAFFIC = {("C2", "policy_forward"): 42.44e6 + 0.39e6, ("C3", "policy_forward"): 1.176e9 + 29.1e6,
+               ("C2", "fd_reduce"): 24.55e6, ("C3", "fd_reduce"): 571.3e6 + 7.8e6}
 TABLE_SIZE = 25_000_000
 TABLE_SEED = 124
 SIGMA = 0.02
@@ -536,7 +540,9 @@ def b200_main(args, w):
     dominant = "policy_forward" if us_forward >= us_reduce else "fd_reduce"
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": dk["achieved_GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": dk["achieved_GBps"] / hbm_peak,
+                "traffic": NCU_TRAFFIC.get((args.workload, dominant)) if (E == WORKLOADS[args.workload]["E"] and not args.pairs) else None,
+                "traffic_source": "profiles/r01/SUMMARY.md (ncu --set full, one launch)", "peak_source": peak_src,
                 "share_of_step": dk["us"] / (ms_step * 1e3),
                 "fd_reduce": {"achieved": kernels["fd_reduce"]["achieved_GBps"], "frac": kernels["fd_reduce"]["achieved_GBps"] / hbm_peak,
                               "us": us_reduce, "algorithmic_bytes": red_bytes}}
