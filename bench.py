@@ -400,14 +400,17 @@ def b200_main(args, w):
         device_step(k)
     torch.cuda.synchronize()
     graphs = None
+    launches_per_graph = LAUNCHES_PER_STEP
     if use_graph:
         try:
             graphs = []
             k0 = n_warm
             for c in range(CYC):
                 gr = torch.cuda.CUDAGraph()
+                l0 = ctx.launch_count()
                 with torch.cuda.graph(gr):
                     device_step(k0 + c)
+                launches_per_graph = ctx.launch_count() - l0      # this library's kernels captured into one step
                 graphs.append(gr)
             torch.cuda.synchronize()
             n_warm += CYC          # capture advanced the learner's ring bookkeeping by CYC steps
@@ -625,7 +628,7 @@ def b200_main(args, w):
         "fd_estimates_per_s": 1e3 / ms_step,
         "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
         "roofline": roofline, "kernels": kernels, "e2e": e2e,
-        "gpu_launches": int(launches_plain if graphs is None else args.steps * LAUNCHES_PER_STEP),
+        "gpu_launches": int(launches_plain if graphs is None else args.steps * launches_per_graph),
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
@@ -659,7 +662,8 @@ def _finish(world):
     os._exit(0)
 
 
-# forward, synthetic return, fd_coef, fd_reduce, sumsq, dsgd_update  (fd_return mode: no dots pass)
+# forward, synthetic return, fd_coef, fd_reduce, [sumsq,] dsgd_update  (fd_return mode: no dots pass); the value
+# reported is counted from the library's launch counter during graph capture, this is only the fallback
 LAUNCHES_PER_STEP = 6
 
 

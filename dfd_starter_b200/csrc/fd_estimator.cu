@@ -501,7 +501,24 @@ __global__ void __launch_bounds__(DSGD_THREADS) dsgd_update_kernel(float* __rest
     __shared__ double sh[DSGD_THREADS / 32];
     __shared__ float coef_s;
     __shared__ unsigned ticket_s;
-    if (threadIdx.x < 32) {
+    if (n_partial == 0) {
+        // short gradients: every CTA sums g.g itself (same order in every CTA -> identical coefficient) instead of
+        // paying a separate launch for the partial sums
+        double a2 = 0.0;
+        for (int64_t p = threadIdx.x; p < P; p += DSGD_THREADS) {
+            const double x = (double)__ldcg(g + p);
+            a2 += x * x;
+        }
+        a2 = warp_sum(a2);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < DSGD_THREADS / 32; ++i) t += sh[i];
+            const double norm = sqrt(t);
+            coef_s = norm > 0.0 ? (float)(step / norm) : 0.f;
+        }
+    } else if (threadIdx.x < 32) {
         double t = 0.0;
         for (int i = threadIdx.x; i < n_partial; i += 32) t += gnorm_partial[i];
         t = warp_sum(t);
@@ -571,11 +588,14 @@ extern "C" int dfd_dsgd_step(dfd_ctx* ctx, float* theta, const float* grad, int6
     double* gpart = (double*)scratch;
     double* upart = gpart + DSGD_MAX_CTAS;
     unsigned* counter = (unsigned*)(upart + DSGD_MAX_CTAS);  // zero on entry (self-resetting)
-    sumsq_partial_kernel<<<ctas, DSGD_THREADS, 0, st>>>(grad, n_params, gpart);
-    DFD_LAUNCHED(ctx);
+    const bool fused_norm = n_params <= 32768;     // <= 128 KB of gradient: cheaper to re-sum per CTA than to launch
+    if (!fused_norm) {
+        sumsq_partial_kernel<<<ctas, DSGD_THREADS, 0, st>>>(grad, n_params, gpart);
+        DFD_LAUNCHED(ctx);
+    }
     // dynamic_sgd.py:30  coef = lr * sqrt(d) * lr_scale / norm  (python floats = fp64)
     const double step = lr * sqrt((double)n_params) * lr_scale;
-    dsgd_update_kernel<<<ctas, DSGD_THREADS, 0, st>>>(theta, grad, n_params, step, gpart, ctas, hist, dist, hist_stride,
+    dsgd_update_kernel<<<ctas, DSGD_THREADS, 0, st>>>(theta, grad, n_params, step, gpart, fused_norm ? 0 : ctas, hist, dist, hist_stride,
                                                       n_hist_valid, hist_write_row, upart, counter, update_size_out);
     DFD_LAUNCHED(ctx);
     return 0;

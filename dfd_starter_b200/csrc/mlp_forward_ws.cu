@@ -1,16 +1,16 @@
 // Warp-specialised, software-pipelined per-member MLP forward for the 64x64 MuJoCo nets
 // (policies/mujoco.py:35-41 + utils/torch_helpers.py:20-25; perturbation worker/worker.py:28).
 //
-// One persistent CTA per SM, 16 warps (512 threads x 128 registers), up to three members in flight:
+// One persistent CTA per SM, 8 builder warps + up to three MMA/epilogue groups of 4 warps (640 threads x 96 registers):
 //   * producer duty (no warp of its own): cp.async.bulk (TMA bulk copy) of eps(member) - one contiguous,
 //     16-byte aligned slice of a table replica - and of the member's observation tile into a shared-memory
 //     ring, completion on an mbarrier (expect_tx).  The LAST builder warp to finish reading a ring slot
 //     (shared-memory counter) refills it with the item NE ahead, so the copies run NE items ahead;
 //   * builder warps (8): own theta in REGISTERS for the whole kernel (each thread always builds the same
-//     elements), read eps from the ring, form theta + s*sigma*eps with the reference's two roundings, round to
+//     elements), read eps from the ring, form theta + s*sigma*eps (one FMA: see tf32_fma), round to
 //     tf32 and write the UMMA K-major canonical B operands of all three layers into one of NST operand
 //     stages (bank-conflict-free diagonal lane mapping);
-//   * two epilogue/MMA groups (4 warps each, ping-pong).  Every A operand lives in TENSOR MEMORY: thread r
+//   * two or three epilogue/MMA groups (4 warps each; three whenever 3 x 168 TMEM columns suffice).  Every A operand lives in TENSOR MEMORY: thread r
 //     owns row r of the 128-observation tile, copies its observation row from the group's own TMA-fed ring
 //     into TMEM (tcgen05.st), one elected lane issues tcgen05.mma (kind::tf32, A from TMEM, B from shared
 //     memory), then each thread reads its accumulator row, applies tanh, rounds to tf32 and writes it back
@@ -26,16 +26,16 @@ namespace {
 
 constexpr int WS_HID = 64;        // hidden width served by this kernel
 constexpr int WS_KH = 72;         // K of layers 1 and 2: 64 activations + the bias/ones column block
-constexpr int WS_GROUP_THREADS = 256;   // two groups of 4 warps
+constexpr int WS_MAXG = 3;         // MMA/epilogue groups (runtime: 2 or 3)
 constexpr int WS_NBUILD = 256;
-constexpr int WS_THREADS = WS_GROUP_THREADS + WS_NBUILD;
-constexpr int WS_A0C = 40;        // TMEM columns reserved for the observation operand (K0p <= 40)
-constexpr int WS_TCOLS = WS_A0C + 2 * WS_KH + 32;   // per group: A0 40 | A1/D1 72 | A2/D2 72 | D3 32  (2 x 216 <= 512)
+constexpr int WS_THREADS = WS_NBUILD + 128 * WS_MAXG;
+// TMEM columns per group: A0 (a0c) | A1/D1 72 | A2/D2 72 | D3.  Two groups: a0c = 40, D3 = 32 own columns (2 x 216);
+// three groups: a0c = 24 and D3 (<= 16 columns) aliases A0, which is dead once layer 0 has run (3 x 168 = 504 <= 512).
 
 struct WsParams {
     int K0, K0p, nkq, nout, N3, A;
     int w_off1, w_off2, b_off0, b_off1, b_off2;
-    int E, tiles, n_work, nst, ne, obs_vec;
+    int E, tiles, n_work, nst, ne, obs_vec, ng, a0c, tcols, d3_off;
     int st_floats, o_w0, o_w1, o_w2;
     int o_ring, ring_floats, eps_floats, o_obs, obs_floats;
     float sigma;
@@ -45,6 +45,11 @@ struct WsParams {
 // operand and ignores the low 13 bits, so adding half a tf32 ulp (one integer add) turns that truncation into
 // round-to-nearest, ties away - the same value cvt.rna.tf32.f32 produces, without its conversion-pipe cost.
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+
+// operand element of the tensor path: theta + s*sigma*eps rounded to tf32.  One FMA instead of the reference's mul-then-add:
+// the two differ by at most one fp32 ulp, 2^13 times below the tf32 rounding applied right after (the exact fp32
+// path and dfd_perturb_members keep the bit-exact two-rounding form of worker/worker.py:28).
+__device__ __forceinline__ float tf32_fma(float theta, float sg, float eps) { return tf32_rn(fmaf(sg, eps, theta)); }
 
 template <bool APPROX>
 __device__ __forceinline__ float ws_tanh(float x) {
@@ -140,7 +145,7 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // barrier slots
-enum { B_WFULL = 0, B_WEMPTY = 3, B_MMA = 6, B_EFULL = 8, B_OFULL = 12, B_COUNT = 16 };
+enum { B_WFULL = 0, B_WEMPTY = 3, B_MMA = 6, B_EFULL = 9, B_OFULL = 13, B_COUNT = 19 };
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
@@ -186,12 +191,9 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(WS_BAR(B_WFULL + s)), "r"(WS_NBUILD / 32));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_WEMPTY + s)));
         }
-        for (int s = 0; s < 4; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_EFULL + s)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_OFULL + s)));
-        }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_MMA)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_MMA + 1)));
+        for (int s = 0; s < 4; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_EFULL + s)));
+        for (int s = 0; s < 2 * WS_MAXG; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_OFULL + s)));
+        for (int s = 0; s < WS_MAXG; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(WS_BAR(B_MMA + s)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // first NE eps rows: requested before anything else so the HBM latency overlaps the prologue
         for (int kk = 0; kk < p.ne && kk < n_my; ++kk) {
@@ -211,7 +213,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
     }
     // zero the operand stages once (padding rows / columns stay zero for the whole kernel) and the zero word
     // at the tail of every eps ring slot (the source of every "no such element" in the builders)
-    for (int i = tid; i < p.nst * p.st_floats; i += WS_THREADS) smem[i] = 0.f;
+    for (int i = tid; i < p.nst * p.st_floats; i += (int)blockDim.x) smem[i] = 0.f;
     if (tid < p.ne) smem[p.o_ring + tid * p.ring_floats + p.eps_floats] = 0.f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -219,7 +221,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (warp < WS_NBUILD / 32) {   // warp order: builders 0-7, groups 8-15
+    if (warp < WS_NBUILD / 32) {   // warp order: builders 0-7, groups 8-11, 12-15 (, 16-19)
         // =============================== builders ===============================================
         const int bt = tid;
         const int li = lane & 7, lq = lane >> 3;
@@ -315,10 +317,18 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             const uint32_t eps = smem0 + 4u * (uint32_t)(p.o_ring + slot * p.ring_floats);
             const float sg = sg_s[slot];
             // ---- phase A: every read of the ring first, phase B: perturb, round, store
-            float4 e1[4], e2[2];
-            float ew[2][4];
+            // (two rounds, so at most 17 ring values are live at a time: 96-register budget)
+            {
+                float4 e1[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) e1[b] = lds128(eps + s1[b]);
+                for (int b = 0; b < 4; ++b) e1[b] = lds128(eps + s1[b]);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    sts128(S + d1[b], tf32_fma(th1[b].x, sg, e1[b].x), tf32_fma(th1[b].y, sg, e1[b].y),
+                           tf32_fma(th1[b].z, sg, e1[b].z), tf32_fma(th1[b].w, sg, e1[b].w));
+            }
+            float4 e2[2];
+            float ew[2][4];
 #pragma unroll
             for (int b = 0; b < 2; ++b) e2[b] = lds128(eps + s2[b]);
 #pragma unroll
@@ -327,20 +337,16 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
                 for (int c = 0; c < 4; ++c) ew[b][c] = lds32(eps + src0[b][c]);
             const float ebias = lds32(eps + bsrc_b);
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                sts128(S + d1[b], tf32_rn(perturb1(th1[b].x, sg, e1[b].x)), tf32_rn(perturb1(th1[b].y, sg, e1[b].y)),
-                       tf32_rn(perturb1(th1[b].z, sg, e1[b].z)), tf32_rn(perturb1(th1[b].w, sg, e1[b].w)));
-#pragma unroll
             for (int b = 0; b < 2; ++b)
                 if (v2[b])
-                    sts128(S + d2[b], tf32_rn(perturb1(th2[b].x, sg, e2[b].x)), tf32_rn(perturb1(th2[b].y, sg, e2[b].y)),
-                           tf32_rn(perturb1(th2[b].z, sg, e2[b].z)), tf32_rn(perturb1(th2[b].w, sg, e2[b].w)));
+                    sts128(S + d2[b], tf32_fma(th2[b].x, sg, e2[b].x), tf32_fma(th2[b].y, sg, e2[b].y),
+                           tf32_fma(th2[b].z, sg, e2[b].z), tf32_fma(th2[b].w, sg, e2[b].w));
 #pragma unroll
             for (int b = 0; b < 2; ++b)
                 if (v0[b])
-                    sts128(S + d0[b], tf32_rn(perturb1(th0[b].x, sg, ew[b][0])), tf32_rn(perturb1(th0[b].y, sg, ew[b][1])),
-                           tf32_rn(perturb1(th0[b].z, sg, ew[b][2])), tf32_rn(perturb1(th0[b].w, sg, ew[b][3])));
-            if (bsrc >= 0) sts32(S + bdst, tf32_rn(perturb1(thb, sg, ebias)));
+                    sts128(S + d0[b], tf32_fma(th0[b].x, sg, ew[b][0]), tf32_fma(th0[b].y, sg, ew[b][1]),
+                           tf32_fma(th0[b].z, sg, ew[b][2]), tf32_fma(th0[b].w, sg, ew[b][3]));
+            if (bsrc >= 0) sts32(S + bdst, tf32_fma(thb, sg, ebias));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -360,7 +366,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
         const int gt = tid & 127;                 // row of this thread inside the tile
         const uint32_t mbar = WS_BAR(B_MMA + g);
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const uint32_t tA0 = tmem + (uint32_t)(g * WS_TCOLS), tA1 = tA0 + WS_A0C, tA2 = tA1 + WS_KH, tD3 = tA2 + WS_KH;
+        const uint32_t tA0 = tmem + (uint32_t)(g * p.tcols), tA1 = tA0 + (uint32_t)p.a0c, tA2 = tA1 + WS_KH, tD3 = tA0 + (uint32_t)p.d3_off;
         const uint32_t idesc_h = make_idesc_tf32(WS_HID), idesc_o = make_idesc_tf32(p.N3);
         uint32_t mph = 0;
         const int bar_id = 1 + g;
@@ -382,7 +388,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
         };
         if (p.obs_vec && q == 0 && lane == 0) {
             if (g < n_my) produce_obs(g, 0);
-            if (g + 2 < n_my) produce_obs(g + 2, 1);
+            if (g + p.ng < n_my) produce_obs(g + p.ng, 1);
         }
 
         // TMEM row -> tanh -> tf32 -> the same TMEM columns (they become the next layer's A operand)
@@ -404,10 +410,12 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         };
 
-        int s = g;                // nst >= 2
+        int s = 0;
         uint32_t par = 0, opar = 0;
+        for (int i = 0; i < g; ++i)
+            if (++s == p.nst) { s = 0; par ^= 1u; }
         int oslot = 0;
-        for (int k = g; k < n_my; k += 2) {
+        for (int k = g; k < n_my; k += p.ng) {
             const int work = (int)blockIdx.x + k * (int)gridDim.x;
             const int m = p.tiles == 1 ? work : work / p.tiles, tile = work - m * p.tiles;
             const int e0i = tile * 128, ne = min(128, p.E - e0i);
@@ -440,7 +448,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ring slot consumed, A0 complete
             WS_TL(gt == 0, k, 1);
-            if (p.obs_vec && q == 1 && lane == 0 && k + 4 < n_my) produce_obs(k + 4, oslot);   // off the issuing warp
+            if (p.obs_vec && q == 1 && lane == 0 && k + 2 * p.ng < n_my) produce_obs(k + 2 * p.ng, oslot);   // off the issuing warp
             if (++oslot == 2) { oslot = 0; opar ^= 1u; }
 
             mbar_wait_park(WS_BAR(B_WFULL + s), par);           // weights of item k are in stage s
@@ -517,8 +525,8 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (++s == p.nst) { s = 0; par ^= 1u; }
-            if (++s == p.nst) { s = 0; par ^= 1u; }
+            for (int i = 0; i < p.ng; ++i)
+                if (++s == p.nst) { s = 0; par ^= 1u; }
             WS_TL(gt == 0, k, 6);
         }
     }
@@ -568,15 +576,22 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     p.ring_floats = p.eps_floats + 4;                     // + the zero word
     p.obs_floats = 128 * K0;
     // W0 items 64 * nkq must fit the fixed per-thread item count; the observation operand its TMEM columns
-    if (8 * p.nkq * 8 > 2 * WS_NBUILD || p.K0p > WS_A0C) return -1;
+    if (8 * p.nkq * 8 > 2 * WS_NBUILD || p.K0p > 40) return -1;
     const size_t cap = 226 * 1024;
     p.nst = 3;
     p.ne = 4;
-    auto bytes = [&]() { return ((size_t)p.nst * p.st_floats + (size_t)p.ne * p.ring_floats + 4 * (size_t)p.obs_floats) * sizeof(float); };
+    // three groups when the TMEM columns (3 x (24 + 72 + 72), head accumulator aliased onto the dead observation
+    // operand) and shared memory (six observation slots) allow it
+    p.ng = (p.K0p <= 24 && p.N3 <= 16 && !getenv("DFD_WS_2GROUPS")) ? 3 : 2;
+    auto bytes = [&]() { return ((size_t)p.nst * p.st_floats + (size_t)p.ne * p.ring_floats + 2 * (size_t)p.ng * p.obs_floats) * sizeof(float); };
     if (bytes() > cap) p.ne = 3;
+    if (bytes() > cap && p.ng == 3) { p.ng = 2; p.ne = 4; if (bytes() > cap) p.ne = 3; }
     if (bytes() > cap) p.nst = 2;
     if (bytes() > cap) p.ne = 2;
     if (bytes() > cap) return -1;
+    p.a0c = p.ng == 3 ? 24 : 40;
+    p.tcols = p.ng == 3 ? 24 + 2 * WS_KH : 40 + 2 * WS_KH + 32;
+    p.d3_off = p.ng == 3 ? 0 : 40 + 2 * WS_KH;
     p.o_ring = p.nst * p.st_floats;
     p.o_obs = p.o_ring + p.ne * p.ring_floats;
     const size_t smem = bytes();
@@ -590,10 +605,10 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     }
     if (approx_tanh) {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_ws_kernel<true><<<grid, WS_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        mlp_forward_ws_kernel<true><<<grid, WS_NBUILD + 128 * p.ng, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     } else {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_ws_kernel<false><<<grid, WS_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        mlp_forward_ws_kernel<false><<<grid, WS_NBUILD + 128 * p.ng, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     }
     DFD_LAUNCHED(ctx);
     if (want_prof) {
