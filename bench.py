@@ -616,6 +616,7 @@ def b200_main(args, w):
                "api": "Worker.evaluate -> ReturnBatch (sequence of FDReturn) -> FiniteDifferences.step (host observations, host returns, theta mirrored to host)"}
 
     if rank != 0:
+        _xchg_profile(ctx, rank)
         _finish(world)
         return
     value = M * E * world / (ms_step * 1e-3)
@@ -645,7 +646,18 @@ def b200_main(args, w):
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port",
                                     "sample": "failed: %s" % e}
     print(json.dumps(line), flush=True)
+    _xchg_profile(ctx, rank)
     _finish(world)
+
+
+def _xchg_profile(ctx, rank):
+    if not os.environ.get("DFD_XCHG_PROF"):
+        return
+    import ctypes as C
+    out = (C.c_double * 5)()
+    if ctx.lib.dfd_xchg_profile(out) == 0:
+        sys.stderr.write("[xchg prof] rank %d: push %.0f ns, publish %.0f ns, wait for peers %.0f ns, combine %.0f ns (mean of %d launches)\n"
+                         % (rank, out[0], out[1], out[2], out[3], int(out[4])))
 
 
 def _finish(world):

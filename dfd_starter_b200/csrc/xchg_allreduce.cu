@@ -17,6 +17,7 @@
 // peer still reads.  The step counter lives in the mailbox, so the launch is CUDA-graph replayable.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -40,7 +41,12 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
                                                                       int world, int64_t P,
                                                                       const float* __restrict__ grad_partial,
                                                                       const double* __restrict__ stats5,
-                                                                      float* __restrict__ grad_out) {
+                                                                      float* __restrict__ grad_out,
+                                                                      unsigned long long* __restrict__ prof) {
+    // debugging aid (DFD_XCHG_PROF): accumulated nanoseconds of the four phases as seen by CTA 0
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    auto now = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) t0 = now();
     __shared__ unsigned ticket_s;
     __shared__ double inv_sd_s;
     char* const mine = mailboxes[rank];
@@ -74,12 +80,19 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
             *reinterpret_cast<double*>(mailboxes[w] + my_slot_off + 16 * (size_t)n4 + 8 * threadIdx.x) = s;
     }
     // ---- 2. publish --------------------------------------------------------------------------------------
-    __threadfence_system();
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) t1 = now();
+    // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (fences are
+    // cumulative), so ONE fence per CTA - not one per thread - makes the whole CTA's pushes visible before its
+    // arrival is counted; the last CTA to arrive then publishes
     __syncthreads();
-    if (threadIdx.x == 0) ticket_s = atomicAdd(bar_ctr, 1u);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        ticket_s = atomicAdd(bar_ctr, 1u);
+    }
     __syncthreads();
     if (ticket_s == gridDim.x - 1) {
-        __threadfence_system();
+        if (threadIdx.x == 0) __threadfence_system();
+        __syncthreads();
         if (threadIdx.x < world) {
             unsigned long long* f = reinterpret_cast<unsigned long long*>(mailboxes[threadIdx.x] + XCHG_HDR) +
                                     par * XCHG_MAX_WORLD + rank;
@@ -91,30 +104,39 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
         }
     }
     // ---- 3. combine --------------------------------------------------------------------------------------
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) t2 = now();
     if (threadIdx.x < world) {
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCHG_HDR) + par * XCHG_MAX_WORLD +
                                       threadIdx.x;
         unsigned spins = 0;
         while (ld_acquire_sys(f) < step + 1ull) {
-            if (++spins > (1u << 24)) __trap();    // a missing peer must fault, not hang the GPU
-            __nanosleep(64);
+            if (++spins > (1u << 26)) __trap();    // a missing peer must fault, not hang the GPU
         }
     }
     __syncthreads();
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) t3 = now();
     const size_t slots0 = XCHG_HDR + XCHG_FLAGS + (size_t)par * world * slot;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         // standardize_arr over the whole population (utils/math_helpers.py:127-134): population std,
-        // identity when all rewards are equal
+        // identity when all rewards are equal.  Lane w loads rank w's five statistics (all loads in flight
+        // together), lane 0 combines them in rank order.
+        double v[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+        if (threadIdx.x < world) {
+            const double* st = reinterpret_cast<const double*>(mine + slots0 + (size_t)threadIdx.x * slot + 16 * (size_t)n4);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] = __ldcg(st + k);
+        }
         double s = 0.0, ss = 0.0, n = 0.0, mn = 1e300, mx = -1e300;
         for (int w = 0; w < world; ++w) {
-            const double* st = reinterpret_cast<const double*>(mine + slots0 + (size_t)w * slot + 16 * (size_t)n4);
-            const double nw = __ldcg(st + 2);
-            if (nw > 0.0) {
-                s += __ldcg(st + 0);
-                ss += __ldcg(st + 1);
-                n += nw;
-                mn = fmin(mn, __ldcg(st + 3));
-                mx = fmax(mx, __ldcg(st + 4));
+            const double a0 = __shfl_sync(0xffffffffu, v[0], w), a1 = __shfl_sync(0xffffffffu, v[1], w);
+            const double a2 = __shfl_sync(0xffffffffu, v[2], w), a3 = __shfl_sync(0xffffffffu, v[3], w);
+            const double a4 = __shfl_sync(0xffffffffu, v[4], w);
+            if (a2 > 0.0) {
+                s += a0;
+                ss += a1;
+                n += a2;
+                mn = fmin(mn, a3);
+                mx = fmax(mx, a4);
             }
         }
         double inv = 1.0;
@@ -123,7 +145,7 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
             const double var = fmax(ss / n - mean * mean, 0.0);
             if (var > 0.0) inv = 1.0 / sqrt(var);
         }
-        inv_sd_s = inv;
+        if (threadIdx.x == 0) inv_sd_s = inv;
     }
     __syncthreads();
     const float inv_sd = (float)inv_sd_s;
@@ -139,9 +161,15 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
         const float t[4] = {g.x * inv_sd, g.y * inv_sd, g.z * inv_sd, g.w * inv_sd};
         for (int k = 0; k < 4 && 4 * i + k < P; ++k) grad_out[4 * i + k] = t[k];
     }
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long t4 = now();
+        prof[0] += t1 - t0; prof[1] += t2 - t1; prof[2] += t3 - t2; prof[3] += t4 - t3; prof[4] += 1;
+    }
 }
 
 }  // namespace
+
+static unsigned long long* g_xchg_prof = nullptr;
 
 extern "C" size_t dfd_xchg_mailbox_bytes(int64_t n_params, int world) {
     if (n_params <= 0 || world <= 0 || world > XCHG_MAX_WORLD) return 0;
@@ -189,8 +217,25 @@ extern "C" int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank
     const int64_t n4 = (n_params + 3) / 4;
     int grid = (int)((n4 + XCHG_THREADS - 1) / XCHG_THREADS);
     if (grid > ctx->sm_count) grid = ctx->sm_count;   // all CTAs co-resident: the in-kernel arrival count cannot deadlock
+    static const bool want_prof = getenv("DFD_XCHG_PROF") != nullptr;
+    if (want_prof && !g_xchg_prof) {
+        cudaMalloc(&g_xchg_prof, 64);
+        cudaMemset(g_xchg_prof, 0, 64);
+    }
+    unsigned long long* prof = g_xchg_prof;
     xchg_allreduce_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params,
-                                                                           grad_partial, stats5, grad_out);
+                                                                           grad_partial, stats5, grad_out, prof);
     DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+// debugging aid: mean nanoseconds per phase (push, publish, wait for peers, combine) accumulated so far
+extern "C" int dfd_xchg_profile(double* out5) {
+    if (!g_xchg_prof || !out5) return 1;
+    unsigned long long h[5];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, g_xchg_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < 4; ++i) out5[i] = h[4] ? (double)h[i] / (double)h[4] : 0.0;
+    out5[4] = (double)h[4];
     return 0;
 }
