@@ -18,6 +18,7 @@ SYMBOLS = [
     "dfd_fd_prepare", "dfd_fd_reduce_scratch_bytes", "dfd_fd_reduce", "dfd_dsgd_step", "dfd_dsgd_scratch_bytes", "dfd_synthetic_reward",
     "dfd_fd_prepare_partial", "dfd_xchg_mailbox_bytes", "dfd_xchg_mailbox_create", "dfd_xchg_mailbox_open",
     "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
+    "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused",
 ]
 
 
@@ -87,6 +88,9 @@ def load():
     proto("dfd_xchg_mailbox_close", i32, [vp, vp])
     proto("dfd_xchg_mailbox_destroy", i32, [vp, vp])
     proto("dfd_xchg_allreduce", i32, [vp, vp, i32, i32, i64, vp, vp, vp, vp])
+    proto("dfd_fd_step_fused_scratch_bytes", sz, [vp, i64, i32, i32])
+    proto("dfd_fd_step_fused", i32, [vp, P(DfdTable), i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, f64, f64, vp, vp, i64,
+                                     i32, i32, vp, vp, i32, i32, vp, sz, vp])
     _lib = L
     return L
 

@@ -52,7 +52,7 @@ class _Staging(object):
 class FiniteDifferences(object):
     def __init__(self, policy, gradient_optimizer, omega, noise_source, noise_std=0.1, batch_size=100, ent_coef=0.0,
                  max_delayed_return=10, paired=False, process_group=None, device=None, sync_policy=True,
-                 peer_exchange=None):
+                 peer_exchange=None, fused_step=True):
         self.max_delayed_return = max_delayed_return
         self.ent_coef = ent_coef
         self.noise_std = noise_std
@@ -65,6 +65,9 @@ class FiniteDifferences(object):
         # dist.PeerExchange: the exchange runs as one peer-memory kernel instead of NCCL calls whenever the batch
         # is antithetic pairs of the current epoch (otherwise: rewards all-gather + NCCL all_reduce)
         self.peer_exchange = peer_exchange
+        # short parameter vectors: prepare + reduce [+ exchange] + DSGD run as ONE kernel (csrc/fd_tail.cu)
+        self.fused_step = fused_step
+        self._fused_scratch = {}
         self.sync_policy = sync_policy
         self.using_dsgd = is_dsgd(gradient_optimizer)
 
@@ -195,6 +198,10 @@ class FiniteDifferences(object):
             else:
                 self._ensure_capacity(n)
                 d = self._stage.upload(n, reward=rewards, idx=idx, hist_row=hist_row, sign=sign)
+                scratch = self._fused_scratch_for(n, 1)
+                if scratch is not None:
+                    return self._apply_update(fused_call=self._fused_step_call(scratch, d["idx"], d["sign"], d["reward"], n, 1,
+                                                                               policy_reward))
                 self._fused_exchange(d["idx"], d["sign"], d["reward"], d["hist_row"], n, policy_reward)
             return self._apply_update()
         if pg is not None:
@@ -212,6 +219,11 @@ class FiniteDifferences(object):
         if n > 0:
             d = self._stage.upload(n, reward=rewards, idx=idx, hist_row=hist_row, sign=sign)
             paired = 1 if (self.paired and n % 2 == 0) else 0
+            if pg is None and bool((hist_row == -1).all()):
+                scratch = self._fused_scratch_for(n, paired)
+                if scratch is not None:
+                    return self._apply_update(fused_call=self._fused_step_call(scratch, d["idx"], d["sign"], d["reward"], n,
+                                                                               paired, policy_reward))
             _lib.check(self.lib.dfd_fd_prepare(
                 self.ctx.handle, self.table.ref(), self.P, ptr(d["reward"]), ptr(d["idx"]), ptr(d["sign"]),
                 ptr(d["hist_row"]), n, paired, float(policy_reward), float(self.noise_std), ptr(self.dist), self.Ps,
@@ -227,6 +239,30 @@ class FiniteDifferences(object):
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=pg)     # the one parameter-sized exchange
         return self._apply_update()
+
+    def _fused_scratch_for(self, n, paired):
+        """Zero-filled scratch of the one-kernel step for this batch shape, or None when the shape is not served."""
+        if not (self.fused_step and self.using_dsgd):
+            return None
+        key = (int(n), int(paired))
+        if key not in self._fused_scratch:
+            nbytes = int(self.lib.dfd_fd_step_fused_scratch_bytes(self.ctx.handle, self.P, int(n), int(paired)))
+            self._fused_scratch[key] = self.ctx.zeros_bytes(nbytes) if nbytes else None
+        return self._fused_scratch[key]
+
+    def _fused_step_call(self, scratch, idx_d, sign_d, reward_d, n, paired, policy_reward):
+        """Closure handed to _apply_update: launches dfd_fd_step_fused with the optimizer's current step size."""
+        world = 1 if self.process_group is None else self.peer_exchange.world
+        rank = 0 if self.process_group is None else self.peer_exchange.rank
+        boxes = None if self.process_group is None else ptr(self.peer_exchange.table)
+
+        def call(lr, lr_scale, n_valid, write_row):
+            _lib.check(self.lib.dfd_fd_step_fused(
+                self.ctx.handle, self.table.ref(), self.P, ptr(reward_d), ptr(idx_d), ptr(sign_d), int(n), int(paired),
+                float(policy_reward), float(self.noise_std), ptr(self.theta), ptr(self.grad), lr, lr_scale, ptr(self.hist),
+                ptr(self.dist), self.Ps, n_valid, write_row, ptr(self._update_size), boxes, rank, world,
+                aligned_ptr(scratch), scratch.numel() - 256, self.ctx.stream), "dfd_fd_step_fused")
+        return call
 
     def _fused_exchange(self, idx_d, sign_d, reward_d, hist_row_d, n, policy_reward):
         """prepare (standardisation deferred) -> reduce -> ONE peer-memory exchange kernel -> self.grad."""
@@ -259,9 +295,19 @@ class FiniteDifferences(object):
         if self.process_group is not None and self.peer_exchange is not None:
             if not (paired and n_hist == 0 and stats_d is None):
                 raise _lib.DfdError("a learner with peer_exchange takes antithetic pairs of the current epoch only")
+            scratch = self._fused_scratch_for(n, 1)
+            if scratch is not None:
+                self._apply_update(sync=False, fused_call=self._fused_step_call(scratch, idx_d, sign_d, reward_d, n, 1, policy_reward))
+                return
             self._fused_exchange(idx_d, sign_d, reward_d, hist_row_d, n, policy_reward)
             self._apply_update(sync=False)
             return
+        if self.process_group is None and n_hist == 0:
+            scratch = self._fused_scratch_for(n, paired)
+            if scratch is not None:
+                self._apply_update(sync=False, fused_call=self._fused_step_call(scratch, idx_d, sign_d, reward_d, n, paired,
+                                                                               policy_reward))
+                return
         _lib.check(self.lib.dfd_fd_prepare(
             self.ctx.handle, self.table.ref(), self.P, ptr(reward_d), ptr(idx_d), ptr(sign_d), ptr(hist_row_d), n,
             paired, float(policy_reward), float(self.noise_std), ptr(self.dist), self.Ps, int(n_hist), ptr(stats_d),
@@ -285,17 +331,20 @@ class FiniteDifferences(object):
             return len(self._hist_epoch)
         return int(np.argmin(self._hist_epoch))
 
-    def _apply_update(self, sync=True):
+    def _apply_update(self, sync=True, fused_call=None):
         st = self.ctx.stream
         n_valid = len(self._hist_epoch)
         write_row = self._ring_write_row()
         if self.using_dsgd:
             self.gradient_optimizer.adjust_lr(self.omega)                    # :51-52
             lr, lr_scale = float(self.gradient_optimizer.lr), float(self.gradient_optimizer.lr_scale)
-            _lib.check(self.lib.dfd_dsgd_step(
-                self.ctx.handle, ptr(self.theta), ptr(self.grad), self.P, lr, lr_scale, ptr(self.hist), ptr(self.dist),
-                self.Ps, n_valid, write_row, ptr(self._update_size), aligned_ptr(self._dsgd_scratch),
-                self._dsgd_scratch.numel() - 256, st), "dfd_dsgd_step")
+            if fused_call is not None:
+                fused_call(lr, lr_scale, n_valid, write_row)
+            else:
+                _lib.check(self.lib.dfd_dsgd_step(
+                    self.ctx.handle, ptr(self.theta), ptr(self.grad), self.P, lr, lr_scale, ptr(self.hist), ptr(self.dist),
+                    self.Ps, n_valid, write_row, ptr(self._update_size), aligned_ptr(self._dsgd_scratch),
+                    self._dsgd_scratch.numel() - 256, st), "dfd_dsgd_step")
             if hasattr(self.gradient_optimizer, "steps"):
                 self.gradient_optimizer.steps += 1
             if not sync:

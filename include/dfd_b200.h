@@ -194,6 +194,21 @@ int dfd_xchg_mailbox_destroy(dfd_ctx* ctx, void* mailbox);
 int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params,
                        const float* grad_partial, const double* stats5, float* grad_out, dfd_stream stream);
 
+/* ---- the whole step after the returns are known, as ONE kernel (short parameter vectors) ---------------
+ * dfd_fd_step_fused = dfd_fd_prepare + dfd_fd_reduce [+ dfd_xchg_allreduce] + dfd_dsgd_step for fd_return-mode
+ * batches (all returns from the current epoch) with n_params <= 32 768: learner/finite_differences.py:40-49,
+ * 54-78 and dsgd/dynamic_sgd.py:18-39 in one grid of co-resident CTAs (csrc/fd_tail.cu).  world == 1: single
+ * GPU, mailboxes may be NULL.  world > 1: antithetic pairs only; mailboxes as for dfd_xchg_allreduce (the two
+ * entry points share the mailbox layout and step counter, a learner may use either on any step).
+ * dfd_fd_step_fused_scratch_bytes returns 0 when the shape is not served (the caller then uses the separate
+ * calls); scratch must be zero-filled once when allocated. */
+size_t dfd_fd_step_fused_scratch_bytes(const dfd_ctx* ctx, int64_t n_params, int n_returns, int paired);
+int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, const double* reward, const int64_t* idx,
+                      const int8_t* sign, int n_returns, int paired, double baseline, float sigma, float* theta,
+                      float* grad, double lr, double lr_scale, float* hist, float* dist, int64_t hist_stride,
+                      int n_hist_valid, int hist_write_row, float* update_size_out, void* const* mailboxes, int rank,
+                      int world, void* scratch, size_t scratch_bytes, dfd_stream stream);
+
 /* ---- synthetic return (bench / tests only) ------------------------------- */
 /* Stand-in for the environment, which is outside this path (worker/agent.py is
  * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */
