@@ -528,6 +528,16 @@ def b200_main(args, w):
                                       0, C.byref(rows), aligned_ptr(learner._prep_scratch),
                                       learner._prep_scratch.numel() - 256, ctx.stream))
 
+    us_tail = None
+    tail_scratch = learner._fused_scratch_for(M, 1) if world == 1 else None
+    if tail_scratch is not None:
+        def k_tail(r):      # the one-kernel learner step with lr = 0 (theta and the ring are left as they are)
+            _lib.check(lib.dfd_fd_step_fused(ctx.handle, table.device_table.ref(), P, ptr(reward_d), ptr(idx_d[r % CYC]),
+                                             ptr(sign_d), M, 1, 0.0, SIGMA, ptr(learner.theta), ptr(grad_tmp), 0.0, 1.0,
+                                             ptr(learner.hist), ptr(learner.dist), learner.Ps, len(learner._hist_epoch), -1,
+                                             ptr(learner._update_size), None, 0, 1, aligned_ptr(tail_scratch),
+                                             tail_scratch.numel() - 256, ctx.stream))
+        us_tail = time_calls(k_tail, reps)
     us_forward = time_calls(k_forward, reps)
     us_reduce = time_calls(k_reduce, reps)
     us_prepare = time_calls(k_prepare, reps)
@@ -540,6 +550,8 @@ def b200_main(args, w):
                            "achieved_GBps": fwd_bytes / us_forward * 1e-3, "achieved_TFLOPs": fwd_flops / us_forward * 1e-6},
         "fd_prepare": {"us": us_prepare},
     }
+    if us_tail is not None:     # what the step actually launches for short parameter vectors (replaces prepare + reduce + DSGD)
+        kernels["fd_step_fused"] = {"us": us_tail, "algorithmic_bytes": red_bytes, "achieved_GBps": red_bytes / us_tail * 1e-3}
     dominant = "policy_forward" if us_forward >= us_reduce else "fd_reduce"
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
