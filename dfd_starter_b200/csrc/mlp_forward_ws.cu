@@ -30,7 +30,7 @@ constexpr int WS_MAXG = 3;         // MMA/epilogue groups (runtime: 2 or 3)
 constexpr int WS_NBUILD = 256;
 constexpr int WS_THREADS = WS_NBUILD + 128 * WS_MAXG;
 // TMEM columns per group: A0 (a0c) | A1/D1 72 | A2/D2 72 | D3.  Two groups: a0c = 40, D3 = 32 own columns (2 x 216);
-// three groups: a0c = 24 and D3 (<= 16 columns) aliases A0, which is dead once layer 0 has run (3 x 168 = 504 <= 512).
+// three groups: a0c = 24 and D3 (<= 16 columns) aliases the head of A1/D1, dead once layer 1 has run (3 x 168 = 504 <= 512).
 
 struct WsParams {
     int K0, K0p, nkq, nout, N3, A;
@@ -415,18 +415,16 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
         for (int i = 0; i < g; ++i)
             if (++s == p.nst) { s = 0; par ^= 1u; }
         int oslot = 0;
-        for (int k = g; k < n_my; k += p.ng) {
-            const int work = (int)blockIdx.x + k * (int)gridDim.x;
+        // observation row of item kk -> TMEM (A operand of layer 0): columns [0, K0) = x, K0 = 1, rest 0.  Called for the
+        // group's first item before the loop and for item k + ng right after layer 1 of item k has been issued, so the
+        // ring wait, the shared-memory reads and the TMEM stores hide under that MMA.  The barrier that orders these
+        // stores before the next layer-0 issue (and the slot refill) is the one at the end of the layer-1 epilogue.
+        auto load_obs = [&](int kk) {
+            const int work = (int)blockIdx.x + kk * (int)gridDim.x;
             const int m = p.tiles == 1 ? work : work / p.tiles, tile = work - m * p.tiles;
             const int e0i = tile * 128, ne = min(128, p.E - e0i);
-            const bool active = q * 32 < ne;     // whole-warp skip of padding rows
-            const uint32_t s_addr = smem0 + 4u * (uint32_t)(s * p.st_floats);
-            const bool st = gt == 0 && k == 6;
-
-            WS_TL(gt == 0, k, 0);
-            // ---- observation row -> TMEM (A operand of layer 0): columns [0, K0) = x, K0 = 1, rest 0
             if (p.obs_vec) mbar_wait_park(WS_BAR(B_OFULL + g * 2 + oslot), opar);
-            if (active) {
+            if (q * 32 < ne) {
                 // straight-line, branch-free: clamped unconditional loads (batched by the compiler), selects after
                 const float* src = p.obs_vec ? smem + p.o_obs + (g * 2 + oslot) * p.obs_floats + gt * p.K0
                                              : obs + ((int64_t)m * p.E + e0i + min(gt, ne - 1)) * p.K0;
@@ -438,19 +436,33 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
                     uint32_t x[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const int kk = c0 + c;
-                        x[c] = __float_as_uint(tf32_rn(kk < p.K0 ? v[c] : (kk == p.K0 ? 1.0f : 0.f)));
+                        const int kk2 = c0 + c;
+                        x[c] = __float_as_uint(tf32_rn(kk2 < p.K0 ? v[c] : (kk2 == p.K0 ? 1.0f : 0.f)));
                     }
                     tmem_st8(tA0 + lane_sel + (uint32_t)c0, x);
                 }
                 tmem_st_wait();
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // ring slot consumed, A0 complete
-            WS_TL(gt == 0, k, 1);
-            if (p.obs_vec && q == 1 && lane == 0 && k + 2 * p.ng < n_my) produce_obs(k + 2 * p.ng, oslot);   // off the issuing warp
+        };
+        auto obs_consumed = [&](int kk) {      // after a group barrier: refill the slot item kk used, two group items ahead
+            if (p.obs_vec && q == 1 && lane == 0 && kk + 2 * p.ng < n_my) produce_obs(kk + 2 * p.ng, oslot);
             if (++oslot == 2) { oslot = 0; opar ^= 1u; }
+        };
+        if (g < n_my) {
+            load_obs(g);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            obs_consumed(g);
+        }
+        for (int k = g; k < n_my; k += p.ng) {
+            const int work = (int)blockIdx.x + k * (int)gridDim.x;
+            const int m = p.tiles == 1 ? work : work / p.tiles, tile = work - m * p.tiles;
+            const int e0i = tile * 128, ne = min(128, p.E - e0i);
+            const bool active = q * 32 < ne;     // whole-warp skip of padding rows
+            const uint32_t s_addr = smem0 + 4u * (uint32_t)(s * p.st_floats);
+            const bool st = gt == 0 && k == 6;
 
+            WS_TL(gt == 0, k, 0);
             mbar_wait_park(WS_BAR(B_WFULL + s), par);           // weights of item k are in stage s
             WS_TL(gt == 0, k, 2);
             // MMA issue is warp-uniform (descriptors live in uniform registers), one elected lane issues
@@ -479,10 +491,13 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
                 __syncwarp();
             }
             WS_STAMP(st, 5);
+            const bool has_next = k + p.ng < n_my;
+            if (has_next) load_obs(k + p.ng);                  // hidden under the layer-1 MMA
             mbar_wait_park(mbar, mph); mph ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             WS_STAMP(st, 6);
             epilogue_hidden(tA2, active);
+            if (has_next) obs_consumed(k + p.ng);
             WS_TL(gt == 0, k, 4);
 
             if (q == 0) {          // layer 2 (head); its completion also frees operand stage s
@@ -525,6 +540,7 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // head read out before the next layer 0 reuses its columns
             for (int i = 0; i < p.ng; ++i)
                 if (++s == p.nst) { s = 0; par ^= 1u; }
             WS_TL(gt == 0, k, 6);
@@ -591,7 +607,7 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     if (bytes() > cap) return -1;
     p.a0c = p.ng == 3 ? 24 : 40;
     p.tcols = p.ng == 3 ? 24 + 2 * WS_KH : 40 + 2 * WS_KH + 32;
-    p.d3_off = p.ng == 3 ? 0 : 40 + 2 * WS_KH;
+    p.d3_off = p.ng == 3 ? 24 : 40 + 2 * WS_KH;   // three groups: the head accumulator aliases the first columns of A1/D1
     p.o_ring = p.nst * p.st_floats;
     p.o_obs = p.o_ring + p.ne * p.ring_floats;
     const size_t smem = bytes();
