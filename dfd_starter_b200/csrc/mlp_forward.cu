@@ -5,6 +5,7 @@
 // the perturbed weights are produced in shared memory from the theta tile and the
 // table-row tile and are never written to HBM.
 #include "common.cuh"
+#include <stdlib.h>
 
 struct MlpLayout {
     int kind, K, h1, h2, nout, A;
@@ -188,6 +189,165 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_forward_fp32_kernel(MlpLayout
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small-batch exact path (E <= 8 observations per member, P <= 12 288): the reference-faithful operating point -
+// one observation per policy call (policies/*.py get_action) - is a per-member GEMV whose cost is the member's
+// eps row.  One CTA per (member, observation tile): ALL 16-byte loads of theta and eps are issued before the first
+// use - two cp.async.bulk (TMA bulk) copies per member, theta and the eps row, straight into shared memory: one
+// exposed memory latency per member instead of one per layer, and no L1 line reservations (register-staged loads
+// were capped by the ~28 KB of L1 left beside shared memory: 53 -> 28 us; bulk copies: see DESIGN.md).  The perturbed
+// vector is built in place (two roundings, bit-identical to worker/worker.py:28), then the three layers run from shared memory
+// with 4 lanes per output neuron (k interleaved, rotated by the neuron index so weight and activation reads are
+// bank-conflict-free for the 64-wide layers) and a 2-step shuffle reduction.
+// ---------------------------------------------------------------------------------------------------------------
+template <int ET>
+__global__ void __launch_bounds__(MLP_THREADS) mlp_forward_small_kernel(MlpLayout L, const float* __restrict__ replicas,
+                                                                        int64_t stride, const float* __restrict__ theta,
+                                                                        const float* __restrict__ bnbuf,
+                                                                        const int64_t* __restrict__ idx,
+                                                                        const int8_t* __restrict__ sign, float sigma,
+                                                                        const float* __restrict__ obs, int E,
+                                                                        float* __restrict__ out, int maxdim, int P4) {
+    extern __shared__ __align__(16) float smem[];
+    float* W = smem;                         // [P4] theta, then the member's perturbed flat parameter vector
+    float* EPS = W + P4;                     // [P4] the member's table row
+    float* actA = EPS + P4;                  // [ET][maxdim]
+    float* actB = actA + ET * maxdim;
+    float* bnS = actB + ET * maxdim;         // BN scale / shift of the current layer input (Discrete)
+    float* bnB = bnS + maxdim;
+
+    const int m = blockIdx.x, e0 = blockIdx.y * ET, ne = min(ET, E - e0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float sg = sigma * (float)sign[m];
+    const float* row = table_row_ptr(replicas, stride, idx[m]);
+    const int P = (int)L.P, nv = P >> 2;
+    // ---- the whole parameter vector: two bulk copies, completion on an mbarrier -------------------------------
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)nv * 16u;
+        if (bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(W)), "l"(theta), "r"(bytes), "r"(bar_a) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(EPS)), "l"(row), "r"(bytes), "r"(bar_a) : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+        }
+    }
+    // observations (row-major [e][k]) -> actA, zero rows for the padding of the tile
+    const float* ob = obs + ((int64_t)m * E + e0) * L.K;
+    for (int t = tid; t < ET * L.K; t += MLP_THREADS) {
+        const int e = t / L.K, k = t - e * L.K;
+        actA[e * maxdim + k] = e < ne ? ob[t] : 0.f;
+    }
+    float* ain = actA;
+    float* aout = actB;
+    __syncthreads();           // barrier initialised (and observations staged) before anyone waits on it
+    {
+        uint32_t ok, spins = 0;
+        do {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t"
+                "}\n"
+                : "=r"(ok)
+                : "r"(bar_a)
+                : "memory");
+            if (!ok && ++spins > (1u << 26)) __trap();
+        } while (!ok);
+    }
+    for (int i = tid; i < nv; i += MLP_THREADS) {          // perturb in place: theta + sg * eps, two roundings
+        const float4 a = reinterpret_cast<const float4*>(W)[i];
+        const float4 e = reinterpret_cast<const float4*>(EPS)[i];
+        reinterpret_cast<float4*>(W)[i] = make_float4(perturb1(a.x, sg, e.x), perturb1(a.y, sg, e.y), perturb1(a.z, sg, e.z),
+                                                      perturb1(a.w, sg, e.w));
+    }
+    if (tid < P - 4 * nv) W[4 * nv + tid] = perturb1(theta[4 * nv + tid], sg, row[4 * nv + tid]);
+    __syncthreads();
+
+    for (int l = 0; l < 3; ++l) {
+        const int in = L.in[l], no = L.out[l];
+        if (L.kind == DFD_POLICY_DISCRETE) {
+            // eval-mode BatchNorm1d on the layer input, gamma/beta perturbed per member, running stats shared
+            for (int k = tid; k < in; k += MLP_THREADS) {
+                const float invstd = 1.0f / sqrtf(bnbuf[L.bn_var[l] + k] + 1e-5f);
+                const float a = W[L.bn_g[l] + k] * invstd;
+                bnS[k] = a;
+                bnB[k] = W[L.bn_b[l] + k] - bnbuf[L.bn_mean[l] + k] * a;
+            }
+            __syncthreads();
+            for (int t = tid; t < in * ET; t += MLP_THREADS) {
+                const int e = t / in, k = t - e * in;
+                ain[e * maxdim + k] = fmaf(ain[e * maxdim + k], bnS[k], bnB[k]);
+            }
+            __syncthreads();
+        }
+        const int ks = lane & 3, o8 = lane >> 2;
+        const int rot = (in & 31) == 0 ? 4 * o8 : 0;      // bank rotation for the 32-multiple widths
+        const int kiter = (in + 3) >> 2;
+        for (int o = warp * 8 + o8; o < ((no + 7) & ~7); o += (MLP_THREADS / 32) * 8) {
+            float acc[ET];
+#pragma unroll
+            for (int e = 0; e < ET; ++e) acc[e] = 0.f;
+            if (o < no) {
+                const float* wr = W + L.w[l] + o * in;
+                for (int j = 0; j < kiter; ++j) {
+                    int k = ks + 4 * j + rot;
+                    if (k >= in) k -= in;                  // rot < in and ks + 4j < in + 3
+                    if (ks + 4 * j < in) {
+                        const float wv = wr[k];
+#pragma unroll
+                        for (int e = 0; e < ET; ++e) acc[e] = fmaf(wv, ain[e * maxdim + k], acc[e]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < ET; ++e) {
+                acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+                acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
+            }
+            if (ks == 0 && o < no) {
+                const float bv = W[L.b[l] + o];
+#pragma unroll
+                for (int e = 0; e < ET; ++e) {
+                    float y = acc[e] + bv;
+                    if (L.kind == DFD_POLICY_MUJOCO) y = tanhf(y);
+                    else if (l < 2) y = fmaxf(y, 0.f);
+                    aout[e * maxdim + o] = y;
+                }
+            }
+        }
+        __syncthreads();
+        float* t = ain; ain = aout; aout = t;
+    }
+    // ain now holds the head outputs [e][nout]
+    float* o = out + ((int64_t)m * E + e0) * L.nout;
+    if (L.kind == DFD_POLICY_MUJOCO) {
+        // MapContinuousToAction (torch_helpers.py:20-25): mean = y[:A], std = 0.55 + 0.45*y[A:]
+        for (int t = tid; t < ne * L.nout; t += MLP_THREADS) {
+            const int e = t / L.nout, j = t - e * L.nout;
+            const float y = ain[e * maxdim + j];
+            o[t] = j < L.A ? y : 0.55f + 0.45f * y;
+        }
+    } else {
+        for (int e = tid; e < ne; e += MLP_THREADS) {
+            float mx = -INFINITY;
+            for (int j = 0; j < L.nout; ++j) mx = fmaxf(mx, ain[e * maxdim + j]);
+            float s = 0.f;
+            for (int j = 0; j < L.nout; ++j) s += expf(ain[e * maxdim + j] - mx);
+            const float inv = 1.0f / s;
+            for (int j = 0; j < L.nout; ++j) o[(int64_t)e * L.nout + j] = expf(ain[e * maxdim + j] - mx) * inv;
+        }
+    }
+}
+
 int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                            const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
                            const float* obs, int obs_per_member, float* out, cudaStream_t st);
@@ -237,6 +397,24 @@ extern "C" int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     if (L.nout > maxdim) maxdim = L.nout;
     DFD_CHECK_ARG(maxdim + 1 <= MLP_WBUF, "dfd_policy_forward: layer width %d too large", maxdim);
     DFD_CHECK_ARG(n_members <= 2147483647 / 1 && (obs_per_member + 3) / 4 <= 65535, "dfd_policy_forward: grid too large");
+    // small batches of observations: the one-latency GEMV kernel (whole perturbed vector resident in shared memory)
+    if (obs_per_member <= 8 && L.P <= 12288 && (((uintptr_t)theta) & 15) == 0 && !getenv("DFD_MLP_NO_SMALL")) {
+        const int P4 = (int)((L.P + 3) / 4 * 4);
+        dim3 grid(n_members, obs_per_member <= 2 ? (obs_per_member + 1) / 2 : (obs_per_member + 7) / 8);
+        if (obs_per_member <= 2) {
+            const size_t sm = ((size_t)2 * P4 + 2 * 2 * maxdim + 2 * maxdim) * sizeof(float);
+            DFD_CUDA(cudaFuncSetAttribute(mlp_forward_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            mlp_forward_small_kernel<2><<<grid, MLP_THREADS, sm, st>>>(L, table->replicas, table->replica_stride, theta, bn_buffers,
+                                                                       idx, sign, sigma, obs, obs_per_member, out, maxdim, P4);
+        } else {
+            const size_t sm = ((size_t)2 * P4 + 2 * 8 * maxdim + 2 * maxdim) * sizeof(float);
+            DFD_CUDA(cudaFuncSetAttribute(mlp_forward_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            mlp_forward_small_kernel<8><<<grid, MLP_THREADS, sm, st>>>(L, table->replicas, table->replica_stride, theta, bn_buffers,
+                                                                       idx, sign, sigma, obs, obs_per_member, out, maxdim, P4);
+        }
+        DFD_LAUNCHED(ctx);
+        return 0;
+    }
     const int ET = obs_per_member <= 4 ? 4 : 16;
     const size_t smem = ((size_t)2 * maxdim * ET + MLP_WBUF + 3 * (size_t)maxdim) * sizeof(float);
     DFD_CHECK_ARG(smem <= 227 * 1024, "dfd_policy_forward: layer width %d needs %zu B of shared memory", maxdim, smem);
