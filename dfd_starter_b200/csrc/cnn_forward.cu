@@ -4,11 +4,21 @@
 // theta + sign[m]*sigma*table[idx[m]:idx[m]+P] (worker/worker.py:28); the perturbed weights only ever exist in
 // shared memory / registers.  98 % of the parameters are the first Linear (663 552 weights), so at small E the
 // kernel is a stream of that weight block through the SM: HBM-bound on pairs*P*4 bytes.
+// The first Linear streams through shared-memory slots fed by cp.async.bulk (TMA bulk copies, half a theta row and
+// half an eps row of 5 184 bytes each per item, completion on mbarriers) issued by a producer warp: 14 consumer warps
+// own one slot each (items w, w + 14, ...), the slots live in the frame / conv buffers that are dead by then
+// (145 KB in flight per SM, no L1 line reservations - register-staged loads were capped by the ~28 KB of L1 left
+// beside 200 KB of shared memory).
+// Consecutive CTAs take the two members of an antithetic pair, so HBM serves their shared eps row once.
 #include "common.cuh"
 
 namespace {
 
-constexpr int AT_THREADS = 512;
+constexpr int AT_THREADS = 512;       // worker threads; one more warp feeds the first Linear's ring
+constexpr int AT_LAUNCH = AT_THREADS + 32;
+constexpr int AT_HALF = 1296;         // half an FC1 weight row
+constexpr int AT_SLOT = 2 * AT_HALF;  // floats per ring slot: theta half-row | eps half-row (10 368 B)
+constexpr int AT_NSLOT = 14;          // one slot per consumer warp; 14 * 10 368 B + partial sums <= frame + w0 + sc0 + a0 (155 008 B)
 constexpr int AT_ET = 4;              // observations per CTA pass (FC1 weights are streamed once per pass)
 constexpr int FRAME = 4 * 84 * 84;    // 28224
 constexpr int A0N = 16 * 20 * 20;     // 6400
@@ -19,13 +29,14 @@ constexpr int O_W0 = 0, O_B0 = 4096, O_G1 = 4112, O_BE1 = 4128, O_W3 = 4144, O_B
               O_BE4 = 12400, O_W7 = 12432, O_B7 = 675984, O_G8 = 676240, O_BE8 = 676496, O_W10 = 676752;
 constexpr int BU_M1 = 0, BU_V1 = 16, BU_M4 = 33, BU_V4 = 65, BU_M8 = 98, BU_V8 = 354;
 
-__global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const float* __restrict__ replicas, int64_t stride,
+__global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float* __restrict__ replicas, int64_t stride,
                                                                       const float* __restrict__ theta,
                                                                       const float* __restrict__ bnbuf,
                                                                       const int64_t* __restrict__ idx,
                                                                       const int8_t* __restrict__ sign, float sigma,
                                                                       const float* __restrict__ obs, int E, int tiles,
-                                                                      int A, float* __restrict__ out) {
+                                                                      int A, float* __restrict__ out, int n_members,
+                                                                      int pair_order) {
     extern __shared__ __align__(16) float sm[];
     float* frame = sm;                     // 28224; conv3 weights alias it once conv0 is done with the frame
     float* w0 = frame + FRAME;             // [256 k][16 oc]
@@ -37,8 +48,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
     float* w3 = frame;                     // [256 k][32 oc]
     float* sc3 = frame + 8192;             // 32 scale | 32 shift
 
+    __shared__ __align__(8) uint64_t bars[2 * AT_NSLOT];      // full[slot], empty[slot]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const bool worker = tid < AT_THREADS;                    // warp 16 only feeds the ring (and joins the barriers)
+    const int mb = blockIdx.x / tiles, tile = blockIdx.x % tiles;
+    const int m = pair_order ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
+    if (tid == 0) {
+        for (int i = 0; i < AT_NSLOT; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (AT_NSLOT + i)));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int e0 = tile * AT_ET;
     const int ne = min(AT_ET, E - e0);
     const float sg = sigma * (float)sign[m];
@@ -46,7 +68,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
     auto par = [&](int p) { return perturb1(theta[p], sg, row[p]); };
 
     // conv0 weights -> [k][oc]; bias + BN1 folded into per-channel scale / shift
-    for (int t = tid; t < 4096; t += AT_THREADS) {
+    for (int t = tid; t < 4096 && worker; t += AT_THREADS) {
         const int oc = t >> 8, k = t & 255;
         w0[k * 16 + oc] = par(O_W0 + t);
     }
@@ -60,7 +82,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
     for (int e = 0; e < ne; ++e) {
         __syncthreads();   // previous observation is done with frame / w3 / a0
         const float* fr = obs + ((int64_t)m * E + e0 + e) * FRAME;
-        for (int t = tid; t < FRAME / 4; t += AT_THREADS)
+        for (int t = tid; t < FRAME / 4 && worker; t += AT_THREADS)
             reinterpret_cast<float4*>(frame)[t] = ldg_stream_f4(fr + 4 * t);
         __syncthreads();
         // ---- conv0: one output pixel x 16 channels per thread (400 threads)
@@ -95,7 +117,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
         }
         __syncthreads();
         // ---- conv3 weights -> [k][oc] over the (now free) frame region; bias + BN4 folded
-        for (int t = tid; t < 8192; t += AT_THREADS) {
+        for (int t = tid; t < 8192 && worker; t += AT_THREADS) {
             const int oc = t >> 8, k = t & 255;
             w3[k * 32 + oc] = par(O_W3 + t);
         }
@@ -143,37 +165,57 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
             }
         }
     }
-    for (int t = tid; t < (AT_ET - ne) * A1N; t += AT_THREADS) a1[ne * A1N + t] = 0.f;   // ragged tile
-    __syncthreads();
+    for (int t = tid; t < (AT_ET - ne) * A1N && worker; t += AT_THREADS) a1[ne * A1N + t] = 0.f;   // ragged tile
+    __syncthreads();       // a1 complete; frame / w0 / a0 are dead from here on: they become the weight ring
 
-    // ---- Linear 2592 -> 256: each warp streams 16 weight rows (theta + sg*eps, 16-byte vectors), AT_ET
-    //      observations share every weight; then bias + BN8 + ReLU
-    for (int o = warp; o < 256; o += AT_THREADS / 32) {
-        const int64_t base = O_W7 + (int64_t)o * A1N;
-        float acc[AT_ET];
-#pragma unroll
-        for (int e = 0; e < AT_ET; ++e) acc[e] = 0.f;
-        for (int it0 = 0; it0 < 648; it0 += 32 * 4) {
-            float4 tw[4], ew[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = it0 + u * 32 + lane;
-                tw[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                ew[u] = tw[u];
-                if (v < 648) {
-                    tw[u] = *reinterpret_cast<const float4*>(theta + base + 4 * v);
-                    ew[u] = ldg_stream_f4(row + base + 4 * v);
-                }
+    // ---- Linear 2592 -> 256: item h = (neuron h >> 1, half h & 1) -> slot h % 14, owned by consumer warp h % 14 (one
+    //      waiter per barrier, phases strictly in order); the producer warp issues one theta and one eps bulk copy per
+    //      item; AT_ET observations share every weight; the two halves meet in shared memory, then bias + BN8 + ReLU
+    float* ring = sm;
+    float* pacc = sm + AT_NSLOT * AT_SLOT;     // [AT_ET][512] partial dot products
+    auto wait_bar = [&](uint32_t addr, uint32_t parity) {
+        uint32_t ok, spins = 0;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            if (!ok && ++spins > (1u << 26)) __trap();
+        } while (!ok);
+    };
+    if (!worker) {
+        if (lane == 0) {
+            // the ring region was last written through the generic proxy (frame, conv weights, activations)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int h = 0; h < 512; ++h) {
+                const int slot = h % AT_NSLOT, it = h / AT_NSLOT;
+                wait_bar(bar0 + 8u * (AT_NSLOT + slot), (uint32_t)((it & 1) ^ 1));
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + slot * AT_SLOT);
+                const uint32_t fb = bar0 + 8u * slot;
+                const int64_t base = O_W7 + (int64_t)(h >> 1) * A1N + (h & 1) * AT_HALF;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(2u * AT_HALF * 4u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                             "l"(theta + base), "r"((uint32_t)(AT_HALF * 4)), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 dst + AT_HALF * 4u), "l"(row + base), "r"((uint32_t)(AT_HALF * 4)), "r"(fb) : "memory");
             }
+        }
+    } else if (warp < AT_NSLOT) {
+        int it = 0;
+        for (int h = warp; h < 512; h += AT_NSLOT, ++it) {
+            wait_bar(bar0 + 8u * warp, (uint32_t)(it & 1));
+            const float4* tw4 = reinterpret_cast<const float4*>(ring + warp * AT_SLOT);
+            const float4* ew4 = tw4 + AT_HALF / 4;
+            const float* xa = a1 + (h & 1) * AT_HALF;
+            float acc[AT_ET];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = it0 + u * 32 + lane;
-                if (v < 648) {
-                    const float4 w = make_float4(perturb1(tw[u].x, sg, ew[u].x), perturb1(tw[u].y, sg, ew[u].y),
-                                                 perturb1(tw[u].z, sg, ew[u].z), perturb1(tw[u].w, sg, ew[u].w));
+            for (int e = 0; e < AT_ET; ++e) acc[e] = 0.f;
+            for (int v = lane; v < AT_HALF / 4; v += 32) {
+                const float4 t4 = tw4[v], e4 = ew4[v];
+                const float4 w = make_float4(perturb1(t4.x, sg, e4.x), perturb1(t4.y, sg, e4.y), perturb1(t4.z, sg, e4.z),
+                                             perturb1(t4.w, sg, e4.w));
 #pragma unroll
-                    for (int e = 0; e < AT_ET; ++e) {
-                        const float4 x = *reinterpret_cast<const float4*>(a1 + e * A1N + 4 * v);
+                for (int e = 0; e < AT_ET; ++e) {
+                    if (e < ne) {
+                        const float4 x = *reinterpret_cast<const float4*>(xa + e * A1N + 4 * v);
                         acc[e] = fmaf(w.x, x.x, acc[e]);
                         acc[e] = fmaf(w.y, x.y, acc[e]);
                         acc[e] = fmaf(w.z, x.z, acc[e]);
@@ -181,20 +223,28 @@ __global__ void __launch_bounds__(AT_THREADS, 1) atari_forward_kernel(const floa
                     }
                 }
             }
-        }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (AT_NSLOT + warp)) : "memory");
 #pragma unroll
-        for (int e = 0; e < AT_ET; ++e) acc[e] = warp_sum(acc[e]);
-        if (lane == 0) {
-            const float inv = 1.0f / sqrtf(bnbuf[BU_V8 + o] + 1e-5f);
-            const float s = par(O_G8 + o) * inv;
-            const float sh = (par(O_B7 + o) - bnbuf[BU_M8 + o]) * s + par(O_BE8 + o);
+            for (int e = 0; e < AT_ET; ++e) acc[e] = warp_sum(acc[e]);
+            if (lane == 0) {
 #pragma unroll
-            for (int e = 0; e < AT_ET; ++e) a2[e * 256 + o] = fmaxf(fmaf(acc[e], s, sh), 0.f);
+                for (int e = 0; e < AT_ET; ++e) pacc[e * 512 + h] = acc[e];
+            }
         }
     }
     __syncthreads();
+    if (tid < 256) {
+        const int o = tid;
+        const float inv = 1.0f / sqrtf(bnbuf[BU_V8 + o] + 1e-5f);
+        const float s = par(O_G8 + o) * inv;
+        const float sh = (par(O_B7 + o) - bnbuf[BU_M8 + o]) * s + par(O_BE8 + o);
+#pragma unroll
+        for (int e = 0; e < AT_ET; ++e) a2[e * 256 + o] = fmaxf(fmaf(pacc[e * 512 + 2 * o] + pacc[e * 512 + 2 * o + 1], s, sh), 0.f);
+    }
+    __syncthreads();
     // ---- Linear 256 -> A (warp per action), softmax per observation
-    for (int a = warp; a < A; a += AT_THREADS / 32) {
+    for (int a = warp; a < A && worker; a += AT_THREADS / 32) {
         float w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = par(O_W10 + a * 256 + lane + 32 * j);
@@ -234,9 +284,10 @@ int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_
     DFD_CHECK_ARG((int64_t)n_members * tiles < 2147483647LL, "dfd_policy_forward: grid too large");
     const size_t smem = (size_t)(FRAME + 4096 + 32 + A0N + AT_ET * A1N + AT_ET * 256 + AT_ET * 32) * sizeof(float);
     DFD_CUDA(cudaFuncSetAttribute(atari_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    atari_forward_kernel<<<n_members * tiles, AT_THREADS, smem, st>>>(table->replicas, table->replica_stride, theta,
-                                                                      bn_buffers, idx, sign, sigma, obs, obs_per_member,
-                                                                      tiles, desc->n_act, out);
+    atari_forward_kernel<<<n_members * tiles, AT_LAUNCH, smem, st>>>(table->replicas, table->replica_stride, theta,
+                                                                     bn_buffers, idx, sign, sigma, obs, obs_per_member,
+                                                                     tiles, desc->n_act, out, n_members,
+                                                                     (n_members % 2 == 0) ? 1 : 0);
     DFD_LAUNCHED(ctx);
     return 0;
 }
