@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/dfd_b200.h"
 
@@ -44,6 +45,28 @@ void dfd_set_error(const char* fmt, ...);
     } while (0)
 
 static inline size_t dfd_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor on the stream is still draining
+// (its CTAs start as the predecessor's CTAs exit), so launch latency and the dependent's prologue overlap the
+// predecessor's tail.  Every kernel launched this way executes dfd_grid_dependency_wait() before it touches anything
+// the predecessor wrote - the semantics stay those of an ordinary stream-ordered launch.  DFD_NO_PDL=1 disables it.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dfd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args... args) {
+    static const bool off = getenv("DFD_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void dfd_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // 16-byte streaming load: read-only path, do not allocate in L1 (rows are touched once per kernel)
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {

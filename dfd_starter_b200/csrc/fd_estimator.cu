@@ -638,10 +638,50 @@ __global__ void __launch_bounds__(256) synthetic_reward_kernel(const float* __re
     }
 }
 
+// short per-member outputs (<= 16 KB, 16-byte aligned, width a multiple of 4): one WARP per member, every lane issues
+// all of its 16-byte loads before the first use -> one exposed memory latency, eight members per CTA
+__global__ void __launch_bounds__(256) synthetic_reward_warp_kernel(const float* __restrict__ out, int per_member, int width,
+                                                                    const float* __restrict__ target,
+                                                                    double* __restrict__ reward, int n_members) {
+    const int lane = threadIdx.x & 31, m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    dfd_grid_dependency_wait();        // launched with programmatic stream serialisation: `out` comes from the forward
+    if (m >= n_members) return;
+    const float* o = out + (int64_t)m * per_member;
+    const int nq = per_member >> 2;          // <= 1024 quads: at most 32 per lane
+    float acc = 0.f;
+    for (int q0 = 0; q0 < nq; q0 += 32 * 16) {
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int q = q0 + u * 32 + lane;
+            v[u] = q < nq ? ldg_stream_f4(o + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int q = q0 + u * 32 + lane;
+            if (q < nq) {
+                const int j = (4 * q) % width;
+                const float d0 = v[u].x - target[j], d1 = v[u].y - target[j + 1], d2 = v[u].z - target[j + 2],
+                            d3 = v[u].w - target[j + 3];
+                acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            }
+        }
+    }
+    const double a = warp_sum((double)acc);
+    if (lane == 0) reward[m] = -a / (double)per_member;
+}
+
 extern "C" int dfd_synthetic_reward(dfd_ctx* ctx, const float* out, int n_members, int obs_per_member, int out_width,
                                     const float* target, double* reward, dfd_stream stream) {
     DFD_CHECK_ARG(ctx && out && target && reward, "dfd_synthetic_reward: NULL argument");
     if (n_members <= 0) return 0;
+    const int64_t per_member = (int64_t)obs_per_member * out_width;
+    if (per_member <= 4096 && (per_member & 3) == 0 && (out_width & 3) == 0 && (((uintptr_t)out) & 15) == 0) {
+        DFD_CUDA(dfd_launch_pdl(synthetic_reward_warp_kernel, dim3((n_members + 7) / 8), dim3(256), 0, (cudaStream_t)stream, out,
+                                (int)per_member, out_width, target, reward, n_members));
+        DFD_LAUNCHED(ctx);
+        return 0;
+    }
     synthetic_reward_kernel<<<n_members, 256, 0, (cudaStream_t)stream>>>(out, obs_per_member * out_width, out_width,
                                                                          target, reward);
     DFD_LAUNCHED(ctx);

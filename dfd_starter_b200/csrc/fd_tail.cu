@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
     const int nrows = r_end - r_begin;
     const double sig = (double)p.sigma;
     const int nk = p.paired ? 2 : 1;
+    dfd_grid_dependency_wait();        // launched with programmatic stream serialisation: rewards come from the predecessor
     unsigned long long xstep = 0;
     if (p.world > 1) xstep = *reinterpret_cast<volatile unsigned long long*>(p.mailboxes[p.rank] + 8);
 
@@ -425,7 +426,7 @@ extern "C" int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n
     p.partial_stride = t.partial_stride;
     p.mailboxes = (char* const*)mailboxes; p.rank = rank; p.world = world;
     dim3 grid(t.tiles, t.splits);
-    fd_tail_kernel<<<grid, TL_THREADS, 0, (cudaStream_t)stream>>>(p);
+    DFD_CUDA(dfd_launch_pdl(fd_tail_kernel, grid, dim3(TL_THREADS), 0, (cudaStream_t)stream, p));
     DFD_LAUNCHED(ctx);
     return 0;
 }

@@ -215,6 +215,10 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
     // at the tail of every eps ring slot (the source of every "no such element" in the builders)
     for (int i = tid; i < p.nst * p.st_floats; i += (int)blockDim.x) smem[i] = 0.f;
     if (tid < p.ne) smem[p.o_ring + tid * p.ring_floats + p.eps_floats] = 0.f;
+    // launched with programmatic stream serialisation: everything above (barriers, the first eps copies - they read
+    // only the table and the index / sign arrays -, TMEM allocation, zeroing) overlaps the predecessor's tail; theta
+    // and the observations are read below
+    dfd_grid_dependency_wait();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -621,10 +625,12 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     }
     if (approx_tanh) {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_ws_kernel<true><<<grid, WS_NBUILD + 128 * p.ng, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        DFD_CUDA(dfd_launch_pdl(mlp_forward_ws_kernel<true>, dim3(grid), dim3(WS_NBUILD + 128 * p.ng), smem, st, p, table->replicas,
+                                table->replica_stride, theta, idx, sign, obs, out, prof));
     } else {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_ws_kernel<false><<<grid, WS_NBUILD + 128 * p.ng, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        DFD_CUDA(dfd_launch_pdl(mlp_forward_ws_kernel<false>, dim3(grid), dim3(WS_NBUILD + 128 * p.ng), smem, st, p, table->replicas,
+                                table->replica_stride, theta, idx, sign, obs, out, prof));
     }
     DFD_LAUNCHED(ctx);
     if (want_prof) {

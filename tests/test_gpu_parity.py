@@ -469,3 +469,19 @@ def test_one_kernel_step_equals_three_call_path(D, table1m, P, N, paired):
     for L in (c, d):
         L.step_arrays(np.zeros(N, np.int64), idx, sign, rew + np.arange(N), 0.0)
     assert torch.equal(c.grad, d.grad) and torch.equal(c.theta, d.theta)
+
+
+@pytest.mark.parametrize("M,E,W", [(37, 128, 12), (5, 3, 9), (2048, 128, 12), (9, 1, 12), (3, 700, 12)])
+def test_synthetic_reward_kernels(D, M, E, W):
+    """bench / smoke stand-in for the environment: reward[m] = -mean_{e,j}(out - target)^2 in fp64 accumulation of
+    fp32 squares (both the warp-per-member and the CTA-per-member kernels)."""
+    from dfd_starter_b200 import _lib
+    from dfd_starter_b200.device import get_context, ptr
+    ctx = get_context(0)
+    g = torch.Generator().manual_seed(M + E)
+    out = torch.rand(M, E, W, generator=g).cuda()
+    target = torch.rand(W, generator=g).cuda()
+    rew = torch.zeros(M, dtype=torch.float64, device="cuda")
+    _lib.check(ctx.lib.dfd_synthetic_reward(ctx.handle, ptr(out), M, E, W, ptr(target), ptr(rew), ctx.stream))
+    ref = -((out.double() - target.double()) ** 2).mean(dim=(1, 2))
+    np.testing.assert_allclose(rew.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=1e-9)
