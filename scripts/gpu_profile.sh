@@ -11,6 +11,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:fd_reduce -s 12 -c 1 -o gpurun_out/prof_reduce_c3 -f python bench.py --workload C3 --obs-per-member 128 $A > gpurun_out/ncu_full_reduce.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mlp_forward_ws -s 12 -c 1 -o gpurun_out/prof_fwd_c2 -f python bench.py --workload C2 $A > gpurun_out/ncu_full_fwd.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mlp_forward_stream -s 12 -c 1 -o gpurun_out/prof_fwd_c3 -f python bench.py --workload C3 --obs-per-member 128 $A > gpurun_out/ncu_full_fwd_c3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fd_reduce -s 12 -c 1 -o gpurun_out/prof_reduce_c2 -f python bench.py --workload C2 $A > gpurun_out/ncu_full_reduce_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fd_tail -s 6 -c 1 -o gpurun_out/prof_tail_c2 -f python bench.py --workload C2 $A > gpurun_out/ncu_full_tail_c2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
 tail -n 2 gpurun_out/ncu_c2.log gpurun_out/ncu_full_reduce.log gpurun_out/ncu_full_fwd.log gpurun_out/ncu_full_fwd_c3.log
