@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                                                                        const float* __restrict__ h_in,
                                                                        const float* __restrict__ c_in, int E,
                                                                        float* __restrict__ probs, float* __restrict__ h_out,
-                                                                       float* __restrict__ c_out) {
+                                                                       float* __restrict__ c_out, int n_members, int pair_order) {
     extern __shared__ __align__(16) float sm[];
     float* bufA = sm;
     float* bufB = bufA + MAP;
@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
     float* vec = bias + 32;        // 2048 + 257 + 256 + 1024 + 32 scratch for the dense tail
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int inst = blockIdx.x;            // (member, env)
-    const int m = inst / E;
+    // consecutive CTAs take the two members of an antithetic pair ([plus | minus] batches: members j and j + M/2 share
+    // their table row), so the pair streams the same eps row at the same time and HBM serves it once
+    const int mb = blockIdx.x / E, env = blockIdx.x - mb * E;
+    const int m = pair_order ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
+    const int inst = m * E + env;           // (member, env)
     Ctx c;
     c.theta = theta;
     c.bn = bnbuf;
@@ -336,7 +339,7 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     impala_forward_kernel<<<n_members * obs_per_member, IM_THREADS, smem, (cudaStream_t)stream>>>(
         L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
-        obs_per_member, probs, h_out, c_out);
+        obs_per_member, probs, h_out, c_out, n_members, (n_members % 2 == 0) ? 1 : 0);
     DFD_LAUNCHED(ctx);
     return 0;
 }
