@@ -9,8 +9,12 @@
 // own one slot each (items w, w + 14, ...), the slots live in the frame / conv buffers that are dead by then
 // (145 KB in flight per SM, no L1 line reservations - register-staged loads were capped by the ~28 KB of L1 left
 // beside 200 KB of shared memory).
-// Consecutive CTAs take the two members of an antithetic pair, so HBM serves their shared eps row once.
+// Pair mode (E <= 2, even member count): one CTA evaluates members j and j + M/2 - the two members of an antithetic
+// pair in [plus | minus] batches -, runs the conv stack for each and then streams theta and the SHARED eps row once for
+// both (if the two indices differ, the first Linear simply runs one pass per member).  Otherwise consecutive CTAs take
+// the two members of a pair, so HBM at least serves their shared eps row once.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -51,8 +55,10 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
     __shared__ __align__(8) uint64_t bars[2 * AT_NSLOT];      // full[slot], empty[slot]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool worker = tid < AT_THREADS;                    // warp 16 only feeds the ring (and joins the barriers)
-    const int mb = blockIdx.x / tiles, tile = blockIdx.x % tiles;
-    const int m = pair_order ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
+    const int nmem = pair_order == 2 ? 2 : 1;                // members evaluated by this CTA
+    const int mb = pair_order == 2 ? (int)blockIdx.x : blockIdx.x / tiles, tile = pair_order == 2 ? 0 : blockIdx.x % tiles;
+    const int m0 = pair_order == 1 ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
+    const int ms[2] = {m0, pair_order == 2 ? m0 + (n_members >> 1) : m0};
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bars[0]);
     if (tid == 0) {
         for (int i = 0; i < AT_NSLOT; ++i) {
@@ -62,10 +68,20 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const int e0 = tile * AT_ET;
-    const int ne = min(AT_ET, E - e0);
-    const float sg = sigma * (float)sign[m];
-    const float* row = table_row_ptr(replicas, stride, idx[m]);
+    const int ne = min(AT_ET, E - e0);                       // pair mode: ne <= 2, activation slot = member * 2 + e
+    const float sgs[2] = {sigma * (float)sign[ms[0]], sigma * (float)sign[ms[1]]};
+    const float* rows[2] = {table_row_ptr(replicas, stride, idx[ms[0]]), table_row_ptr(replicas, stride, idx[ms[1]])};
+    float sg = sgs[0];
+    const float* row = rows[0];
+    int m = ms[0];
     auto par = [&](int p) { return perturb1(theta[p], sg, row[p]); };
+    auto slot_of = [&](int mem, int e) { return nmem == 2 ? mem * 2 + e : e; };
+
+    for (int mem = 0; mem < nmem; ++mem) {
+    sg = sgs[mem];
+    row = rows[mem];
+    m = ms[mem];
+    __syncthreads();       // the previous member's conv stack is done with w0 / sc0 / frame / a0
 
     // conv0 weights -> [k][oc]; bias + BN1 folded into per-channel scale / shift
     for (int t = tid; t < 4096 && worker; t += AT_THREADS) {
@@ -161,12 +177,17 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int oc = og * 8 + i;
-                a1[e * A1N + oc * 81 + pix] = fmaxf(fmaf(acc[i], sc3[oc], sc3[32 + oc]), 0.f);   // flatten (C,H,W)
+                a1[slot_of(mem, e) * A1N + oc * 81 + pix] = fmaxf(fmaf(acc[i], sc3[oc], sc3[32 + oc]), 0.f);   // flatten (C,H,W)
             }
         }
     }
-    for (int t = tid; t < (AT_ET - ne) * A1N && worker; t += AT_THREADS) a1[ne * A1N + t] = 0.f;   // ragged tile
+    }   // members
     __syncthreads();       // a1 complete; frame / w0 / a0 are dead from here on: they become the weight ring
+    bool act[AT_ET];                                         // which activation slots hold an observation
+#pragma unroll
+    for (int sl = 0; sl < AT_ET; ++sl) act[sl] = nmem == 2 ? ((sl & 1) < ne) : (sl < ne);
+    const bool shared_row = nmem == 2 && rows[0] == rows[1];
+    const int npass = (nmem == 2 && !shared_row) ? 2 : 1;    // pair with one table row: ONE pass feeds both members
 
     // ---- Linear 2592 -> 256: item h = (neuron h >> 1, half h & 1) -> slot h % 14, owned by consumer warp h % 14 (one
     //      waiter per barrier, phases strictly in order); the producer warp issues one theta and one eps bulk copy per
@@ -185,8 +206,10 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
         if (lane == 0) {
             // the ring region was last written through the generic proxy (frame, conv weights, activations)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int h = 0; h < 512; ++h) {
-                const int slot = h % AT_NSLOT, it = h / AT_NSLOT;
+            for (int hg = 0; hg < npass * 512; ++hg) {
+                const int h = hg & 511, pass = hg >> 9;
+                const float* row = rows[pass];               // pass 0: member 0's row (= member 1's in a true pair)
+                const int slot = hg % AT_NSLOT, it = hg / AT_NSLOT;
                 wait_bar(bar0 + 8u * (AT_NSLOT + slot), (uint32_t)((it & 1) ^ 1));
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + slot * AT_SLOT);
                 const uint32_t fb = bar0 + 8u * slot;
@@ -200,21 +223,32 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
         }
     } else if (warp < AT_NSLOT) {
         int it = 0;
-        for (int h = warp; h < 512; h += AT_NSLOT, ++it) {
+        for (int hg = warp; hg < npass * 512; hg += AT_NSLOT, ++it) {
+            const int h = hg & 511, pass = hg >> 9;
             wait_bar(bar0 + 8u * warp, (uint32_t)(it & 1));
             const float4* tw4 = reinterpret_cast<const float4*>(ring + warp * AT_SLOT);
             const float4* ew4 = tw4 + AT_HALF / 4;
             const float* xa = a1 + (h & 1) * AT_HALF;
+            // which slots this pass serves and with which signed sigma: single member: all; true pair: both members
+            // from the one row; two unrelated members: the pass's own member only
+            bool on[AT_ET];
+            float sgl[AT_ET];
+#pragma unroll
+            for (int sl = 0; sl < AT_ET; ++sl) {
+                const int mem = nmem == 2 ? (sl >> 1) : 0;
+                on[sl] = act[sl] && (npass == 1 || mem == pass);
+                sgl[sl] = sgs[mem];
+            }
             float acc[AT_ET];
 #pragma unroll
             for (int e = 0; e < AT_ET; ++e) acc[e] = 0.f;
             for (int v = lane; v < AT_HALF / 4; v += 32) {
                 const float4 t4 = tw4[v], e4 = ew4[v];
-                const float4 w = make_float4(perturb1(t4.x, sg, e4.x), perturb1(t4.y, sg, e4.y), perturb1(t4.z, sg, e4.z),
-                                             perturb1(t4.w, sg, e4.w));
 #pragma unroll
                 for (int e = 0; e < AT_ET; ++e) {
-                    if (e < ne) {
+                    if (on[e]) {
+                        const float4 w = make_float4(perturb1(t4.x, sgl[e], e4.x), perturb1(t4.y, sgl[e], e4.y),
+                                                     perturb1(t4.z, sgl[e], e4.z), perturb1(t4.w, sgl[e], e4.w));
                         const float4 x = *reinterpret_cast<const float4*>(xa + e * A1N + 4 * v);
                         acc[e] = fmaf(w.x, x.x, acc[e]);
                         acc[e] = fmaf(w.y, x.y, acc[e]);
@@ -229,7 +263,8 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
             for (int e = 0; e < AT_ET; ++e) acc[e] = warp_sum(acc[e]);
             if (lane == 0) {
 #pragma unroll
-                for (int e = 0; e < AT_ET; ++e) pacc[e * 512 + h] = acc[e];
+                for (int e = 0; e < AT_ET; ++e)
+                    if (on[e]) pacc[e * 512 + h] = acc[e];
             }
         }
     }
@@ -237,35 +272,48 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
     if (tid < 256) {
         const int o = tid;
         const float inv = 1.0f / sqrtf(bnbuf[BU_V8 + o] + 1e-5f);
-        const float s = par(O_G8 + o) * inv;
-        const float sh = (par(O_B7 + o) - bnbuf[BU_M8 + o]) * s + par(O_BE8 + o);
+        for (int mem = 0; mem < nmem; ++mem) {
+            sg = sgs[mem];
+            row = rows[mem];
+            const float s = par(O_G8 + o) * inv;
+            const float sh = (par(O_B7 + o) - bnbuf[BU_M8 + o]) * s + par(O_BE8 + o);
 #pragma unroll
-        for (int e = 0; e < AT_ET; ++e) a2[e * 256 + o] = fmaxf(fmaf(pacc[e * 512 + 2 * o] + pacc[e * 512 + 2 * o + 1], s, sh), 0.f);
+            for (int sl = 0; sl < AT_ET; ++sl) {
+                const bool mine = nmem == 2 ? (sl >> 1) == mem : true;
+                if (mine && act[sl]) a2[sl * 256 + o] = fmaxf(fmaf(pacc[sl * 512 + 2 * o] + pacc[sl * 512 + 2 * o + 1], s, sh), 0.f);
+            }
+        }
     }
     __syncthreads();
     // ---- Linear 256 -> A (warp per action), softmax per observation
     for (int a = warp; a < A && worker; a += AT_THREADS / 32) {
-        float w[8];
+        for (int mem = 0; mem < nmem; ++mem) {
+            sg = sgs[mem];
+            row = rows[mem];
+            float w[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = par(O_W10 + a * 256 + lane + 32 * j);
-        const float b = par(O_W10 + A * 256 + a);
-        for (int e = 0; e < ne; ++e) {
-            float s = 0.f;
+            for (int j = 0; j < 8; ++j) w[j] = par(O_W10 + a * 256 + lane + 32 * j);
+            const float b = par(O_W10 + A * 256 + a);
+            for (int e = 0; e < ne; ++e) {
+                const int sl = slot_of(mem, e);
+                float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = fmaf(w[j], a2[e * 256 + lane + 32 * j], s);
-            s = warp_sum(s);
-            if (lane == 0) lg[e * 32 + a] = s + b;
+                for (int j = 0; j < 8; ++j) s = fmaf(w[j], a2[sl * 256 + lane + 32 * j], s);
+                s = warp_sum(s);
+                if (lane == 0) lg[sl * 32 + a] = s + b;
+            }
         }
     }
     __syncthreads();
-    if (tid < ne) {
+    if (tid < AT_ET && act[tid]) {
+        const int mem = nmem == 2 ? (tid >> 1) : 0, e = nmem == 2 ? (tid & 1) : tid;
         const float* l = lg + tid * 32;
         float mx = -INFINITY;
         for (int a = 0; a < A; ++a) mx = fmaxf(mx, l[a]);
         float s = 0.f;
         for (int a = 0; a < A; ++a) s += expf(l[a] - mx);
         const float inv = 1.0f / s;
-        float* o = out + ((int64_t)m * E + e0 + tid) * A;
+        float* o = out + ((int64_t)ms[mem] * E + e0 + e) * A;
         for (int a = 0; a < A; ++a) o[a] = expf(l[a] - mx) * inv;
     }
 }
@@ -284,10 +332,11 @@ int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_
     DFD_CHECK_ARG((int64_t)n_members * tiles < 2147483647LL, "dfd_policy_forward: grid too large");
     const size_t smem = (size_t)(FRAME + 4096 + 32 + A0N + AT_ET * A1N + AT_ET * 256 + AT_ET * 32) * sizeof(float);
     DFD_CUDA(cudaFuncSetAttribute(atari_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    atari_forward_kernel<<<n_members * tiles, AT_LAUNCH, smem, st>>>(table->replicas, table->replica_stride, theta,
-                                                                     bn_buffers, idx, sign, sigma, obs, obs_per_member,
-                                                                     tiles, desc->n_act, out, n_members,
-                                                                     (n_members % 2 == 0) ? 1 : 0);
+    // 2: one CTA per pair of members (E <= 2); 1: one CTA per member, pair-adjacent order; 0: plain order
+    int mode = (n_members % 2 == 0) ? ((obs_per_member <= 2 && !getenv("DFD_ATARI_NO_PAIR")) ? 2 : 1) : 0;
+    const int grid = mode == 2 ? n_members / 2 : n_members * tiles;
+    atari_forward_kernel<<<grid, AT_LAUNCH, smem, st>>>(table->replicas, table->replica_stride, theta, bn_buffers, idx, sign,
+                                                        sigma, obs, obs_per_member, tiles, desc->n_act, out, n_members, mode);
     DFD_LAUNCHED(ctx);
     return 0;
 }

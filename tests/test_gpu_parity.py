@@ -393,6 +393,29 @@ def test_atari_forward_vs_oracle_ragged(D, E):
     assert 0 <= pol.get_action(obs[0, 0], deterministic=True) < 6
 
 
+@pytest.mark.parametrize("E,shared", [(1, True), (2, True), (1, False), (2, False)])
+def test_atari_pair_mode_vs_oracle(D, E, shared):
+    """E <= 2 with an even member count: one CTA evaluates members j and j + M/2 and streams theta / the eps row of
+    the first Linear once for both when they share their table index (antithetic pair), otherwise one pass each."""
+    L = O.atari_layout(6)
+    table = D.SharedNoiseTable(1_000_000, L.num_params, 123, device=0)
+    pol = D.AtariPolicy((84, 84), 6, seed=124, device=0).bind_table(table)
+    theta, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
+    pol.set_trainable_flat(theta)
+    pol.set_buffers(buf)
+    rng = np.random.RandomState(10 * E + shared)
+    M = 4
+    half = rng.randint(0, 1_000_000 - L.num_params, size=M // 2).astype(np.int64)
+    idx = np.concatenate([half, half]) if shared else rng.randint(0, 1_000_000 - L.num_params, size=M).astype(np.int64)
+    sign = np.array([1, 1, -1, -1] if shared else [1, 0, -1, 1], dtype=np.int8)
+    obs = rng.rand(M, E, 4, 84, 84).astype(np.float32)
+    out = pol.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(),
+                              0.02).cpu().numpy()
+    for m in range(M):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + L.num_params], int(sign[m]))
+        np.testing.assert_allclose(out[m], O.atari_forward(L, th, buf, obs[m]), rtol=0, atol=1e-5)
+
+
 # ---------------------------------------------------------------- a10 IMPALA CNN + LSTM
 def test_impala_forward_golden(D, golden_dir):
     """policies/impala.py:136-186 against the reference's own outputs: probs and the carried (h, c),
