@@ -15,7 +15,9 @@ from dfd_starter_b200.dist import PeerExchange, shard_pairs
 from dfd_starter_b200.device import get_context
 from oracle import dfd_oracle as O
 
-P_IN, ACT, PAIRS, SIG, LR, STEPS = 17, 6, 96, 0.02, 0.01, 5
+# XCHG_SHAPE=odd: a parameter count that is not a multiple of 4 (P = 4934) and a ragged shard split
+ODD = os.environ.get("XCHG_SHAPE", "") == "odd"
+P_IN, ACT, PAIRS, SIG, LR, STEPS = (5, 3, 101, 0.02, 0.01, 4) if ODD else (17, 6, 96, 0.02, 0.01, 5)
 ctx = get_context(local)
 L = O.mujoco_layout(P_IN, ACT, 64, 64)
 P = L.num_params

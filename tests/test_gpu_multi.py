@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.timeout(300)
-def test_peer_exchange_matches_nccl_and_oracle():
+@pytest.mark.parametrize("shape", ["", "odd"])
+def test_peer_exchange_matches_nccl_and_oracle(shape):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import __graft_entry__ as G
@@ -21,5 +22,5 @@ def test_peer_exchange_matches_nccl_and_oracle():
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "xchg_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=280, cwd=ROOT, env=dict(os.environ, XCHG_SHAPE=shape))
     assert out.returncode == 0 and "xchg ok" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
