@@ -16,10 +16,14 @@ from dfd_starter_b200.device import get_context
 from oracle import dfd_oracle as O
 
 # XCHG_SHAPE=odd: a parameter count that is not a multiple of 4 (P = 4934) and a ragged shard split
-ODD = os.environ.get("XCHG_SHAPE", "") == "odd"
-P_IN, ACT, PAIRS, SIG, LR, STEPS = (5, 3, 101, 0.02, 0.01, 4) if ODD else (17, 6, 96, 0.02, 0.01, 5)
+#            wide: P = 69 218 > 32 768, so the step runs prepare_partial -> reduce -> the standalone exchange kernel -> DSGD
+SHAPE = os.environ.get("XCHG_SHAPE", "")
+P_IN, ACT, PAIRS, SIG, LR, STEPS = (5, 3, 101, 0.02, 0.01, 4) if SHAPE == "odd" else (17, 6, 96, 0.02, 0.01, 5)
+HID = 64
+if SHAPE == "wide":
+    P_IN, ACT, PAIRS, HID, STEPS = 376, 17, 64, 128, 3
 ctx = get_context(local)
-L = O.mujoco_layout(P_IN, ACT, 64, 64)
+L = O.mujoco_layout(P_IN, ACT, HID, HID)
 P = L.num_params
 noise = O.NoiseTableOracle(1_000_000, P, 123)
 theta0 = O.synthetic_theta(L, 3)
@@ -31,7 +35,7 @@ class Omega(object):
 
 def make_learner(xchg):
     table = D.SharedNoiseTable(1_000_000, P, 123, device=local)
-    pol = D.MujocoPolicy(P_IN, ACT, seed=3, device=local).bind_table(table)
+    pol = D.MujocoPolicy(P_IN, ACT, seed=3, h1=HID, h2=HID, device=local).bind_table(table)
     pol.set_trainable_flat(theta0)
     opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
     opt.coef = np.sqrt(P)
