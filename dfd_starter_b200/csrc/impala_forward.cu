@@ -37,9 +37,29 @@ struct Ctx {
 // weights -> wsm[(ci*9+tap)*cout + oc]; input-side BN folded to per-input-channel scale/shift; conv bias
 __device__ void load_conv(const Ctx& c, const ConvP& p, float* wsm, float* s_in, float* sh_in, float* bias) {
     const int n = p.cout * p.cin * 9;
-    for (int t = threadIdx.x; t < n; t += IM_THREADS) {
-        const int oc = t / (p.cin * 9), k = t - oc * (p.cin * 9);
-        wsm[k * p.cout + oc] = c.par(p.w + t);
+    // all of a thread's loads of a batch are issued before the first shared-memory store (the compiler cannot hoist
+    // global loads over stores it cannot prove disjoint, which would expose one memory latency per element)
+    constexpr int U = 8;
+    for (int t0 = threadIdx.x; t0 < n; t0 += IM_THREADS * U) {
+        float a[U], e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * IM_THREADS;
+            a[u] = 0.f;
+            e[u] = 0.f;
+            if (t < n) {
+                a[u] = c.theta[p.w + t];
+                e[u] = c.row[p.w + t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * IM_THREADS;
+            if (t < n) {
+                const int oc = t / (p.cin * 9), k = t - oc * (p.cin * 9);
+                wsm[k * p.cout + oc] = perturb1(a[u], c.sg, e[u]);
+            }
+        }
     }
     for (int t = threadIdx.x; t < p.cin; t += IM_THREADS) {
         const float inv = 1.0f / sqrtf(c.bn[p.bv + t] + 1e-5f);

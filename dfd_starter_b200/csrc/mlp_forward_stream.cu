@@ -62,24 +62,8 @@ __device__ __forceinline__ float st_tanh(float x) {
     }
 }
 
-__device__ int st_spin_mode;   // experiment switch: 1 = plain try_wait loop, 0 = try_wait with a suspend-time hint
 __device__ __forceinline__ void st_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok, spins = 0;
-    if (st_spin_mode) {
-        do {
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t"
-                "}\n"
-                : "=r"(ok)
-                : "r"(bar), "r"(parity)
-                : "memory");
-            if (!ok && ++spins > (1u << 26)) __trap();
-        } while (!ok);
-        return;
-    }
     do {
         asm volatile(
             "{\n\t"
@@ -191,7 +175,7 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
             const float sg = p.sigma * (float)sign[m];
             const float* row = table_row_ptr(replicas, stride, idx[m]);
             const float* ob = obs + ((int64_t)m * p.E + e0i) * p.K0;
-            if ((p.prefetch & 1) && tid == 0 && u + 1 < n_my) {      // next member's eps row and observation tile -> L2
+            if (p.prefetch && tid == 0 && u + 1 < n_my) {      // next member's eps row and observation tile -> L2
                 int nm, nt;
                 st_item(p, work + (int)gridDim.x, nm, nt);
                 l2_prefetch(table_row_ptr(replicas, stride, idx[nm]), (size_t)p.P * 4);
@@ -239,8 +223,8 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                         e[h] = a[h];
                         if (rg < nrg && n < nreal && k < kin) {      // kin % 4 == 0: whole quads only
                             const int q = n * kin + k;
-                            if (!(p.prefetch & 2)) a[h] = *reinterpret_cast<const float4*>(th_l + q);
-                            if (!(p.prefetch & 4)) e[h] = ldg_stream_f4(ep_l + q);
+                            a[h] = ldg_stream_f4(th_l + q);
+                            e[h] = ldg_stream_f4(ep_l + q);
                         }
                     }
                     if (l == 0) {     // observation chunk [128 x 16]: 16 row groups
@@ -248,7 +232,7 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                         for (int h = 0; h < 16 / ST_TEAM_WARPS; ++h) {
                             const int r = (tw + h * ST_TEAM_WARPS) * 8 + li;
                             o4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (r < ne && k < p.K0 && !(p.prefetch & 8)) o4[h] = ldg_stream_f4(ob + (int64_t)r * p.K0 + k);
+                            if (r < ne && k < p.K0) o4[h] = ldg_stream_f4(ob + (int64_t)r * p.K0 + k);
                         }
                     }
 #pragma unroll
@@ -434,7 +418,6 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     p.sigma = sigma;
     p.pair_order = (n_members % 2 == 0 && !getenv("DFD_ST_NOPAIR")) ? 1 : 0;
     p.prefetch = getenv("DFD_ST_NOPF") ? 0 : 1;
-    if (getenv("DFD_ST_DBG")) p.prefetch |= atoi(getenv("DFD_ST_DBG"));   // experiments: 2 no theta, 4 no eps, 8 no obs loads
     // 4 x 24 KB + biases: shared memory stays near 100 KB so ~96 KB of the SM's 228 KB remain L1 - measured on B200:
     // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
     p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : ST_NS;
@@ -442,10 +425,6 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768) * sizeof(float);
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
-    {
-        const int sm = getenv("DFD_ST_SPIN") ? 1 : 0;
-        cudaMemcpyToSymbolAsync(st_spin_mode, &sm, sizeof(int), 0, cudaMemcpyHostToDevice, st);
-    }
     long long* prof = nullptr;
     if (getenv("DFD_ST_PROF")) { cudaMalloc(&prof, (size_t)grid * 32 * 8); cudaMemset(prof, 0, (size_t)grid * 32 * 8); }
     if (approx_tanh) {
