@@ -1,0 +1,49 @@
+"""bench.py contract checks that need no GPU: the reference arm (the CPU restatement of the reference's path, the one
+place besides tests/ and smoke() that may execute oracle/) prints ONE JSON line with the keys the driver reads, and
+the B200 arm refuses to run without a CUDA device instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args):
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=300,
+                          cwd=ROOT, env=env)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _run(["--impl", "reference", "--workload", "C1", "--obs-per-member", "2", "--steps", "1", "--warmup", "0",
+                "--cpu-sample-members", "4", "--table-size", "200000"])
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "perturbed-policy env-steps/sec" and d["unit"] == "env-steps/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env_rank = dict(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, **env_rank))
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_b200_arm_has_no_cpu_fallback():
+    if torch.cuda.is_available():
+        return          # on a GPU box the arm runs; the refusal is what is checked here
+    out = _run(["--steps", "1", "--warmup", "1"])
+    assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
