@@ -56,8 +56,8 @@ def test_halfcheetah_shape_tf32(D, E):
 
 @pytest.mark.parametrize("E", [128, 1, 37, 200, 300])
 def test_halfcheetah_shape_tf32_tanh_approx(D, E):
-    """precision=2: tf32 operands + tanh.approx.f32 (2^-11 relative per activation); stated tolerance
-    max-abs 4e-3, mean-abs 3e-4 (checked inside _check)."""
+    """precision=2: tf32 operands + tanh.approx.f32 (2^-11 relative per activation, activations truncated - not
+    rounded - to tf32 by the tensor core); stated tolerance max-abs 4e-3, mean-abs 3e-4 (checked inside _check)."""
     _check(D, 17, 64, 6, E, M=300, seed=4, atol=4e-3, precision=2)
 
 
