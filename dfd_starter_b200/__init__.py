@@ -4,10 +4,10 @@ neither the shared library nor a GPU; using it needs both (no CPU fallback)."""
 from .fd_return import FDReturn, ReturnBatch
 from .fd_state import FDState
 from .dsgd import DSGD
-from .noise_sources import SharedNoiseTable
+from .noise_sources import SharedNoiseTable, RNGNoiseSource, SimpleNoiseSource
 from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
 from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
-__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "FiniteDifferences", "Worker", "SyntheticAgent",
+__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent",
            "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

@@ -32,7 +32,7 @@ class ReturnBatch(object):
     and falls back to the per-record path (learner/finite_differences.py:94-114 semantics) as soon as
     any record object has been handed out, because callers may have edited it."""
 
-    def __init__(self, epoch, idx, sign, reward, entropy, timesteps, is_eval, states=None):
+    def __init__(self, epoch, idx, sign, reward, entropy, timesteps, is_eval, states=None, keys=None):
         n = len(idx)
         self.epoch = np.full(n, int(epoch), dtype=np.int64) if np.isscalar(epoch) else np.asarray(epoch, dtype=np.int64)
         self.idx = np.asarray(idx, dtype=np.int64)
@@ -42,6 +42,7 @@ class ReturnBatch(object):
         self.timesteps = np.asarray(timesteps, dtype=np.int64)
         self.is_eval = np.asarray(is_eval, dtype=bool)
         self.states = states
+        self.keys = keys            # explicit `encoded_noise` values (noise sources whose key is not a table index)
         self.antithetic = bool((self.sign < 0).any())
         self._records = None
 
@@ -53,6 +54,8 @@ class ReturnBatch(object):
         antithetic extension: '+i' / '-i')."""
         if self.is_eval[j]:
             return "0"
+        if self.keys is not None:
+            return self.keys[j]
         if self.antithetic:
             return ("+%d" if self.sign[j] > 0 else "-%d") % self.idx[j]
         return "%d" % self.idx[j]
@@ -79,7 +82,7 @@ class ReturnBatch(object):
     @property
     def soa(self):
         """(epoch, idx, sign, reward) when no record object has been handed out, else None."""
-        if self._records is not None:
+        if self._records is not None or self.keys is not None:
             return None
         return self.epoch, self.idx, self.sign, self.reward
 

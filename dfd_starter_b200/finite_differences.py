@@ -74,7 +74,9 @@ class FiniteDifferences(object):
         self.ctx = get_context(device if device is not None else getattr(getattr(policy, "ctx", None), "device", None))
         self.lib = self.ctx.lib
         dev = self.ctx.device
-        self.table = noise_source.device_table
+        # a shared table lives on the device for the whole run; other noise sources (RNGNoiseSource, SimpleNoiseSource:
+        # utils/noise_sources.py:4-33) are decoded on the host per batch and staged as a RowTable
+        self.table = noise_source.device_table if hasattr(noise_source, "device_table") else None
         P = int(policy.num_params)
         self.P = P
         self.Ps = (P + 3) // 4 * 4              # row stride of history / dist rows (16-byte aligned rows)
@@ -144,12 +146,35 @@ class FiniteDifferences(object):
         soa = getattr(batch, "soa", None)
         if soa is not None:                      # untouched ReturnBatch from the batched Worker: arrays as they are
             return self.step_arrays(soa[0], soa[1], soa[2], soa[3], policy_reward)
+        if self.table is None:
+            return self._step_host_noise(batch, policy_reward)
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
         keys = [parse_key(r.encoded_noise) for r in batch]
         idx = np.fromiter((k[0] for k in keys), dtype=np.int64, count=len(batch))
         sign = np.fromiter((k[1] for k in keys), dtype=np.int8, count=len(batch))
         return self.step_arrays(epochs, idx, sign, rewards, policy_reward)
+
+    def _step_host_noise(self, batch, policy_reward):
+        """Noise sources without a device table: `decode` every ACCEPTED return on the host, in batch order like
+        finite_differences.py:87 (too-old returns are rejected before they are decoded, :82-85), stage the fp32 vectors
+        as a RowTable and run the ordinary device step over it."""
+        from .noise_sources import RowTable
+        batch = list(batch)
+        epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
+        rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
+        ok = np.array([(e == self.epoch) or (e in self._dist_epoch) for e in epochs], dtype=bool)
+        rows = [np.asarray(self.noise_source.decode(r.encoded_noise), dtype=np.float32) for r, k in zip(batch, ok) if k]
+        if not rows:
+            return self.step_arrays(epochs, np.zeros(len(batch), np.int64), np.ones(len(batch), np.int8), rewards, policy_reward)
+        rt = RowTable(self.ctx, np.stack(rows))
+        idx = np.zeros(len(batch), dtype=np.int64)
+        idx[ok] = rt.idx
+        self.table = rt
+        try:
+            return self.step_arrays(epochs, idx, np.ones(len(batch), dtype=np.int8), rewards, policy_reward)
+        finally:
+            self.table = None
 
     def step_arrays(self, epochs, idx, sign, rewards, policy_reward, all_rewards=None):
         """SoA form of `step`: int64 epochs/idx, int8 sign, float64 rewards (host arrays).

@@ -76,6 +76,76 @@ class SharedNoiseTable(object):
         return self.to_device()
 
 
+class RNGNoiseSource(object):
+    """utils/noise_sources.py:4-20 restated for numpy >= 2 (the reference reads `rng.__getstate__()['state']`, which
+    newer numpy no longer lays out that way; the PCG64 words themselves are the same).  The key is the generator's
+    `state,inc` BEFORE the draw, the noise is `standard_normal(P)` in fp64; `decode` rewinds the SAME generator to the
+    key and redraws (so, as in the reference, it also moves the stream `sample()` continues from).
+    Noise is generated on the host; the learner and the worker stage the vectors on the device per batch
+    (`RowTable`).  In-kernel PCG64 + ziggurat generation is SURVEY.md §8(f) row N4."""
+
+    def __init__(self, n_params, random_seed=123):
+        self.rng = np.random.default_rng(np.random.SeedSequence(random_seed))
+        self.n_params = n_params
+
+    def sample(self):
+        st = self.rng.bit_generator.state["state"]
+        state = "{},{}".format(st["state"], st["inc"])
+        noise = self.rng.standard_normal(size=self.n_params)
+        return state, noise
+
+    def decode(self, state):
+        state_data = str(state).split(",")
+        self.rng.bit_generator.state = {"bit_generator": "PCG64",
+                                        "state": {"state": int(state_data[0]), "inc": int(state_data[1])},
+                                        "has_uint32": 0, "uinteger": 0}
+        return self.rng.standard_normal(size=self.n_params)
+
+
+class SimpleNoiseSource(object):
+    """utils/noise_sources.py:23-33: the key IS the noise vector."""
+
+    def __init__(self, n_params, random_seed=123):
+        self.rng = np.random.RandomState(random_seed)
+        self.n_params = n_params
+
+    def sample(self):
+        noise = self.rng.randn(self.n_params)
+        return noise, noise
+
+    def decode(self, noise):
+        return noise
+
+
+class RowTable(object):
+    """N host vectors staged as a throw-away device table: row j lives at entries [j*Ps, j*Ps + P) with Ps = P rounded
+    up to 4, so every row starts 16-byte aligned in replica 0 and all kernels (forward, prepare, reduce, one-kernel
+    step) run unchanged with idx[j] = j*Ps.  Used for noise sources that are not a shared table."""
+
+    def __init__(self, ctx, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        n, P = rows.shape
+        self.Ps = (P + 3) // 4 * 4
+        size = n * self.Ps + self.Ps + 8          # strictly larger than any row end; the tail is zero
+        host = np.zeros(size, dtype=np.float32)
+        host[:n * self.Ps].reshape(n, self.Ps)[:, :P] = rows
+        lib = ctx.lib
+        stride = int(lib.dfd_table_replica_stride(size))
+        with torch.cuda.device(ctx.device):
+            raw = torch.from_numpy(host).to(ctx.device)
+            replicas = torch.empty(4 * stride, dtype=torch.float32, device=ctx.device)
+            prefix = torch.empty(size + 1, dtype=torch.float64, device=ctx.device)
+            scratch = ctx.zeros_bytes(lib.dfd_table_scratch_bytes(size))
+            _lib.check(lib.dfd_table_build(ctx.handle, ptr(raw), size, ptr(replicas), stride, ptr(prefix),
+                                           aligned_ptr(scratch), scratch.numel() - 256, ctx.stream), "dfd_table_build")
+        self._keep = (raw, scratch)               # stream-ordered: freed with the object
+        self.table = DeviceTable(ctx, replicas, stride, prefix, size)
+        self.idx = np.arange(n, dtype=np.int64) * self.Ps
+
+    def ref(self):
+        return self.table.ref()
+
+
 class DeviceTable(object):
     def __init__(self, ctx, replicas, stride, prefix, size):
         self.ctx, self.replicas, self.stride, self.prefix, self.size = ctx, replicas, stride, prefix, size

@@ -247,12 +247,18 @@ class Policy(object):
     def bind_table(self, noise_source):
         """The table whose rows perturb the members (needed even for the unperturbed
         M=1 wrappers: the kernel signature always carries a table)."""
+        if not hasattr(noise_source, "device_table"):       # RNG / Simple noise sources: nothing to bind, rows are staged per batch
+            return self
         self._table = noise_source.device_table
         return self
 
-    def forward_members(self, idx, sign, obs, sigma, out=None):
-        """idx int64 [M], sign int8 [M] (0 = unperturbed), obs float32 [M, E, ...] — device tensors."""
-        if self._table is None:
+    def forward_members(self, idx, sign, obs, sigma, out=None, theta=None, table=None):
+        """idx int64 [M], sign int8 [M] (0 = unperturbed), obs float32 [M, E, ...] — device tensors.
+        theta / table override the policy's own parameter vector and bound table (used for noise sources that are
+        not a shared table: the members' perturbed vectors are staged as a RowTable and evaluated against theta = 0)."""
+        table = table if table is not None else self._table
+        theta = theta if theta is not None else self.theta
+        if table is None:
             raise _lib.DfdError("policy.bind_table(noise_source) must be called before forward_members")
         M = idx.shape[0]
         E = obs.shape[1]
@@ -260,7 +266,7 @@ class Policy(object):
             out = torch.empty(M, E, self.out_width, dtype=torch.float32, device=self.ctx.device)
         obs = obs.contiguous()
         _lib.check(self.ctx.lib.dfd_policy_forward(
-            self.ctx.handle, C.byref(self.desc), self._table.ref(), ptr(self.theta), ptr(self.buffers), ptr(idx),
+            self.ctx.handle, C.byref(self.desc), table.ref(), ptr(theta), ptr(self.buffers), ptr(idx),
             ptr(sign), M, float(sigma), ptr(obs), E, ptr(out), self.ctx.stream), "dfd_policy_forward")
         return out
 

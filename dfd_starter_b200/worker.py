@@ -58,8 +58,37 @@ class Worker(object):
 
     @torch.no_grad()
     def collect_returns(self, n=1, antithetic=False):
+        if not hasattr(self.noise_source, "device_table"):
+            return self._collect_returns_host_noise(n)
         flags, idx = self.draw(n)
         return self.evaluate(flags, idx, antithetic=antithetic)
+
+    @torch.no_grad()
+    def _collect_returns_host_noise(self, n):
+        """`RNGNoiseSource` / `SimpleNoiseSource` (utils/noise_sources.py:4-33): the noise is generated on the host, so
+        the members' perturbed vectors are formed exactly as the reference does it - `flat + sigma * eps` with fp64
+        noise, cast to fp32 by `set_trainable_flat` (worker/worker.py:28-29, policies/policy.py:40-42) - staged on the
+        device as a RowTable and evaluated in ONE batched launch against theta = 0 (0 + 1 * x == x bit for bit).
+        Same two draws per member, in the same order, as the reference loop."""
+        from .noise_sources import RowTable
+        flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32)
+        rows = np.empty((n, flat.shape[0]), dtype=np.float32)
+        keys, is_eval = [], np.zeros(n, dtype=bool)
+        for j in range(n):
+            is_eval[j] = self.rng.uniform(0, 1) < self.eval_prob
+            if is_eval[j]:
+                rows[j] = flat
+                keys.append("0")
+            else:
+                key, eps = self.noise_source.sample()
+                rows[j] = (flat + self.sigma * eps).astype(np.float32)
+                keys.append(key)
+        ctx = self.policy.ctx
+        rt = RowTable(ctx, rows)
+        view = _RowPolicyView(self.policy, rt, torch.zeros(flat.shape[0], dtype=torch.float32, device=ctx.device))
+        res = self.agent.collect_returns(view, rt.idx, np.ones(n, dtype=np.int8), 1.0)
+        return ReturnBatch(self.epoch, rt.idx, np.ones(n, dtype=np.int8), res["reward"], res["entropy"], res["timesteps"],
+                           is_eval, states=res.get("states"), keys=keys)
 
     @torch.no_grad()
     def evaluate(self, flags, idx, antithetic=False):
@@ -88,6 +117,20 @@ class Worker(object):
         """worker.py:40-43: load the learner's snapshot (flattened state_dict incl. BN buffers)."""
         self.policy.deserialize(state.policy_params)
         self.epoch = state.epoch
+
+
+class _RowPolicyView(object):
+    """What a batched agent sees when the members' parameter vectors were staged as rows: the policy's attributes,
+    with `forward_members` evaluating row j (theta = 0, sigma = 1) instead of theta + sigma * table[idx]."""
+
+    def __init__(self, policy, row_table, zero_theta):
+        self._policy, self._rows, self._zero = policy, row_table, zero_theta
+
+    def __getattr__(self, name):
+        return getattr(self._policy, name)
+
+    def forward_members(self, idx, sign, obs, sigma, out=None):
+        return self._policy.forward_members(idx, sign, obs, 1.0, out=out, theta=self._zero, table=self._rows)
 
 
 class SyntheticAgent(object):

@@ -31,6 +31,43 @@ import numpy as np
 # --------------------------------------------------------------------------
 
 
+class RNGNoiseSourceOracle(object):
+    """`RNGNoiseSource` restated (utils/noise_sources.py:4-20) for numpy >= 2: key = PCG64 `state,inc` before the
+    draw, noise = `standard_normal(P)` (fp64); `decode` rewinds the same generator and redraws.  The reference reads
+    the words through `Generator.__getstate__()`, whose layout changed in numpy 2; the generator
+    words and the normal stream are pinned by SURVEY.md App. C."""
+
+    def __init__(self, n_params, random_seed=123):
+        self.rng = np.random.default_rng(np.random.SeedSequence(random_seed))
+        self.n_params = n_params
+
+    def sample(self):
+        st = self.rng.bit_generator.state["state"]
+        return "{},{}".format(st["state"], st["inc"]), self.rng.standard_normal(size=self.n_params)
+
+    def decode(self, key):
+        s, i = str(key).split(",")
+        self.rng.bit_generator.state = {"bit_generator": "PCG64", "state": {"state": int(s), "inc": int(i)},
+                                        "has_uint32": 0, "uinteger": 0}
+        return self.rng.standard_normal(size=self.n_params)
+
+
+class SimpleNoiseSourceOracle(object):
+    """`SimpleNoiseSource` restated (utils/noise_sources.py:23-33): `RandomState(seed).randn(P)` per draw (fp64), the key
+    is the vector itself and `decode` is the identity."""
+
+    def __init__(self, n_params, random_seed=123):
+        self.rng = np.random.RandomState(random_seed)
+        self.n_params = n_params
+
+    def sample(self):
+        noise = self.rng.randn(self.n_params)
+        return noise, noise
+
+    def decode(self, noise):
+        return noise
+
+
 class NoiseTableOracle(object):
     """`SharedNoiseTable` restated (utils/noise_sources.py:36-51).
 

@@ -356,6 +356,81 @@ def gen_fd_steps():
     np.savez_compressed(os.path.join(HERE, "fd_steps.npz"), **rec)
 
 
+class _Numpy2Generator(object):
+    """numpy >= 2 dropped the dict `Generator.__getstate__()` the reference RNGNoiseSource reads
+    (utils/noise_sources.py:7,11,18).  This proxy gives the UNMODIFIED reference class the
+    old protocol on top of `bit_generator.state`, so its own sample()/decode() code runs."""
+
+    def __init__(self, gen):
+        self._g = gen
+
+    def __getstate__(self):
+        return dict(self._g.bit_generator.state)
+
+    def __setstate__(self, st):
+        self._g.bit_generator.state = st
+
+    def standard_normal(self, size=None):
+        return self._g.standard_normal(size=size)
+
+
+def gen_fd_steps_hostnoise():
+    """Unmodified FiniteDifferences.step + DSGD driven by the two noise sources whose key is NOT a table index
+    (utils/noise_sources.py:4-33): SimpleNoiseSource as shipped, RNGNoiseSource through the numpy-2 proxy above.
+    Only seeds, keys (RNG), rewards and epochs are stored; the tests regenerate the noise from the seeds."""
+    import io
+    import contextlib
+    from utils.noise_sources import RNGNoiseSource, SimpleNoiseSource
+    rec = {}
+    for name in ("simple", "rng"):
+        torch.manual_seed(124)
+        pol = MujocoPolicy(17, 6, seed=124)
+        P = pol.num_params
+        if name == "simple":
+            src = SimpleNoiseSource(P, 321)
+        else:
+            src = RNGNoiseSource.__new__(RNGNoiseSource)
+            src.rng = _Numpy2Generator(np.random.default_rng(np.random.SeedSequence(321)))
+            src.base_state = src.rng.__getstate__()
+            src.n_params = P
+        H = 2
+        opt = DSGD(pol.parameters(), lr=0.01)
+        fd = FiniteDifferences(pol, opt, _Omega(0.3), src, noise_std=0.02, batch_size=12, ent_coef=0.0, max_delayed_return=H)
+        rrng = np.random.RandomState(7)
+        erng = np.random.RandomState(8)
+        rec[name + "_theta0"] = pol.get_trainable_flat().copy()
+        n_steps = 5
+        for s in range(n_steps):
+            N = 12
+            keys = [src.sample()[0] for _ in range(N)]
+            rewards = (rrng.randn(N) * 2.0 - 1.0).tolist()
+            if s < 2:
+                epochs = [fd.epoch] * N
+            else:                      # delayed returns, one of them too old (discarded before it is decoded)
+                epochs = [fd.epoch - int(k) for k in erng.randint(0, H + 1, size=N)]
+                if s == 3:
+                    epochs[5] = fd.epoch - H - 1
+            batch = [mkret(e, k, r) for e, k, r in zip(epochs, keys, rewards)]
+            with contextlib.redirect_stdout(io.StringIO()):
+                upd = fd.step(batch, 0.05 * s, 0.0, 0.0)
+            if name == "rng":
+                rec["rng_s%d_keys" % s] = np.array(keys)
+            rec["%s_s%d_epochs" % (name, s)] = np.array(epochs)
+            rec["%s_s%d_rewards" % (name, s)] = np.array(rewards)
+            rec["%s_s%d_grad" % (name, s)] = fd.gradient_memory.copy()
+            rec["%s_s%d_theta" % (name, s)] = pol.get_trainable_flat().copy()
+            rec["%s_s%d_update" % (name, s)] = float(upd)
+            rec["%s_s%d_discarded" % (name, s)] = fd.discarded_returns
+    rec.update(n_steps=5, H=2, sigma=0.02, lr=0.01, omega=0.3, seed=321, N=12)
+    # RNGNoiseSource stream pins (SURVEY.md App. C uses seed 123)
+    g = np.random.default_rng(np.random.SeedSequence(123))
+    st = g.bit_generator.state["state"]
+    rec["pcg_seed123_state"] = np.array(str(st["state"]))
+    rec["pcg_seed123_inc"] = np.array(str(st["inc"]))
+    rec["pcg_seed123_normals"] = g.standard_normal(8)
+    np.savez_compressed(os.path.join(HERE, "fd_steps_hostnoise.npz"), **rec)
+
+
 def main():
     with open(os.path.join(HERE, "noise.json"), "w") as f:
         json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
@@ -365,6 +440,7 @@ def main():
     gen_atari()
     gen_impala()
     gen_fd_steps()
+    gen_fd_steps_hostnoise()
     print("golden fixtures written to", HERE)
 
 

@@ -354,6 +354,76 @@ def test_worker_batched_collect_and_learning(D, table1m):
     assert eval_reward() > r0 + 1e-3
 
 
+# ---------------------------------------------------------------- a4 RNGNoiseSource / SimpleNoiseSource
+@pytest.mark.parametrize("name", ["simple", "rng"])
+def test_estimator_steps_host_noise_sources_golden(D, golden_dir, name):
+    """The unmodified reference learner driven by the noise sources whose key is not a table index
+    (utils/noise_sources.py:4-33; fp64 noise, delayed and too-old returns): decoded on the host in batch order,
+    staged as device rows, same kernels.  Bars as for the table: gradient rel-max 1e-5, theta atol 2e-6."""
+    g = np.load(os.path.join(golden_dir, "fd_steps_hostnoise.npz"))
+    P = g[name + "_theta0"].shape[0]
+    src = (D.SimpleNoiseSource if name == "simple" else D.RNGNoiseSource)(P, int(g["seed"]))
+    fd = make_learner(D, src, g[name + "_theta0"], float(g["sigma"]), H=int(g["H"]), lr=float(g["lr"]), omega=float(g["omega"]))
+    for s in range(int(g["n_steps"])):
+        batch = []
+        for e, r in zip(g["%s_s%d_epochs" % (name, s)], g["%s_s%d_rewards" % (name, s)]):
+            ret = D.FDReturn()
+            ret.epoch, ret.encoded_noise, ret.reward = int(e), src.sample()[0], float(r)
+            batch.append(ret)
+        if name == "rng":
+            assert [b.encoded_noise for b in batch] == [str(k) for k in g["rng_s%d_keys" % s]]
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step(batch, 0.05 * s, 0.0, 0.0)
+        assert rel_max(fd.gradient_memory, g["%s_s%d_grad" % (name, s)]) <= 1e-5, s
+        assert abs(upd - float(g["%s_s%d_update" % (name, s)])) <= 1e-5 * upd, s
+        assert np.max(np.abs(fd.policy.get_trainable_flat() - g["%s_s%d_theta" % (name, s)])) <= 2e-6, s
+        assert fd.discarded_returns == int(g["%s_s%d_discarded" % (name, s)]), s
+
+
+@pytest.mark.parametrize("name", ["simple", "rng"])
+def test_worker_with_host_noise_sources(D, name):
+    """worker/worker.py:19-38 with RNGNoiseSource / SimpleNoiseSource: same flag and noise draws as the reference loop,
+    members' vectors `fp32(flat + sigma * eps_fp64)` evaluated in one batched launch; outputs vs the oracle forward of
+    exactly those vectors (atol 1e-5), eval members unperturbed with key "0"."""
+    torch.manual_seed(124)
+    pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+    P = pol.num_params
+    mk = (lambda: D.SimpleNoiseSource(P, 9)) if name == "simple" else (lambda: D.RNGNoiseSource(P, 9))
+    src = mk()
+    seen = {}
+
+    class Agent(object):
+        saved_states = []
+
+        def collect_returns(self, view, idx, sign, sigma):
+            g = torch.Generator().manual_seed(3)
+            obs = torch.randn(len(idx), 4, 17, generator=g)
+            out = view.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), obs.cuda(), sigma)
+            seen["obs"], seen["out"] = obs.numpy(), out.cpu().numpy()
+            return {"reward": out.double().mean(dim=(1, 2)).cpu().numpy(), "entropy": np.zeros(len(idx)),
+                    "timesteps": np.full(len(idx), 4), "states": None}
+    w = D.Worker(pol, Agent(), src, None, sigma=0.02, eval_prob=0.3, random_seed=5)
+    w.epoch = 3
+    rets = w.collect_returns(24)
+    # the reference loop, restated: one uniform per member, one noise draw per non-eval member
+    rng, ref_src = np.random.RandomState(5), mk()
+    flat = pol.get_trainable_flat()
+    lay = O.mujoco_layout(17, 6)
+    assert len(rets) == 24
+    for j, r in enumerate(rets):
+        is_eval = rng.uniform(0, 1) < 0.3
+        assert r.is_eval == is_eval and r.epoch == 3
+        if is_eval:
+            assert r.encoded_noise == "0"
+            vec = flat
+        else:
+            key, eps = ref_src.sample()
+            assert (r.encoded_noise is not None) and (np.array_equal(r.encoded_noise, key) if name == "simple" else r.encoded_noise == key)
+            vec = (flat + 0.02 * eps).astype(np.float32)
+        ref = O.mujoco_forward(lay, vec, seen["obs"][j])
+        np.testing.assert_allclose(seen["out"][j], ref, rtol=0, atol=1e-5)
+
+
 # ---------------------------------------------------------------- a9 Atari CNN
 def test_atari_forward_golden(D, golden_dir):
     """policies/atari.py:35-51 against the reference's own outputs (synthetic seeded theta / BN stats)."""

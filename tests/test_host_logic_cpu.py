@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from dfd_starter_b200.noise_sources import SharedNoiseTable, parse_key
+from dfd_starter_b200.noise_sources import SharedNoiseTable, RNGNoiseSource, SimpleNoiseSource, parse_key
 from dfd_starter_b200 import policies as P
 from dfd_starter_b200.dsgd import DSGD, affine_transform, is_dsgd
 from dfd_starter_b200.worker import Worker
@@ -41,6 +41,23 @@ def test_sample_indices_is_the_same_stream(noise_json):
     g = noise_json["tables"]["200000_5197_124"]
     t = SharedNoiseTable(g["size"], g["n_params"], g["seed"], upload=False)
     assert [str(i) for i in t.sample_indices(8)] == g["keys"]
+
+
+def test_rng_and_simple_noise_sources_follow_the_reference(golden_dir):
+    """utils/noise_sources.py:4-33: RNGNoiseSource keys are the PCG64 `state,inc` before the draw
+    (App. C words; keys recorded from the reference class itself), SimpleNoiseSource's key is the vector."""
+    g = np.load(os.path.join(golden_dir, "fd_steps_hostnoise.npz"))
+    src = RNGNoiseSource(8, 123)
+    key, noise = src.sample()
+    assert key == "%s,%s" % (str(g["pcg_seed123_state"]), str(g["pcg_seed123_inc"]))
+    assert noise.dtype == np.float64 and np.array_equal(noise, g["pcg_seed123_normals"])
+    assert np.array_equal(src.decode(key), noise)
+    src = RNGNoiseSource(6092, int(g["seed"]))
+    keys = [src.sample()[0] for _ in range(int(g["N"]))]
+    assert keys == [str(k) for k in g["rng_s0_keys"]]
+    s = SimpleNoiseSource(5, 77)
+    k, v = s.sample()
+    assert k is v and s.decode(k) is k and np.array_equal(v, np.random.RandomState(77).randn(5))
 
 
 class _StubPolicy(object):

@@ -148,6 +148,44 @@ def test_estimator_steps_match_reference(golden_dir):
     assert fd.step([], 0.0) == 0 and fd.epoch == int(g["n_steps"])
 
 
+def test_rng_noise_source_stream_pins(golden_dir):
+    """utils/noise_sources.py:4-20: key = PCG64 `state,inc` before the draw; SURVEY.md App. C words and normals."""
+    g = _load(golden_dir, "fd_steps_hostnoise.npz")
+    src = O.RNGNoiseSourceOracle(8, 123)
+    key, noise = src.sample()
+    assert key == "%s,%s" % (str(g["pcg_seed123_state"]), str(g["pcg_seed123_inc"]))
+    assert key == "160078363690744033601390112987726904141,17686443629577124697969402389330893883"
+    assert np.array_equal(noise, g["pcg_seed123_normals"])
+    np.testing.assert_allclose(noise[:5], [-0.98912135, -0.36778665, 1.28792526, 0.19397442, 0.9202309], atol=5e-9)
+    k2, n2 = src.sample()
+    assert np.array_equal(src.decode(key), noise) and np.array_equal(src.decode(k2), n2)
+    # decode rewinds the SAME generator (as the reference does): the next sample continues after the decoded vector
+    assert src.sample()[0] != k2
+
+
+@pytest.mark.parametrize("name", ["simple", "rng"])
+def test_estimator_steps_with_host_noise_sources_match_reference(golden_dir, name):
+    """Unmodified reference FiniteDifferences.step driven by SimpleNoiseSource / RNGNoiseSource (fp64 noise,
+    delayed and too-old returns): the restatement follows it to fp64 rounding."""
+    g = _load(golden_dir, "fd_steps_hostnoise.npz")
+    P = g[name + "_theta0"].shape[0]
+    src = (O.SimpleNoiseSourceOracle if name == "simple" else O.RNGNoiseSourceOracle)(P, int(g["seed"]))
+    fd = O.FiniteDifferencesOracle(g[name + "_theta0"], src, float(g["sigma"]), float(g["lr"]),
+                                   max_delayed_return=int(g["H"]), omega=float(g["omega"]))
+    for s in range(int(g["n_steps"])):
+        keys = [src.sample()[0] for _ in range(int(g["N"]))]
+        if name == "rng":
+            assert keys == [str(k) for k in g["rng_s%d_keys" % s]], s
+        batch = [O.Ret(int(e), k, float(r)) for e, k, r in
+                 zip(g["%s_s%d_epochs" % (name, s)], keys, g["%s_s%d_rewards" % (name, s)])]
+        upd = fd.step(batch, 0.05 * s)
+        ref_g = g["%s_s%d_grad" % (name, s)]
+        assert np.max(np.abs(fd.gradient_memory - ref_g)) <= 1e-12 * np.max(np.abs(ref_g)), s
+        assert np.array_equal(fd.theta, g["%s_s%d_theta" % (name, s)]), s
+        assert abs(upd - float(g["%s_s%d_update" % (name, s)])) <= 1e-7 * abs(upd)
+        assert fd.discarded_returns == int(g["%s_s%d_discarded" % (name, s)])
+
+
 def test_closed_form_matches_stepwise(golden_dir):
     g = _load(golden_dir, "fd_steps.npz")
     noise = O.NoiseTableOracle(int(g["table_size"]), 6092, int(g["table_seed"]))
