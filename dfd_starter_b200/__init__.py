@@ -7,7 +7,9 @@ from .dsgd import DSGD
 from .noise_sources import SharedNoiseTable, RNGNoiseSource, SimpleNoiseSource
 from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
+from .grpc_worker import GRPCWorker, RPCServer, RPCClient
+from . import wire
 from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
-__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent",
+__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent", "GRPCWorker", "RPCServer", "RPCClient", "wire",
            "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

@@ -18,7 +18,7 @@ SYMBOLS = [
     "dfd_fd_prepare", "dfd_fd_reduce_scratch_bytes", "dfd_fd_reduce", "dfd_dsgd_step", "dfd_dsgd_scratch_bytes", "dfd_synthetic_reward",
     "dfd_fd_prepare_partial", "dfd_xchg_mailbox_bytes", "dfd_xchg_mailbox_create", "dfd_xchg_mailbox_open",
     "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
-    "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused",
+    "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused", "dfd_wire_count_returns", "dfd_wire_decode_returns",
 ]
 
 
@@ -34,6 +34,12 @@ class DfdPolicyDesc(C.Structure):
 
 class DfdFdRows(C.Structure):
     _fields_ = [("row_ptr", C.c_void_p), ("row_coef", C.c_void_p), ("max_rows", C.c_int)]
+
+
+class DfdReturnSoa(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("epoch", "idx", "sign", "reward", "novelty", "entropy", "timesteps", "is_eval",
+                                          "key_off", "key_len", "states_off", "states_len", "shape_off", "shape_len",
+                                          "stats_off", "stats_len")]
 
 
 class DfdError(RuntimeError):
@@ -91,6 +97,8 @@ def load():
     proto("dfd_fd_step_fused_scratch_bytes", sz, [vp, i64, i32, i32])
     proto("dfd_fd_step_fused", i32, [vp, P(DfdTable), i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, f64, f64, vp, vp, i64,
                                      i32, i32, vp, vp, i32, i32, vp, sz, vp])
+    proto("dfd_wire_count_returns", i64, [C.c_char_p, sz])
+    proto("dfd_wire_decode_returns", i64, [C.c_char_p, sz, i32, i64, P(DfdReturnSoa)])
     _lib = L
     return L
 

@@ -209,6 +209,44 @@ int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, co
                       int n_hist_valid, int hist_write_row, float* update_size_out, void* const* mailboxes, int rank,
                       int world, void* scratch, size_t scratch_bytes, dfd_stream stream);
 
+/* ---- return ingestion from the RPC loop (host only) -------------------------------
+ * Replaces the per-return object path networking/server.py:151-162 (SubmitReturn / SubmitReturns ->
+ * FDReturn.deserialize_from_grpc, learner/fd_return.py:41-56) feeding learner/finite_differences.py:94-114:
+ * the serialized proto3 `Return` / `ReturnArray` bytes
+ * (networking/rpc_misc/proto/client_server_interface.proto:30-47) are decoded straight into the
+ * structure-of-arrays batch the device learner uploads.  All pointers are HOST pointers owned by the caller; no
+ * CUDA call is made.  `encoded_noise` keys that are a decimal table index (optionally '+' / '-' prefixed, the
+ * antithetic extension) are parsed into idx / sign; any other key leaves idx = -1, sign = 0 and is found at
+ * buf[key_off .. key_off + key_len).  eval_states / eval_states_shape / obs_stats_update are returned as the byte
+ * range of their packed payload inside buf (little-endian fp32 / varints), length 0 when absent.
+ * dfd_wire_count_returns: number of `rets` in a ReturnArray.  dfd_wire_decode_returns: number of returns decoded
+ * (is_array = 0: buf is ONE Return).  Negative results: DFD_WIRE_MALFORMED, or DFD_WIRE_UNSUPPORTED for the legal
+ * but unpacked / split repeated-field encodings no proto3 writer of the reference produces (the caller then takes
+ * its general decoder). */
+#define DFD_WIRE_MALFORMED (-1)
+#define DFD_WIRE_UNSUPPORTED (-2)
+typedef struct dfd_return_soa {
+    int64_t* epoch;
+    int64_t* idx;
+    int8_t* sign;
+    double* reward;
+    float* novelty;
+    float* entropy;
+    int32_t* timesteps;
+    uint8_t* is_eval;
+    int64_t* key_off;
+    int32_t* key_len;
+    int64_t* states_off;
+    int32_t* states_len;
+    int64_t* shape_off;
+    int32_t* shape_len;
+    int64_t* stats_off;
+    int32_t* stats_len;
+} dfd_return_soa;
+int64_t dfd_wire_count_returns(const uint8_t* host_buf, size_t len);
+int64_t dfd_wire_decode_returns(const uint8_t* host_buf, size_t len, int is_array, int64_t max_returns,
+                                const dfd_return_soa* out);
+
 /* ---- synthetic return (bench / tests only) ------------------------------- */
 /* Stand-in for the environment, which is outside this path (worker/agent.py is
  * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */

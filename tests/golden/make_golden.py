@@ -431,6 +431,93 @@ def gen_fd_steps_hostnoise():
     np.savez_compressed(os.path.join(HERE, "fd_steps_hostnoise.npz"), **rec)
 
 
+
+def gen_wire():
+    """Bytes written by the reference's own message classes (learner/fd_return.py:25-39, networking/client.py:39-44,
+    networking/server.py:128-142) and the outcome of its `ServerInterface.get_returns_batch` (server.py:64-95) on a
+    scripted arrival sequence."""
+    from networking.rpc_misc import client_server_interface_pb2 as pb
+    from networking.server import ServerInterface
+    from learner import FDState
+    rng = np.random.RandomState(3)
+    rets = []
+    for j in range(40):
+        r = FDReturn()
+        r.epoch = int(rng.randint(-1, 9))
+        kind = j % 5
+        r.encoded_noise = ["%d" % rng.randint(0, 10 ** 7), "+%d" % rng.randint(0, 10 ** 7), "-%d" % rng.randint(0, 10 ** 7),
+                           "%d,%d" % (rng.randint(1, 2 ** 62), rng.randint(1, 2 ** 62)), "0"][kind]
+        r.reward = float(rng.randn() * 100)
+        r.novelty = float(rng.rand()) if j % 3 else 0
+        r.entropy = float(rng.randn()) if j % 4 else 0.0
+        r.timesteps = int(rng.randint(0, 1000))
+        r.is_eval = kind == 4
+        if r.is_eval:
+            r.eval_states = rng.randn(int(rng.randint(1, 4)), 3, 2).astype(np.float32) if j % 10 == 4 else []
+        if j % 6 == 0:
+            r.obs_stats_update = rng.randn(7).astype(np.float32).tolist()
+        rets.append(r)
+    rets[7].reward = -0.0
+    rets[8].epoch = 0
+    rets[8].timesteps = 0
+    rec = {"n": len(rets)}
+    msgs = [r.serialize_to_grpc() for r in rets]
+    arr = pb.ReturnArray(rets=msgs)
+    rec["array_bytes"] = np.frombuffer(arr.SerializeToString(), dtype=np.uint8)
+    for j, m in enumerate(msgs):
+        rec["ret%d_bytes" % j] = np.frombuffer(m.SerializeToString(), dtype=np.uint8)
+    back = []
+    for m in pb.ReturnArray.FromString(arr.SerializeToString()).rets:    # what the reference server reads back
+        r = FDReturn()
+        r.deserialize_from_grpc(m)
+        back.append(r)
+    rec["epoch"] = np.array([r.epoch for r in back])
+    rec["key"] = np.array([r.encoded_noise for r in back])
+    rec["reward"] = np.array([r.reward for r in back], dtype=np.float64)
+    rec["novelty"] = np.array([r.novelty for r in back], dtype=np.float64)
+    rec["entropy"] = np.array([r.entropy for r in back], dtype=np.float64)
+    rec["timesteps"] = np.array([r.timesteps for r in back])
+    rec["is_eval"] = np.array([r.is_eval for r in back])
+    for j, r in enumerate(back):
+        rec["ret%d_states" % j] = np.asarray(r.eval_states, dtype=np.float32)
+        rec["ret%d_stats" % j] = np.asarray(list(r.obs_stats_update), dtype=np.float32)
+    # an unpacked encoding of the repeated fields (legal proto3 input; exercises the general decoder)
+    # ServerState as the servicer builds it
+    st = FDState()
+    st.strategy_frames = rng.randn(3, 2).astype(np.float32)
+    st.strategy_history = rng.randn(2, 3, 4).astype(np.float32)
+    st.policy_params = rng.randn(50).astype(np.float32).tolist()
+    st.epoch = 17
+    st.experiment_id = "exp-a1"
+    st.obs_stats = rng.randn(5).astype(np.float32).tolist()
+    st.cfg = {"env_id": "Walker2d-v2", "noise_std": 0.02, "normalize_obs": True, "random_seed": 124, "eval_prob": 0.05}
+    si = ServerInterface(st)
+    ss = si.server_state
+    msg = pb.ServerState(strategy_frames=ss.strategy_frames, strategy_frames_shape=ss.strategy_frames_shape,
+                         strategy_history=ss.strategy_history, strategy_history_shape=ss.strategy_history_shape,
+                         policy_parameters=ss.policy_params, epoch=ss.epoch, experiment_id=ss.experiment_id,
+                         obs_stats=ss.obs_stats)
+    rec["state_bytes"] = np.frombuffer(msg.SerializeToString(), dtype=np.uint8)
+    rec["state_frames"] = st.strategy_frames
+    rec["state_history"] = st.strategy_history
+    rec["state_params"] = np.asarray(st.policy_params, dtype=np.float32)
+    rec["state_obs_stats"] = np.asarray(st.obs_stats, dtype=np.float32)
+    si.grpc_cfg.params["random_seed"] += 1
+    rec["config_bytes"] = np.frombuffer(si.grpc_cfg.SerializeToString(deterministic=True), dtype=np.uint8)
+    # get_returns_batch scenarios: arrivals in order 0..39 (ids = position), then three pulls
+    for r in back:
+        si.submit_return(r)
+    ids = {id(r): j for j, r in enumerate(back)}
+    pulls = [(5, 8, 3), (6, 8, None), (4, None, None)]
+    for q, (bs, cur, mdr) in enumerate(pulls):
+        got, ts, n_del, n_disc = si.get_returns_batch(batch_size=bs, current_epoch=cur, max_delayed_return=mdr)
+        rec["pull%d_ids" % q] = np.array([ids[id(r)] for r in got])
+        rec["pull%d_stats" % q] = np.array([ts, n_del, n_disc])
+    rec["pulls"] = np.array([[bs, -99 if cur is None else cur, -99 if mdr is None else mdr] for bs, cur, mdr in pulls])
+    rec["left"] = len(si.waiting_returns)
+    np.savez_compressed(os.path.join(HERE, "wire.npz"), **rec)
+
+
 def main():
     with open(os.path.join(HERE, "noise.json"), "w") as f:
         json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
@@ -441,6 +528,7 @@ def main():
     gen_impala()
     gen_fd_steps()
     gen_fd_steps_hostnoise()
+    gen_wire()
     print("golden fixtures written to", HERE)
 
 

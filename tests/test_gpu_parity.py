@@ -424,6 +424,47 @@ def test_worker_with_host_noise_sources(D, name):
         np.testing.assert_allclose(seen["out"][j], ref, rtol=0, atol=1e-5)
 
 
+# ---------------------------------------------------------------- N2 ingestion from the RPC loop
+def test_ingested_wire_batch_steps_like_the_oracle(D, table1m):
+    """SubmitReturns bytes -> C decoder -> ServerInterface (LIFO, staleness) -> ReturnBatch.non_eval() -> learner.step:
+    the arrays reach the device learner without per-return objects, and the step equals the oracle's on the same
+    returns (rewards are fp32 on the wire, as in the reference: proto:33)."""
+    from dfd_starter_b200.grpc_worker import ServerInterface
+    P, sigma = 6092, 0.02
+    theta = np.random.RandomState(2).randn(P).astype(np.float32) * 0.1
+    fd = make_learner(D, table1m, theta, sigma, H=3)
+    on = O.NoiseTableOracle(1_000_000, P, 123)
+    of = O.FiniteDifferencesOracle(theta, on, sigma, 0.01, max_delayed_return=3, omega=0.3)
+    rng = np.random.RandomState(4)
+    st = D.FDState()
+    st.policy_params, st.epoch, st.experiment_id, st.obs_stats, st.cfg = [], 0, "x", [], {}
+    st.strategy_frames, st.strategy_history = np.zeros((1, 1), np.float32), np.zeros((1, 1), np.float32)
+    si = ServerInterface(st)
+    for step in range(5):
+        rets = []
+        for j in range(40):
+            r = D.FDReturn()
+            r.epoch = fd.epoch - int(rng.randint(0, 6)) if step >= 2 else fd.epoch
+            r.is_eval = j % 9 == 0
+            r.encoded_noise = "0" if r.is_eval else "%d" % rng.randint(0, 1_000_000 - P)
+            r.reward, r.timesteps = float(rng.randn() * 5), 10
+            rets.append(r)
+        si.submit_batch(D.wire.decode_returns(D.wire.encode_return_array(rets[:25])))
+        si.submit_batch(D.wire.decode_returns(D.wire.encode_return_array(rets[25:])))
+        got, ts, n_del, n_disc = si.get_returns_batch(batch_size=18, current_epoch=fd.epoch, max_delayed_return=3, timeout=5)
+        ne = got.non_eval()
+        assert ne.soa is not None and len(ne) == 18 and ts >= 180
+        ref_batch = [O.Ret(int(e), "%d" % i, float(r)) for e, i, r in zip(ne.epoch, ne.idx, ne.reward)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step(ne, 0.1, 0.0, 0.0)
+            upd_o = of.step(ref_batch, 0.1)
+        assert rel_max(fd.gradient_memory, of.gradient_memory) <= 1e-5, step
+        assert abs(upd - upd_o) <= 1e-5 * upd_o
+        assert np.max(np.abs(fd.policy.get_trainable_flat() - of.theta)) <= 2e-6
+        assert fd.discarded_returns == of.discarded_returns           # (epochs before 0 pass the queue, not the learner)
+        si.waiting_returns = []
+
+
 # ---------------------------------------------------------------- a9 Atari CNN
 def test_atari_forward_golden(D, golden_dir):
     """policies/atari.py:35-51 against the reference's own outputs (synthetic seeded theta / BN stats)."""
