@@ -9,7 +9,8 @@ from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
 from .grpc_worker import GRPCWorker, RPCServer, RPCClient
 from . import wire
+from .strategy import StrategyHandler, SparseHistoryManager, StrategyPoint, strategy_distances
 from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
-__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent", "GRPCWorker", "RPCServer", "RPCClient", "wire",
+__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent", "GRPCWorker", "RPCServer", "RPCClient", "wire", "StrategyHandler", "SparseHistoryManager", "StrategyPoint", "strategy_distances",
            "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

@@ -108,10 +108,14 @@ class Worker(object):
             m_sign = np.where(flags, 0, 1).astype(np.int8)
             is_eval = flags.copy()                                           # worker.py:34: eval key is "0"
         res = self.agent.collect_returns(self.policy, m_idx, m_sign, self.sigma)
+        novelty = None
+        if self.strategy_handler is not None and hasattr(self.strategy_handler, "compute_novelty_members"):
+            # worker.py:53: the novelty of every member's (perturbed) policy, here in one batched evaluation
+            novelty = self.strategy_handler.compute_novelty_members(m_idx, m_sign, self.sigma)
         # records are built lazily (ReturnBatch): the learner consumes the arrays, any other caller
         # still sees a sequence of FDReturn objects
         return ReturnBatch(self.epoch, m_idx, m_sign, res["reward"], res["entropy"], res["timesteps"], is_eval,
-                           states=res.get("states"))
+                           states=res.get("states"), novelty=novelty)
 
     def update(self, state):
         """worker.py:40-43: load the learner's snapshot (flattened state_dict incl. BN buffers)."""

@@ -247,6 +247,29 @@ int64_t dfd_wire_count_returns(const uint8_t* host_buf, size_t len);
 int64_t dfd_wire_decode_returns(const uint8_t* host_buf, size_t len, int is_array, int64_t max_returns,
                                 const dfd_return_soa* out);
 
+/* ---- strategy distances / novelty of many members --------------------------------
+ * A strategy is a policy head evaluated on the zeta frames: [n_frames, width] floats (`get_strategy`,
+ * policies/mujoco.py:29-30, discrete.py:31-32; produced here by dfd_policy_forward with the zeta frames as
+ * observations).  dist(a_i, b_j) follows utils/math_helpers.py:166-222 (the per-frame term in fp32, in the
+ * reference's operation order; the mean over frames in fp64):
+ *   DFD_DIST_L2                         l2_dist                                    :166-170
+ *   DFD_DIST_CATEGORICAL_TVD            categorical_tvd                            :218-221
+ *   DFD_DIST_GAUSSIAN_WASSERSTEIN       gaussian_wasserstein_dist_from_strategies  :200-216 (mean | std halves)
+ *   DFD_DIST_CATEGORICAL_BHATTACHARYYA  categorical_bhattacharrya_dist             :194-197
+ *   DFD_DIST_GAUSSIAN_BHATTACHARYYA     gaussian_bhattacharrya_dist                :173-191 (as written there)
+ * a: [n_a, n_frames, width], b: [n_b, n_frames, width] (device).  dists (nullable): [n_a, n_b] doubles.
+ * row_min (nullable): [n_a] doubles = min_j dist(a_i, b_j), i.e. `compute_strategy_novelty` (:147-155,
+ * strategy/strategy_handler.py:25-30) of every member against the history in one launch; +inf when n_b == 0.
+ * exclude_diagonal != 0 leaves j == i out of row_min (nearest OTHER point when a and b are the same set:
+ * strategy/sparse_history_manager.py:48-70, 111-149). */
+#define DFD_DIST_L2 0
+#define DFD_DIST_CATEGORICAL_TVD 1
+#define DFD_DIST_GAUSSIAN_WASSERSTEIN 2
+#define DFD_DIST_CATEGORICAL_BHATTACHARYYA 3
+#define DFD_DIST_GAUSSIAN_BHATTACHARYYA 4
+int dfd_strategy_distances(dfd_ctx* ctx, const float* a, int n_a, const float* b, int n_b, int n_frames, int width,
+                           int kind, double* dists, double* row_min, int exclude_diagonal, dfd_stream stream);
+
 /* ---- synthetic return (bench / tests only) ------------------------------- */
 /* Stand-in for the environment, which is outside this path (worker/agent.py is
  * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */

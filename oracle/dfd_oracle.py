@@ -566,3 +566,112 @@ def fd_partial_gradient(table, idx, sign, rewards, all_rewards, sigma, n_params,
         lam = (table[idx[i]:idx[i] + n_params] * sig32 * np.float32(sign[i])).astype(np.float64)
         g += w[i] * lam / np.dot(lam, lam)
     return g
+
+
+# --------------------------------------------------------------------------
+# Strategy distances / novelty / history
+# --------------------------------------------------------------------------
+def strategy_distance(name, a, b):
+    """utils/math_helpers.py:166-222 restated (numpy, the input dtype's arithmetic): a (Z, W) or (n, Z, W) against
+    b (m, Z, W) with numpy broadcasting; returns one distance per leading entry."""
+    a, b = np.asarray(a), np.asarray(b)
+    if name == "l2_dist":                                               # :166-170
+        return np.linalg.norm(b - a, axis=-1).mean(axis=-1)
+    if name == "categorical_tvd":                                       # :218-221
+        return np.abs(np.subtract(a, b)).sum(axis=-1).mean(axis=-1)
+    if name == "categorical_bhattacharrya_dist":                        # :194-197
+        return (-np.log(np.sum(np.sqrt(a * b), axis=-1) + 1e-12)).mean(axis=-1)
+    n = a.shape[-1] // 2
+    m1, s1, m2, s2 = a[..., :n], a[..., n:], b[..., :n], b[..., n:]
+    if name == "gaussian_wasserstein_dist_from_strategies":             # :200-216
+        inside = s1 + s2 - 2 * np.sqrt(s1 * s2)
+        return (np.square(np.linalg.norm(m1 - m2, axis=-1)) + inside.sum(axis=-1)).mean(axis=-1)
+    if name == "gaussian_bhattacharrya_dist":                           # :173-191 (as written: no log on the "log term")
+        s3 = (s1 + s2) / 2
+        d = m1 - m2
+        return ((d * d / s3).sum(axis=-1) / 8 + (s3.prod(axis=-1) / np.sqrt(s1.prod(axis=-1) * s2.prod(axis=-1))) / 4).mean(axis=-1)
+    raise ValueError(name)
+
+
+def strategy_novelty(name, strategy, others):
+    """compute_strategy_novelty (math_helpers.py:147-155): distance to the nearest history strategy."""
+    return float(np.min(strategy_distance(name, strategy, others)))
+
+
+class StrategyHistoryOracle(object):
+    """StrategyHandler + SparseHistoryManager + StrategyPoint restated (strategy/strategy_handler.py:6-30,
+    sparse_history_manager.py:6-149, strategy_point.py:6-39).  `evaluate(flat, zeta)` is the policy's `get_strategy`
+    with the given parameter vector (one of the forward restatements above)."""
+
+    def __init__(self, evaluate, distance_name, max_history_size=200):
+        self.evaluate, self.name, self.max = evaluate, distance_name, max_history_size
+        self.flats, self.strategies = [], []
+        self.closest, self.second = [], []
+        self.strategy_tensor = np.zeros(0)
+        self.zeta = None
+        self.known = {}
+        self.worst_point_idx = 0
+
+    def add_policy(self, flat):
+        flat = np.array(flat, dtype=np.float32)
+        if len(self.flats) >= self.max and self.zeta is not None and len(self.zeta) > 0:   # manager :25-26
+            return self._replace(flat)
+        self.flats.append(flat)
+        self.strategies.append(None)
+        return None
+
+    def set_zeta(self, zeta):
+        if zeta is None or len(zeta) == 0:                               # handler :17-19
+            return
+        self.zeta = zeta
+        self.strategies = [self.evaluate(f, zeta) for f in self.flats]   # manager :40-44
+        n = len(self.flats)
+        self.known = {(i, j): float(strategy_distance(self.name, self.strategies[i], self.strategies[j]))
+                      for i in range(n) for j in range(i + 1, n)}       # :51-66
+        self._update()
+        self.strategy_tensor = np.asarray(self.strategies)
+
+    def compute_novelty(self, flat):
+        if self.zeta is None or len(self.zeta) == 0 or self.strategy_tensor is None or len(self.strategy_tensor) < 2:
+            return 0                                                     # handler :26-27
+        return strategy_novelty(self.name, self.evaluate(np.asarray(flat, np.float32), self.zeta), self.strategy_tensor)
+
+    def _replace(self, flat):                                            # manager :72-109
+        strategy = self.evaluate(flat, self.zeta)
+        dists = strategy_distance(self.name, strategy, self.strategy_tensor)
+        novelty = float(np.min(dists))
+        idx = self.worst_point_idx
+        current_worst = self.closest[idx][1]
+        if novelty > current_worst or current_worst == np.inf:
+            self.flats[idx] = flat
+            self.strategies[idx] = strategy
+            self.strategy_tensor[idx] = strategy
+            for pair in self.known:
+                if idx in pair:
+                    self.known[pair] = float(dists[pair[1 - pair.index(idx)]])
+            self._update()
+            return idx
+        return -1
+
+    def _update(self):                                                   # manager :111-149, strategy_point.py:27-39
+        n = len(self.flats)
+        self.closest = [[None, np.inf] for _ in range(n)]
+        self.second = [[None, np.inf] for _ in range(n)]
+        for i in range(n):
+            for key, val in self.known.items():
+                if i in key:
+                    if val < self.closest[i][1]:
+                        self.second[i] = self.closest[i][:]
+                        self.closest[i] = [key, val]
+                    elif val < self.second[i][1] and key != self.closest[i][0]:
+                        self.second[i] = [key, val]
+        worst = np.inf
+        for i in range(n):
+            c = self.closest[i]
+            if c[1] < worst:
+                if c[0] is None:
+                    self.worst_point_idx = i
+                    continue
+                j = c[0][1 - c[0].index(i)]
+                worst = c[1]
+                self.worst_point_idx = i if self.second[i][1] < self.second[j][1] else j

@@ -518,6 +518,65 @@ def gen_wire():
     np.savez_compressed(os.path.join(HERE, "wire.npz"), **rec)
 
 
+
+def gen_strategy():
+    """The reference's StrategyHandler / SparseHistoryManager (strategy/*.py) driven through a scripted sequence with a
+    small history (so replacements happen), for the two driver configurations (init_helper.py:12-30): MuJoCo MLP with
+    the Gaussian Wasserstein distance and the discrete MLP with the categorical TVD; plus every distance function of
+    utils/math_helpers.py:166-222 on random strategies."""
+    from strategy import StrategyHandler
+    from utils import math_helpers
+    rec = {}
+    for name in ("mujoco", "discrete"):
+        torch.manual_seed(124)
+        if name == "mujoco":
+            pol = MujocoPolicy(17, 6, seed=124)
+            fn = math_helpers.gaussian_wasserstein_dist_from_strategies
+            zeta = np.random.RandomState(5).randn(7, 17).astype(np.float32)
+        else:
+            pol = DiscretePolicy(2, 9, seed=124)
+            fn = math_helpers.categorical_tvd
+            zeta = np.random.RandomState(5).rand(7, 2).astype(np.float32)
+            rec["discrete_serialized"] = np.asarray(pol.serialize(), dtype=np.float32)
+        P = pol.num_params
+        rng = np.random.RandomState(6)
+        handler = StrategyHandler(pol, fn, max_history_size=4)
+        rec[name + "_theta0"] = pol.get_trainable_flat().copy()
+        rec[name + "_zeta"] = zeta
+        n_events = 12
+        for t in range(n_events):
+            flat = (pol.get_trainable_flat() + (0.02 if t % 3 else 0.2) * rng.randn(P)).astype(np.float32)
+            pol.set_trainable_flat(flat)
+            rec["%s_e%d_flat" % (name, t)] = flat
+            n_before = len(handler.strategy_history_manager.strategy_points)
+            res = handler.strategy_history_manager.submit_policy(pol)
+            rec["%s_e%d_submit" % (name, t)] = -2 if res is None else int(res)
+            if t in (1, 3, 6, 9):
+                handler.set_zeta(zeta)
+            rec["%s_e%d_tensor" % (name, t)] = np.asarray(handler.strategy_tensor, dtype=np.float32).copy()
+            rec["%s_e%d_worst" % (name, t)] = handler.strategy_history_manager.worst_point_idx
+            probe = (flat + 0.05 * rng.randn(P)).astype(np.float32)
+            keep = pol.get_trainable_flat().copy()
+            pol.set_trainable_flat(probe)
+            rec["%s_e%d_probe" % (name, t)] = probe
+            rec["%s_e%d_novelty" % (name, t)] = float(handler.compute_novelty(pol))
+            pol.set_trainable_flat(keep)
+        rec[name + "_n_events"] = n_events
+    rng = np.random.RandomState(9)
+    cat_a = rng.dirichlet(np.ones(9), size=(11,)).astype(np.float32)
+    cat_b = rng.dirichlet(np.ones(9), size=(5, 11)).astype(np.float32)
+    ga = np.concatenate([rng.randn(11, 6), 0.1 + rng.rand(11, 6)], -1).astype(np.float32)
+    gb = np.concatenate([rng.randn(5, 11, 6), 0.1 + rng.rand(5, 11, 6)], -1).astype(np.float32)
+    rec.update(cat_a=cat_a, cat_b=cat_b, gauss_a=ga, gauss_b=gb)
+    rec["d_l2_dist"] = math_helpers.l2_dist(ga, gb)
+    rec["d_categorical_tvd"] = math_helpers.categorical_tvd(cat_a, cat_b)
+    rec["d_gaussian_wasserstein_dist_from_strategies"] = math_helpers.gaussian_wasserstein_dist_from_strategies(ga, gb)
+    rec["d_categorical_bhattacharrya_dist"] = math_helpers.categorical_bhattacharrya_dist(cat_a, cat_b)
+    rec["d_gaussian_bhattacharrya_dist"] = math_helpers.gaussian_bhattacharrya_dist(ga[None], gb)
+    rec["novelty_tvd"] = math_helpers.compute_strategy_novelty(cat_a, cat_b, distance_fn=math_helpers.categorical_tvd)
+    np.savez_compressed(os.path.join(HERE, "strategy.npz"), **rec)
+
+
 def main():
     with open(os.path.join(HERE, "noise.json"), "w") as f:
         json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
@@ -529,6 +588,7 @@ def main():
     gen_fd_steps()
     gen_fd_steps_hostnoise()
     gen_wire()
+    gen_strategy()
     print("golden fixtures written to", HERE)
 
 

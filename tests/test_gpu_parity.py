@@ -420,8 +420,8 @@ def test_worker_with_host_noise_sources(D, name):
             key, eps = ref_src.sample()
             assert (r.encoded_noise is not None) and (np.array_equal(r.encoded_noise, key) if name == "simple" else r.encoded_noise == key)
             vec = (flat + 0.02 * eps).astype(np.float32)
-        ref = O.mujoco_forward(lay, vec, seen["obs"][j])
-        np.testing.assert_allclose(seen["out"][j], ref, rtol=0, atol=1e-5)
+        mean, std = O.mujoco_forward(lay, vec, seen["obs"][j])
+        np.testing.assert_allclose(seen["out"][j], np.concatenate([mean, std], -1), rtol=0, atol=1e-5)
 
 
 # ---------------------------------------------------------------- N2 ingestion from the RPC loop
@@ -463,6 +463,95 @@ def test_ingested_wire_batch_steps_like_the_oracle(D, table1m):
         assert np.max(np.abs(fd.policy.get_trainable_flat() - of.theta)) <= 2e-6
         assert fd.discarded_returns == of.discarded_returns           # (epochs before 0 pass the queue, not the learner)
         si.waiting_returns = []
+
+
+# ---------------------------------------------------------------- N3 strategy distances / novelty / history
+STRATEGY_DISTANCES = ["l2_dist", "categorical_tvd", "gaussian_wasserstein_dist_from_strategies",
+                      "categorical_bhattacharrya_dist", "gaussian_bhattacharrya_dist"]
+
+
+@pytest.mark.parametrize("name", STRATEGY_DISTANCES)
+def test_strategy_distance_kernel_golden(D, golden_dir, name):
+    """dfd_strategy_distances against utils/math_helpers.py:166-222 run by the reference (fp32 there; rel 1e-5)."""
+    from dfd_starter_b200.strategy import DISTANCES
+    from dfd_starter_b200.device import get_context
+    g = np.load(os.path.join(golden_dir, "strategy.npz"))
+    a, b = (g["cat_a"], g["cat_b"]) if name.startswith("categorical") else (g["gauss_a"], g["gauss_b"])
+    ctx = get_context(0)
+    dists, rmin = D.strategy_distances(ctx, torch.from_numpy(a[None]).cuda(), torch.from_numpy(b).cuda(), DISTANCES[name])
+    np.testing.assert_allclose(dists.cpu().numpy()[0], g["d_" + name], rtol=1e-5, atol=1e-7)
+    assert abs(float(rmin[0]) - float(np.min(g["d_" + name]))) <= 1e-5 * abs(float(np.min(g["d_" + name])))
+    # a table of many rows, odd sizes, rows too large for the shared-memory staging: against the oracle
+    rng = np.random.RandomState(3)
+    for Z, W, na, nb in ((1, 2, 3, 1), (37, 12, 19, 23), (700, 18, 4, 9)):
+        if name.startswith("categorical"):
+            A, B = rng.dirichlet(np.ones(W), size=(na, Z)).astype(np.float32), rng.dirichlet(np.ones(W), size=(nb, Z)).astype(np.float32)
+        else:
+            A = np.concatenate([rng.randn(na, Z, W // 2), 0.1 + rng.rand(na, Z, W // 2)], -1).astype(np.float32)
+            B = np.concatenate([rng.randn(nb, Z, W // 2), 0.1 + rng.rand(nb, Z, W // 2)], -1).astype(np.float32)
+        dists, rmin = D.strategy_distances(ctx, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), DISTANCES[name])
+        ref = np.stack([O.strategy_distance(name, A[i].astype(np.float64)[None] if name == "gaussian_bhattacharrya_dist"
+                                            else A[i].astype(np.float64), B.astype(np.float64)) for i in range(na)])
+        np.testing.assert_allclose(dists.cpu().numpy(), ref, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(rmin.cpu().numpy(), ref.min(axis=1), rtol=2e-5, atol=1e-6)
+    same = torch.from_numpy(B).cuda()
+    d2, m2 = D.strategy_distances(ctx, same, same, DISTANCES[name], exclude_diagonal=True)
+    d2 = d2.cpu().numpy()
+    np.fill_diagonal(d2, np.inf)
+    np.testing.assert_allclose(m2.cpu().numpy(), d2.min(axis=1), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("name", ["mujoco", "discrete"])
+def test_strategy_history_golden(D, golden_dir, name):
+    """The reference StrategyHandler replayed (12 submissions, 4-entry history, both driver configurations): same
+    replacement decisions and next-to-replace point, strategy tensor atol 1e-5, novelty rel 1e-5; then the novelty of a
+    batch of perturbed members equals the one-policy-at-a-time value."""
+    g = np.load(os.path.join(golden_dir, "strategy.npz"))
+    table = D.SharedNoiseTable(1_000_000, 6092 if name == "mujoco" else 5197, 123, device=0)
+    if name == "mujoco":
+        pol = D.MujocoPolicy(17, 6, seed=124, device=0).bind_table(table)
+        dist = "gaussian_wasserstein_dist_from_strategies"
+    else:
+        pol = D.DiscretePolicy(2, 9, seed=124, device=0).bind_table(table)
+        pol.deserialize(g["discrete_serialized"])
+        dist = "categorical_tvd"
+    h = D.StrategyHandler(pol, dist, max_history_size=4)
+    zeta = g[name + "_zeta"]
+
+    class Holder(object):
+        def get_trainable_flat(self):
+            return self.flat
+    holder = Holder()
+    for t in range(int(g[name + "_n_events"])):
+        holder.flat = g["%s_e%d_flat" % (name, t)]
+        res = h.strategy_history_manager.submit_policy(holder)
+        assert (-2 if res is None else res) == int(g["%s_e%d_submit" % (name, t)]), t
+        if t in (1, 3, 6, 9):
+            h.set_zeta(zeta)
+        want = g["%s_e%d_tensor" % (name, t)]
+        assert np.asarray(h.strategy_tensor).shape == want.shape, t
+        if want.size:
+            np.testing.assert_allclose(h.strategy_tensor, want, rtol=0, atol=1e-5)
+        assert h.strategy_history_manager.worst_point_idx == int(g["%s_e%d_worst" % (name, t)]), t
+        holder.flat = g["%s_e%d_probe" % (name, t)]
+        nov = h.compute_novelty(holder)
+        assert abs(nov - float(g["%s_e%d_novelty" % (name, t)])) <= 1e-5 * max(1.0, abs(nov)), t
+    # batched members: theta + sign * sigma * table[idx], all at once, against one policy at a time
+    pol.set_trainable_flat(g["%s_e%d_flat" % (name, 11)])
+    theta = pol.get_trainable_flat()
+    rng = np.random.RandomState(1)
+    idx = rng.randint(0, 1_000_000 - pol.num_params, size=13).astype(np.int64)
+    sign = rng.choice([-1, 0, 1], size=13).astype(np.int8)
+    nov = h.compute_novelty_members(idx, sign, 0.05)
+    for m in range(13):
+        holder.flat = theta if sign[m] == 0 else O.perturb(theta, 0.05, table._table[idx[m]:idx[m] + pol.num_params], int(sign[m]))
+        one = h.compute_novelty(holder)
+        assert abs(nov[m] - one) <= 1e-6 * max(1.0, abs(one)), m
+    # ... and the batched Worker ships it with every return (worker/worker.py:53)
+    agent = D.SyntheticAgent(pol, obs_per_member=2, seed=0)
+    w = D.Worker(pol, agent, table, h, sigma=0.05, eval_prob=0.0, random_seed=1)
+    rets = w.evaluate(np.zeros(13, dtype=bool), idx)
+    np.testing.assert_allclose([r.novelty for r in rets], h.compute_novelty_members(idx, np.ones(13, np.int8), 0.05), rtol=0, atol=0)
 
 
 # ---------------------------------------------------------------- a9 Atari CNN

@@ -204,3 +204,50 @@ def test_dsgd_sanity():
     g = rng.randn(6092).astype(np.float32)
     new = O.dsgd_step(th, g, 0.01, O.dsgd_lr_scale(0.0, 0.0, 1.0))
     assert abs(np.linalg.norm(th - new) - 0.1795179) < 2e-5
+
+
+# ---------------------------------------------------------------- N3 strategy distances / novelty / history
+STRATEGY_DISTANCES = ["l2_dist", "categorical_tvd", "gaussian_wasserstein_dist_from_strategies",
+                      "categorical_bhattacharrya_dist", "gaussian_bhattacharrya_dist"]
+
+
+@pytest.mark.parametrize("name", STRATEGY_DISTANCES)
+def test_strategy_distance_functions_match_reference(golden_dir, name):
+    g = _load(golden_dir, "strategy.npz")
+    a, b = (g["cat_a"], g["cat_b"]) if name.startswith("categorical") else (g["gauss_a"], g["gauss_b"])
+    if name == "gaussian_bhattacharrya_dist":        # the reference sums with einsum there: last-ulp fp32 differences
+        np.testing.assert_allclose(O.strategy_distance(name, a[None], b), g["d_" + name], rtol=1e-6, atol=0)
+    else:
+        np.testing.assert_array_equal(O.strategy_distance(name, a, b), g["d_" + name])
+    if name == "categorical_tvd":
+        assert O.strategy_novelty(name, a, b) == float(g["novelty_tvd"])
+
+
+@pytest.mark.parametrize("name", ["mujoco", "discrete"])
+def test_strategy_history_follows_reference(golden_dir, name):
+    """The reference StrategyHandler through 12 submissions with a 4-entry history: same replacement decisions, same
+    next point to replace, same strategy tensor, same novelties."""
+    g = _load(golden_dir, "strategy.npz")
+    if name == "mujoco":
+        lay = O.mujoco_layout(17, 6)
+        ev = lambda flat, zeta: np.concatenate(O.mujoco_forward(lay, flat, zeta), -1)          # noqa: E731
+        dist = "gaussian_wasserstein_dist_from_strategies"
+    else:
+        lay = O.discrete_layout(2, 9)
+        _, buffers = lay.split_state(g["discrete_serialized"])
+        ev = lambda flat, zeta: O.discrete_forward(lay, flat, buffers, zeta)                  # noqa: E731
+        dist = "categorical_tvd"
+    h = O.StrategyHistoryOracle(ev, dist, max_history_size=4)
+    zeta = g[name + "_zeta"]
+    for t in range(int(g[name + "_n_events"])):
+        res = h.add_policy(g["%s_e%d_flat" % (name, t)])
+        assert (-2 if res is None else res) == int(g["%s_e%d_submit" % (name, t)]), t
+        if t in (1, 3, 6, 9):
+            h.set_zeta(zeta)
+        want = g["%s_e%d_tensor" % (name, t)]
+        assert np.asarray(h.strategy_tensor).shape == want.shape, t
+        if want.size:
+            np.testing.assert_allclose(h.strategy_tensor, want, rtol=0, atol=2e-6)
+        assert h.worst_point_idx == int(g["%s_e%d_worst" % (name, t)]), t
+        nov = h.compute_novelty(g["%s_e%d_probe" % (name, t)])
+        assert abs(nov - float(g["%s_e%d_novelty" % (name, t)])) <= 1e-5 * max(1.0, abs(nov)), t
