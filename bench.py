@@ -577,11 +577,13 @@ def b200_main(args, w):
     # ---------------- e2e through the reference-facing objects, host buffers ---------------------------
     e2e = None
     if not args.no_e2e:
+        TRACE = [] if os.environ.get("DFD_E2E_TRACE") else None
+
         class HostObsAgent(object):
             """obs from pinned host memory every call; returns come back to the host.  `prefetch`: the observations are
-            double-buffered - step k+1's host->device copy is issued on a copy stream right after step k's forward has
-            been launched, so it overlaps step k's return read-back and learner step (an input pipeline; every step's
-            copy still happens inside the timed region).  Without it the copy sits in front of the forward."""
+            double-buffered - step k+1's host->device copy is queued on a copy stream behind step k's, so it overlaps step
+            k's forward, return read-back and learner step (an input pipeline; every step's copy still happens inside the
+            timed region and the copy engine is the bound).  Without it the copy sits in front of the forward."""
             saved_states = []
             prefetch = True
 
@@ -590,26 +592,44 @@ def b200_main(args, w):
                 self.bufs = [torch.empty_like(obs_d[0]) for _ in range(2)]
                 self.ready = [torch.cuda.Event(), torch.cuda.Event()]
                 self.staged = [None, None]            # which step's observations each buffer holds
+                # member indices / signs go up through a pinned buffer read by a kernel (dfd_host_stage): a pageable
+                # cudaMemcpyAsync would block the host behind the observation upload in flight on the copy engine
+                self.small_host = torch.empty(M * 9 + 16, dtype=torch.uint8).pin_memory()
+                self.small_dev = torch.empty(M * 9 + 16, dtype=torch.uint8, device=dev)
+                self.reward_host = torch.empty(M, dtype=torch.float64).pin_memory()
+                sh = self.small_host.numpy()
+                self.idx_np, self.sign_np = sh[:M * 8].view(np.int64), sh[M * 8:M * 9].view(np.int8)
+                self.i_d = self.small_dev[:M * 8].view(torch.int64)
+                self.s_d = self.small_dev[M * 8:M * 9].view(torch.int8)
+                self.reward_np = self.reward_host.numpy()
 
             def stage(self, k):
                 b = k % 2
                 if self.staged[b] == k:
                     return
                 with torch.cuda.stream(self.copy_stream):
+                    if TRACE is not None:
+                        e = torch.cuda.Event(enable_timing=True); e.record(self.copy_stream); TRACE.append(("copy_start", k, e))
                     self.bufs[b].copy_(obs_host[(k % CYC) % n_obs_buf], non_blocking=True)
                     self.ready[b].record(self.copy_stream)
+                    if TRACE is not None:
+                        e = torch.cuda.Event(enable_timing=True); e.record(self.copy_stream); TRACE.append(("copy_end", k, e))
                 self.staged[b] = k
 
             def collect_returns(self, pol, m_idx, m_sign, sigma):
                 k = self.k
                 if self.prefetch:
                     self.stage(k)
+                    self.stage(k + 1)             # queued right behind step k's copy: its buffer was last read by step
+                    #                               k-1's forward, which finished before step k-1's returns were read
                     torch.cuda.current_stream(dev).wait_event(self.ready[k % 2])
                     o = self.bufs[k % 2]
                 else:
                     o = obs_host[(k % CYC) % n_obs_buf].to(dev, non_blocking=True)
-                i_d = torch.from_numpy(m_idx).to(dev, non_blocking=True)
-                s_d = torch.from_numpy(m_sign).to(dev, non_blocking=True)
+                self.idx_np[:] = m_idx
+                self.sign_np[:] = m_sign
+                ctx.host_stage(self.small_host, self.small_dev)
+                i_d, s_d = self.i_d, self.s_d
                 if is_impala:
                     _lib.check(lib.dfd_impala_forward(ctx.handle, C.byref(pol.desc), table.device_table.ref(), ptr(pol.theta),
                                                       ptr(pol.buffers), ptr(i_d), ptr(s_d), M, sigma, ptr(o), ptr(zero_r),
@@ -619,9 +639,18 @@ def b200_main(args, w):
                     pol.forward_members(i_d, s_d, o, sigma, out=out_d)
                 _lib.check(lib.dfd_synthetic_reward(ctx.handle, ptr(out_d), M, E, w["out_width"], ptr(target),
                                                     ptr(reward_d), ctx.stream))
-                if self.prefetch:
-                    self.stage(k + 1)             # its buffer was last read by step k-1's forward, long finished
-                rew = reward_d.cpu().numpy()
+                # the returns come back through SM writes into pinned memory (dfd_host_stage): a device-to-host
+                # cudaMemcpyAsync completed only after the observation upload in flight (measured)
+                if TRACE is not None:
+                    e = torch.cuda.Event(enable_timing=True); e.record(); TRACE.append(("fwd_reward_end", k, e))
+                ctx.host_stage(reward_d, self.reward_host)
+                if TRACE is not None:
+                    e = torch.cuda.Event(enable_timing=True); e.record(); TRACE.append(("reward_staged", k, e))
+                    TRACE.append(("host_launched_all", k, time.perf_counter()))
+                torch.cuda.current_stream(dev).synchronize()
+                if TRACE is not None:
+                    TRACE.append(("host_has_rewards", k, time.perf_counter()))
+                rew = self.reward_np.copy()
                 return {"reward": rew, "entropy": np.zeros(M), "timesteps": np.full(M, E), "states": None}
         agent = HostObsAgent()
         worker = D.Worker(policy, agent, table, None, sigma=SIGMA, eval_prob=0.0, random_seed=TABLE_SEED)
@@ -630,6 +659,9 @@ def b200_main(args, w):
 
         def e2e_step(k):
             agent.k = k
+            if TRACE is not None:
+                TRACE.append(("host_step_start", k, time.perf_counter()))
+                e = torch.cuda.Event(enable_timing=True); e.record(); TRACE.append(("step_start", k, e))
             worker.epoch = learner.epoch
             flags = np.zeros(R, dtype=bool)
             idx = idx_sets[k % CYC]
@@ -664,8 +696,28 @@ def b200_main(args, w):
                 dt = float(t.item())
             return dt
         n_e2e = max(3, min(args.steps, 30))
+        # a pinned page reaches full DMA speed only after the device has read it a few times (first reads of fresh pinned
+        # memory ran at 34-47 GB/s on this box, 54.8 GB/s from the third pass on: scripts/h2d_probe.py); a long-running
+        # worker reuses its staging buffers, so the staging buffers are read through before the timed loops
+        for _ in range(4):
+            for b in range(n_obs_buf):
+                agent.bufs[0].copy_(obs_host[b], non_blocking=True)
+        torch.cuda.synchronize()
         dt_serial = e2e_run(n_done, False)
+        if TRACE is not None:
+            del TRACE[:]
         dt = e2e_run(n_done + 3 + n_e2e, True)
+        if TRACE is not None and rank == 0:
+            torch.cuda.synchronize()
+            base_e = next(t for t in TRACE if t[0] == "step_start")
+            base_h = next(t for t in TRACE if t[0] == "host_step_start")
+            k_lo = base_e[1] + 8
+            for name, k, v in TRACE:
+                if k_lo <= k < k_lo + 4:
+                    if isinstance(v, float):
+                        sys.stderr.write("trace host   %-18s k=%d %9.1f us\n" % (name, k, (v - base_h[2]) * 1e6))
+                    else:
+                        sys.stderr.write("trace device %-18s k=%d %9.1f us\n" % (name, k, base_e[2].elapsed_time(v) * 1e3))
         h2d = obs_host[0].numel() * 4 + M * 8 + M + M * (8 + 8 + 4 + 1)
         d2h = M * 8 + 4 + P * 4
         e2e = {"value": M * E * world * n_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),

@@ -261,3 +261,68 @@ extern "C" int dfd_perturb_members(dfd_ctx* ctx, const dfd_table* table, const f
     DFD_LAUNCHED(ctx);
     return 0;
 }
+
+// ---------------------------------------------------------------------------
+// small host -> device staging that does not use the copy engine
+// ---------------------------------------------------------------------------
+// The learner's per-step batch (rewards | indices | history rows | signs, ~21 bytes per return) is tens of KB.  As a
+// cudaMemcpyAsync it queues on the host-to-device copy engine BEHIND whatever large upload is in flight there (the
+// next step's observations, 18 MB = 0.33 ms over PCIe 5 x16), which put that whole transfer on the learner step's
+// critical path.  Here the SMs read the pinned buffer directly through its device alias (unified addressing) and
+// write the device copy: a few PCIe read round trips, independent of the copy engine's queue.  The same holds for the
+// small results going back (rewards, update size, theta of a short parameter vector): measured on B200, a 16 KB
+// device-to-host cudaMemcpyAsync issued while an 18 MB host-to-device copy was in flight completed only after it; here
+// the SMs write the pinned destination directly (posted PCIe writes).
+__global__ void __launch_bounds__(256) host_stage_kernel(const int4* __restrict__ src, int4* __restrict__ dst, int64_t n16,
+                                                         const unsigned char* __restrict__ src_tail,
+                                                         unsigned char* __restrict__ dst_tail, int n_tail) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        int4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(src + i));
+        dst[i] = v;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+// device-visible address of a device pointer or of PINNED host memory (its alias under unified addressing)
+static int dfd_device_view(const void* p, void** out) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dfd_set_error("dfd_host_stage: cudaPointerGetAttributes: %s", cudaGetErrorString(e));
+        return 2;
+    }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+        *out = const_cast<void*>(p);
+        return 0;
+    }
+    if (a.type == cudaMemoryTypeHost && a.devicePointer) {
+        *out = a.devicePointer;
+        return 0;
+    }
+    dfd_set_error("dfd_host_stage: %p is neither device memory nor pinned (page-locked) host memory", p);
+    return 1;
+}
+
+extern "C" int dfd_host_stage(dfd_ctx* ctx, const void* src, void* dst, size_t bytes, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && src && dst, "dfd_host_stage: NULL argument");
+    DFD_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "dfd_host_stage: buffers must be 16-byte aligned");
+    if (bytes == 0) return 0;
+    void *s = nullptr, *d = nullptr;
+    int rc = dfd_device_view(src, &s);
+    if (rc) return rc;
+    rc = dfd_device_view(dst, &d);
+    if (rc) return rc;
+    const int64_t n16 = (int64_t)(bytes / 16);
+    const int n_tail = (int)(bytes % 16);
+    int grid = (int)((n16 + 255) / 256);
+    grid = grid < 1 ? 1 : (grid > 2 * ctx->sm_count ? 2 * ctx->sm_count : grid);
+    host_stage_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4*)s, (int4*)d, n16,
+                                                              (const unsigned char*)s + n16 * 16,
+                                                              (unsigned char*)d + n16 * 16, n_tail);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}

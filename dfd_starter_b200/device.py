@@ -31,6 +31,16 @@ class Context(object):
     def launch_count(self):
         return int(self.lib.dfd_ctx_launch_count(self.handle))
 
+    def host_stage(self, src, dst):
+        """Small transfer between a PINNED host tensor and a device tensor (either direction) with `dfd_host_stage`: a
+        kernel accessing the pinned buffer through its device alias.  Stream-ordered like `dst.copy_(src,
+        non_blocking=True)`, but it neither queues on a DMA copy engine behind a large upload nor blocks the host."""
+        nbytes = src.numel() * src.element_size()
+        assert dst.numel() * dst.element_size() == nbytes and (src.is_cuda or src.is_pinned()) and (dst.is_cuda or dst.is_pinned())
+        _lib.check(self.lib.dfd_host_stage(self.handle, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), nbytes,
+                                           self.stream), "dfd_host_stage")
+        return dst
+
     def zeros_bytes(self, nbytes):
         """Zero-filled, 256-byte aligned scratch (the library's counters self-reset)."""
         return torch.zeros(max(int(nbytes), 256) + 256, dtype=torch.uint8, device=self.device)

@@ -30,22 +30,30 @@ from .noise_sources import parse_key
 class _Staging(object):
     """Pinned host + device staging for one batch: rewards f64 | idx i64 | hist_row i32 | sign i8."""
 
-    def __init__(self, device, cap):
+    def __init__(self, device, cap, ctx=None):
         self.cap = cap
+        self.ctx = ctx
         nbytes = cap * (8 + 8 + 4 + 1)
         self.host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         self.dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
         o = 0
         self.views = {}
-        for name, dt, sz in (("reward", torch.float64, 8), ("idx", torch.int64, 8), ("hist_row", torch.int32, 4),
-                             ("sign", torch.int8, 1)):
-            self.views[name] = (self.host[o:o + cap * sz].view(dt), self.dev[o:o + cap * sz].view(dt))
+        host_np = self.host.numpy()                 # numpy views of the pinned buffer: filling them costs ~1 us per array
+        for name, dt, ndt, sz in (("reward", torch.float64, np.float64, 8), ("idx", torch.int64, np.int64, 8),
+                                  ("hist_row", torch.int32, np.int32, 4), ("sign", torch.int8, np.int8, 1)):
+            self.views[name] = (host_np[o:o + cap * sz].view(ndt), self.dev[o:o + cap * sz].view(dt))
             o += cap * sz
 
     def upload(self, n, **arrays):
         for k, a in arrays.items():
-            self.views[k][0][:n].copy_(torch.from_numpy(np.ascontiguousarray(a)))
-        self.dev.copy_(self.host, non_blocking=True)
+            self.views[k][0][:n] = a
+        if self.ctx is not None:
+            # read by the SMs through the pinned buffer's device alias: does not queue on the host-to-device copy engine
+            # behind a large upload (the next step's observations) - include/dfd_b200.h, dfd_host_stage
+            _lib.check(self.ctx.lib.dfd_host_stage(self.ctx.handle, self.host.data_ptr(), self.dev.data_ptr(),
+                                                   self.host.numel(), self.ctx.stream), "dfd_host_stage")
+        else:
+            self.dev.copy_(self.host, non_blocking=True)
         return {k: v[1] for k, v in self.views.items()}
 
 
@@ -100,8 +108,8 @@ class FiniteDifferences(object):
         self._dist_epoch = {}                                    # epoch -> dist row (delayed epochs only)
         self.epoch = 0
         self.discarded_returns = 0
-        self._update_size = torch.zeros(1, dtype=torch.float32, device=dev)
-        self._update_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._update_size = torch.zeros(4, dtype=torch.float32, device=dev)   # [0] is written by the kernels (16-byte unit)
+        self._update_host16 = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._theta_host = torch.zeros(P, dtype=torch.float32).pin_memory()
         self._stage = None
         self._rows_cap = 0
@@ -114,7 +122,7 @@ class FiniteDifferences(object):
             return
         cap = max(n, 16)
         dev = self.ctx.device
-        self._stage = _Staging(dev, cap)
+        self._stage = _Staging(dev, cap, self.ctx)
         self._rows_cap = cap + self.H
         self._row_ptr = torch.zeros(self._rows_cap, dtype=torch.int64, device=dev)
         self._row_coef = torch.zeros(self._rows_cap, dtype=torch.float32, device=dev)
@@ -374,11 +382,16 @@ class FiniteDifferences(object):
                 self.gradient_optimizer.steps += 1
             if not sync:
                 return self._advance_epoch(write_row, None)
-            self._update_host.copy_(self._update_size, non_blocking=True)
+            # small read-backs go through dfd_host_stage (SM writes into pinned memory), not the DMA engine, so they do
+            # not wait behind a large upload in flight; long parameter vectors keep the copy engine
+            self.ctx.host_stage(self._update_size, self._update_host16)
             if self._host_policy and self.sync_policy:
-                self._theta_host.copy_(self.theta, non_blocking=True)
+                if self.P * 4 <= (1 << 20) and self.theta.data_ptr() % 16 == 0:
+                    self.ctx.host_stage(self.theta, self._theta_host)
+                else:
+                    self._theta_host.copy_(self.theta, non_blocking=True)
             torch.cuda.current_stream(self.ctx.device).synchronize()
-            update_size = float(self._update_host[0])
+            update_size = float(self._update_host16[0])
             if self._host_policy and self.sync_policy:
                 self.policy.set_trainable_flat(self._theta_host.numpy())
         else:

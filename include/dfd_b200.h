@@ -209,6 +209,16 @@ int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, co
                       int n_hist_valid, int hist_write_row, float* update_size_out, void* const* mailboxes, int rank,
                       int world, void* scratch, size_t scratch_bytes, dfd_stream stream);
 
+/* ---- small host <-> device staging without the copy engine ------------------------------------------------
+ * The per-step small transfers of this path - the batch arrays going up (the FDReturn fields the estimator reads,
+ * learner/finite_differences.py:94-114) and the results coming back (rewards, `update_size`, theta for
+ * `get_trainable_flat`, finite_differences.py:54-59) - are moved by a kernel that accesses the PINNED host buffer
+ * through its device alias, so they neither queue on a DMA copy engine behind a large observation upload nor block
+ * the host.  src / dst: each either device memory or page-locked host memory (cudaHostAlloc / torch pin_memory),
+ * both 16-byte aligned.  Stream-ordered like cudaMemcpyAsync: the host may touch a pinned source again / read a
+ * pinned destination once the stream has passed this call. */
+int dfd_host_stage(dfd_ctx* ctx, const void* src, void* dst, size_t bytes, dfd_stream stream);
+
 /* ---- return ingestion from the RPC loop (host only) -------------------------------
  * Replaces the per-return object path networking/server.py:151-162 (SubmitReturn / SubmitReturns ->
  * FDReturn.deserialize_from_grpc, learner/fd_return.py:41-56) feeding learner/finite_differences.py:94-114:
