@@ -574,6 +574,37 @@ def b200_main(args, w):
                 "fd_reduce": {"achieved": kernels["fd_reduce"]["achieved_GBps"], "frac": kernels["fd_reduce"]["achieved_GBps"] / hbm_peak,
                               "us": us_reduce, "algorithmic_bytes": red_bytes}}
 
+    # ---------------- the reduction at a size where HBM, not launch latency, is the bound ----------------------
+    # The default workload's reduction streams 25 MB (3.8 us of HBM time): it is latency bound.  The same kernel entry
+    # point on the per-GPU reduction of BASELINE config 3 (1024 table rows x 171 042 parameters, 700 MB per launch, row
+    # sets rotated so a launch never finds its rows in L2) shows what it does when bandwidth is the limit.
+    if rank == 0 and not args.profile_mode and args.table_size > 171042 + 1024:
+        try:
+            Pb, Rb, NSET = 171042, 1024, 6
+            dt_ = table.device_table
+            rng_b = np.random.RandomState(1)
+            gb = torch.empty(Pb, device=dev)
+            sb = ctx.zeros_bytes(lib.dfd_fd_reduce_scratch_bytes(ctx.handle, Pb, Rb))
+            big_sets = []
+            for c in range(NSET):
+                ix = rng_b.randint(0, args.table_size - Pb, size=Rb).astype(np.int64)
+                rp = torch.from_numpy(dt_.replicas.data_ptr() + 4 * ((ix & 3) * dt_.stride + (ix - (ix & 3)))).to(dev)
+                rc = torch.from_numpy(rng_b.randn(Rb).astype(np.float32)).to(dev)
+                big_sets.append((rp, rc, _lib.DfdFdRows(rp.data_ptr(), rc.data_ptr(), Rb)))
+
+            def k_reduce_big(r):
+                _lib.check(lib.dfd_fd_reduce(ctx.handle, C.byref(big_sets[r % NSET][2]), Rb, Pb, ptr(gb), aligned_ptr(sb),
+                                             sb.numel() - 256, ctx.stream))
+            us_big = min(time_calls(k_reduce_big, 4 * NSET) for _ in range(3))
+            big_bytes = Rb * Pb * 4 + Pb * 4
+            roofline["fd_reduce_at_scale"] = {
+                "workload": "C3 per-GPU reduction: 1024 table rows x 171042 parameters (8192 pairs over 8 GPUs)",
+                "algorithmic_bytes": big_bytes, "us": us_big, "achieved": big_bytes / us_big * 1e-3,
+                "frac": big_bytes / us_big * 1e-3 / hbm_peak, "unit": "GB/s"}
+            del big_sets, gb, sb
+        except Exception as e:      # reported, never fatal for the headline
+            roofline["fd_reduce_at_scale"] = {"error": str(e)}
+
     # ---------------- e2e through the reference-facing objects, host buffers ---------------------------
     e2e = None
     if not args.no_e2e:

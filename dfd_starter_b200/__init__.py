@@ -9,8 +9,9 @@ from .finite_differences import FiniteDifferences
 from .worker import Worker, SyntheticAgent
 from .grpc_worker import GRPCWorker, RPCServer, RPCClient
 from . import wire
+from .obs_stats import WelfordRunningStat, normalize_obs, member_obs_stats
 from .strategy import StrategyHandler, SparseHistoryManager, StrategyPoint, strategy_distances
 from .policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy, Policy
 
-__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent", "GRPCWorker", "RPCServer", "RPCClient", "wire", "StrategyHandler", "SparseHistoryManager", "StrategyPoint", "strategy_distances",
+__all__ = ["FDReturn", "ReturnBatch", "FDState", "DSGD", "SharedNoiseTable", "RNGNoiseSource", "SimpleNoiseSource", "FiniteDifferences", "Worker", "SyntheticAgent", "GRPCWorker", "RPCServer", "RPCClient", "wire", "WelfordRunningStat", "normalize_obs", "member_obs_stats", "StrategyHandler", "SparseHistoryManager", "StrategyPoint", "strategy_distances",
            "MujocoPolicy", "DiscretePolicy", "AtariPolicy", "ImpalaPolicy", "Policy"]

@@ -19,7 +19,7 @@ SYMBOLS = [
     "dfd_fd_prepare_partial", "dfd_xchg_mailbox_bytes", "dfd_xchg_mailbox_create", "dfd_xchg_mailbox_open",
     "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
     "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused", "dfd_wire_count_returns", "dfd_wire_decode_returns",
-    "dfd_strategy_distances", "dfd_host_stage",
+    "dfd_strategy_distances", "dfd_host_stage", "dfd_normalize_obs", "dfd_member_obs_stats",
 ]
 
 
@@ -99,6 +99,8 @@ def load():
     proto("dfd_fd_step_fused", i32, [vp, P(DfdTable), i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, f64, f64, vp, vp, i64,
                                      i32, i32, vp, vp, i32, i32, vp, sz, vp])
     proto("dfd_strategy_distances", i32, [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp])
+    proto("dfd_normalize_obs", i32, [vp, vp, i64, i32, vp, vp, f32, vp, vp])
+    proto("dfd_member_obs_stats", i32, [vp, vp, vp, i32, i32, i32, vp, vp])
     proto("dfd_host_stage", i32, [vp, vp, vp, sz, vp])
     proto("dfd_wire_count_returns", i64, [C.c_char_p, sz])
     proto("dfd_wire_decode_returns", i64, [C.c_char_p, sz, i32, i64, P(DfdReturnSoa)])

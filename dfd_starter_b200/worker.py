@@ -30,6 +30,8 @@ class Worker(object):
         self.epoch = -1
         self.rng = np.random.RandomState(random_seed)
         self.eval_prob = eval_prob
+        from .obs_stats import WelfordRunningStat
+        self.fixed_obs_stats = WelfordRunningStat(policy.input_shape)      # worker.py:17
         if hasattr(policy, "bind_table"):
             policy.bind_table(noise_source)
 
@@ -107,6 +109,9 @@ class Worker(object):
             m_idx = idx.copy()
             m_sign = np.where(flags, 0, 1).astype(np.int8)
             is_eval = flags.copy()                                           # worker.py:34: eval key is "0"
+        if getattr(self.agent, "normalize_obs", False):
+            # worker.py:47-48: the rollout normalises with the learner-wide statistics of the last FDState
+            self.agent.obs_mean, self.agent.obs_std = self.fixed_obs_stats.mean, self.fixed_obs_stats.std
         res = self.agent.collect_returns(self.policy, m_idx, m_sign, self.sigma)
         novelty = None
         if self.strategy_handler is not None and hasattr(self.strategy_handler, "compute_novelty_members"):
@@ -115,12 +120,14 @@ class Worker(object):
         # records are built lazily (ReturnBatch): the learner consumes the arrays, any other caller
         # still sees a sequence of FDReturn objects
         return ReturnBatch(self.epoch, m_idx, m_sign, res["reward"], res["entropy"], res["timesteps"], is_eval,
-                           states=res.get("states"), novelty=novelty)
+                           states=res.get("states"), novelty=novelty, obs_stats_updates=res.get("obs_stats_updates"))
 
     def update(self, state):
         """worker.py:40-43: load the learner's snapshot (flattened state_dict incl. BN buffers)."""
         self.policy.deserialize(state.policy_params)
         self.epoch = state.epoch
+        if state.obs_stats is not None and len(state.obs_stats):
+            self.fixed_obs_stats.deserialize(np.asarray(state.obs_stats))
 
 
 class _RowPolicyView(object):
@@ -144,8 +151,16 @@ class SyntheticAgent(object):
     the device; `host_obs=True` re-uploads them from pinned host memory each call
     (the end-to-end path)."""
 
-    def __init__(self, policy, obs_per_member, seed=0, shared_obs=True, host_obs=False, members_hint=1):
+    def __init__(self, policy, obs_per_member, seed=0, shared_obs=True, host_obs=False, members_hint=1,
+                 normalize_obs=False, obs_stats_update_chance=0.01):
         self.E = int(obs_per_member)
+        # worker/agent.py:26-41: observations are normalised with the learner-wide statistics (set by the Worker before
+        # every evaluation) and every member folds the observations it draws (probability obs_stats_update_chance, from
+        # the agent's own RandomState stream) into its own statistics, which travel as FDReturn.obs_stats_update
+        self.normalize_obs = bool(normalize_obs)
+        self.obs_stats_update_chance = obs_stats_update_chance
+        self.obs_mean, self.obs_std = None, None
+        self.rng = np.random.RandomState(seed)
         g = torch.Generator().manual_seed(seed)
         shape = policy._obs_shape()
         self.shape = shape
@@ -172,7 +187,15 @@ class SyntheticAgent(object):
         M = len(idx)
         idx_d = torch.from_numpy(np.ascontiguousarray(idx)).to(dev)
         sign_d = torch.from_numpy(np.ascontiguousarray(sign)).to(dev)
-        out = policy.forward_members(idx_d, sign_d, self._obs(policy, M), sigma)
+        obs = self._obs(policy, M)
+        stats = None
+        if self.normalize_obs:
+            from .obs_stats import normalize_obs, member_obs_stats
+            select = torch.from_numpy(self.rng.uniform(0, 1, size=(M, self.E)) < self.obs_stats_update_chance)
+            stats = member_obs_stats(policy.ctx, obs, select)                    # raw observations (agent.py:38-39)
+            if self.obs_mean is not None:
+                obs = normalize_obs(policy.ctx, obs, self.obs_mean, self.obs_std)    # agent.py:40-41
+        out = policy.forward_members(idx_d, sign_d, obs, sigma)
         err = (out - self.target_dev) ** 2
         reward = -err.mean(dim=(1, 2))
         if policy.kind == "mujoco":
@@ -181,4 +204,5 @@ class SyntheticAgent(object):
         else:
             ent = -(out * torch.log(out.clamp_min(1e-30))).sum(-1).mean(-1)
         return {"reward": reward.double().cpu().numpy(), "entropy": ent.double().cpu().numpy(),
-                "timesteps": np.full(M, self.E), "states": None}
+                "timesteps": np.full(M, self.E), "states": None,
+                "obs_stats_updates": None if stats is None else [r.tolist() for r in stats.cpu().numpy()]}

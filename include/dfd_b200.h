@@ -209,6 +209,21 @@ int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, co
                       int n_hist_valid, int hist_write_row, float* update_size_out, void* const* mailboxes, int rank,
                       int world, void* scratch, size_t scratch_bytes, dfd_stream stream);
 
+/* ---- observation normalisation and per-member observation statistics -----------------
+ * dfd_normalize_obs: out = clip((obs - mean) / std, -clip, clip), worker/agent.py:40-41 applied to a whole batch of
+ * observations [n_rows, width] (in place allowed); mean / std: [width] device floats (the learner-wide
+ * WelfordRunningStat.mean / .std, utils/math_helpers.py:46-66).  fp32, IEEE subtract and divide: bit-identical to
+ * numpy on fp32 inputs.
+ * dfd_member_obs_stats: the statistics every member's agent accumulates over its own observations
+ * (agent.py:38-39 -> WelfordRunningStat.update, math_helpers.py:29-39): obs [n_members, obs_per_member, width],
+ * select [n_members, obs_per_member] (non-zero = this observation was drawn for the update), out
+ * [n_members, 2*width + 1] = running_mean | running_variance | count, the layout of `serialize()` (:89-90) that
+ * travels as FDReturn.obs_stats_update.  Sequential fp32 in the reference's order: bit-identical. */
+int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows, int width, const float* mean, const float* stdv,
+                      float clip, float* out, dfd_stream stream);
+int dfd_member_obs_stats(dfd_ctx* ctx, const float* obs, const uint8_t* select, int n_members, int obs_per_member,
+                         int width, float* out, dfd_stream stream);
+
 /* ---- small host <-> device staging without the copy engine ------------------------------------------------
  * The per-step small transfers of this path - the batch arrays going up (the FDReturn fields the estimator reads,
  * learner/finite_differences.py:94-114) and the results coming back (rewards, `update_size`, theta for

@@ -577,6 +577,42 @@ def gen_strategy():
     np.savez_compressed(os.path.join(HERE, "strategy.npz"), **rec)
 
 
+
+def gen_obs_stats():
+    """WelfordRunningStat (utils/math_helpers.py:7-105) and the rollout loop's normalisation (worker/agent.py:37-41) run by
+    the reference on fp32 observations: per-member sequential updates, the learner-wide merge, mean / std, and the
+    normalised observations."""
+    from utils.math_helpers import WelfordRunningStat
+    rng = np.random.RandomState(11)
+    M, E, K = 6, 23, 17
+    obs = (rng.randn(M, E, K) * np.linspace(0.1, 30, K) + np.linspace(-5, 5, K)).astype(np.float32)
+    obs[:, :, 3] = 2.5                                    # a constant feature: variance 0 -> std 1 (math_helpers.py:62)
+    select = rng.uniform(0, 1, size=(M, E)) < 0.4
+    select[1, :] = False                                  # a member that drew nothing: count 0, merge skipped
+    select[2, :] = False
+    select[2, 5] = True                                   # a single sample: count 1
+    rows = []
+    for m in range(M):
+        st = WelfordRunningStat(K)
+        for e in range(E):
+            if select[m, e]:
+                st.increment(obs[m, e], 1)
+        rows.append(st.serialize())
+    glob = WelfordRunningStat(K)
+    snaps = []
+    for r in rows:
+        glob.increment_from_obs_stats_update(r)
+        snaps.append(np.asarray(glob.serialize(), dtype=np.float64))
+    mean, std = np.asarray(glob.mean), np.asarray(glob.std)
+    normed = np.clip(np.subtract(obs, mean) / std, -10, 10)
+    assert normed.dtype == np.float32
+    back = WelfordRunningStat(K)
+    back.deserialize(glob.serialize())
+    np.savez_compressed(os.path.join(HERE, "obs_stats.npz"), obs=obs, select=select, rows=np.asarray(rows, dtype=np.float64),
+                        merged=np.asarray(snaps), mean=mean, std=std, normed=normed,
+                        back_mean=np.asarray(back.mean, dtype=np.float64), back_std=np.asarray(back.std, dtype=np.float64))
+
+
 def main():
     with open(os.path.join(HERE, "noise.json"), "w") as f:
         json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
@@ -589,6 +625,7 @@ def main():
     gen_fd_steps_hostnoise()
     gen_wire()
     gen_strategy()
+    gen_obs_stats()
     print("golden fixtures written to", HERE)
 
 

@@ -554,6 +554,65 @@ def test_strategy_history_golden(D, golden_dir, name):
     np.testing.assert_allclose([r.novelty for r in rets], h.compute_novelty_members(idx, np.ones(13, np.int8), 0.05), rtol=0, atol=0)
 
 
+# ---------------------------------------------------------------- N4 observation normalisation / statistics
+def test_obs_normalisation_and_member_stats_bit_exact(D, golden_dir):
+    """worker/agent.py:37-41 + WelfordRunningStat.update run by the reference on fp32 observations: the batched kernels
+    give the same BITS (normalised observations; every member's mean | variance | count row)."""
+    from dfd_starter_b200.device import get_context
+    g = np.load(os.path.join(golden_dir, "obs_stats.npz"))
+    ctx = get_context(0)
+    obs = torch.from_numpy(g["obs"]).cuda()
+    rows = D.member_obs_stats(ctx, obs, torch.from_numpy(g["select"])).cpu().numpy()
+    assert np.array_equal(rows.astype(np.float64), g["rows"])
+    normed = D.normalize_obs(ctx, obs, g["mean"], g["std"]).cpu().numpy()
+    assert np.array_equal(normed, g["normed"])
+    # clipping at +-10 and in-place use
+    big = torch.from_numpy((g["obs"] * 1000).astype(np.float32)).cuda()
+    want = np.clip(np.subtract(g["obs"] * np.float32(1000), g["mean"]) / g["std"], -10, 10)
+    D.normalize_obs(ctx, big, g["mean"], g["std"], out=big)
+    assert np.array_equal(big.cpu().numpy(), want) and float(big.abs().max()) == 10.0
+    # the learner-wide merge of the device rows equals the reference's merged statistics
+    glob = D.WelfordRunningStat(17)
+    for m, r in enumerate(rows):
+        glob.increment_from_obs_stats_update(r.tolist())
+        assert np.array_equal(np.asarray(glob.serialize(), dtype=np.float64), g["merged"][m]), m
+
+
+def test_worker_normalises_observations_and_ships_member_statistics(D, table1m):
+    """Worker.update loads FDState.obs_stats (worker.py:43); the batched agent normalises with them, and every return
+    carries its member's obs_stats_update (worker.py:56)."""
+    torch.manual_seed(124)
+    pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+    agent = D.SyntheticAgent(pol, obs_per_member=8, seed=0, shared_obs=False, members_hint=12, normalize_obs=True,
+                             obs_stats_update_chance=0.5)
+    w = D.Worker(pol, agent, table1m, None, sigma=0.02, eval_prob=0.0, random_seed=1)
+    glob = D.WelfordRunningStat(17)
+    rng = np.random.RandomState(0)
+    for _ in range(40):
+        glob.increment((rng.randn(17) * 3 + 1).astype(np.float32), 1)
+    st = D.FDState()
+    st.policy_params, st.epoch, st.obs_stats = pol.serialize(), 5, glob.serialize()
+    w.update(st)
+    assert w.epoch == 5 and np.array_equal(w.fixed_obs_stats.std, glob.std)
+    idx = np.arange(12, dtype=np.int64) * 1000
+    rets = w.evaluate(np.zeros(12, dtype=bool), idx)
+    sel = np.random.RandomState(0).uniform(0, 1, size=(12, 8)) < 0.5
+    obs = agent.obs_host.numpy()
+    lay = O.mujoco_layout(17, 6)
+    theta = pol.get_trainable_flat()
+    for m, r in enumerate(rets):
+        ref = D.WelfordRunningStat(17)
+        for e in range(8):
+            if sel[m, e]:
+                ref.increment(obs[m, e], 1)
+        assert np.array_equal(np.float32(r.obs_stats_update), np.float32(ref.serialize())), m
+        x = np.clip(np.subtract(obs[m], glob.mean) / glob.std, -10, 10)
+        th = O.perturb(theta, 0.02, table1m._table[idx[m]:idx[m] + 6092], 1)
+        mean, std = O.mujoco_forward(lay, th, x)
+        reward = -np.mean((np.concatenate([mean, std], -1) - agent.target.numpy()) ** 2)
+        assert abs(r.reward - reward) <= 1e-5, m
+
+
 # ---------------------------------------------------------------- a9 Atari CNN
 def test_atari_forward_golden(D, golden_dir):
     """policies/atari.py:35-51 against the reference's own outputs (synthetic seeded theta / BN stats)."""

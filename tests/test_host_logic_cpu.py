@@ -142,3 +142,29 @@ def test_return_batch_is_a_sequence_of_fdreturns_and_keeps_the_arrays():
     assert recs[2].reward == 1.0 and recs[2].epoch == 7 and recs[2].timesteps == 3
     one_sided = ReturnBatch(0, idx[1:3], np.ones(2, np.int8), np.zeros(2), np.zeros(2), np.ones(2), np.zeros(2, bool))
     assert [one_sided.key(j) for j in range(2)] == ["11", "22"]
+
+
+def test_welford_running_stat_follows_the_reference(golden_dir):
+    """utils/math_helpers.py:7-105 run by the reference: per-member sequential updates, learner-wide merge, mean / std
+    (constant feature -> std 1), (de)serialisation.  Bit-exact (same numpy fp32 operations)."""
+    from dfd_starter_b200.obs_stats import WelfordRunningStat
+    g = np.load(os.path.join(golden_dir, "obs_stats.npz"))
+    obs, select = g["obs"], g["select"]
+    M, E, K = obs.shape
+    glob = WelfordRunningStat(K)
+    for m in range(M):
+        st = WelfordRunningStat(K)
+        for e in range(E):
+            if select[m, e]:
+                st.increment(obs[m, e], 1)
+        assert np.array_equal(np.asarray(st.serialize(), dtype=np.float64), g["rows"][m]), m
+        glob.increment_from_obs_stats_update(st.serialize())
+        assert np.array_equal(np.asarray(glob.serialize(), dtype=np.float64), g["merged"][m]), m
+    assert np.array_equal(glob.mean, g["mean"]) and np.array_equal(glob.std, g["std"])
+    assert np.array_equal(np.clip(np.subtract(obs, glob.mean) / glob.std, -10, 10), g["normed"])
+    back = WelfordRunningStat(K)
+    back.deserialize(glob.serialize())
+    assert np.array_equal(np.asarray(back.mean, dtype=np.float64), g["back_mean"])
+    assert np.array_equal(np.asarray(back.std, dtype=np.float64), g["back_std"])
+    fresh = WelfordRunningStat(K)
+    assert np.array_equal(fresh.mean, np.zeros(K)) and np.array_equal(fresh.std, np.ones(K))     # count < 2
