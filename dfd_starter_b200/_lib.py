@@ -99,7 +99,7 @@ def load():
     proto("dfd_fd_step_fused", i32, [vp, P(DfdTable), i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, f64, f64, vp, vp, i64,
                                      i32, i32, vp, vp, i32, i32, vp, sz, vp])
     proto("dfd_strategy_distances", i32, [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp])
-    proto("dfd_normalize_obs", i32, [vp, vp, i64, i32, vp, vp, f32, vp, vp])
+    proto("dfd_normalize_obs", i32, [vp, vp, i64, i32, vp, vp, i32, f32, vp, vp])
     proto("dfd_member_obs_stats", i32, [vp, vp, vp, i32, i32, i32, vp, vp])
     proto("dfd_host_stage", i32, [vp, vp, vp, sz, vp])
     proto("dfd_wire_count_returns", i64, [C.c_char_p, sz])

@@ -23,6 +23,21 @@ __global__ void __launch_bounds__(256) normalize_obs_kernel(const float* __restr
     }
 }
 
+// The reference WORKER normalises with statistics it deserialised from the learner's FDState (worker/worker.py:43,47):
+// WelfordRunningStat.deserialize rebuilds them from a Python list, i.e. as float64 arrays, so `(obs - mean) / std` runs in
+// fp64 there and is rounded to fp32 once, when the observation enters the policy (policies/policy.py:28).
+__global__ void __launch_bounds__(256) normalize_obs_f64_kernel(const float* __restrict__ obs, int64_t n, int width,
+                                                                const double* __restrict__ mean,
+                                                                const double* __restrict__ stdv, float clip,
+                                                                float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % width);
+        double v = __ddiv_rn(__dsub_rn((double)obs[i], mean[k]), stdv[k]);
+        v = fmin(fmax(v, -(double)clip), (double)clip);
+        out[i] = (float)v;
+    }
+}
+
 // one thread per (member, feature): the member's selected observations folded in order, exactly as
 // WelfordRunningStat.update does it (math_helpers.py:29-39)
 __global__ void __launch_bounds__(128) member_obs_stats_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ select,
@@ -52,8 +67,8 @@ __global__ void __launch_bounds__(128) member_obs_stats_kernel(const float* __re
 
 }  // namespace
 
-extern "C" int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows, int width, const float* mean,
-                                 const float* stdv, float clip, float* out, dfd_stream stream) {
+extern "C" int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows, int width, const void* mean,
+                                 const void* stdv, int stats_f64, float clip, float* out, dfd_stream stream) {
     DFD_CHECK_ARG(ctx && obs && mean && stdv && out, "dfd_normalize_obs: NULL argument");
     DFD_CHECK_ARG(width > 0 && n_rows >= 0, "dfd_normalize_obs: bad shape");
     const int64_t n = n_rows * width;
@@ -61,7 +76,12 @@ extern "C" int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows,
     int64_t grid = (n + 255) / 256;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (grid > cap) grid = cap;
-    normalize_obs_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, n, width, mean, stdv, clip, out);
+    if (stats_f64)
+        normalize_obs_f64_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, n, width, (const double*)mean,
+                                                                                   (const double*)stdv, clip, out);
+    else
+        normalize_obs_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(obs, n, width, (const float*)mean,
+                                                                               (const float*)stdv, clip, out);
     DFD_LAUNCHED(ctx);
     return 0;
 }

@@ -85,17 +85,26 @@ class WelfordRunningStat(object):
 
 
 def normalize_obs(ctx, obs, mean, std, clip=10.0, out=None):
-    """obs: device fp32 [..., K]; mean / std: host or device [K] -> clip((obs - mean) / std, -clip, clip)."""
-    K = obs.shape[-1] if obs.dim() > 1 else obs.numel()
+    """obs: device fp32 [..., K]; mean / std: [K] host arrays or device tensors -> clip((obs - mean) / std, -clip, clip).
+    The arithmetic follows the statistics' dtype, as numpy's does: float32 statistics -> fp32 subtract / divide;
+    float64 statistics (what a Worker holds after `update(state)`: worker.py:43) -> fp64, rounded to fp32 once."""
+    def dev(x):
+        t = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(np.asarray(x).ravel()))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.double()
+        return t.to(ctx.device).contiguous()
     obs = obs.contiguous()
-    mean_d = torch.as_tensor(np.asarray(mean, dtype=np.float32).ravel() if not torch.is_tensor(mean) else mean).to(ctx.device)
-    std_d = torch.as_tensor(np.asarray(std, dtype=np.float32).ravel() if not torch.is_tensor(std) else std).to(ctx.device)
+    mean_d, std_d = dev(mean), dev(std)
+    f64 = mean_d.dtype == torch.float64 or std_d.dtype == torch.float64
+    if f64:
+        mean_d, std_d = mean_d.double(), std_d.double()
     K = int(mean_d.numel())
-    if obs.numel() % K:
-        raise _lib.DfdError("normalize_obs: %d observation values are not a multiple of the %d features" % (obs.numel(), K))
+    if obs.numel() % K or std_d.numel() != K:
+        raise _lib.DfdError("normalize_obs: %d observation values / %d std values do not match %d features"
+                            % (obs.numel(), std_d.numel(), K))
     out = torch.empty_like(obs) if out is None else out
-    _lib.check(ctx.lib.dfd_normalize_obs(ctx.handle, ptr(obs), obs.numel() // K, K, ptr(mean_d), ptr(std_d), float(clip),
-                                         ptr(out), ctx.stream), "dfd_normalize_obs")
+    _lib.check(ctx.lib.dfd_normalize_obs(ctx.handle, ptr(obs), obs.numel() // K, K, ptr(mean_d), ptr(std_d), 1 if f64 else 0,
+                                         float(clip), ptr(out), ctx.stream), "dfd_normalize_obs")
     return out
 
 

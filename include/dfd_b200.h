@@ -211,16 +211,19 @@ int dfd_fd_step_fused(dfd_ctx* ctx, const dfd_table* table, int64_t n_params, co
 
 /* ---- observation normalisation and per-member observation statistics -----------------
  * dfd_normalize_obs: out = clip((obs - mean) / std, -clip, clip), worker/agent.py:40-41 applied to a whole batch of
- * observations [n_rows, width] (in place allowed); mean / std: [width] device floats (the learner-wide
- * WelfordRunningStat.mean / .std, utils/math_helpers.py:46-66).  fp32, IEEE subtract and divide: bit-identical to
- * numpy on fp32 inputs.
+ * observations [n_rows, width] (in place allowed); mean / std: [width] device values (the learner-wide
+ * WelfordRunningStat.mean / .std, utils/math_helpers.py:46-66), float when stats_f64 == 0, double otherwise.
+ * stats_f64 == 0: fp32 IEEE subtract and divide, bit-identical to numpy on fp32 inputs.  stats_f64 != 0: the
+ * reference WORKER's arithmetic - its statistics were deserialised from FDState.obs_stats as float64 arrays
+ * (worker/worker.py:43, math_helpers.py:92-101), so it normalises in fp64 and rounds to fp32 once
+ * (policies/policy.py:28); bit-identical to that.
  * dfd_member_obs_stats: the statistics every member's agent accumulates over its own observations
  * (agent.py:38-39 -> WelfordRunningStat.update, math_helpers.py:29-39): obs [n_members, obs_per_member, width],
  * select [n_members, obs_per_member] (non-zero = this observation was drawn for the update), out
  * [n_members, 2*width + 1] = running_mean | running_variance | count, the layout of `serialize()` (:89-90) that
  * travels as FDReturn.obs_stats_update.  Sequential fp32 in the reference's order: bit-identical. */
-int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows, int width, const float* mean, const float* stdv,
-                      float clip, float* out, dfd_stream stream);
+int dfd_normalize_obs(dfd_ctx* ctx, const float* obs, int64_t n_rows, int width, const void* mean, const void* stdv,
+                      int stats_f64, float clip, float* out, dfd_stream stream);
 int dfd_member_obs_stats(dfd_ctx* ctx, const float* obs, const uint8_t* select, int n_members, int obs_per_member,
                          int width, float* out, dfd_stream stream);
 

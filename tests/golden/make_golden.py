@@ -608,7 +608,16 @@ def gen_obs_stats():
     assert normed.dtype == np.float32
     back = WelfordRunningStat(K)
     back.deserialize(glob.serialize())
+    # the worker's own path: statistics deserialised from the state (float64 arrays), fp64 normalisation, one rounding
+    # to fp32 when the observation enters the policy (worker.py:43,47; agent.py:40-41; policy.py:28)
+    wire_stats = np.asarray(glob.serialize(), dtype=np.float32).tolist()      # `repeated float` on the wire (proto:27)
+    wst = WelfordRunningStat(K)
+    wst.deserialize(wire_stats)
+    normed_worker = torch.as_tensor(np.clip(np.subtract(obs, wst.mean) / wst.std, -10, 10), dtype=torch.float32).numpy()
+    assert np.asarray(wst.std).dtype == np.float64
     np.savez_compressed(os.path.join(HERE, "obs_stats.npz"), obs=obs, select=select, rows=np.asarray(rows, dtype=np.float64),
+                        wire_stats=np.asarray(wire_stats, dtype=np.float64), normed_worker=normed_worker,
+                        worker_mean=np.asarray(wst.mean), worker_std=np.asarray(wst.std),
                         merged=np.asarray(snaps), mean=mean, std=std, normed=normed,
                         back_mean=np.asarray(back.mean, dtype=np.float64), back_std=np.asarray(back.std, dtype=np.float64))
 

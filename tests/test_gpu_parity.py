@@ -566,6 +566,11 @@ def test_obs_normalisation_and_member_stats_bit_exact(D, golden_dir):
     assert np.array_equal(rows.astype(np.float64), g["rows"])
     normed = D.normalize_obs(ctx, obs, g["mean"], g["std"]).cpu().numpy()
     assert np.array_equal(normed, g["normed"])
+    # the reference worker's path: statistics deserialised from FDState.obs_stats (float64), fp64 arithmetic, one rounding
+    wst = D.WelfordRunningStat(17)
+    wst.deserialize(g["wire_stats"].tolist())
+    assert np.asarray(wst.std).dtype == np.float64 and np.array_equal(wst.std, g["worker_std"])
+    assert np.array_equal(D.normalize_obs(ctx, obs, wst.mean, wst.std).cpu().numpy(), g["normed_worker"])
     # clipping at +-10 and in-place use
     big = torch.from_numpy((g["obs"] * 1000).astype(np.float32)).cuda()
     want = np.clip(np.subtract(g["obs"] * np.float32(1000), g["mean"]) / g["std"], -10, 10)
@@ -593,7 +598,8 @@ def test_worker_normalises_observations_and_ships_member_statistics(D, table1m):
     st = D.FDState()
     st.policy_params, st.epoch, st.obs_stats = pol.serialize(), 5, glob.serialize()
     w.update(st)
-    assert w.epoch == 5 and np.array_equal(w.fixed_obs_stats.std, glob.std)
+    assert w.epoch == 5 and np.allclose(w.fixed_obs_stats.std, glob.std, rtol=1e-6)
+    wmean, wstd = w.fixed_obs_stats.mean, w.fixed_obs_stats.std          # float64 after deserialize, as in the reference
     idx = np.arange(12, dtype=np.int64) * 1000
     rets = w.evaluate(np.zeros(12, dtype=bool), idx)
     sel = np.random.RandomState(0).uniform(0, 1, size=(12, 8)) < 0.5
@@ -606,7 +612,7 @@ def test_worker_normalises_observations_and_ships_member_statistics(D, table1m):
             if sel[m, e]:
                 ref.increment(obs[m, e], 1)
         assert np.array_equal(np.float32(r.obs_stats_update), np.float32(ref.serialize())), m
-        x = np.clip(np.subtract(obs[m], glob.mean) / glob.std, -10, 10)
+        x = np.clip(np.subtract(obs[m], wmean) / wstd, -10, 10).astype(np.float32)
         th = O.perturb(theta, 0.02, table1m._table[idx[m]:idx[m] + 6092], 1)
         mean, std = O.mujoco_forward(lay, th, x)
         reward = -np.mean((np.concatenate([mean, std], -1) - agent.target.numpy()) ** 2)
