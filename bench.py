@@ -734,6 +734,14 @@ def b200_main(args, w):
             for b in range(n_obs_buf):
                 agent.bufs[0].copy_(obs_host[b], non_blocking=True)
         torch.cuda.synchronize()
+        # the bound of the end-to-end step: its observations crossing PCIe (measured here, same buffers, copy engine)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for b in range(8):
+            agent.bufs[0].copy_(obs_host[b % n_obs_buf], non_blocking=True)
+        eb.record()
+        torch.cuda.synchronize()
+        h2d_gbps = obs_host[0].numel() * 4 * 8 / (ea.elapsed_time(eb) * 1e-3) / 1e9
         dt_serial = e2e_run(n_done, False)
         if TRACE is not None:
             del TRACE[:]
@@ -754,6 +762,8 @@ def b200_main(args, w):
         e2e = {"value": M * E * world * n_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e,
                "serial_ms_per_step": dt_serial / n_e2e * 1e3,
+               "pcie": {"h2d_GBps_measured": h2d_gbps, "floor_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3,
+                        "frac_of_floor": (h2d / (h2d_gbps * 1e9)) / (dt / n_e2e)},
                "api": "Worker.evaluate -> ReturnBatch (sequence of FDReturn) -> FiniteDifferences.step (host observations, host "
                       "returns, theta mirrored to host); observations double-buffered: step k+1's pinned host->device copy is "
                       "issued on a copy stream while step k's returns are read back and the learner steps "

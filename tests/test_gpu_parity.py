@@ -323,6 +323,66 @@ def test_atari_sized_reduction_full_config(D):
     assert cos >= 1 - 1e-8
 
 
+def test_humanoid_sized_reduction_full_config(D):
+    """BASELINE config 3, one GPU's share: P = 171 042 (376-256-256-17), 1 024 antithetic pairs, fp64 closed form."""
+    P, R = 171042, 1024
+    table = D.SharedNoiseTable(25_000_000, P, 124, device=0)
+    rng = np.random.RandomState(0)
+    theta = rng.randn(P).astype(np.float32) * 0.05
+    idx = table.sample_indices(R)
+    assert idx[:3].tolist() == [10700291, 7636593, 9022969]      # SURVEY.md App. C
+    rew = rng.randn(2 * R)
+    sign = np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)
+    fd = make_learner(D, table, theta, 0.02, paired=True, batch=2 * R)
+    fd.step_arrays(np.zeros(2 * R, np.int64), np.concatenate([idx, idx]), sign, rew, 0.0)
+    g1 = fd.gradient_memory.copy()
+    ref = O.fd_gradient_closed_form(table._table, np.concatenate([idx, idx]), sign, rew, 0.02, P)
+    assert rel_max(g1, ref) <= 1e-5
+    assert np.dot(g1, ref) / np.linalg.norm(g1) / np.linalg.norm(ref) >= 1 - 1e-8
+    # size-independent properties at the full size: the estimate does not depend on the order of the pairs, and
+    # shifting / scaling all rewards leaves the standardised estimate unchanged
+    perm = rng.permutation(R)
+    fd2 = make_learner(D, table, theta, 0.02, paired=True, batch=2 * R)
+    fd2.step_arrays(np.zeros(2 * R, np.int64), np.concatenate([idx[perm], idx[perm]]), sign,
+                    3.0 * np.concatenate([rew[:R][perm], rew[R:][perm]]) + 7.0, 0.0)
+    assert rel_max(fd2.gradient_memory, g1) <= 2e-6
+
+
+def test_impala_sized_fd_state_full_config(D):
+    """BASELINE config 5, one GPU's share: P = 1 158 709, 256 pairs' worth of returns (512) spread over the accepted
+    epochs (fd_state mode: lambda = sigma * eps + (theta_e - theta_now)), against an independent fp64 evaluation of
+    learner/finite_differences.py:80-114,40-49 with torch on the device."""
+    P, N, H = 1158709, 512, 10
+    table = D.SharedNoiseTable(25_000_000, P, 124, device=0)
+    rng = np.random.RandomState(2)
+    theta0 = (rng.randn(P) * 0.05).astype(np.float32)
+    fd = make_learner(D, table, theta0, 0.02, H=H, lr=0.01, batch=N)
+    thetas = {0: theta0.copy()}
+    for s in range(5):                                           # build a history of parameter vectors
+        idx = table.sample_indices(8)
+        fd.step_arrays(np.full(8, fd.epoch), idx, np.ones(8, np.int8), rng.randn(8), 0.0)
+        thetas[fd.epoch] = fd.policy.get_trainable_flat().copy()
+    idx = table.sample_indices(N)
+    epochs = fd.epoch - rng.randint(0, 5, size=N)
+    rew = rng.randn(N) * 2 + 1
+    now = fd.epoch
+    fd.step_arrays(epochs, idx, np.ones(N, np.int8), rew, 0.25)
+    w = rew - 0.25
+    w = (w - w.mean()) / w.std()
+    tab = torch.from_numpy(table._table).cuda()
+    th_now = torch.from_numpy(thetas[now]).cuda()
+    g = torch.zeros(P, dtype=torch.float64, device="cuda")
+    for i in range(N):
+        lam = tab[idx[i]:idx[i] + P] * np.float32(0.02)
+        if epochs[i] != now:
+            lam = lam + (torch.from_numpy(thetas[int(epochs[i])]).cuda() - th_now)       # fp32, as the reference
+        lam64 = lam.double()
+        g += float(w[i]) * lam64 / (lam64 * lam64).sum()
+    ref = g.cpu().numpy()
+    assert rel_max(fd.gradient_memory, ref) <= 1e-5
+    assert np.dot(fd.gradient_memory, ref) / np.linalg.norm(fd.gradient_memory) / np.linalg.norm(ref) >= 1 - 1e-8
+
+
 def test_worker_batched_collect_and_learning(D, table1m):
     """Worker.collect_returns(n) -> FDReturns -> learner.step: flags/keys follow the reference streams and
     the synthetic objective improves."""
