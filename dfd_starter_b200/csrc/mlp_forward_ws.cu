@@ -126,6 +126,19 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -183,7 +196,13 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
 #define WS_BAR(i) (bar0 + 8u * (uint32_t)(i))
 // debugging aid (DFD_WS_PROF=1): clock64 stamps of one steady-state item per role
 #define WS_STAMP(cond, slot) do { } while (0)
-#define WS_TL(cond, item, slot) do { if (prof && (cond) && (item) < 16) prof[(size_t)blockIdx.x * 256 + (item) * 16 + (slot)] = clock64(); } while (0)
+// (compiled in with -DDFD_WS_TIMELINE only: the group chain is instruction-latency bound, ~5 cycles per instruction,
+// and eleven guarded stamps per item are not free)
+#ifdef DFD_WS_TIMELINE
+#define WS_TL(cond, item, slot) do { if (prof && (cond) && (item) >= 0 && (item) < 16) prof[(size_t)blockIdx.x * 256 + (item) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define WS_TL(cond, item, slot) do { } while (0)
+#endif
 
     if (tid < 4) ring_cnt[tid] = 0;
     if (tid == 0) {
@@ -398,18 +417,26 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
         // TMEM row -> tanh -> tf32 -> the same TMEM columns (they become the next layer's A operand).  Accurate-tanh path:
         // rounded to nearest; tanh.approx path: left as they are - the tensor core truncates the low 13 mantissa bits, an
         // error of the same 2^-11 class as tanh.approx itself, and one integer add per activation is saved (-5 % kernel time)
+        // The TMEM read port (64 B/clk per SM) and the SFU (16 tanh/clk per SM) each need ~512 cycles per group and
+        // layer; used one after the other (read everything, then tanh everything) the groups fall into lockstep and the
+        // two phases ADD (measured: ~7 000-cycle item chain = 3 groups x 2 layers x (read + tanh)).  Pipelined form: 16
+        // columns at a time, the read of chunk c+1 is in flight while chunk c goes through the SFU, so every group keeps
+        // both resources busy and the per-item cost tends to max(read, tanh) instead of their sum.
         auto epilogue_hidden = [&](uint32_t t_reg, bool active) {
             if (active) {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t_reg + lane_sel, ra);
-                tmem_ld32_issue(t_reg + lane_sel + 32u, rb);
+                uint32_t r0[16], r1[16];
+                tmem_ld16_issue(t_reg + lane_sel, r0);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint((APPROX ? ws_tanh<APPROX>(__uint_as_float(ra[i])) : tf32_rn(ws_tanh<APPROX>(__uint_as_float(ra[i])))));
-                tmem_st32(t_reg + lane_sel, ra);
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t* cur = (c & 1) ? r1 : r0;
+                    uint32_t* nxt = (c & 1) ? r0 : r1;
+                    if (c < 3) tmem_ld16_issue(t_reg + lane_sel + 16u * (uint32_t)(c + 1), nxt);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) rb[i] = __float_as_uint((APPROX ? ws_tanh<APPROX>(__uint_as_float(rb[i])) : tf32_rn(ws_tanh<APPROX>(__uint_as_float(rb[i])))));
-                tmem_st32(t_reg + lane_sel + 32u, rb);
+                    for (int i = 0; i < 16; ++i) cur[i] = __float_as_uint((APPROX ? ws_tanh<APPROX>(__uint_as_float(cur[i])) : tf32_rn(ws_tanh<APPROX>(__uint_as_float(cur[i])))));
+                    tmem_st16(t_reg + lane_sel + 16u * (uint32_t)c, cur);
+                    if (c < 3) tmem_ld_wait();
+                }
                 tmem_st_wait();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -429,24 +456,47 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             const int work = (int)blockIdx.x + kk * (int)gridDim.x;
             const int m = p.tiles == 1 ? work : work / p.tiles, tile = work - m * p.tiles;
             const int e0i = tile * 128, ne = min(128, p.E - e0i);
+            WS_TL(gt == 0, kk - p.ng, 12);
             if (p.obs_vec) mbar_wait_park(WS_BAR(B_OFULL + g * 2 + oslot), opar);
+            WS_TL(gt == 0, kk - p.ng, 13);
             if (q * 32 < ne) {
-                // straight-line, branch-free: clamped unconditional loads (batched by the compiler), selects after
-                const float* src = p.obs_vec ? smem + p.o_obs + (g * 2 + oslot) * p.obs_floats + gt * p.K0
-                                             : obs + ((int64_t)m * p.E + e0i + min(gt, ne - 1)) * p.K0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < p.K0p; c0 += 8) {
-                    float v[8];
+                if (p.obs_vec) {
+                    // row gt of the TMA-landed tile: fully unrolled, immediate offsets, independent loads (the group chain is
+                    // instruction-latency bound; the clamped generic-pointer form cost ~1 000 cycles per item).  Columns past
+                    // K0 are replaced after the load, so reading up to 7 floats past the row is harmless - it stays inside
+                    // the ring (the allocation carries 32 floats of slack behind the last slot).
+                    const uint32_t srow = obs_ring + 4u * (uint32_t)(oslot * p.obs_floats + gt * p.K0);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[c] = src[min(c0 + c, p.K0 - 1)];
-                    uint32_t x[8];
+                    for (int c0 = 0; c0 < 40; c0 += 8) {
+                        if (c0 < p.K0p) {
+                            uint32_t x[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int kk2 = c0 + c;
-                        x[c] = __float_as_uint(tf32_rn(kk2 < p.K0 ? v[c] : (kk2 == p.K0 ? 1.0f : 0.f)));
+                            for (int c = 0; c < 8; ++c) {
+                                const int kk2 = c0 + c;
+                                const float v = lds32(srow + 4u * (uint32_t)kk2);
+                                x[c] = __float_as_uint(tf32_rn(kk2 < p.K0 ? v : (kk2 == p.K0 ? 1.0f : 0.f)));
+                            }
+                            tmem_st8(tA0 + lane_sel + (uint32_t)c0, x);
+                        }
                     }
-                    tmem_st8(tA0 + lane_sel + (uint32_t)c0, x);
+                } else {
+                    // rows straight from global memory (unaligned observation buffers): clamped loads, selects after
+                    const float* src = obs + ((int64_t)m * p.E + e0i + min(gt, ne - 1)) * p.K0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < p.K0p; c0 += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = src[min(c0 + c, p.K0 - 1)];
+                        uint32_t x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int kk2 = c0 + c;
+                            x[c] = __float_as_uint(tf32_rn(kk2 < p.K0 ? v[c] : (kk2 == p.K0 ? 1.0f : 0.f)));
+                        }
+                        tmem_st8(tA0 + lane_sel + (uint32_t)c0, x);
+                    }
                 }
+                WS_TL(gt == 0, kk - p.ng, 14);
                 tmem_st_wait();
             }
         };
@@ -498,9 +548,11 @@ mlp_forward_ws_kernel(const WsParams p, const float* __restrict__ replicas, int6
             }
             WS_STAMP(st, 5);
             const bool has_next = k + p.ng < n_my;
-            if (has_next) load_obs(k + p.ng);                  // hidden under the layer-1 MMA
+            if (has_next) load_obs(k + p.ng);                  // issued behind the layer-1 MMA
+            WS_TL(gt == 0, k, 1);
             mbar_wait_park(mbar, mph); mph ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            WS_TL(gt == 0, k, 7);
             WS_STAMP(st, 6);
             epilogue_hidden(tA2, active);
             if (has_next) obs_consumed(k + p.ng);
@@ -599,7 +651,7 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     p.obs_floats = 128 * K0;
     // W0 items 64 * nkq must fit the fixed per-thread item count; the observation operand its TMEM columns
     if (8 * p.nkq * 8 > 2 * WS_NBUILD || p.K0p > 40) return -1;
-    const size_t cap = 226 * 1024;
+    const size_t cap = 226 * 1024 - 128;
     p.nst = 3;
     p.ne = 4;
     // three groups when the TMEM columns (3 x (24 + 72 + 72), head accumulator aliased onto the dead observation
@@ -616,11 +668,15 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
     p.d3_off = p.ng == 3 ? 24 : 40 + 2 * WS_KH;   // three groups: the head accumulator aliases the first columns of A1/D1
     p.o_ring = p.nst * p.st_floats;
     p.o_obs = p.o_ring + p.ne * p.ring_floats;
-    const size_t smem = bytes();
+    const size_t smem = bytes() + 128;              // slack behind the last observation slot (load_obs over-read)
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
     long long* prof = nullptr;
+#ifdef DFD_WS_TIMELINE
     static const bool want_prof = getenv("DFD_WS_PROF") != nullptr;
+#else
+    static const bool want_prof = false;
+#endif
     if (want_prof) {
         cudaMalloc(&prof, (size_t)grid * 256 * sizeof(long long));
         cudaMemset(prof, 0, (size_t)grid * 256 * sizeof(long long));
@@ -641,10 +697,12 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
         cudaMemcpy(h, prof + 256 * 5, 256 * sizeof(long long), cudaMemcpyDeviceToHost);   // CTA 5
         long long t0 = 0;
         for (int i = 0; i < 256; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
-        fprintf(stderr, "[ws timeline] CTA 5, cycles since first stamp; G: top, obs done, weights ready, E0 done, E1 done, L2 issued, end | B: top, eps ready, stage free, built\n");
+        fprintf(stderr, "[ws timeline] CTA 5, cycles since first stamp; G: top, next obs staged, weights ready, E0 done, E1 done, L2 issued, end, L1 MMA done | B: top, eps ready, stage free, built\n");
         for (int k = 0; k < 16; ++k) {
-            fprintf(stderr, "  item %2d G%d:", k, k & 1);
-            for (int j = 0; j < 7; ++j) fprintf(stderr, " %7lld", h[k * 16 + j] ? h[k * 16 + j] - t0 : -1LL);
+            fprintf(stderr, "  item %2d G%d:", k, k % p.ng);
+            for (int j = 0; j < 8; ++j) fprintf(stderr, " %7lld", h[k * 16 + j] ? h[k * 16 + j] - t0 : -1LL);
+            fprintf(stderr, "  | obs: enter, landed, stores issued:");
+            for (int j = 12; j < 15; ++j) fprintf(stderr, " %7lld", h[k * 16 + j] ? h[k * 16 + j] - t0 : -1LL);
             fprintf(stderr, "  | B:");
             for (int j = 8; j < 12; ++j) fprintf(stderr, " %7lld", h[k * 16 + j] ? h[k * 16 + j] - t0 : -1LL);
             fprintf(stderr, "\n");
