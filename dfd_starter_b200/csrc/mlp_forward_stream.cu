@@ -6,8 +6,10 @@
 //                      flight (the chunk is small on purpose: shared memory stays under 100 KB and the rest of the
 //                      SM's 228 KB is L1, whose capacity bounds how many load bytes can be outstanding);
 //                      theta and eps(member) straight from global memory, theta + s*sigma*eps with the reference's
-//                      two roundings, tf32, stored as the UMMA K-major canonical B operand chunk [N x 16]; for layer 0
-//                      also the observation chunk [128 x 16] (A);
+//                      two roundings, tf32, stored as the UMMA K-major SWIZZLE_128B B operand chunk [N x 32] (every row
+//                      is one 128-byte line: a quarter-warp reads one full line of theta / eps and writes one full
+//                      swizzled row, so global requests touch 4 lines instead of 8 half-lines and the stores are
+//                      conflict-free); for layer 0 also the observation chunk [128 x 32] (A);
 //   MMA warp (1 lane)  tcgen05.mma kind::tf32, M = 128 observations, N = layer width, 2 instructions per chunk;
 //                      layer 0 takes A from shared memory, layers 1 and 2 take A from TENSOR MEMORY;
 //   epilogue warps (4) TMEM accumulator -> + perturbed bias -> tanh -> tf32 -> the same TMEM columns (the next
@@ -20,7 +22,7 @@
 
 namespace {
 
-constexpr int ST_KC = 16;                 // K columns per chunk
+constexpr int ST_KC = 32;                 // K columns per chunk: one 128-byte swizzle atom row
 constexpr int ST_TEAMS = 2;               // builder teams: team t builds chunks t, t+2, ... so two chunks' loads are in flight
 constexpr int ST_TEAM_WARPS = 4;
 constexpr int ST_NS = 4;                  // ring stages (max; the launcher may use fewer to leave L1 for in-flight loads)
@@ -131,8 +133,10 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int n_my = ((int)blockIdx.x < p.n_work) ? (p.n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t bar0 = smem_u32(&bars[0]);
-    const uint32_t smem0 = smem_u32(smem);
-    float* bias_s = smem + p.ns * ST_STAGE;
+    // stages are SWIZZLE_128B operands: 1024-byte aligned atoms (the launcher allocates 1 KB of slack)
+    const uint32_t smem_raw = smem_u32(smem);
+    const uint32_t smem0 = (smem_raw + 1023u) & ~1023u;
+    float* bias_s = smem + ((smem0 - smem_raw) >> 2) + p.ns * ST_STAGE;
 #define ST_BAR(i) (bar0 + 8u * (uint32_t)(i))
 
     if (tid == 0) {
@@ -162,9 +166,9 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
 
     if (warp < ST_NBUILD / 32) {
         // =============================== builders ===============================================
-        // lane -> (row-in-group i = lane & 7, k-quad j = lane >> 3): a warp reads 8 rows x 64 contiguous bytes
-        // (full 32-byte sectors) and every quarter-warp stores 128 contiguous bytes (conflict-free)
-        const int li = lane & 7, lj = lane >> 3;
+        // lane -> (row-in-item li = lane >> 3, 16-byte chunk lc = lane & 7): a warp item is 4 rows x 128 contiguous bytes
+        // (4 full lines per request); row r's chunk lc lands at r * 128 + ((lc ^ (r & 7)) << 4) - the 128-byte swizzle
+        const int li = lane >> 3, lc = lane & 7;
         const int team = warp / ST_TEAM_WARPS, tw = warp % ST_TEAM_WARPS;
         int g = 0;           // running chunk number over layers and members: stage = g % ns, team = g % ST_TEAMS
         for (int u = 0; u < n_my; ++u) {
@@ -200,7 +204,7 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
             }
 #pragma unroll
             for (int l = 0; l < 3; ++l) {      // unrolled: every p.xxx[l] is a compile-time constant-bank read
-                const int kin = p.kin[l], nreal = p.nreal[l], nrg = p.npad[l] >> 3, nchunk = p.nchunk[l];
+                const int kin = p.kin[l], nreal = p.nreal[l], npad = p.npad[l], nchunk = p.nchunk[l];
                 const float* th_l = theta + p.w_off[l];
                 const float* ep_l = row + p.w_off[l];
 #pragma unroll 1
@@ -210,47 +214,49 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                     st_wait(ST_BAR(SB_EMPTY + s), (uint32_t)((g / p.ns) & 1) ^ 1u);
                     const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
                     const uint32_t Ad = Wd + 4u * ST_WCHUNK;
-                    const int k0 = c * ST_KC, k = k0 + lj * 4;
-                    // W chunk [N x 16]: one warp item = one row group (8 rows x 4 k-quads); ALL of a thread's loads
-                    // of the chunk are issued before the first use
-                    constexpr int NI = 32 / ST_TEAM_WARPS;       // row groups per warp (N <= 256)
-                    float4 a[NI], e[NI], o4[16 / ST_TEAM_WARPS];
+                    const int k = c * ST_KC + lc * 4;
+                    // W chunk [N x 32]: 4 rows per warp item, 16 items per warp for N = 256, in two passes of 8 so that at
+                    // most 16 x 16 bytes of loads are live per thread; every load of a pass is issued before the first use
+                    constexpr int NI = 8;
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        float4 a[NI], e[NI];
+                        if ((half * NI * ST_TEAM_WARPS) * 4 >= npad) break;
 #pragma unroll
-                    for (int h = 0; h < NI; ++h) {
-                        const int rg = tw + h * ST_TEAM_WARPS;
-                        const int n = rg * 8 + li;
-                        a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        e[h] = a[h];
-                        if (rg < nrg && n < nreal && k < kin) {      // kin % 4 == 0: whole quads only
-                            const int q = n * kin + k;
-                            a[h] = ldg_stream_f4(th_l + q);
-                            e[h] = ldg_stream_f4(ep_l + q);
+                        for (int h = 0; h < NI; ++h) {
+                            const int n = ((half * NI + h) * ST_TEAM_WARPS + tw) * 4 + li;
+                            a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            e[h] = a[h];
+                            if (n < nreal && k < kin) {      // kin % 4 == 0: whole quads only
+                                const int q = n * kin + k;
+                                a[h] = ldg_stream_f4(th_l + q);
+                                e[h] = ldg_stream_f4(ep_l + q);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < NI; ++h) {
+                            const int n = ((half * NI + h) * ST_TEAM_WARPS + tw) * 4 + li;
+                            if (n < npad) {
+                                const uint32_t d = Wd + (uint32_t)(n * 128 + ((lc ^ (n & 7)) << 4));
+                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
+                                             "f"(st_tf32(perturb1(a[h].x, sg, e[h].x))), "f"(st_tf32(perturb1(a[h].y, sg, e[h].y))),
+                                             "f"(st_tf32(perturb1(a[h].z, sg, e[h].z))), "f"(st_tf32(perturb1(a[h].w, sg, e[h].w)))
+                                             : "memory");
+                            }
                         }
                     }
-                    if (l == 0) {     // observation chunk [128 x 16]: 16 row groups
+                    if (l == 0) {     // observation chunk [128 x 32]: 8 items per warp
+                        float4 o4[8];
 #pragma unroll
-                        for (int h = 0; h < 16 / ST_TEAM_WARPS; ++h) {
-                            const int r = (tw + h * ST_TEAM_WARPS) * 8 + li;
+                        for (int h = 0; h < 8; ++h) {
+                            const int r = (h * ST_TEAM_WARPS + tw) * 4 + li;
                             o4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (r < ne && k < p.K0) o4[h] = ldg_stream_f4(ob + (int64_t)r * p.K0 + k);
                         }
-                    }
 #pragma unroll
-                    for (int h = 0; h < NI; ++h) {
-                        const int rg = tw + h * ST_TEAM_WARPS;
-                        if (rg < nrg) {
-                            const uint32_t d = Wd + 4u * (uint32_t)(rg * (ST_KC * 8) + lj * 32 + li * 4);
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
-                                         "f"(st_tf32(perturb1(a[h].x, sg, e[h].x))), "f"(st_tf32(perturb1(a[h].y, sg, e[h].y))),
-                                         "f"(st_tf32(perturb1(a[h].z, sg, e[h].z))), "f"(st_tf32(perturb1(a[h].w, sg, e[h].w)))
-                                         : "memory");
-                        }
-                    }
-                    if (l == 0) {
-#pragma unroll
-                        for (int h = 0; h < 16 / ST_TEAM_WARPS; ++h) {
-                            const int rg = tw + h * ST_TEAM_WARPS;
-                            const uint32_t d = Ad + 4u * (uint32_t)(rg * (ST_KC * 8) + lj * 32 + li * 4);
+                        for (int h = 0; h < 8; ++h) {
+                            const int r = (h * ST_TEAM_WARPS + tw) * 4 + li;
+                            const uint32_t d = Ad + (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4));
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d), "f"(st_tf32(o4[h].x)),
                                          "f"(st_tf32(o4[h].y)), "f"(st_tf32(o4[h].z)), "f"(st_tf32(o4[h].w))
                                          : "memory");
@@ -355,16 +361,18 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                     st_wait(ST_BAR(SB_FULL + s), (uint32_t)((g / p.ns) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
-                    const uint64_t bdesc = make_desc(Wd, 128, ST_KC * 32u);
+                    // SWIZZLE_128B K-major operands: 8-row atoms of 1024 bytes; a K step of 8 tf32 (32 bytes) inside the atom
+                    // advances the start-address field by 2
+                    const uint64_t bdesc = make_desc_sw128(Wd);
                     if (l == 0) {
-                        const uint64_t adesc = make_desc(Wd + 4u * ST_WCHUNK, 128, ST_KC * 32u);
+                        const uint64_t adesc = make_desc_sw128(Wd + 4u * ST_WCHUNK);
 #pragma unroll
                         for (int j = 0; j < ST_KC / 8; ++j)
-                            umma_tf32_elect(d_tmem, adesc + (uint64_t)(j * 16), bdesc + (uint64_t)(j * 16), idesc, (c | j) ? 1u : 0u);
+                            umma_tf32_elect(d_tmem, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (c | j) ? 1u : 0u);
                     } else {
 #pragma unroll
                         for (int j = 0; j < ST_KC / 8; ++j)
-                            st_umma_ts(d_tmem, a_tmem + (uint32_t)(c * ST_KC + j * 8), bdesc + (uint64_t)(j * 16), idesc, (c | j) ? 1u : 0u);
+                            st_umma_ts(d_tmem, a_tmem + (uint32_t)(c * ST_KC + j * 8), bdesc + (uint64_t)(j * 2), idesc, (c | j) ? 1u : 0u);
                     }
                     umma_commit_elect(ST_BAR(SB_EMPTY + s));
                     if (c == p.nchunk[l] - 1) umma_commit_elect(ST_BAR(SB_DFULL + l));
@@ -418,11 +426,11 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     p.sigma = sigma;
     p.pair_order = (n_members % 2 == 0 && !getenv("DFD_ST_NOPAIR")) ? 1 : 0;
     p.prefetch = getenv("DFD_ST_NOPF") ? 0 : 1;
-    // 4 x 24 KB + biases: shared memory stays near 100 KB so ~96 KB of the SM's 228 KB remain L1 - measured on B200:
+    // ns x 48 KB + biases - measured on B200:
     // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
-    p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : ST_NS;
-    if (p.ns < 2 || p.ns > ST_NS) p.ns = ST_NS;
-    const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768) * sizeof(float);
+    p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : 3;
+    if (p.ns < 2 || p.ns > ST_NS) p.ns = 3;
+    const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768) * sizeof(float) + 1024;   // + alignment slack of the swizzled stages
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
     long long* prof = nullptr;

@@ -36,6 +36,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;                // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
 }
 
+// K-major operand in the 128-byte swizzled layout (rows of 128 bytes, 16-byte chunks XOR-ed with row & 7, 8-row atoms
+// of 1024 bytes, atoms 1024-byte aligned): stride-byte-offset 1024, leading-byte-offset unused (1), layout_type 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
