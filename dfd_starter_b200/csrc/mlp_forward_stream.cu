@@ -137,6 +137,7 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
     const uint32_t smem_raw = smem_u32(smem);
     const uint32_t smem0 = (smem_raw + 1023u) & ~1023u;
     float* bias_s = smem + ((smem0 - smem_raw) >> 2) + p.ns * ST_STAGE;
+    float* ostage = bias_s + 2 * 768;            // [128 x nout] output rows of the member being finished (16-byte aligned)
 #define ST_BAR(i) (bar0 + 8u * (uint32_t)(i))
 
     if (tid == 0) {
@@ -309,37 +310,63 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                     if (lane == 0) st_arrive(ST_BAR(SB_HREADY + l * 8 + (c0 >> 5)));   // these 32 activations are an A chunk now
                 }
             }
-            // head: accumulator in R1 columns [0, N3)
+            // head: accumulator in R1 columns [0, N3).  The member's [ne x nout] output block is contiguous in global
+            // memory, so the rows are staged in shared memory and leave with ONE bulk store: per-thread row stores touch 32
+            // lines per instruction (34 of them per thread: ~9 000 cycles of the SM's single L1 wavefront queue per member,
+            // taken from the builders' loads, and the next member's layer 0 waited that long for region R1).  R1 is
+            // released as soon as the accumulator is in registers.
             ST_TL(gt == 0, 12);
             st_wait(ST_BAR(SB_DFULL + 2), pd[2]); pd[2] ^= 1u;
             ST_TL(gt == 0, 13);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
                 float* o = out + ((int64_t)m * p.E + e0i + gt) * p.nout;
+                float* og = out + ((int64_t)m * p.E + e0i) * p.nout;
+                const uint32_t obytes = (uint32_t)(ne * p.nout) * 4u;
+                const bool bulk = (obytes & 15u) == 0 && (((uintptr_t)og) & 15) == 0;
+                if (bulk) {
+                    // the previous member's bulk store must have finished READING the staging rows
+                    if (gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                }
+                float* os = ostage + gt * p.nout;
 #pragma unroll 1
                 for (int c = 0; c < p.N3; c += 16) {
                     float v[16];
                     tmem_ld16(tR1 + lane_sel + (uint32_t)c, v);
+                    if (c + 16 >= p.N3) {       // last read of R1: the next member's layer 0 may overwrite it
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) st_arrive(ST_BAR(SB_R1FREE));
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float y = st_tanh<APPROX>(v[i] + bs[512 + c + i]);
                         v[i] = c + i < p.A ? y : 0.55f + 0.45f * y;   // MapContinuousToAction
                     }
                     if (gt < ne) {
+                        float* dst = bulk ? os : o;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c + i < p.nout) o[c + i] = v[i];
+                            if (c + i < p.nout) dst[c + i] = v[i];
+                    }
+                }
+                if (bulk) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (gt == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(og),
+                                     "r"(smem_u32(ostage)), "r"(obytes)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             ST_TL(gt == 0, 14);
-            if (lane == 0) {
-                st_arrive(ST_BAR(SB_R1FREE));
-                st_arrive(ST_BAR(SB_BEMPTY + bb));
-            }
+            if (lane == 0) st_arrive(ST_BAR(SB_BEMPTY + bb));
         }
+        if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the last block has left shared memory
     } else {
         // =============================== MMA issue warp =========================================
         int g = 0;
@@ -430,7 +457,7 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
     p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : 3;
     if (p.ns < 2 || p.ns > ST_NS) p.ns = 3;
-    const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768) * sizeof(float) + 1024;   // + alignment slack of the swizzled stages
+    const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768 + 128 * (size_t)nout) * sizeof(float) + 1024;   // + alignment slack of the swizzled stages
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
     long long* prof = nullptr;
