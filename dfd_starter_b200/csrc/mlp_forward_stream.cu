@@ -2,14 +2,12 @@
 // Humanoid-shaped 376-256-256-17 of BASELINE config 3; policies/mujoco.py:35-41, perturbation worker/worker.py:28).
 // A member's weights (171 042 floats) do not fit on chip, so they stream through a shared-memory ring in K chunks:
 //
-//   builder warps (8)  two teams of four warps alternate chunks, so the global loads of two chunks are always in
-//                      flight (the chunk is small on purpose: shared memory stays under 100 KB and the rest of the
-//                      SM's 228 KB is L1, whose capacity bounds how many load bytes can be outstanding);
-//                      theta and eps(member) straight from global memory, theta + s*sigma*eps with the reference's
-//                      two roundings, tf32, stored as the UMMA K-major SWIZZLE_128B B operand chunk [N x 32] (every row
-//                      is one 128-byte line: a quarter-warp reads one full line of theta / eps and writes one full
-//                      swizzled row, so global requests touch 4 lines instead of 8 half-lines and the stores are
-//                      conflict-free); for layer 0 also the observation chunk [128 x 32] (A);
+//   builder warps (8)  two teams of four warps alternate chunks, so two chunks are always being built.  The theta tile
+//                      [N x 32] of the chunk - and for layer 0 the observation chunk [128 x 32] (A) - arrive by TMA tensor
+//                      copy (SWIZZLE_128B tensor maps) straight in the UMMA K-major operand layout, never touching L1;
+//                      the builders load eps(member) from global memory (every row of the chunk is one 128-byte line: a
+//                      quarter-warp reads one full line, all 16 loads of a thread in flight before the first use) and add
+//                      s*sigma*eps IN PLACE with the reference's two roundings, tf32;
 //   MMA warp (1 lane)  tcgen05.mma kind::tf32, M = 128 observations, N = layer width, 2 instructions per chunk;
 //                      layer 0 takes A from shared memory, layers 1 and 2 take A from TENSOR MEMORY;
 //   epilogue warps (4) TMEM accumulator -> + perturbed bias -> tanh -> tf32 -> the same TMEM columns (the next
@@ -19,6 +17,7 @@
 //       region R2 (columns 256-511) = layer-1 accumulator / layer-2 A operand.
 // The builders run ahead of the MMA warp by the depth of the ring, across layer and member boundaries.
 #include "tc_common.cuh"
+#include <cuda.h>
 
 namespace {
 
@@ -40,6 +39,23 @@ struct StParams {
     int64_t P;
     float sigma;
 };
+
+// theta tiles (one map per layer: [n_out rows, k_in columns] row-major, box 32 columns x npad rows) and observation chunks
+// ([members * E rows, K0 columns], box 32 x 128), both SWIZZLE_128B: the copy lands in the operand layout directly and
+// never passes through L1.  Out-of-bounds rows / columns (k >= k_in, padded rows) are filled with zeros.
+struct StMaps {
+    CUtensorMap w[3];
+    CUtensorMap obs;
+};
+
+__device__ __forceinline__ void st_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 
 // work item -> (member, tile).  pair_order: consecutive work items are the two members of an antithetic pair
 // ([plus | minus] batches: members j and j + M/2 share their table row), so the CTAs b and b+1 stream the same eps
@@ -117,11 +133,11 @@ __device__ __forceinline__ void st_tmem_st32(uint32_t taddr, const uint32_t* r) 
 }
 
 // barrier slots
-enum { SB_FULL = 0, SB_EMPTY = 4, SB_DFULL = 8, SB_HREADY = 11 /* [2 layers][8 chunks] */, SB_R1FREE = 27, SB_BFULL = 28, SB_BEMPTY = 30, SB_COUNT = 32 };
+enum { SB_FULL = 0, SB_EMPTY = 4, SB_DFULL = 8, SB_HREADY = 11 /* [2 layers][8 chunks] */, SB_R1FREE = 27, SB_BFULL = 28, SB_BEMPTY = 30, SB_TFULL = 32, SB_COUNT = 36 };
 
 template <bool APPROX>
 __global__ void __launch_bounds__(ST_THREADS, 1)
-mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, int64_t stride, const float* __restrict__ theta,
+mlp_forward_stream_kernel(const StParams p, const __grid_constant__ StMaps maps, const float* __restrict__ replicas, int64_t stride, const float* __restrict__ theta,
                           const int64_t* __restrict__ idx, const int8_t* __restrict__ sign, const float* __restrict__ obs,
                           float* __restrict__ out, long long* __restrict__ prof) {
 #define ST_TL(cond, slot) do { if (prof && (cond) && u == 3) prof[(size_t)blockIdx.x * 32 + (slot)] = clock64(); } while (0)
@@ -144,6 +160,7 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
         for (int s = 0; s < ST_NS; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ST_BAR(SB_FULL + s)), "r"(ST_TEAM_WARPS));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ST_BAR(SB_EMPTY + s)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ST_BAR(SB_TFULL + s)));
         }
         for (int l = 0; l < 3; ++l) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ST_BAR(SB_DFULL + l)));
         for (int j = 0; j < 16; ++j) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(ST_BAR(SB_HREADY + j)));
@@ -179,7 +196,6 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
             const int e0i = tile * 128, ne = min(128, p.E - e0i);
             const float sg = p.sigma * (float)sign[m];
             const float* row = table_row_ptr(replicas, stride, idx[m]);
-            const float* ob = obs + ((int64_t)m * p.E + e0i) * p.K0;
             if (p.prefetch && tid == 0 && u + 1 < n_my) {      // next member's eps row and observation tile -> L2
                 int nm, nt;
                 st_item(p, work + (int)gridDim.x, nm, nt);
@@ -206,7 +222,6 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
 #pragma unroll
             for (int l = 0; l < 3; ++l) {      // unrolled: every p.xxx[l] is a compile-time constant-bank read
                 const int kin = p.kin[l], nreal = p.nreal[l], npad = p.npad[l], nchunk = p.nchunk[l];
-                const float* th_l = theta + p.w_off[l];
                 const float* ep_l = row + p.w_off[l];
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c, ++g) {
@@ -216,50 +231,36 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
                     const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
                     const uint32_t Ad = Wd + 4u * ST_WCHUNK;
                     const int k = c * ST_KC + lc * 4;
-                    // W chunk [N x 32]: 4 rows per warp item, 16 items per warp for N = 256, in two passes of 8 so that at
-                    // most 16 x 16 bytes of loads are live per thread; every load of a pass is issued before the first use
-                    constexpr int NI = 8;
-#pragma unroll 1
-                    for (int half = 0; half < 2; ++half) {
-                        float4 a[NI], e[NI];
-                        if ((half * NI * ST_TEAM_WARPS) * 4 >= npad) break;
-#pragma unroll
-                        for (int h = 0; h < NI; ++h) {
-                            const int n = ((half * NI + h) * ST_TEAM_WARPS + tw) * 4 + li;
-                            a[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            e[h] = a[h];
-                            if (n < nreal && k < kin) {      // kin % 4 == 0: whole quads only
-                                const int q = n * kin + k;
-                                a[h] = ldg_stream_f4(th_l + q);
-                                e[h] = ldg_stream_f4(ep_l + q);
-                            }
-                        }
-#pragma unroll
-                        for (int h = 0; h < NI; ++h) {
-                            const int n = ((half * NI + h) * ST_TEAM_WARPS + tw) * 4 + li;
-                            if (n < npad) {
-                                const uint32_t d = Wd + (uint32_t)(n * 128 + ((lc ^ (n & 7)) << 4));
-                                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
-                                             "f"(st_tf32(perturb1(a[h].x, sg, e[h].x))), "f"(st_tf32(perturb1(a[h].y, sg, e[h].y))),
-                                             "f"(st_tf32(perturb1(a[h].z, sg, e[h].z))), "f"(st_tf32(perturb1(a[h].w, sg, e[h].w)))
-                                             : "memory");
-                            }
-                        }
+                    // theta tile (and, for layer 0, the observation chunk) by tensor copy straight into the stage; the
+                    // builders then add s*sigma*eps IN PLACE: eps from global memory (the only loads left on the L1 path),
+                    // theta from the swizzled position they write back to
+                    if (tw == 0 && lane == 0) {
+                        const uint32_t bytes = (uint32_t)npad * 128u + (l == 0 ? 128u * 128u : 0u);
+                        st_expect_tx(ST_BAR(SB_TFULL + s), bytes);
+                        st_tma_2d(Wd, &maps.w[l], c * ST_KC, 0, ST_BAR(SB_TFULL + s));
+                        if (l == 0) st_tma_2d(Ad, &maps.obs, c * ST_KC, m * p.E + e0i, ST_BAR(SB_TFULL + s));
                     }
-                    if (l == 0) {     // observation chunk [128 x 32]: 8 items per warp
-                        float4 o4[8];
+                    // ALL of the chunk's eps loads (16 x 16 bytes per thread for N = 256) are in flight before the first use:
+                    // one memory round trip per chunk
+                    constexpr int NI = 16;
+                    float4 e[NI];
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            const int r = (h * ST_TEAM_WARPS + tw) * 4 + li;
-                            o4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (r < ne && k < p.K0) o4[h] = ldg_stream_f4(ob + (int64_t)r * p.K0 + k);
-                        }
+                    for (int h = 0; h < NI; ++h) {
+                        const int n = (h * ST_TEAM_WARPS + tw) * 4 + li;
+                        e[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n < nreal && k < kin) e[h] = ldg_stream_f4(ep_l + n * kin + k);      // kin % 4 == 0: whole quads
+                    }
+                    st_wait(ST_BAR(SB_TFULL + s), (uint32_t)((g / p.ns) & 1));    // theta tile (and observations) landed
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            const int r = (h * ST_TEAM_WARPS + tw) * 4 + li;
-                            const uint32_t d = Ad + (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4));
-                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d), "f"(st_tf32(o4[h].x)),
-                                         "f"(st_tf32(o4[h].y)), "f"(st_tf32(o4[h].z)), "f"(st_tf32(o4[h].w))
+                    for (int h = 0; h < NI; ++h) {
+                        const int n = (h * ST_TEAM_WARPS + tw) * 4 + li;
+                        if (n < npad) {
+                            const uint32_t d = Wd + (uint32_t)(n * 128 + ((lc ^ (n & 7)) << 4));
+                            float4 a;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(d));
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
+                                         "f"(st_tf32(perturb1(a.x, sg, e[h].x))), "f"(st_tf32(perturb1(a.y, sg, e[h].y))),
+                                         "f"(st_tf32(perturb1(a.z, sg, e[h].z))), "f"(st_tf32(perturb1(a.w, sg, e[h].w)))
                                          : "memory");
                         }
                     }
@@ -422,6 +423,31 @@ mlp_forward_stream_kernel(const StParams p, const float* __restrict__ replicas, 
 
 }  // namespace
 
+typedef CUresult (*st_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// fp32 [rows, cols] row-major -> boxes of 32 columns x box_rows rows in the 128-byte swizzle; 0 on success
+static int st_make_map(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    static st_encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            return 1;
+        }
+        encode = (st_encode_fn)fn;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)ST_KC, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 2;
+}
+
 // returns -1 when the shape is not served by this kernel (the caller falls back to the generic tcgen05 kernel)
 int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                                 const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
@@ -456,18 +482,24 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     // ns x 48 KB + biases - measured on B200:
     // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
     p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : 3;
-    if (p.ns < 2 || p.ns > ST_NS) p.ns = 3;
+    if (p.ns < 3 || p.ns > ST_NS) p.ns = 3;
     const size_t smem = ((size_t)p.ns * ST_STAGE + 2 * 768 + 128 * (size_t)nout) * sizeof(float) + 1024;   // + alignment slack of the swizzled stages
+    StMaps maps;
+    for (int l = 0; l < 3; ++l)
+        DFD_CHECK_ARG(st_make_map(&maps.w[l], theta + p.w_off[l], (uint64_t)p.kin[l], (uint64_t)p.nreal[l], (uint32_t)p.npad[l]) == 0,
+                      "tcgen05 MLP path: cuTensorMapEncodeTiled failed for the layer-%d weights", l);
+    DFD_CHECK_ARG(st_make_map(&maps.obs, obs, (uint64_t)K0, (uint64_t)n_members * (uint64_t)obs_per_member, 128u) == 0,
+                  "tcgen05 MLP path: cuTensorMapEncodeTiled failed for the observations");
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
     long long* prof = nullptr;
     if (getenv("DFD_ST_PROF")) { cudaMalloc(&prof, (size_t)grid * 32 * 8); cudaMemset(prof, 0, (size_t)grid * 32 * 8); }
     if (approx_tanh) {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_stream_kernel<true><<<grid, ST_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        mlp_forward_stream_kernel<true><<<grid, ST_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     } else {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_stream_kernel<false><<<grid, ST_THREADS, smem, st>>>(p, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
+        mlp_forward_stream_kernel<false><<<grid, ST_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     }
     DFD_LAUNCHED(ctx);
     if (prof) {
