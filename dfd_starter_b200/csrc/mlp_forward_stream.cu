@@ -35,7 +35,7 @@ constexpr int ST_STAGE = ST_WCHUNK + ST_ACHUNK;
 struct StParams {
     int K0, N1, N2, nout, N3, A;
     int w_off[3], b_off[3], kin[3], nreal[3], npad[3], nchunk[3];
-    int E, tiles, n_work, pair_order, prefetch, ns;
+    int E, tiles, n_work, pair_order, prefetch, ns, head_fused;
     int64_t P;
     float sigma;
 };
@@ -223,6 +223,59 @@ mlp_forward_stream_kernel(const StParams p, const __grid_constant__ StMaps maps,
             for (int l = 0; l < 3; ++l) {      // unrolled: every p.xxx[l] is a compile-time constant-bank read
                 const int kin = p.kin[l], nreal = p.nreal[l], npad = p.npad[l], nchunk = p.nchunk[l];
                 const float* ep_l = row + p.w_off[l];
+                if (l == 2 && p.head_fused) {
+                    // the whole head layer ([npad x kin] <= 48 KB) as ONE ring entry: kin / 32 swizzle atoms of npad rows,
+                    // one tensor copy each, instead of kin / 32 dependent chunk round trips of a few KB
+                    if (g % ST_TEAMS == team) {
+                        const int s = g % p.ns;
+                        st_wait(ST_BAR(SB_EMPTY + s), (uint32_t)((g / p.ns) & 1) ^ 1u);
+                        const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
+                        const int natoms = kin / ST_KC, ri = npad >> 2, items = natoms * ri;
+                        const uint32_t atom_bytes = (uint32_t)npad * 128u;
+                        if (tw == 0 && lane == 0) {
+                            st_expect_tx(ST_BAR(SB_TFULL + s), (uint32_t)natoms * atom_bytes);
+                            for (int a = 0; a < natoms; ++a)
+                                st_tma_2d(Wd + (uint32_t)a * atom_bytes, &maps.w[2], a * ST_KC, 0, ST_BAR(SB_TFULL + s));
+                        }
+                        int atom0 = 0, ritem0 = tw;          // item t = h * 4 + tw -> (atom, row item) = (t / ri, t % ri); ri >= 4
+#pragma unroll 1
+                        for (int t0 = 0; t0 < items; t0 += 16 * ST_TEAM_WARPS) {
+                            float4 e[16];
+                            int atom = atom0, ritem = ritem0;
+#pragma unroll
+                            for (int h = 0; h < 16; ++h) {
+                                const int n = ritem * 4 + li, k = atom * ST_KC + lc * 4;
+                                e[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (atom < natoms && n < nreal) e[h] = ldg_stream_f4(ep_l + n * kin + k);
+                                ritem += ST_TEAM_WARPS;
+                                if (ritem >= ri) { ritem -= ri; ++atom; }
+                            }
+                            if (t0 == 0) st_wait(ST_BAR(SB_TFULL + s), (uint32_t)((g / p.ns) & 1));
+                            atom = atom0; ritem = ritem0;
+#pragma unroll
+                            for (int h = 0; h < 16; ++h) {
+                                const int n = ritem * 4 + li;
+                                if (atom < natoms) {
+                                    const uint32_t d = Wd + (uint32_t)atom * atom_bytes + (uint32_t)(n * 128 + ((lc ^ (n & 7)) << 4));
+                                    float4 a;
+                                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(d));
+                                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(d),
+                                                 "f"(st_tf32(perturb1(a.x, sg, e[h].x))), "f"(st_tf32(perturb1(a.y, sg, e[h].y))),
+                                                 "f"(st_tf32(perturb1(a.z, sg, e[h].z))), "f"(st_tf32(perturb1(a.w, sg, e[h].w)))
+                                                 : "memory");
+                                }
+                                ritem += ST_TEAM_WARPS;
+                                if (ritem >= ri) { ritem -= ri; ++atom; }
+                            }
+                            atom0 = atom; ritem0 = ritem;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) st_arrive(ST_BAR(SB_FULL + s));
+                    }
+                    ++g;
+                    continue;
+                }
 #pragma unroll 1
                 for (int c = 0; c < nchunk; ++c, ++g) {
                     if (g % ST_TEAMS != team) continue;
@@ -381,6 +434,26 @@ mlp_forward_stream_kernel(const StParams p, const __grid_constant__ StMaps maps,
                 ST_TL(lane == 0, 2 * l);
                 if (l == 0 && u > 0) { st_wait(ST_BAR(SB_R1FREE), pr1); pr1 ^= 1u; }   // head of the previous member read out
                 ST_TL(lane == 0 && l == 0, 6);
+                if (l == 2 && p.head_fused) {
+                    const int s = g % p.ns, natoms = p.kin[2] / ST_KC;
+                    st_wait(ST_BAR(SB_FULL + s), (uint32_t)((g / p.ns) & 1));
+                    const uint32_t Wd = smem0 + 4u * (uint32_t)(s * ST_STAGE);
+#pragma unroll 1
+                    for (int a = 0; a < natoms; ++a) {
+                        st_wait(ST_BAR(SB_HREADY + 8 + a), ph);          // activations [32a, 32a + 32) of layer 1 are in TMEM
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t bdesc = make_desc_sw128(Wd + (uint32_t)a * (uint32_t)p.npad[2] * 128u);
+#pragma unroll
+                        for (int j = 0; j < ST_KC / 8; ++j)
+                            st_umma_ts(d_tmem, a_tmem + (uint32_t)(a * ST_KC + j * 8), bdesc + (uint64_t)(j * 2), idesc, (a | j) ? 1u : 0u);
+                    }
+                    umma_commit_elect(ST_BAR(SB_EMPTY + s));
+                    umma_commit_elect(ST_BAR(SB_DFULL + 2));
+                    __syncwarp();
+                    ++g;
+                    ST_TL(lane == 0, 2 * l + 1);
+                    continue;
+                }
 #pragma unroll 1
                 for (int c = 0; c < p.nchunk[l]; ++c, ++g) {
                     const int s = g % p.ns;
@@ -479,6 +552,8 @@ int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     p.sigma = sigma;
     p.pair_order = (n_members % 2 == 0 && !getenv("DFD_ST_NOPAIR")) ? 1 : 0;
     p.prefetch = getenv("DFD_ST_NOPF") ? 0 : 1;
+    // the head layer as one ring entry when it fits a stage (whole 32-column atoms, atoms 1024-byte aligned)
+    p.head_fused = (!getenv("DFD_ST_NOFUSE") && N2 % ST_KC == 0 && p.N3 % 8 == 0 && p.N3 >= 16 && (size_t)p.N3 * N2 * 4 <= (size_t)ST_STAGE * 4) ? 1 : 0;
     // ns x 48 KB + biases - measured on B200:
     // the bytes of global loads in flight (and with them the builders' throughput) scale with the L1 that is left
     p.ns = getenv("DFD_ST_NS") ? atoi(getenv("DFD_ST_NS")) : 3;
