@@ -72,7 +72,8 @@ def parse_args():
                     help="forward arithmetic: fp32 CUDA cores (exact path, atol 1e-5), tf32 = tcgen05 tensor cores with "
                          "tf32 operands / fp32 accumulate / ~1e-6 tanh (max-abs 2e-3 vs fp32), tf32a = the same with the "
                          "single-instruction tanh.approx.f32 (2^-11 relative; max-abs 4e-3 vs fp32); "
-                         "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, fp32 otherwise")
+                         "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, tf32 convolutions for IMPALA "
+                         "(max-abs 2e-3 on the action probabilities vs fp32), fp32 otherwise")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: timed steps only (no clock-load loop, per-kernel timing, e2e or CPU baseline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -320,8 +321,9 @@ def b200_main(args, w):
 
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
-    use_tc = w["kind"] == "mujoco" and (args.precision in ("tf32", "tf32a") or (args.precision == "auto" and E >= 32))
-    tc_level = 1 if args.precision == "tf32" else 2
+    use_tc = (w["kind"] == "mujoco" and (args.precision in ("tf32", "tf32a") or (args.precision == "auto" and E >= 32))) or \
+             (w["kind"] == "impala" and args.precision != "fp32")
+    tc_level = 1 if (args.precision == "tf32" or w["kind"] == "impala") else 2
     if w["kind"] in ("mujoco", "discrete"):
         cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
         policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,
@@ -331,7 +333,7 @@ def b200_main(args, w):
         policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local)
         obs_shape = (4, 84, 84)
     else:
-        policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local)
+        policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local, precision=1 if use_tc else 0)
         obs_shape = (3, 64, 64)
     is_impala = w["kind"] == "impala"
     P = policy.num_params
@@ -777,7 +779,9 @@ def b200_main(args, w):
     line = {
         "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ("tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"))
+        "vs_baseline": None, "dtype": ("tf32 convolution operands (mma.sync), fp32 accumulate, fp32 first convolution / dense tail; f32 estimator"
+                                       if w["kind"] == "impala" else
+                                       "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"))
         if use_tc else "f32",
         "data": "synthetic", "config": bench_config(args, w),
         "fd_estimates_per_s": 1e3 / ms_step,

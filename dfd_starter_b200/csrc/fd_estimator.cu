@@ -22,47 +22,92 @@ extern "C" size_t dfd_fd_prepare_scratch_bytes(int n_returns, int n_hist) {
     return dfd_align_up((size_t)(n_returns + 2 * n_hist + 2) * sizeof(double), 256);
 }
 
-// blockIdx.y < n_returns: dot of table row i with its dist row (skipped when hist_row < 0)
-// blockIdx.y >= n_returns: ||dist row||^2
+// blockIdx.y < RB: dots of one table row with the distance rows of its returns (skipped when hist_row < 0).  RB = n_returns,
+// or, with antithetic pairs ([plus | minus] batches: returns y and y + R share their table row by contract), RB = R: the row
+// is streamed from HBM ONCE for both members - when the two returns come from the same epoch (the usual case: a worker
+// evaluates a pair against one FDState) the dot itself is shared too.  Four 16-byte row loads in flight per thread.
+// blockIdx.y >= RB: ||dist row||^2
 __global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __restrict__ replicas, int64_t stride,
                                                               const int64_t* __restrict__ idx,
-                                                              const int32_t* __restrict__ hist_row, int n_returns,
+                                                              const int32_t* __restrict__ hist_row, int n_returns, int R_pairs,
                                                               const float* __restrict__ dist, int64_t dist_stride,
                                                               int64_t P, double* __restrict__ out) {
-    __shared__ double sh[DOT_THREADS / 32];
-    const int r = blockIdx.y;
+    __shared__ double sh[2][DOT_THREADS / 32];
+    const int y = blockIdx.y;
+    const int RB = R_pairs > 0 ? R_pairs : n_returns;
     const float* a;
-    const float* b;
-    if (r < n_returns) {
-        const int h = hist_row[r];
-        if (h < 0) return;
-        a = table_row_ptr(replicas, stride, idx[r]);
-        b = dist + (int64_t)h * dist_stride;
+    const float* b0;
+    const float* b1 = nullptr;
+    int h[2] = {-1, -1};
+    if (y < RB) {
+        h[0] = hist_row[y];
+        if (R_pairs > 0) h[1] = hist_row[y + R_pairs];
+        const int ha = h[0] >= 0 ? h[0] : h[1];
+        if (ha < 0) return;
+        a = table_row_ptr(replicas, stride, idx[y]);
+        b0 = dist + (int64_t)ha * dist_stride;
+        if (h[1] >= 0 && h[1] != ha) b1 = dist + (int64_t)h[1] * dist_stride;
     } else {
-        a = b = dist + (int64_t)(r - n_returns) * dist_stride;
+        a = b0 = dist + (int64_t)(y - RB) * dist_stride;
     }
     const int64_t c0 = (int64_t)blockIdx.x * DOT_CHUNK;
     const int64_t c1 = min(c0 + (int64_t)DOT_CHUNK, P);
-    double acc = 0.0;
-    // both bases are 16-byte aligned (replica rows by construction, dist rows because dist_stride % 4 == 0)
+    double acc0 = 0.0, acc1 = 0.0;
+    // all bases are 16-byte aligned (replica rows by construction, dist rows because dist_stride % 4 == 0)
     const int64_t v1 = c0 + ((c1 - c0) & ~(int64_t)3);
-    for (int64_t c = c0 + 4 * threadIdx.x; c < v1; c += 4 * DOT_THREADS) {
-        const float4 x = ldg_stream_f4(a + c);
-        const float4 y = *reinterpret_cast<const float4*>(b + c);
-        float s = x.x * y.x;
-        s = fmaf(x.y, y.y, s);
-        s = fmaf(x.z, y.z, s);
-        s = fmaf(x.w, y.w, s);
-        acc += (double)s;
+    constexpr int U = 4;
+    for (int64_t cb = c0 + 4 * threadIdx.x; cb < v1; cb += 4 * DOT_THREADS * U) {
+        float4 x[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t c = cb + (int64_t)u * 4 * DOT_THREADS;
+            x[u] = c < v1 ? ldg_stream_f4(a + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t c = cb + (int64_t)u * 4 * DOT_THREADS;
+            if (c < v1) {
+                const float4 y0 = *reinterpret_cast<const float4*>(b0 + c);
+                float s = x[u].x * y0.x;
+                s = fmaf(x[u].y, y0.y, s);
+                s = fmaf(x[u].z, y0.z, s);
+                s = fmaf(x[u].w, y0.w, s);
+                acc0 += (double)s;
+                if (b1) {
+                    const float4 y1 = *reinterpret_cast<const float4*>(b1 + c);
+                    float s1 = x[u].x * y1.x;
+                    s1 = fmaf(x[u].y, y1.y, s1);
+                    s1 = fmaf(x[u].z, y1.z, s1);
+                    s1 = fmaf(x[u].w, y1.w, s1);
+                    acc1 += (double)s1;
+                }
+            }
+        }
     }
-    for (int64_t c = v1 + threadIdx.x; c < c1; c += DOT_THREADS) acc += (double)a[c] * (double)b[c];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    for (int64_t c = v1 + threadIdx.x; c < c1; c += DOT_THREADS) {
+        acc0 += (double)a[c] * (double)b0[c];
+        if (b1) acc1 += (double)a[c] * (double)b1[c];
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = acc0;
+        sh[1][threadIdx.x >> 5] = acc1;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int i = 0; i < DOT_THREADS / 32; ++i) t += sh[i];
-        atomicAdd(out + r, t);
+        double t0 = 0.0, t1 = 0.0;
+        for (int i = 0; i < DOT_THREADS / 32; ++i) {
+            t0 += sh[0][i];
+            t1 += sh[1][i];
+        }
+        if (y >= RB) {
+            atomicAdd(out + n_returns + (y - RB), t0);
+        } else {
+            const int ha = h[0] >= 0 ? h[0] : h[1];
+            if (h[0] >= 0) atomicAdd(out + y, t0);                                  // h[0] >= 0 implies ha == h[0]
+            if (h[1] >= 0) atomicAdd(out + y + R_pairs, h[1] == ha ? t0 : t1);
+        }
     }
 }
 
@@ -219,9 +264,9 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
     unsigned* counter = (unsigned*)((double*)scratch + (dfd_fd_prepare_scratch_bytes(n_returns, n_hist) / sizeof(double) - 1));
     if (n_hist > 0) {
         DFD_CUDA(cudaMemsetAsync(dots, 0, (size_t)(n_returns + 2 * n_hist) * sizeof(double), st));
-        dim3 grid((unsigned)((n_params + DOT_CHUNK - 1) / DOT_CHUNK), (unsigned)(n_returns + n_hist));
+        dim3 grid((unsigned)((n_params + DOT_CHUNK - 1) / DOT_CHUNK), (unsigned)((paired ? R : n_returns) + n_hist));
         fd_dots_kernel<<<grid, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
-                                                     dist, dist_stride, n_params, dots);
+                                                     paired ? R : 0, dist, dist_stride, n_params, dots);
         DFD_LAUNCHED(ctx);
     }
     fd_coef_kernel<<<(R + COEF_THREADS - 1) / COEF_THREADS, COEF_THREADS, 0, st>>>(

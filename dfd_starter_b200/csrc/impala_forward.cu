@@ -5,7 +5,10 @@
 // BN layers are eval-mode with shared running statistics and per-member (perturbed) gamma / beta; every
 // parameter is theta + sign*sigma*eps generated in-kernel (worker/worker.py:28).  The whole conv trunk keeps its
 // activations in shared memory (two ping-pong maps + a conv-row band for the pooled stages); only the
-// carried LSTM state and the action probabilities touch HBM.  Exact fp32 on CUDA cores (atol 1e-5 against torch CPU):
+// carried LSTM state and the action probabilities touch HBM.  precision 0: exact fp32 on CUDA cores (atol 1e-5 against
+// torch CPU); precision >= 1: the convolutions from the second one on run on the tensor cores (tf32, see conv3x3_mma).
+// One CTA evaluates the two members of an antithetic pair (trunks one after the other, ONE pass over theta and the shared
+// eps row for the dense tail of both).  The fp32 path:
 //   * convolutions are register-tiled: a thread owns 4 neighbouring pixels x OCT output channels (OCT = 8 / 4 / 2 chosen so
 //     that every layer fills the 512 threads), reads its 4 inputs with one 16-byte shared-memory load per (channel, row),
 //     applies the input-side BN (+ReLU) once, takes the two halo pixels from the neighbouring lanes by shuffle, and issues
@@ -23,6 +26,7 @@ namespace {
 
 constexpr int IM_THREADS = 512;
 constexpr int MAP = 16384;    // floats per activation map buffer (16 x 32 x 32)
+constexpr int MAP_TC = 18560; // the same map padded for the tensor-core path: 16 channels x 1160 (34 x 34 = 1156 -> 8 mod 32)
 constexpr int BAND = 9248;    // conv-row band for the pooled stages: 9 rows x (64 x 16 | 32 x 32), 32 x 16 x 16; staging of a
                               // layer's weights (32 rows x 289)
 constexpr int WMAX = 9216;    // largest conv weight block (32 x 32 x 3 x 3)
@@ -52,7 +56,8 @@ struct Ctx {
 // every load of the layer - BN gamma / beta / statistics and the bias included - is issued before the first store.  The
 // perturbed rows go to a staging area (`stage` = the conv band buffer, free while weights are loaded) with an odd row
 // stride, so the transposition into the [k][oc] layout reads and writes shared memory without bank conflicts.
-__device__ void load_conv(const Ctx& c, const ConvP& p, float* wsm, float* stage, float* s_in, float* sh_in, float* bias) {
+__device__ void load_conv(const Ctx& c, const ConvP& p, float* wsm, float* stage, float* s_in, float* sh_in, float* bias,
+                          bool tc_layer) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k9 = p.cin * 9, n = p.cout * k9;
     const int ss = k9 | 1;                     // staging row stride (odd)
@@ -99,9 +104,21 @@ __device__ void load_conv(const Ctx& c, const ConvP& p, float* wsm, float* stage
     }
     __syncthreads();
     const int lc = p.cout == 32 ? 5 : 4;       // cout is 16 or 32
-    for (int t = tid; t < n; t += IM_THREADS) {
-        const int k = t >> lc, oc = t & (p.cout - 1);
-        wsm[t] = stage[oc * ss + k];
+    if (!tc_layer) {
+        for (int t = tid; t < n; t += IM_THREADS) {
+            const int k = t >> lc, oc = t & (p.cout - 1);
+            wsm[t] = stage[oc * ss + k];
+        }
+    } else {
+        // tensor-core layer: weights rounded to tf32, channel index swizzled by the input channel (conv3x3_mma)
+        const int mask = p.cout == 32 ? 3 : 1;
+        for (int t = tid; t < n; t += IM_THREADS) {
+            const int k = t >> lc, oc = t & (p.cout - 1);
+            const int ci = k / 9;
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(stage[oc * ss + k]));
+            wsm[k * p.cout + (oc ^ ((ci & mask) << 3))] = __uint_as_float(u);
+        }
     }
 }
 
@@ -220,6 +237,267 @@ __device__ __forceinline__ void conv3x3(const float* __restrict__ in, int cin, i
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Tensor-core convolution (precision >= 1): implicit GEMM on mma.sync m16n8k8 tf32, fp32 accumulate.
+//   M = 16 neighbouring pixels, N = 8 output channels, K = 8 input channels at one filter tap (9 taps x cin/8 K-steps).
+// The A operand is read straight from the activation map - no im2col copy: maps are stored PADDED ([c][H+2][W+2], channel
+// stride = 8 mod 32 so the (pixel, channel) fragment loads are bank-conflict-free) with a NaN border, the input-side BN + ReLU
+// is applied as the fragment is loaded (fmaxf(NaN, 0) = 0 turns the border into torch's zero padding of the BN output; the
+// ReLU-less stage convolutions use a self-compare), and the value is rounded to tf32 by adding half an ulp (the tensor core
+// ignores the low 13 mantissa bits).  Weights are rounded with cvt.rna.tf32 when the layer is loaded and stored [k][oc] with
+// the channel index XOR-swizzled by (ci & 3) << 3, so the B fragments are conflict-free too.
+// Why mma.sync and not tcgen05 (yet): tcgen05's A operand must sit in shared memory in the UMMA core-matrix layout, i.e.
+// one materialised im2col tile per filter tap (16 KB written + read per 131 k MACs at N = 16 / 32), while this loop feeds the
+// fragments from the map as it is.  Measured on B200 (DFD_IMPALA_PROF timeline): the legacy HMMA.1688.TF32 path sustains
+// about one instruction per 24 cycles per SM sub-partition here, which makes these layers 2x faster than the packed-FMA
+// fp32 ones (16 x 32 x 32 layer: 28 k -> 15 k cycles); halving the MMA count (m16n8k16, fp16 operands) and an im2col-by-TMA
+// tcgen05 variant are the next steps.
+// A warp owns MT m-tiles x NT n-tiles; every layer is cut into exactly 16 such units (one per warp).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <bool RELU_IN>
+__device__ __forceinline__ uint32_t norm_tf32(float v, float s, float sh) {
+    float f = fmaf(v, s, sh);
+    if (RELU_IN) f = fmaxf(f, 0.f);      // NaN border -> 0
+    else f = (f == f) ? f : 0.f;
+    return __float_as_uint(f) + 0x1000u;
+}
+
+// in_o: padded input map at its (0, 0) element, channel stride in_cs, row stride in_rs.  Output rows [r0, r1) of the
+// H x W map; element (oc, r, x) goes to dst[oc*dst_cs + ((r - r0 + dst_r0) % dst_rmod)*dst_rs + x]; ACCUM adds (residual).
+template <int MT, int NT, bool RELU_IN, bool ACCUM>
+__device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, int cin, int in_cs, int in_rs, int W,
+                                            const float* __restrict__ wsm, int cout, const float* __restrict__ s_in,
+                                            const float* __restrict__ sh_in, const float* __restrict__ bias, int r0, int r1,
+                                            float* __restrict__ dst, int dst_cs, int dst_rs, int dst_r0, int dst_rmod) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int lw = 31 - __clz(W);
+    const int mblks = (((r1 - r0) << lw) >> 4) / MT, nblks = (cout >> 3) / NT;
+    const int swz = (cout == 32 ? tig : (tig & 1)) << 3;
+    for (int unit = warp; unit < mblks * nblks; unit += IM_THREADS / 32) {
+        const int mblk = unit % mblks, nblk = unit / mblks;
+        int ao[MT][2], pr[MT][2], px[MT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int pm = ((mblk * MT + i) << 4) + g + 8 * p;
+                pr[i][p] = r0 + (pm >> lw);
+                px[i][p] = pm & (W - 1);
+                ao[i][p] = pr[i][p] * in_rs + px[i][p];
+            }
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float2 b = *reinterpret_cast<const float2*>(bias + ((nblk * NT + j) << 3) + 2 * tig);
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                acc[i][j][0] = b.x; acc[i][j][1] = b.y; acc[i][j][2] = b.x; acc[i][j][3] = b.y;
+            }
+        }
+        int nph[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) nph[j] = ((((nblk * NT + j) << 3) + g) ^ swz);
+        for (int ci0 = 0; ci0 < cin; ci0 += 8) {
+            const float* chA = in_o + (ci0 + tig) * in_cs;
+            const float* chB = chA + 4 * in_cs;
+            const float sA = s_in[ci0 + tig], shA = sh_in[ci0 + tig], sB = s_in[ci0 + tig + 4], shB = sh_in[ci0 + tig + 4];
+            const float* wA = wsm + (ci0 + tig) * 9 * cout;
+            const float* wB = wA + 36 * cout;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int tap = ky * 3 + kx;
+                    const int toff = (ky - 1) * in_rs + (kx - 1);
+                    uint32_t b0[NT], b1[NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        b0[j] = __float_as_uint(wA[tap * cout + nph[j]]);
+                        b1[j] = __float_as_uint(wB[tap * cout + nph[j]]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const uint32_t a0 = norm_tf32<RELU_IN>(chA[ao[i][0] + toff], sA, shA);
+                        const uint32_t a1 = norm_tf32<RELU_IN>(chA[ao[i][1] + toff], sA, shA);
+                        const uint32_t a2 = norm_tf32<RELU_IN>(chB[ao[i][0] + toff], sB, shB);
+                        const uint32_t a3 = norm_tf32<RELU_IN>(chB[ao[i][1] + toff], sB, shB);
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b0[j], b1[j]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const int slot = (pr[i][p] - r0 + dst_r0) % dst_rmod;
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int oc = ((nblk * NT + j) << 3) + 2 * tig + q;
+                        float* d = dst + oc * dst_cs + slot * dst_rs + px[i][p];
+                        if (ACCUM) *d += acc[i][j][2 * p + q]; else *d = acc[i][j][2 * p + q];
+                    }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Dense tail for the NM members of this CTA (NM = 2: the two members of an antithetic pair, whose eps row is streamed ONCE).
+// fc[q]: BN'd flattened trunk output of member q (2048); st: per-member scratch (core 260 | h0 256 | gates 1024 | hn 256 |
+// logits 32 = ST floats).
+constexpr int ST = 260 + 256 + 1024 + 256 + 32;
+template <int NM>
+__device__ __forceinline__ void dense_tail(const ImpalaP& L, const float* __restrict__ theta, const float* __restrict__ row,
+                                           const float* __restrict__ bnbuf, const float (&sg)[2], const int (&inst)[2],
+                                           float* const (&fc)[2], float* st, const float* __restrict__ reward,
+                                           const uint8_t* __restrict__ done, const float* __restrict__ h_in,
+                                           const float* __restrict__ c_in, float* __restrict__ probs,
+                                           float* __restrict__ h_out, float* __restrict__ c_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto par = [&](int q, int64_t p) { return perturb1(theta[p], sg[q], row[p]); };
+    bool dn[NM];
+#pragma unroll
+    for (int q = 0; q < NM; ++q) {
+        dn[q] = done[inst[q]] != 0;
+        float* hst = st + q * ST + 260;
+        for (int k = tid; k < 256; k += IM_THREADS) hst[k] = dn[q] ? 0.f : h_in[(int64_t)inst[q] * 256 + k];
+    }
+    __syncthreads();
+    // Linear 2048 -> 256 (+ReLU): warp per output row, 8-byte loads (row starts are 8-byte aligned only), 16 + 16 loads
+    // (256 B) in flight per lane
+    for (int o = warp; o < 256; o += IM_THREADS / 32) {
+        const int64_t base = L.fc_w + (int64_t)o * 2048;
+        float acc[NM];
+#pragma unroll
+        for (int q = 0; q < NM; ++q) acc[q] = 0.f;
+        for (int v0 = 0; v0 < 1024; v0 += 512) {
+            float2 tw[16], ew[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int v = v0 + u * 32 + lane;
+                tw[u] = *reinterpret_cast<const float2*>(theta + base + 2 * v);
+                ew[u] = *reinterpret_cast<const float2*>(row + base + 2 * v);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int v = v0 + u * 32 + lane;
+#pragma unroll
+                for (int q = 0; q < NM; ++q) {
+                    const float2 f = *reinterpret_cast<const float2*>(fc[q] + 2 * v);
+                    acc[q] = fmaf(perturb1(tw[u].x, sg[q], ew[u].x), f.x, acc[q]);
+                    acc[q] = fmaf(perturb1(tw[u].y, sg[q], ew[u].y), f.y, acc[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NM; ++q) {
+            const float a = warp_sum(acc[q]);
+            if (lane == 0) st[q * ST + o] = fmaxf(a + par(q, L.fc_b + o), 0.f);
+        }
+    }
+    if (tid < NM) st[tid * ST + 256] = fminf(fmaxf(reward[inst[tid]], -1.f), 1.f);   // clamp(reward, -1, 1), impala.py:158
+    __syncthreads();
+    // LSTM gates = W_ih [x;r] + b_ih + W_hh h0 + b_hh   (rows: i | f | g | o, 256 each).  A warp takes two gate rows at a
+    // time and issues all their loads first: W_ih rows (257 floats, 4-byte aligned only) lane-strided, W_hh rows (256
+    // floats, 8-byte aligned) as float2 - 52 loads = 272 B in flight per lane
+    for (int o0 = 2 * warp; o0 < 1024; o0 += 2 * (IM_THREADS / 32)) {
+        float ti[2][9], ei[2][9];
+        float2 th[2][4], eh[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int64_t bi = L.wih + (int64_t)(o0 + r) * 257, bh = L.whh + (int64_t)(o0 + r) * 256;
+#pragma unroll
+            for (int u = 0; u < 9; ++u) {
+                const int k = lane + 32 * u;
+                ti[r][u] = 0.f;
+                ei[r][u] = 0.f;
+                if (k < 257) {
+                    ti[r][u] = theta[bi + k];
+                    ei[r][u] = row[bi + k];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int v = lane + 32 * u;
+                th[r][u] = *reinterpret_cast<const float2*>(theta + bh + 2 * v);
+                eh[r][u] = *reinterpret_cast<const float2*>(row + bh + 2 * v);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < NM; ++q) {
+                const float* core = st + q * ST;
+                const float* hst = core + 260;
+                float acc = 0.f;
+#pragma unroll
+                for (int u = 0; u < 9; ++u) {
+                    const int k = lane + 32 * u;
+                    if (k < 257) acc = fmaf(perturb1(ti[r][u], sg[q], ei[r][u]), core[k], acc);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int v = lane + 32 * u;
+                    const float2 hv = *reinterpret_cast<const float2*>(hst + 2 * v);
+                    acc = fmaf(perturb1(th[r][u].x, sg[q], eh[r][u].x), hv.x, acc);
+                    acc = fmaf(perturb1(th[r][u].y, sg[q], eh[r][u].y), hv.y, acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) st[q * ST + 516 + o0 + r] = acc + par(q, L.bih + o0 + r) + par(q, L.bhh + o0 + r);
+            }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NM; ++q) {
+        const float* gates = st + q * ST + 516;
+        float* hn = st + q * ST + 1540;
+        for (int k = tid; k < 256; k += IM_THREADS) {
+            const float c0 = dn[q] ? 0.f : c_in[(int64_t)inst[q] * 256 + k];
+            const float ig = sigmoidf_(gates[k]), fg = sigmoidf_(gates[256 + k]);
+            const float gg = tanhf(gates[512 + k]), og = sigmoidf_(gates[768 + k]);
+            const float c1 = fg * c0 + ig * gg;
+            const float h1 = og * tanhf(c1);
+            c_out[(int64_t)inst[q] * 256 + k] = c1;
+            h_out[(int64_t)inst[q] * 256 + k] = h1;
+            const float inv = 1.0f / sqrtf(bnbuf[L.pol_bv + k] + 1e-5f);
+            const float s = par(q, L.pol_g + k) * inv;
+            hn[k] = fmaf(h1, s, par(q, L.pol_be + k) - bnbuf[L.pol_bm + k] * s);
+        }
+    }
+    __syncthreads();
+    for (int a = warp; a < NM * L.A; a += IM_THREADS / 32) {
+        const int q = a / L.A, ai = a - q * L.A;
+        const float* hn = st + q * ST + 1540;
+        float acc = 0.f;
+        for (int k = lane; k < 256; k += 32) acc = fmaf(par(q, L.pol_w + ai * 256 + k), hn[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) st[q * ST + 1796 + ai] = acc + par(q, L.pol_b + ai);
+    }
+    __syncthreads();
+    if (tid < NM) {
+        const float* lg = st + tid * ST + 1796;
+        float mx = -INFINITY;
+        for (int a = 0; a < L.A; ++a) mx = fmaxf(mx, lg[a]);
+        float ssum = 0.f;
+        for (int a = 0; a < L.A; ++a) ssum += expf(lg[a] - mx);
+        const float inv = 1.0f / ssum;
+        for (int a = 0; a < L.A; ++a) probs[(int64_t)inst[tid] * L.A + a] = expf(lg[a] - mx) * inv;
+    }
+}
+
+// TC = false: exact fp32 (unpadded maps).  TC = true: tf32 tensor-core convolutions (padded maps with a NaN border); the
+// first convolution (3 input channels, 6 % of the MACs) and the dense tail stay fp32.
+// pair_order: 0 = CTA per (member, env) in plain order; 1 = the same with the two members of an antithetic pair on
+// neighbouring CTAs; 2 = CTA per (pair, env): members j and j + M/2 run their trunks one after the other and share the dense
+// tail, so theta and the pair's eps row (8.4 MB per pair) are streamed once for both.
+template <bool TC>
 __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L, const float* __restrict__ replicas,
                                                                        int64_t stride, const float* __restrict__ theta,
                                                                        const float* __restrict__ bnbuf,
@@ -233,17 +511,18 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                                                                        float* __restrict__ probs, float* __restrict__ h_out,
                                                                        float* __restrict__ c_out, int n_members, int pair_order,
                                                                        long long* __restrict__ prof) {
+    constexpr int MAPF = TC ? MAP_TC : MAP;
     extern __shared__ __align__(16) float sm[];
     float* bufA = sm;
-    float* bufB = bufA + MAP;
-    float* band = bufB + MAP;
+    float* bufB = bufA + MAPF;
+    float* band = bufB + MAPF;
     float* wsm = band + BAND;
     float* s_in = wsm + WMAX;      // 32
     float* sh_in = s_in + 32;      // 32
     float* bias = sh_in + 32;      // 32
-    float* vec = bias + 32;        // 2048 + 257 + 256 + 1024 + 32 scratch for the dense tail
+    float* fc0 = bias + 32;        // 2048: BN'd trunk output of the CTA's first member (the second one's goes to `band`)
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     int stamp_i = 0;
     // DFD_IMPALA_PROF=1: cycle stamps of CTA 7 at the phase boundaries (all stamps follow a CTA barrier)
     auto stamp = [&]() {
@@ -251,237 +530,185 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
         ++stamp_i;
     };
     stamp();
-    // consecutive CTAs take the two members of an antithetic pair ([plus | minus] batches: members j and j + M/2 share
-    // their table row), so the pair streams the same eps row at the same time and HBM serves it once
+    const int nmem = pair_order == 2 ? 2 : 1;
     const int mb = blockIdx.x / E, env = blockIdx.x - mb * E;
-    const int m = pair_order ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
-    const int inst = m * E + env;           // (member, env)
-    Ctx c;
-    c.theta = theta;
-    c.bn = bnbuf;
-    c.sg = sigma * (float)sign[m];
-    c.row = table_row_ptr(replicas, stride, idx[m]);
+    const int m0 = pair_order == 1 ? ((mb & 1) ? (n_members >> 1) + (mb >> 1) : (mb >> 1)) : mb;
+    const int ms[2] = {m0, pair_order == 2 ? m0 + (n_members >> 1) : m0};
+    const int inst[2] = {ms[0] * E + env, ms[1] * E + env};          // (member, env)
+    const float sgs[2] = {sigma * (float)sign[ms[0]], sigma * (float)sign[ms[1]]};
+    const float* rows[2] = {table_row_ptr(replicas, stride, idx[ms[0]]), table_row_ptr(replicas, stride, idx[ms[1]])};
+    float* const fcs[2] = {fc0, band};
 
-    // frame / 255 -> bufA  (impala.py:142); 24 loads per thread in three rounds of 8
-    const float* fr = frame + (int64_t)inst * 12288;
-    for (int t0 = tid; t0 < 12288; t0 += IM_THREADS * 8) {
-        float f[8];
+    for (int mem = 0; mem < nmem; ++mem) {
+        Ctx c;
+        c.theta = theta;
+        c.bn = bnbuf;
+        c.sg = sgs[mem];
+        c.row = rows[mem];
+        __syncthreads();        // the previous member's trunk output has been read
+        // frame / 255 -> bufA  (impala.py:142); 24 loads per thread in three rounds of 8
+        const float* fr = frame + (int64_t)inst[mem] * 12288;
+        for (int t0 = tid; t0 < 12288; t0 += IM_THREADS * 8) {
+            float f[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) f[u] = fr[t0 + u * IM_THREADS];
+            for (int u = 0; u < 8; ++u) f[u] = fr[t0 + u * IM_THREADS];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) bufA[t0 + u * IM_THREADS] = f[u] / 255.0f;
-    }
-
-    __syncthreads();
-    stamp();            // 1: frame in shared memory
-    float* x = bufA;    // current map
-    float* t = bufB;    // the other buffer
-    int H = 64;
-    int li = 0;         // position in the execution-order list of conv layers
-    auto next_layer = [&](const ConvP& p) {
-        load_conv(c, p, wsm, band, s_in, sh_in, bias);
-        ++li;
-        if (li < 15) prefetch_l2(c.row + L.seq_w[li], L.seq_n[li]);
-        else prefetch_l2(c.row + L.fc_w, 65536);      // first 32 rows of the Linear
-    };
-    for (int s = 0; s < 3; ++s) {
-        const ConvP& fp = L.feat[s];
+            for (int u = 0; u < 8; ++u) bufA[t0 + u * IM_THREADS] = f[u] / 255.0f;
+        }
         __syncthreads();
-        next_layer(fp);
-        __syncthreads();
-        // conv (BN on the input, no ReLU) + maxpool 3x3 stride 2 pad 1 (-inf padding)
-        const int W = H, Ho = H / 2, Wo = W / 2;
-        const int lwo = 31 - __clz(Wo);
-        if (s < 2) {
-            // bands of 4 pooled rows: 8 NEW conv rows per band go into a 9-row circular band (conv row r lives in slot
-            // r % 9), the row above them is still there from the previous band
-            for (int py0 = 0; py0 < Ho; py0 += 4) {
-                const int cr0 = 2 * py0;
-                conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, cr0 % 9, 9);
+        if (mem == 0) stamp();            // 1: frame in shared memory
+        float* x = bufA;    // current map
+        float* t = bufB;    // the other buffer
+        int H = 64;
+        int xcs = 64 * 64, xrs = 64, xorg = 0;     // geometry of x: channel stride, row stride, offset of element (0, 0)
+        int li = 0;         // position in the execution-order list of conv layers
+        auto next_layer = [&](const ConvP& p, bool tc_layer) {
+            load_conv(c, p, wsm, band, s_in, sh_in, bias, tc_layer);
+            ++li;
+            if (li < 15) prefetch_l2(c.row + L.seq_w[li], L.seq_n[li]);
+            else prefetch_l2(c.row + L.fc_w, 65536);      // first 32 rows of the Linear
+        };
+        auto nan_fill = [&](float* buf) {
+            for (int i = tid; i < MAPF; i += IM_THREADS) buf[i] = __int_as_float(0x7fc00000);
+        };
+        for (int s = 0; s < 3; ++s) {
+            const ConvP& fp = L.feat[s];
+            const bool tc_conv = TC && s > 0;
+            __syncthreads();
+            next_layer(fp, tc_conv);
+            // conv (BN on the input, no ReLU) + maxpool 3x3 stride 2 pad 1 (-inf padding)
+            const int W = H, Ho = H / 2, Wo = W / 2;
+            const int lwo = 31 - __clz(Wo);
+            // geometry of the pooled map
+            const int trs = TC ? Wo + 2 : Wo;
+            const int tcs = TC ? (((Wo + 2) * (Wo + 2) + 23) / 32 * 32 + 8) : Wo * Wo;
+            const int torg = TC ? trs + 1 : 0;
+            if (TC) nan_fill(t);        // t is free: nobody reads it until the pool below has written the new map
+            __syncthreads();
+            if (s < 2) {
+                // bands of 4 pooled rows: 8 NEW conv rows per band go into a 9-row circular band (conv row r lives in slot
+                // r % 9), the row above them is still there from the previous band
+                for (int py0 = 0; py0 < Ho; py0 += 4) {
+                    const int cr0 = 2 * py0;
+                    if (tc_conv)
+                        conv3x3_mma<1, 4, false, false>(x + xorg, fp.cin, xcs, xrs, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8,
+                                                        band, 9 * W, W, cr0 % 9, 9);
+                    else
+                        conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, cr0 % 9, 9);
+                    __syncthreads();
+                    for (int o = tid; o < fp.cout * 4 * Wo; o += IM_THREADS) {
+                        const int oc = o >> (lwo + 2), rem = o & (4 * Wo - 1);     // Wo is a power of two
+                        const int py = py0 + (rem >> lwo), px = rem & (Wo - 1);
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            const int yy = 2 * py + dy;
+                            if (yy < 0 || yy >= H) continue;
+                            const float* brow = band + oc * 9 * W + (yy % 9) * W;
+#pragma unroll
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int xx = 2 * px + dx;
+                                if (xx < 0 || xx >= W) continue;
+                                mx = fmaxf(mx, brow[xx]);
+                            }
+                        }
+                        t[torg + oc * tcs + py * trs + px] = mx;
+                    }
+                    __syncthreads();
+                }
+            } else {
+                // 16 x 16: the whole conv output (32 x 16 x 16) fits the band buffer
+                if (tc_conv)
+                    conv3x3_mma<1, 4, false, false>(x + xorg, fp.cin, xcs, xrs, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, W, 0, H);
+                else
+                    conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, 0, H);
                 __syncthreads();
-                for (int o = tid; o < fp.cout * 4 * Wo; o += IM_THREADS) {
-                    const int oc = o >> (lwo + 2), rem = o & (4 * Wo - 1);     // Wo is a power of two
-                    const int py = py0 + (rem >> lwo), px = rem & (Wo - 1);
+                for (int o = tid; o < fp.cout * Ho * Wo; o += IM_THREADS) {
+                    const int oc = o >> (2 * lwo), rem = o & (Ho * Wo - 1);
+                    const int py = rem >> lwo, px = rem & (Wo - 1);
                     float mx = -INFINITY;
 #pragma unroll
                     for (int dy = -1; dy <= 1; ++dy) {
                         const int yy = 2 * py + dy;
                         if (yy < 0 || yy >= H) continue;
-                        const float* brow = band + oc * 9 * W + (yy % 9) * W;
 #pragma unroll
                         for (int dx = -1; dx <= 1; ++dx) {
                             const int xx = 2 * px + dx;
                             if (xx < 0 || xx >= W) continue;
-                            mx = fmaxf(mx, brow[xx]);
+                            mx = fmaxf(mx, band[oc * H * W + yy * W + xx]);
                         }
                     }
-                    t[oc * Ho * Wo + py * Wo + px] = mx;
+                    t[torg + oc * tcs + py * trs + px] = mx;
                 }
                 __syncthreads();
             }
-        } else {
-            // 16 x 16: the whole conv output (32 x 16 x 16) fits the band buffer
-            conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, 0, H);
-            __syncthreads();
-            for (int o = tid; o < fp.cout * Ho * Wo; o += IM_THREADS) {
-                const int oc = o >> (2 * lwo), rem = o & (Ho * Wo - 1);
-                const int py = rem >> lwo, px = rem & (Wo - 1);
-                float mx = -INFINITY;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int yy = 2 * py + dy;
-                    if (yy < 0 || yy >= H) continue;
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        const int xx = 2 * px + dx;
-                        if (xx < 0 || xx >= W) continue;
-                        mx = fmaxf(mx, band[oc * H * W + yy * W + xx]);
-                    }
+            { float* tmp = x; x = t; t = tmp; }
+            H = Ho;
+            xcs = tcs; xrs = trs; xorg = torg;
+            if (TC) nan_fill(t);        // the old input map becomes the block-internal map: NaN border in the new geometry
+            if (mem == 0) stamp();        // 2, 5, 8: stage conv + pool done
+            // two residual blocks at this resolution: x += conv_b(relu(BN_b(conv_a(relu(BN_a(x))))))
+            for (int blk = 0; blk < 2; ++blk) {
+                const ConvP& pa = L.res[blk][s][0];
+                const ConvP& pb = L.res[blk][s][1];
+                auto fine = [&](int i) {       // finer stamps inside the first residual block of each stage
+                    if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && blk == 0) prof[16 + 4 * s + i] = clock64();
+                };
+                next_layer(pa, TC);
+                __syncthreads();
+                fine(0);
+                if (TC) {
+                    if (s == 0) conv3x3_mma<4, 2, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    else if (s == 1) conv3x3_mma<1, 4, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    else conv3x3_mma<1, 1, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                } else {
+                    if (s == 0) conv3x3<8, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
+                    else if (s == 1) conv3x3<4, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
+                    else conv3x3<2, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
                 }
-                t[o] = mx;
-            }
-            __syncthreads();
-        }
-        { float* tmp = x; x = t; t = tmp; }
-        H = Ho;
-        stamp();        // 2, 5, 8: stage conv + pool done
-        // two residual blocks at this resolution: x += conv_b(relu(BN_b(conv_a(relu(BN_a(x))))))
-        for (int blk = 0; blk < 2; ++blk) {
-            const ConvP& pa = L.res[blk][s][0];
-            const ConvP& pb = L.res[blk][s][1];
-            next_layer(pa);
-            __syncthreads();
-            if (s == 0) conv3x3<8, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
-            else if (s == 1) conv3x3<4, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
-            else conv3x3<2, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
-            __syncthreads();
-            next_layer(pb);
-            __syncthreads();
-            if (s == 0) conv3x3<8, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
-            else if (s == 1) conv3x3<4, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
-            else conv3x3<2, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
-            __syncthreads();
-            stamp();    // residual block done
-        }
-    }
-    // x: [32][8][8].  relu -> flatten (C,H,W) -> BN1d(2048) -> vec[0..2048)
-    float* fcin = vec;             // 2048
-    float* core = vec + 2048;      // 257: relu(fc) | clamped reward
-    float* hst = core + 260;       // 256: h0
-    float* gates = hst + 256;      // 1024
-    float* hn = gates + 1024;      // 256: BN'd new h for the policy head
-    float* lg = hn + 256;          // 32 logits
-    for (int k = tid; k < 2048; k += IM_THREADS) {
-        const float inv = 1.0f / sqrtf(bnbuf[L.fc_bv + k] + 1e-5f);
-        const float s = c.par(L.fc_g + k) * inv;
-        fcin[k] = fmaf(fmaxf(x[k], 0.f), s, c.par(L.fc_be + k) - bnbuf[L.fc_bm + k] * s);
-    }
-    const bool dn = done[inst] != 0;
-    for (int k = tid; k < 256; k += IM_THREADS) hst[k] = dn ? 0.f : h_in[(int64_t)inst * 256 + k];
-    __syncthreads();
-    // Linear 2048 -> 256 (+ReLU): warp per output row, 8-byte loads (row starts are 8-byte aligned only), 16 + 16 loads
-    // (256 B) in flight per lane
-    for (int o = warp; o < 256; o += IM_THREADS / 32) {
-        const int64_t base = L.fc_w + (int64_t)o * 2048;
-        float acc = 0.f;
-        for (int v0 = 0; v0 < 1024; v0 += 512) {
-            float2 tw[16], ew[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int v = v0 + u * 32 + lane;
-                tw[u] = *reinterpret_cast<const float2*>(theta + base + 2 * v);
-                ew[u] = *reinterpret_cast<const float2*>(c.row + base + 2 * v);
-            }
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int v = v0 + u * 32 + lane;
-                const float2 f = *reinterpret_cast<const float2*>(fcin + 2 * v);
-                acc = fmaf(perturb1(tw[u].x, c.sg, ew[u].x), f.x, acc);
-                acc = fmaf(perturb1(tw[u].y, c.sg, ew[u].y), f.y, acc);
-            }
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) core[o] = fmaxf(acc + c.par(L.fc_b + o), 0.f);
-    }
-    if (tid == 0) core[256] = fminf(fmaxf(reward[inst], -1.f), 1.f);   // clamp(reward, -1, 1), impala.py:158
-    __syncthreads();
-    stamp();            // 11: Linear 2048 -> 256 done
-    // LSTM gates = W_ih [x;r] + b_ih + W_hh h0 + b_hh   (rows: i | f | g | o, 256 each).  A warp takes two gate rows at a
-    // time and issues all their loads first: W_ih rows (257 floats, 4-byte aligned only) lane-strided, W_hh rows (256
-    // floats, 8-byte aligned) as float2 - 52 loads = 272 B in flight per lane
-    for (int o0 = 2 * warp; o0 < 1024; o0 += 2 * (IM_THREADS / 32)) {
-        float ti[2][9], ei[2][9];
-        float2 th[2][4], eh[2][4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int64_t bi = L.wih + (int64_t)(o0 + q) * 257, bh = L.whh + (int64_t)(o0 + q) * 256;
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int k = lane + 32 * u;
-                ti[q][u] = 0.f;
-                ei[q][u] = 0.f;
-                if (k < 257) {
-                    ti[q][u] = theta[bi + k];
-                    ei[q][u] = c.row[bi + k];
+                __syncthreads();
+                fine(1);
+                next_layer(pb, TC);
+                __syncthreads();
+                fine(2);
+                if (TC) {
+                    if (s == 0) conv3x3_mma<4, 2, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    else if (s == 1) conv3x3_mma<1, 4, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    else conv3x3_mma<1, 1, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                } else {
+                    if (s == 0) conv3x3<8, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
+                    else if (s == 1) conv3x3<4, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
+                    else conv3x3<2, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = lane + 32 * u;
-                th[q][u] = *reinterpret_cast<const float2*>(theta + bh + 2 * v);
-                eh[q][u] = *reinterpret_cast<const float2*>(c.row + bh + 2 * v);
+                __syncthreads();
+                fine(3);
+                if (mem == 0) stamp();    // residual block done
             }
         }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float acc = 0.f;
-#pragma unroll
-            for (int u = 0; u < 9; ++u) {
-                const int k = lane + 32 * u;
-                if (k < 257) acc = fmaf(perturb1(ti[q][u], c.sg, ei[q][u]), core[k], acc);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int v = lane + 32 * u;
-                const float2 hv = *reinterpret_cast<const float2*>(hst + 2 * v);
-                acc = fmaf(perturb1(th[q][u].x, c.sg, eh[q][u].x), hv.x, acc);
-                acc = fmaf(perturb1(th[q][u].y, c.sg, eh[q][u].y), hv.y, acc);
-            }
-            acc = warp_sum(acc);
-            if (lane == 0) gates[o0 + q] = acc + c.par(L.bih + o0 + q) + c.par(L.bhh + o0 + q);
+        // x: [32][8][8].  relu -> flatten (C,H,W) -> BN1d(2048)
+        float* fcin = fcs[mem];
+        for (int k = tid; k < 2048; k += IM_THREADS) {
+            const float inv = 1.0f / sqrtf(bnbuf[L.fc_bv + k] + 1e-5f);
+            const float s = c.par(L.fc_g + k) * inv;
+            const float xv = x[xorg + (k >> 6) * xcs + ((k >> 3) & 7) * xrs + (k & 7)];
+            fcin[k] = fmaf(fmaxf(xv, 0.f), s, c.par(L.fc_be + k) - bnbuf[L.fc_bm + k] * s);
         }
     }
-    __syncthreads();
-    stamp();            // 12: LSTM gates done
-    for (int k = tid; k < 256; k += IM_THREADS) {
-        const float c0 = dn ? 0.f : c_in[(int64_t)inst * 256 + k];
-        const float ig = sigmoidf_(gates[k]), fg = sigmoidf_(gates[256 + k]);
-        const float gg = tanhf(gates[512 + k]), og = sigmoidf_(gates[768 + k]);
-        const float c1 = fg * c0 + ig * gg;
-        const float h1 = og * tanhf(c1);
-        c_out[(int64_t)inst * 256 + k] = c1;
-        h_out[(int64_t)inst * 256 + k] = h1;
-        const float inv = 1.0f / sqrtf(bnbuf[L.pol_bv + k] + 1e-5f);
-        const float s = c.par(L.pol_g + k) * inv;
-        hn[k] = fmaf(h1, s, c.par(L.pol_be + k) - bnbuf[L.pol_bm + k] * s);
+    __syncthreads();            // trunks done: the map buffers are dead and hold the dense tail's scratch from here on
+    stamp_i = 11;
+    stamp();                    // 11: trunks done
+    if (nmem == 2 && rows[0] == rows[1]) {
+        dense_tail<2>(L, theta, rows[0], bnbuf, sgs, inst, fcs, bufA, reward, done, h_in, c_in, probs, h_out, c_out);
+    } else {
+        for (int mem = 0; mem < nmem; ++mem) {
+            const float sg1[2] = {sgs[mem], sgs[mem]};
+            const int in1[2] = {inst[mem], inst[mem]};
+            float* const fc1[2] = {fcs[mem], fcs[mem]};
+            dense_tail<1>(L, theta, rows[mem], bnbuf, sg1, in1, fc1, bufA, reward, done, h_in, c_in, probs, h_out, c_out);
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    for (int a = warp; a < L.A; a += IM_THREADS / 32) {
-        float acc = 0.f;
-        for (int k = lane; k < 256; k += 32) acc = fmaf(c.par(L.pol_w + a * 256 + k), hn[k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) lg[a] = acc + c.par(L.pol_b + a);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float mx = -INFINITY;
-        for (int a = 0; a < L.A; ++a) mx = fmaxf(mx, lg[a]);
-        float ssum = 0.f;
-        for (int a = 0; a < L.A; ++a) ssum += expf(lg[a] - mx);
-        const float inv = 1.0f / ssum;
-        for (int a = 0; a < L.A; ++a) probs[(int64_t)inst * L.A + a] = expf(lg[a] - mx) * inv;
-    }
-    stamp();            // 13: end
+    stamp();                    // 12: end
 }
 
 ImpalaP make_impala(int A) {
@@ -559,22 +786,38 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     DFD_CHECK_ARG(L.P == dfd_policy_num_params(desc) && L.P < table->size, "dfd_impala_forward: parameter count mismatch");
     DFD_CHECK_ARG((((uintptr_t)theta) & 15) == 0, "dfd_impala_forward: theta must be 16-byte aligned");
     DFD_CHECK_ARG((int64_t)n_members * obs_per_member < 2147483647LL, "dfd_impala_forward: grid too large");
-    const size_t smem = (size_t)(2 * MAP + BAND + WMAX + 96 + 2048 + 260 + 256 + 1024 + 256 + 32) * sizeof(float);
-    DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool tc = desc->precision >= 1;
+    const size_t smem = (size_t)(2 * (tc ? MAP_TC : MAP) + BAND + WMAX + 96 + 2048) * sizeof(float);
+    // 2: one CTA per (antithetic pair, env) - members j and j + M/2 of [plus | minus] batches; 1: CTA per (member, env),
+    // pair-adjacent order; 0: plain order.  DFD_IMPALA_NO_PAIR=1 keeps mode 1 (A/B measurements)
+    static const bool no_pair = getenv("DFD_IMPALA_NO_PAIR") != nullptr;
+    const int mode = (n_members % 2 == 0) ? (no_pair ? 1 : 2) : 0;
+    const int grid = (mode == 2 ? n_members / 2 : n_members) * obs_per_member;
     long long* prof = nullptr;
-    if (getenv("DFD_IMPALA_PROF")) { cudaMalloc(&prof, 32 * 8); cudaMemset(prof, 0, 32 * 8); }
-    impala_forward_kernel<<<n_members * obs_per_member, IM_THREADS, smem, (cudaStream_t)stream>>>(
-        L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
-        obs_per_member, probs, h_out, c_out, n_members, (n_members % 2 == 0) ? 1 : 0, prof);
+    if (getenv("DFD_IMPALA_PROF")) { cudaMalloc(&prof, 32 * 8); cudaMemset(prof, 0, 32 * 8); }   // 0..12 phases, 16..27 fine stamps
+    if (tc) {
+        DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        impala_forward_kernel<true><<<grid, IM_THREADS, smem, (cudaStream_t)stream>>>(
+            L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
+            obs_per_member, probs, h_out, c_out, n_members, mode, prof);
+    } else {
+        DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        impala_forward_kernel<false><<<grid, IM_THREADS, smem, (cudaStream_t)stream>>>(
+            L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
+            obs_per_member, probs, h_out, c_out, n_members, mode, prof);
+    }
     DFD_LAUNCHED(ctx);
     if (prof) {
         cudaStreamSynchronize((cudaStream_t)stream);
         long long h[32];
         cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[impala timeline] CTA 7, cycles per phase: frame %lld | s0 conv+pool %lld res %lld %lld | s1 conv+pool %lld res %lld %lld | "
-                        "s2 conv+pool %lld res %lld %lld | fc %lld | lstm %lld | head %lld | total %lld\n",
-                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8],
-                h[10] - h[9], h[11] - h[10], h[12] - h[11], h[13] - h[12], h[13] - h[0]);
+        fprintf(stderr, "[impala timeline] CTA 7 (mode %d, %s), cycles per phase of its first member: frame %lld | s0 conv+pool %lld res %lld %lld | "
+                        "s1 conv+pool %lld res %lld %lld | s2 conv+pool %lld res %lld %lld | all trunks done at %lld | dense tail %lld | total %lld\n",
+                mode, tc ? "tf32 mma" : "fp32", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6],
+                h[8] - h[7], h[9] - h[8], h[10] - h[9], h[11] - h[0], h[12] - h[11], h[12] - h[0]);
+        for (int s = 0; s < 3; ++s)
+            fprintf(stderr, "[impala timeline] stage %d first residual block: weights a %lld | conv a %lld | weights b %lld | conv b %lld\n", s,
+                    h[16 + 4 * s] - h[2 + 3 * s], h[17 + 4 * s] - h[16 + 4 * s], h[18 + 4 * s] - h[17 + 4 * s], h[19 + 4 * s] - h[18 + 4 * s]);
         cudaFree(prof);
     }
     return 0;

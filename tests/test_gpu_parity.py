@@ -777,6 +777,45 @@ def test_impala_forward_golden(D, golden_dir):
     np.testing.assert_allclose(p2, ref2, atol=1e-5)
 
 
+@pytest.mark.parametrize("precision,atol", [(0, 1e-5), (1, 2e-3)])
+@pytest.mark.parametrize("shared,M", [(True, 4), (False, 4), (False, 3)])
+def test_impala_pair_mode_vs_oracle(D, shared, M, precision, atol):
+    """One CTA evaluates members j and j + M/2 (trunks one after the other) and streams theta / the eps row of the dense
+    tail once for both when they share their table index (antithetic pair); unrelated indices get one pass each; an odd
+    member count falls back to one CTA per member.  precision 0: exact fp32 (atol 1e-5); precision 1: tf32 tensor-core
+    convolutions (mma.sync m16n8k8, fp32 accumulate) - stated tolerance 2e-3 on the action probabilities and 1e-2 on the
+    carried LSTM state (15 convolutions deep).  Non-zero incoming state, one finished environment, clamped rewards."""
+    L = O.impala_layout(15)
+    table = D.SharedNoiseTable(2_000_000, L.num_params, 123, device=0)
+    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=precision).bind_table(table)
+    theta, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
+    pol.set_trainable_flat(theta)
+    pol.set_buffers(buf)
+    rng = np.random.RandomState(7 * M + shared)
+    E = 2
+    half = rng.randint(0, 2_000_000 - L.num_params, size=M // 2).astype(np.int64)
+    idx = np.concatenate([half, half]) if shared else rng.randint(0, 2_000_000 - L.num_params, size=M).astype(np.int64)
+    sign = np.array([1, 1, -1, -1] if shared else [1, 0, -1, 1][:M], dtype=np.int8)
+    frames = rng.randint(0, 256, size=(M, E, 3, 64, 64)).astype(np.float32)
+    reward = rng.uniform(-2, 2, size=(M, E)).astype(np.float32)
+    done = np.zeros((M, E), bool)
+    done[1, 0] = True
+    h0 = (0.3 * rng.randn(M, E, 256)).astype(np.float32)
+    c0 = (0.3 * rng.randn(M, E, 256)).astype(np.float32)
+    probs, h1, c1 = pol.forward_members_impala(
+        torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(frames).cuda(),
+        torch.from_numpy(reward).cuda(), torch.from_numpy(done).cuda(), torch.from_numpy(h0).cuda(),
+        torch.from_numpy(c0).cuda(), 0.02)
+    probs, h1, c1 = probs.cpu().numpy(), h1.cpu().numpy(), c1.cpu().numpy()
+    err = [0.0, 0.0, 0.0]
+    for m in range(M):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + L.num_params], int(sign[m]))
+        rp, rh, rc = O.impala_forward(L, th, buf, frames[m], reward[m], done[m], h0[m], c0[m])
+        err = [max(err[0], np.abs(probs[m] - rp).max()), max(err[1], np.abs(h1[m] - rh).max()), max(err[2], np.abs(c1[m] - rc).max())]
+    print("impala precision %d max-abs errors: probs %.2e h %.2e c %.2e" % (precision, err[0], err[1], err[2]))
+    assert err[0] <= atol and err[1] <= (2e-5 if precision == 0 else 1e-2) and err[2] <= (2e-5 if precision == 0 else 1e-2), err
+
+
 @pytest.mark.parametrize("P,N,paired", [(6092, 2048, True), (6092, 300, False), (5197, 40, True), (130, 6, False),
                                         (32768, 128, True)])
 def test_one_kernel_step_equals_three_call_path(D, table1m, P, N, paired):
