@@ -82,8 +82,9 @@ typedef struct dfd_policy_desc {
     int n_in;      /* MLPs: observation width K                                            */
     int h1, h2;    /* MLPs: hidden widths (reference: 64, 64; mujoco.py:33-34)             */
     int n_act;     /* actions A (MuJoCo head emits 2A: mean | std)                         */
-    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tcgen05 tensor cores,
-                      2 = tf32 tcgen05 + single-instruction tanh.approx (2^-11 relative)      */
+    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tensor cores (MuJoCo MLPs: tcgen05;
+                      IMPALA: tf32 mma convolutions, fp32 first convolution and dense tail),
+                      2 = MuJoCo: tf32 tcgen05 + single-instruction tanh.approx (2^-11 relative)  */
 } dfd_policy_desc;
 
 int64_t dfd_policy_num_params(const dfd_policy_desc* desc);
@@ -106,7 +107,10 @@ int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_tabl
 /* IMPALA CNN+LSTM (impala.py:136-186): E independent single-step environments
  * per member, each with its own carried (h, c) of 256 floats.
  * frame [M,E,3,64,64] (0..255), reward [M,E], done [M,E] (uint8),
- * h_in/c_in/h_out/c_out [M,E,256], probs [M,E,A]. scratch: dfd_impala_scratch_bytes. */
+ * h_in/c_in/h_out/c_out [M,E,256], probs [M,E,A]. scratch: dfd_impala_scratch_bytes.
+ * With an even member count, members j and j + M/2 are evaluated by one CTA; when they
+ * share their table index (an antithetic pair in [plus | minus] order) theta and the eps
+ * row of the dense tail are streamed once for both. */
 size_t dfd_impala_scratch_bytes(int n_members, int obs_per_member);
 int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                        const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
