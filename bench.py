@@ -72,8 +72,8 @@ def parse_args():
                     help="forward arithmetic: fp32 CUDA cores (exact path, atol 1e-5), tf32 = tcgen05 tensor cores with "
                          "tf32 operands / fp32 accumulate / ~1e-6 tanh (max-abs 2e-3 vs fp32), tf32a = the same with the "
                          "single-instruction tanh.approx.f32 (2^-11 relative; max-abs 4e-3 vs fp32); "
-                         "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, tf32 convolutions for IMPALA "
-                         "(max-abs 2e-3 on the action probabilities vs fp32), fp32 otherwise")
+                         "auto = tf32a for MuJoCo MLPs with >= 32 observations per member, tensor-core convolutions for IMPALA "
+                         "(fp16 operands / fp32 accumulate, max-abs 2e-3 on the action probabilities vs fp32), fp32 otherwise")
     ap.add_argument("--profile-mode", action="store_true",
                     help="for runs under ncu: timed steps only (no clock-load loop, per-kernel timing, e2e or CPU baseline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -779,7 +779,7 @@ def b200_main(args, w):
     line = {
         "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ("tf32 convolution operands (mma.sync), fp32 accumulate, fp32 first convolution / dense tail; f32 estimator"
+        "vs_baseline": None, "dtype": ("fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
                                        if w["kind"] == "impala" else
                                        "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"))
         if use_tc else "f32",

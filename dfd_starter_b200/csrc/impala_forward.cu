@@ -6,7 +6,7 @@
 // parameter is theta + sign*sigma*eps generated in-kernel (worker/worker.py:28).  The whole conv trunk keeps its
 // activations in shared memory (two ping-pong maps + a conv-row band for the pooled stages); only the
 // carried LSTM state and the action probabilities touch HBM.  precision 0: exact fp32 on CUDA cores (atol 1e-5 against
-// torch CPU); precision >= 1: the convolutions from the second one on run on the tensor cores (tf32, see conv3x3_mma).
+// torch CPU); precision >= 1: the convolutions run on the tensor cores (fp16 operands, fp32 accumulate, see conv3x3_mma).
 // One CTA evaluates the two members of an antithetic pair (trunks one after the other, ONE pass over theta and the shared
 // eps row for the dense tail of both).  The fp32 path:
 //   * convolutions are register-tiled: a thread owns 4 neighbouring pixels x OCT output channels (OCT = 8 / 4 / 2 chosen so
@@ -110,14 +110,32 @@ __device__ void load_conv(const Ctx& c, const ConvP& p, float* wsm, float* stage
             wsm[t] = stage[oc * ss + k];
         }
     } else {
-        // tensor-core layer: weights rounded to tf32, channel index swizzled by the input channel (conv3x3_mma)
-        const int mask = p.cout == 32 ? 3 : 1;
-        for (int t = tid; t < n; t += IM_THREADS) {
-            const int k = t >> lc, oc = t & (p.cout - 1);
-            const int ci = k / 9;
+        // tensor-core layer (conv3x3_mma / conv_first_mma): weights as packed fp16 pairs in the order the B fragments of
+        // mma.m16n8k16 want them: the two registers (j = 0, 1) of a lane sit side by side (one 8-byte load), the output
+        // channel is XOR-swizzled by tig (conflict-free).  Word (((kb*4 + tig)*cout + (oc ^ (tig << 2)))*2 + j) =
+        // {lo: W[kk][oc], hi: W[kk + 4][oc]} with
+        //   cin >= 16: kb = (16-channel block)*9 + tap, kk = channel block*16 + 8j + tig at that tap;
+        //   cin = 3 (first convolution): K = 27 (ci, tap) values padded to 32, kb = 16-value step, kk = 16*kb + 8j + tig.
+        uint32_t* wpk = reinterpret_cast<uint32_t*>(wsm);
+        const bool first = p.cin < 16;
+        const int nw = first ? 16 * p.cout : n / 2;
+        for (int t = tid; t < nw; t += IM_THREADS) {
+            const int oc = t & (p.cout - 1), r = t >> lc;
+            const int jj = r & 7, kb = r >> 3, tg = jj & 3, j = jj >> 2;
+            float lo, hi;
+            if (first) {
+                const int kk = 16 * kb + 8 * j + tg;
+                lo = kk < 27 ? stage[oc * ss + kk] : 0.f;
+                hi = kk + 4 < 27 ? stage[oc * ss + kk + 4] : 0.f;
+            } else {
+                const int blk = kb / 9, tap = kb - blk * 9;
+                const int ch = blk * 16 + 8 * j + tg;
+                lo = stage[oc * ss + ch * 9 + tap];
+                hi = stage[oc * ss + (ch + 4) * 9 + tap];
+            }
             uint32_t u;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(stage[oc * ss + k]));
-            wsm[k * p.cout + (oc ^ ((ci & mask) << 3))] = __uint_as_float(u);
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+            wpk[(((kb * 4 + tg) * p.cout + (oc ^ (tg << 2))) << 1) + j] = u;
         }
     }
 }
@@ -238,46 +256,59 @@ __device__ __forceinline__ void conv3x3(const float* __restrict__ in, int cin, i
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Tensor-core convolution (precision >= 1): implicit GEMM on mma.sync m16n8k8 tf32, fp32 accumulate.
-//   M = 16 neighbouring pixels, N = 8 output channels, K = 8 input channels at one filter tap (9 taps x cin/8 K-steps).
+// Tensor-core convolution (precision >= 1): implicit GEMM on mma.sync m16n8k16, fp16 operands (the 10-bit mantissa of tf32;
+// values saturate at +-65504), fp32 accumulate.
+//   M = 16 neighbouring pixels, N = 8 output channels, K = 16 input channels at one filter tap (9 taps x cin/16 K-steps).
 // The A operand is read straight from the activation map - no im2col copy: maps are stored PADDED ([c][H+2][W+2], channel
 // stride = 8 mod 32 so the (pixel, channel) fragment loads are bank-conflict-free) with a NaN border, the input-side BN + ReLU
 // is applied as the fragment is loaded (fmaxf(NaN, 0) = 0 turns the border into torch's zero padding of the BN output; the
-// ReLU-less stage convolutions use a self-compare), and the value is rounded to tf32 by adding half an ulp (the tensor core
-// ignores the low 13 mantissa bits).  Weights are rounded with cvt.rna.tf32 when the layer is loaded and stored [k][oc] with
-// the channel index XOR-swizzled by (ci & 3) << 3, so the B fragments are conflict-free too.
+// ReLU-less stage convolutions use a self-compare), and two channels are packed into one fp16x2 register.  The K index of the
+// MMA is a free permutation of the channels as long as A and B agree: lane (g, tig) takes channels tig, tig + 4 (low / high
+// half of a0, a1) and tig + 8, tig + 12 (a2, a3), so its four loads per pixel hit four different bank groups.  Weights are
+// packed the same way when the layer is loaded (load_conv): one 8-byte load per n-tile fetches both B registers.
 // Why mma.sync and not tcgen05 (yet): tcgen05's A operand must sit in shared memory in the UMMA core-matrix layout, i.e.
-// one materialised im2col tile per filter tap (16 KB written + read per 131 k MACs at N = 16 / 32), while this loop feeds the
-// fragments from the map as it is.  Measured on B200 (DFD_IMPALA_PROF timeline): the legacy HMMA.1688.TF32 path sustains
-// about one instruction per 24 cycles per SM sub-partition here, which makes these layers 2x faster than the packed-FMA
-// fp32 ones (16 x 32 x 32 layer: 28 k -> 15 k cycles); halving the MMA count (m16n8k16, fp16 operands) and an im2col-by-TMA
-// tcgen05 variant are the next steps.
+// one materialised im2col tile per filter tap (or channel-last maps addressed through shifted descriptors), while this loop
+// feeds the fragments from the map as it is.  Measured on B200 (DFD_IMPALA_PROF timeline, 16 -> 16 layer at 32 x 32): packed
+// FMAs 28 k cycles, tf32 m16n8k8 15 k, this loop 10 k - it is bound by instruction issue (fragment loads, BN, packing:
+// ~11 instructions per MMA), not by the legacy HMMA pipe.
 // A warp owns MT m-tiles x NT n-tiles; every layer is cut into exactly 16 such units (one per warp).
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 template <bool RELU_IN>
-__device__ __forceinline__ uint32_t norm_tf32(float v, float s, float sh) {
-    float f = fmaf(v, s, sh);
-    if (RELU_IN) f = fmaxf(f, 0.f);      // NaN border -> 0
-    else f = (f == f) ? f : 0.f;
-    return __float_as_uint(f) + 0x1000u;
+__device__ __forceinline__ float norm_in(float v, float s, float sh) {
+    const float f = fmaf(v, s, sh);
+    if (RELU_IN) return fmaxf(f, 0.f);      // NaN border -> 0
+    return (f == f) ? f : 0.f;
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t u;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+    return u;
 }
 
 // in_o: padded input map at its (0, 0) element, channel stride in_cs, row stride in_rs.  Output rows [r0, r1) of the
 // H x W map; element (oc, r, x) goes to dst[oc*dst_cs + ((r - r0 + dst_r0) % dst_rmod)*dst_rs + x]; ACCUM adds (residual).
-template <int MT, int NT, bool RELU_IN, bool ACCUM>
-__device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, int cin, int in_cs, int in_rs, int W,
-                                            const float* __restrict__ wsm, int cout, const float* __restrict__ s_in,
-                                            const float* __restrict__ sh_in, const float* __restrict__ bias, int r0, int r1,
+// The map geometry (W, CIN, COUT) is a template parameter: every fragment load then carries its tap offset as an immediate
+// and the loop is ~5 instructions per k8-equivalent MMA instead of ~10 (it is issue-bound, not MMA-bound).
+__host__ __device__ constexpr int tc_rs(int W) { return W + 2; }
+__host__ __device__ constexpr int tc_cs(int W) { return ((W + 2) * (W + 2) + 23) / 32 * 32 + 8; }     // = 8 mod 32
+template <int MT, int NT, int W, int CIN, int COUT, bool RELU_IN, bool ACCUM>
+__device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, const float* __restrict__ wsm,
+                                            const float* __restrict__ s_in, const float* __restrict__ sh_in,
+                                            const float* __restrict__ bias, int r0, int r1,
                                             float* __restrict__ dst, int dst_cs, int dst_rs, int dst_r0, int dst_rmod) {
+    constexpr int cin = CIN, cout = COUT, in_cs = tc_cs(W), in_rs = tc_rs(W);
+    const uint32_t* wpk = reinterpret_cast<const uint32_t*>(wsm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, tig = lane & 3;
-    const int lw = 31 - __clz(W);
-    const int mblks = (((r1 - r0) << lw) >> 4) / MT, nblks = (cout >> 3) / NT;
-    const int swz = (cout == 32 ? tig : (tig & 1)) << 3;
+    constexpr int lw = W == 64 ? 6 : (W == 32 ? 5 : (W == 16 ? 4 : 3));
+    static_assert((1 << lw) == W, "W must be 8, 16, 32 or 64");
+    const int mblks = (((r1 - r0) << lw) >> 4) / MT;
+    constexpr int nblks = (cout >> 3) / NT;
+    const int swz = tig << 2;
     for (int unit = warp; unit < mblks * nblks; unit += IM_THREADS / 32) {
         const int mblk = unit % mblks, nblk = unit / mblks;
         int ao[MT][2], pr[MT][2], px[MT][2];
@@ -302,12 +333,16 @@ __device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, int 
         int nph[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) nph[j] = ((((nblk * NT + j) << 3) + g) ^ swz);
-        for (int ci0 = 0; ci0 < cin; ci0 += 8) {
-            const float* chA = in_o + (ci0 + tig) * in_cs;
-            const float* chB = chA + 4 * in_cs;
-            const float sA = s_in[ci0 + tig], shA = sh_in[ci0 + tig], sB = s_in[ci0 + tig + 4], shB = sh_in[ci0 + tig + 4];
-            const float* wA = wsm + (ci0 + tig) * 9 * cout;
-            const float* wB = wA + 36 * cout;
+        for (int cb = 0; cb < cin; cb += 16) {
+            const float* ch[4];
+            float sc[4], sh[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ch[q] = in_o + (cb + tig + 4 * q) * in_cs;
+                sc[q] = s_in[cb + tig + 4 * q];
+                sh[q] = sh_in[cb + tig + 4 * q];
+            }
+            const uint32_t* wb = wpk + ((((cb >> 4) * 9) * 4 + tig) * cout << 1);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -317,17 +352,21 @@ __device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, int 
                     uint32_t b0[NT], b1[NT];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        b0[j] = __float_as_uint(wA[tap * cout + nph[j]]);
-                        b1[j] = __float_as_uint(wB[tap * cout + nph[j]]);
+                        const uint2 bb = *reinterpret_cast<const uint2*>(wb + ((tap * 4 * cout + nph[j]) << 1));
+                        b0[j] = bb.x;
+                        b1[j] = bb.y;
                     }
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        const uint32_t a0 = norm_tf32<RELU_IN>(chA[ao[i][0] + toff], sA, shA);
-                        const uint32_t a1 = norm_tf32<RELU_IN>(chA[ao[i][1] + toff], sA, shA);
-                        const uint32_t a2 = norm_tf32<RELU_IN>(chB[ao[i][0] + toff], sB, shB);
-                        const uint32_t a3 = norm_tf32<RELU_IN>(chB[ao[i][1] + toff], sB, shB);
+                        float v[4][2];
 #pragma unroll
-                        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b0[j], b1[j]);
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int p = 0; p < 2; ++p) v[q][p] = norm_in<RELU_IN>(ch[q][ao[i][p] + toff], sc[q], sh[q]);
+                        const uint32_t a0 = pack_f16(v[0][0], v[1][0]), a1 = pack_f16(v[0][1], v[1][1]);
+                        const uint32_t a2 = pack_f16(v[2][0], v[3][0]), a3 = pack_f16(v[2][1], v[3][1]);
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) mma_f16(acc[i][j], a0, a1, a2, a3, b0[j], b1[j]);
                     }
                 }
         }
@@ -346,6 +385,93 @@ __device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, int 
                     }
             }
     }
+}
+
+// The first convolution (3 input channels, BN without ReLU) on the same MMA: its K = 27 (channel, tap) values are padded to
+// 32 = two K-steps; lane (g, tig) owns the values kk = 16*step + 8j + tig (+ 4), whose map offsets it keeps in registers
+// (padding values point at the pixel itself and meet zero weights).  8 conv rows x 64 pixels = 32 m-tiles, 2 per warp.
+__device__ __forceinline__ void conv_first_mma(const float* __restrict__ in_o, const float* __restrict__ wsm,
+                                               const float* __restrict__ s_in, const float* __restrict__ sh_in,
+                                               const float* __restrict__ bias, int r0, float* __restrict__ dst, int dst_cs,
+                                               int dst_rs, int dst_r0, int dst_rmod) {
+    constexpr int MT = 2, NT = 2, W = 64, COUT = 16, in_cs = tc_cs(64), in_rs = tc_rs(64);
+    const uint32_t* wpk = reinterpret_cast<const uint32_t*>(wsm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int swz = tig << 2;
+    int koff[2][2][2];          // [step][j][half]
+    float ksc[2][2][2], ksh[2][2][2];
+#pragma unroll
+    for (int st = 0; st < 2; ++st)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = 16 * st + 8 * j + tig + 4 * h;
+                const bool ok = kk < 27;
+                const int ci = ok ? kk / 9 : 0, tap = ok ? kk - ci * 9 : 4;
+                koff[st][j][h] = ci * in_cs + (tap / 3 - 1) * in_rs + (tap % 3 - 1);
+                ksc[st][j][h] = s_in[ci];
+                ksh[st][j][h] = sh_in[ci];
+            }
+    int ao[MT][2], pr[MT][2], px[MT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int pm = ((warp * MT + i) << 4) + g + 8 * p;
+            pr[i][p] = r0 + (pm >> 6);
+            px[i][p] = pm & (W - 1);
+            ao[i][p] = pr[i][p] * in_rs + px[i][p];
+        }
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const float2 b = *reinterpret_cast<const float2*>(bias + (j << 3) + 2 * tig);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            acc[i][j][0] = b.x; acc[i][j][1] = b.y; acc[i][j][2] = b.x; acc[i][j][3] = b.y;
+        }
+    }
+#pragma unroll
+    for (int st = 0; st < 2; ++st) {
+        uint32_t b0[NT], b1[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int nph = ((j << 3) + g) ^ swz;
+            const uint2 bb = *reinterpret_cast<const uint2*>(wpk + (((st * 4 + tig) * COUT + nph) << 1));
+            b0[j] = bb.x;
+            b1[j] = bb.y;
+        }
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            float v[2][2][2];       // [j][half][pixel row]
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+                        v[j][h][p] = norm_in<false>(in_o[ao[i][p] + koff[st][j][h]], ksc[st][j][h], ksh[st][j][h]);
+            const uint32_t a0 = pack_f16(v[0][0][0], v[0][1][0]), a1 = pack_f16(v[0][0][1], v[0][1][1]);
+            const uint32_t a2 = pack_f16(v[1][0][0], v[1][1][0]), a3 = pack_f16(v[1][0][1], v[1][1][1]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) mma_f16(acc[i][j], a0, a1, a2, a3, b0[j], b1[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int slot = (pr[i][p] - r0 + dst_r0) % dst_rmod;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int oc = (j << 3) + 2 * tig + q;
+                    dst[oc * dst_cs + slot * dst_rs + px[i][p]] = acc[i][j][2 * p + q];
+                }
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -492,8 +618,8 @@ __device__ __forceinline__ void dense_tail(const ImpalaP& L, const float* __rest
     }
 }
 
-// TC = false: exact fp32 (unpadded maps).  TC = true: tf32 tensor-core convolutions (padded maps with a NaN border); the
-// first convolution (3 input channels, 6 % of the MACs) and the dense tail stay fp32.
+// TC = false: exact fp32 (unpadded maps).  TC = true: tensor-core convolutions (padded maps with a NaN border); the dense
+// tail stays fp32.
 // pair_order: 0 = CTA per (member, env) in plain order; 1 = the same with the two members of an antithetic pair on
 // neighbouring CTAs; 2 = CTA per (pair, env): members j and j + M/2 run their trunks one after the other and share the dense
 // tail, so theta and the pair's eps row (8.4 MB per pair) are streamed once for both.
@@ -546,21 +672,30 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
         c.sg = sgs[mem];
         c.row = rows[mem];
         __syncthreads();        // the previous member's trunk output has been read
-        // frame / 255 -> bufA  (impala.py:142); 24 loads per thread in three rounds of 8
+        // frame / 255 -> bufA  (impala.py:142); 24 loads per thread in three rounds of 8.  Tensor-core path: padded
+        // [3][66][66] (channel stride 4360 = 8 mod 32) inside a NaN border
+        constexpr int FCS = TC ? tc_cs(64) : 4096, FRS = TC ? tc_rs(64) : 64, FORG = TC ? tc_rs(64) + 1 : 0;
+        if (TC) {
+            for (int i = tid; i < 3 * FCS; i += IM_THREADS) bufA[i] = __int_as_float(0x7fc00000);
+            __syncthreads();
+        }
         const float* fr = frame + (int64_t)inst[mem] * 12288;
         for (int t0 = tid; t0 < 12288; t0 += IM_THREADS * 8) {
             float f[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] = fr[t0 + u * IM_THREADS];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) bufA[t0 + u * IM_THREADS] = f[u] / 255.0f;
+            for (int u = 0; u < 8; ++u) {
+                const int e = t0 + u * IM_THREADS;
+                bufA[FORG + (e >> 12) * FCS + ((e >> 6) & 63) * FRS + (e & 63)] = f[u] / 255.0f;
+            }
         }
         __syncthreads();
         if (mem == 0) stamp();            // 1: frame in shared memory
         float* x = bufA;    // current map
         float* t = bufB;    // the other buffer
         int H = 64;
-        int xcs = 64 * 64, xrs = 64, xorg = 0;     // geometry of x: channel stride, row stride, offset of element (0, 0)
+        int xcs = FCS, xrs = FRS, xorg = FORG;     // geometry of x: channel stride, row stride, offset of element (0, 0)
         int li = 0;         // position in the execution-order list of conv layers
         auto next_layer = [&](const ConvP& p, bool tc_layer) {
             load_conv(c, p, wsm, band, s_in, sh_in, bias, tc_layer);
@@ -573,7 +708,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
         };
         for (int s = 0; s < 3; ++s) {
             const ConvP& fp = L.feat[s];
-            const bool tc_conv = TC && s > 0;
+            const bool tc_conv = TC;
             __syncthreads();
             next_layer(fp, tc_conv);
             // conv (BN on the input, no ReLU) + maxpool 3x3 stride 2 pad 1 (-inf padding)
@@ -590,9 +725,10 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 // r % 9), the row above them is still there from the previous band
                 for (int py0 = 0; py0 < Ho; py0 += 4) {
                     const int cr0 = 2 * py0;
-                    if (tc_conv)
-                        conv3x3_mma<1, 4, false, false>(x + xorg, fp.cin, xcs, xrs, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8,
-                                                        band, 9 * W, W, cr0 % 9, 9);
+                    if (tc_conv && s == 0)
+                        conv_first_mma(x + xorg, wsm, s_in, sh_in, bias, cr0, band, 9 * W, W, cr0 % 9, 9);
+                    else if (tc_conv)
+                        conv3x3_mma<1, 4, 32, 16, 32, false, false>(x + xorg, wsm, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, W, cr0 % 9, 9);
                     else
                         conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, cr0 % 9, 9);
                     __syncthreads();
@@ -619,7 +755,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
             } else {
                 // 16 x 16: the whole conv output (32 x 16 x 16) fits the band buffer
                 if (tc_conv)
-                    conv3x3_mma<1, 4, false, false>(x + xorg, fp.cin, xcs, xrs, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, W, 0, H);
+                    conv3x3_mma<1, 4, 16, 32, 32, false, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, band, H * W, W, 0, H);
                 else
                     conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, 0, H);
                 __syncthreads();
@@ -658,9 +794,9 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 __syncthreads();
                 fine(0);
                 if (TC) {
-                    if (s == 0) conv3x3_mma<4, 2, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
-                    else if (s == 1) conv3x3_mma<1, 4, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
-                    else conv3x3_mma<1, 1, true, false>(x + xorg, pa.cin, xcs, xrs, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    else conv3x3_mma<1, 1, 8, 32, 32, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
                 } else {
                     if (s == 0) conv3x3<8, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
                     else if (s == 1) conv3x3<4, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
@@ -672,9 +808,9 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 __syncthreads();
                 fine(2);
                 if (TC) {
-                    if (s == 0) conv3x3_mma<4, 2, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
-                    else if (s == 1) conv3x3_mma<1, 4, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
-                    else conv3x3_mma<1, 1, true, true>(t + xorg, pb.cin, xcs, xrs, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    else conv3x3_mma<1, 1, 8, 32, 32, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
                 } else {
                     if (s == 0) conv3x3<8, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
                     else if (s == 1) conv3x3<4, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
@@ -813,7 +949,7 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
         cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[impala timeline] CTA 7 (mode %d, %s), cycles per phase of its first member: frame %lld | s0 conv+pool %lld res %lld %lld | "
                         "s1 conv+pool %lld res %lld %lld | s2 conv+pool %lld res %lld %lld | all trunks done at %lld | dense tail %lld | total %lld\n",
-                mode, tc ? "tf32 mma" : "fp32", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6],
+                mode, tc ? "fp16 mma" : "fp32", h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6],
                 h[8] - h[7], h[9] - h[8], h[10] - h[9], h[11] - h[0], h[12] - h[11], h[12] - h[0]);
         for (int s = 0; s < 3; ++s)
             fprintf(stderr, "[impala timeline] stage %d first residual block: weights a %lld | conv a %lld | weights b %lld | conv b %lld\n", s,

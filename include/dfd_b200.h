@@ -82,8 +82,9 @@ typedef struct dfd_policy_desc {
     int n_in;      /* MLPs: observation width K                                            */
     int h1, h2;    /* MLPs: hidden widths (reference: 64, 64; mujoco.py:33-34)             */
     int n_act;     /* actions A (MuJoCo head emits 2A: mean | std)                         */
-    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tf32 tensor cores (MuJoCo MLPs: tcgen05;
-                      IMPALA: tf32 mma convolutions, fp32 first convolution and dense tail),
+    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tensor cores (MuJoCo MLPs: tf32 tcgen05;
+                      IMPALA: mma convolutions with fp16 operands - tf32's 10-bit mantissa - and fp32
+                      accumulate, fp32 dense tail),
                       2 = MuJoCo: tf32 tcgen05 + single-instruction tanh.approx (2^-11 relative)  */
 } dfd_policy_desc;
 

@@ -782,8 +782,8 @@ def test_impala_forward_golden(D, golden_dir):
 def test_impala_pair_mode_vs_oracle(D, shared, M, precision, atol):
     """One CTA evaluates members j and j + M/2 (trunks one after the other) and streams theta / the eps row of the dense
     tail once for both when they share their table index (antithetic pair); unrelated indices get one pass each; an odd
-    member count falls back to one CTA per member.  precision 0: exact fp32 (atol 1e-5); precision 1: tf32 tensor-core
-    convolutions (mma.sync m16n8k8, fp32 accumulate) - stated tolerance 2e-3 on the action probabilities and 1e-2 on the
+    member count falls back to one CTA per member.  precision 0: exact fp32 (atol 1e-5); precision 1: tensor-core
+    convolutions (mma.sync m16n8k16, fp16 operands with tf32's 10-bit mantissa, fp32 accumulate) - stated tolerance 2e-3 on the action probabilities and 1e-2 on the
     carried LSTM state (15 convolutions deep).  Non-zero incoming state, one finished environment, clamped rewards."""
     L = O.impala_layout(15)
     table = D.SharedNoiseTable(2_000_000, L.num_params, 123, device=0)
