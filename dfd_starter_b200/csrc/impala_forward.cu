@@ -255,6 +255,32 @@ __device__ __forceinline__ void conv3x3(const float* __restrict__ in, int cin, i
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// maxpool 3x3 stride 2 pad 1 (-inf padding) of conv rows [cr0 - 1, cr0 + 2*npy) held in `src` (row r of channel oc at
+// src[oc*src_cs + (r % src_rmod)*W]) into pooled rows [py0, py0 + npy): a thread owns one (channel, pooled column), takes the
+// 3-wide maximum of each conv row once and rolls the 3-row window down (27 loads for 4 outputs instead of 36, no per-output
+// index arithmetic).  Wo = W/2 = 1 << lwo.
+__device__ __forceinline__ void pool_rows(const float* __restrict__ src, int src_cs, int W, int src_rmod, int cr0, int npy, int py0,
+                                          int cout, int lwo, float* __restrict__ dst_o, int dst_cs, int dst_rs) {
+    const int Wo = 1 << lwo;
+    for (int o = threadIdx.x; o < (cout << lwo); o += IM_THREADS) {
+        const int oc = o >> lwo, px = o & (Wo - 1);
+        const float* sb = src + oc * src_cs + 2 * px;
+        auto hmax = [&](int r) {
+            const float* row = sb + (r % src_rmod) * W;
+            float m = fmaxf(row[0], row[1]);
+            if (px > 0) m = fmaxf(m, row[-1]);
+            return m;
+        };
+        float prev = cr0 > 0 ? hmax(cr0 - 1) : -INFINITY;
+        float* d = dst_o + oc * dst_cs + py0 * dst_rs + px;
+        for (int j = 0; j < npy; ++j) {
+            const float a = hmax(cr0 + 2 * j), b = hmax(cr0 + 2 * j + 1);
+            d[j * dst_rs] = fmaxf(fmaxf(prev, a), b);
+            prev = b;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // Tensor-core convolution (precision >= 1): implicit GEMM on mma.sync m16n8k16, fp16 operands (the 10-bit mantissa of tf32;
 // values saturate at +-65504), fp32 accumulate.
@@ -732,24 +758,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                     else
                         conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, cr0 % 9, 9);
                     __syncthreads();
-                    for (int o = tid; o < fp.cout * 4 * Wo; o += IM_THREADS) {
-                        const int oc = o >> (lwo + 2), rem = o & (4 * Wo - 1);     // Wo is a power of two
-                        const int py = py0 + (rem >> lwo), px = rem & (Wo - 1);
-                        float mx = -INFINITY;
-#pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy) {
-                            const int yy = 2 * py + dy;
-                            if (yy < 0 || yy >= H) continue;
-                            const float* brow = band + oc * 9 * W + (yy % 9) * W;
-#pragma unroll
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int xx = 2 * px + dx;
-                                if (xx < 0 || xx >= W) continue;
-                                mx = fmaxf(mx, brow[xx]);
-                            }
-                        }
-                        t[torg + oc * tcs + py * trs + px] = mx;
-                    }
+                    pool_rows(band, 9 * W, W, 9, cr0, 4, py0, fp.cout, lwo, t + torg, tcs, trs);
                     __syncthreads();
                 }
             } else {
@@ -759,23 +768,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 else
                     conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, 0, H);
                 __syncthreads();
-                for (int o = tid; o < fp.cout * Ho * Wo; o += IM_THREADS) {
-                    const int oc = o >> (2 * lwo), rem = o & (Ho * Wo - 1);
-                    const int py = rem >> lwo, px = rem & (Wo - 1);
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int yy = 2 * py + dy;
-                        if (yy < 0 || yy >= H) continue;
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int xx = 2 * px + dx;
-                            if (xx < 0 || xx >= W) continue;
-                            mx = fmaxf(mx, band[oc * H * W + yy * W + xx]);
-                        }
-                    }
-                    t[torg + oc * tcs + py * trs + px] = mx;
-                }
+                pool_rows(band, H * W, W, H, 0, Ho, 0, fp.cout, lwo, t + torg, tcs, trs);
                 __syncthreads();
             }
             { float* tmp = x; x = t; t = tmp; }
