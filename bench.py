@@ -49,7 +49,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
 # `ncu --set full` capture of this workload (profiles/r01/SUMMARY.md); None where no capture exists
 NCU_TRAFFIC = {("C2", "policy_forward"): 42.45e6 + 0.52e6, ("C3", "policy_forward"): 1.1775e9 + 28.3e6,
-               ("C4", "policy_forward"): 1.2648e9 + 5.2e6, ("C2", "fd_reduce"): 24.55e6, ("C3", "fd_reduce"): 570.2e6 + 7.3e6}
+               ("C4", "policy_forward"): 1.2648e9 + 5.2e6, ("C5", "policy_forward"): 976.7e6 + 10.3e6, ("C2", "fd_reduce"): 24.55e6, ("C3", "fd_reduce"): 570.2e6 + 7.3e6}
 TABLE_SIZE = 25_000_000
 TABLE_SEED = 124
 SIGMA = 0.02
