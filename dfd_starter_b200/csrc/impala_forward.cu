@@ -1,4 +1,4 @@
-// IMPALA CNN + LSTM perturbed forward (policies/impala.py:136-186), one CTA per (member, environment).
+// IMPALA CNN + LSTM perturbed forward (policies/impala.py:136-186), one CTA per (antithetic pair, environment).
 //   x = frame/255; 3 stages {BN -> conv3x3 -> maxpool(3,2,1); 2 x [x += conv(relu(BN(conv(relu(BN(x))))))]};
 //   relu -> flatten(2048) -> relu(Linear(BN1d(x))) -> concat clamp(reward,-1,1) -> LSTM cell (gates i,f,g,o,
 //   state zeroed where done) -> Linear(BN1d(h)) -> softmax.
@@ -17,8 +17,8 @@
 //   * the pooled stages compute exactly 8 new conv rows per band into a 9-row circular band (no row is convolved twice);
 //   * a layer's weights arrive in ONE round of loads (every thread's theta / eps loads issued before the first store) and
 //     the NEXT layer's eps segment is prefetched into L2 while the current layer computes;
-//   * the dense tail (Linear 2048 -> 256, LSTM 513 -> 1024) streams 8.4 MB per member: every warp keeps 256 B (Linear) /
-//     272 B (LSTM, two gate rows at a time) of loads in flight per lane.
+//   * the dense tail (Linear 2048 -> 256, LSTM 513 -> 1024) streams 8.4 MB of theta and eps per pair: every warp keeps
+//     256 B (Linear) / 272 B (LSTM, two gate rows at a time) of loads in flight per lane.
 #include "common.cuh"
 #include <stdlib.h>
 
