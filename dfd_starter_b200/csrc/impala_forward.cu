@@ -316,16 +316,18 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 }
 
 // in_o: padded input map at its (0, 0) element, channel stride in_cs, row stride in_rs.  Output rows [r0, r1) of the
-// H x W map; element (oc, r, x) goes to dst[oc*dst_cs + ((r - r0 + dst_r0) % dst_rmod)*dst_rs + x]; ACCUM adds (residual).
+// H x W map; element (oc, r, x) goes to dst[oc*dst_cs + ((r - r0 + dst_r0) % dst_rmod)*dst_rs + x]; `accum` adds (residual) -
+// a run-time flag, so the two convolutions of a residual block run the SAME code (the second one finds it in the
+// instruction cache; the kernel is ~200 KB of fully unrolled SASS).
 // The map geometry (W, CIN, COUT) is a template parameter: every fragment load then carries its tap offset as an immediate
 // and the loop is ~5 instructions per k8-equivalent MMA instead of ~10 (it is issue-bound, not MMA-bound).
 __host__ __device__ constexpr int tc_rs(int W) { return W + 2; }
 __host__ __device__ constexpr int tc_cs(int W) { return ((W + 2) * (W + 2) + 23) / 32 * 32 + 8; }     // = 8 mod 32
-template <int MT, int NT, int W, int CIN, int COUT, bool RELU_IN, bool ACCUM>
-__device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, const float* __restrict__ wsm,
+template <int MT, int NT, int W, int CIN, int COUT, bool RELU_IN>
+__device__ __noinline__ void conv3x3_mma(const float* __restrict__ in_o, const float* __restrict__ wsm,
                                             const float* __restrict__ s_in, const float* __restrict__ sh_in,
                                             const float* __restrict__ bias, int r0, int r1,
-                                            float* __restrict__ dst, int dst_cs, int dst_rs, int dst_r0, int dst_rmod) {
+                                            float* __restrict__ dst, int dst_cs, int dst_rs, int dst_r0, int dst_rmod, bool accum) {
     constexpr int cin = CIN, cout = COUT, in_cs = tc_cs(W), in_rs = tc_rs(W);
     const uint32_t* wpk = reinterpret_cast<const uint32_t*>(wsm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -407,7 +409,7 @@ __device__ __forceinline__ void conv3x3_mma(const float* __restrict__ in_o, cons
                     for (int q = 0; q < 2; ++q) {
                         const int oc = ((nblk * NT + j) << 3) + 2 * tig + q;
                         float* d = dst + oc * dst_cs + slot * dst_rs + px[i][p];
-                        if (ACCUM) *d += acc[i][j][2 * p + q]; else *d = acc[i][j][2 * p + q];
+                        if (accum) *d += acc[i][j][2 * p + q]; else *d = acc[i][j][2 * p + q];
                     }
             }
     }
@@ -754,7 +756,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                     if (tc_conv && s == 0)
                         conv_first_mma(x + xorg, wsm, s_in, sh_in, bias, cr0, band, 9 * W, W, cr0 % 9, 9);
                     else if (tc_conv)
-                        conv3x3_mma<1, 4, 32, 16, 32, false, false>(x + xorg, wsm, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, W, cr0 % 9, 9);
+                        conv3x3_mma<1, 4, 32, 16, 32, false>(x + xorg, wsm, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, W, cr0 % 9, 9, false);
                     else
                         conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, cr0, cr0 + 8, band, 9 * W, cr0 % 9, 9);
                     __syncthreads();
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
             } else {
                 // 16 x 16: the whole conv output (32 x 16 x 16) fits the band buffer
                 if (tc_conv)
-                    conv3x3_mma<1, 4, 16, 32, 32, false, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, band, H * W, W, 0, H);
+                    conv3x3_mma<1, 4, 16, 32, 32, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, band, H * W, W, 0, H, false);
                 else
                     conv3x3<4, false, false>(x, fp.cin, H, W, wsm, fp.cout, s_in, sh_in, bias, 0, H, band, H * W, 0, H);
                 __syncthreads();
@@ -787,9 +789,9 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 __syncthreads();
                 fine(0);
                 if (TC) {
-                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
-                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
-                    else conv3x3_mma<1, 1, 8, 32, 32, true, false>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H);
+                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H, false);
+                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H, false);
+                    else conv3x3_mma<1, 1, 8, 32, 32, true>(x + xorg, wsm, s_in, sh_in, bias, 0, H, t + xorg, xcs, xrs, 0, H, false);
                 } else {
                     if (s == 0) conv3x3<8, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
                     else if (s == 1) conv3x3<4, true, false>(x, pa.cin, H, H, wsm, pa.cout, s_in, sh_in, bias, 0, H, t, H * H, 0, H);
@@ -801,9 +803,9 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                 __syncthreads();
                 fine(2);
                 if (TC) {
-                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
-                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
-                    else conv3x3_mma<1, 1, 8, 32, 32, true, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H);
+                    if (s == 0) conv3x3_mma<4, 2, 32, 16, 16, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H, true);
+                    else if (s == 1) conv3x3_mma<1, 4, 16, 32, 32, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H, true);
+                    else conv3x3_mma<1, 1, 8, 32, 32, true>(t + xorg, wsm, s_in, sh_in, bias, 0, H, x + xorg, xcs, xrs, 0, H, true);
                 } else {
                     if (s == 0) conv3x3<8, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
                     else if (s == 1) conv3x3<4, true, true>(t, pb.cin, H, H, wsm, pb.cout, s_in, sh_in, bias, 0, H, x, H * H, 0, H);
