@@ -95,6 +95,18 @@ def workload(args):
     return w
 
 
+def forward_precision(kind, precision, E):
+    """--precision -> (tensor path on?, dfd_policy_desc.precision level).  MuJoCo MLPs: tcgen05 tf32 (level 1: accurate
+    tanh, level 2: tanh.approx) when asked for, or by default from 32 observations per member; IMPALA: tensor-core
+    convolutions (level 1) unless fp32 is asked for; Discrete / Atari: the exact fp32 kernels only."""
+    if kind == "mujoco":
+        on = precision in ("tf32", "tf32a") or (precision == "auto" and E >= 32)
+        return on, (1 if precision == "tf32" else 2)
+    if kind == "impala":
+        return precision != "fp32", 1
+    return False, 0
+
+
 def layer_flops_per_obs(w):
     if w["kind"] == "atari":
         return 5934080          # SURVEY.md §8a a9
@@ -321,9 +333,7 @@ def b200_main(args, w):
 
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
-    use_tc = (w["kind"] == "mujoco" and (args.precision in ("tf32", "tf32a") or (args.precision == "auto" and E >= 32))) or \
-             (w["kind"] == "impala" and args.precision != "fp32")
-    tc_level = 1 if (args.precision == "tf32" or w["kind"] == "impala") else 2
+    use_tc, tc_level = forward_precision(w["kind"], args.precision, E)
     if w["kind"] in ("mujoco", "discrete"):
         cls = D.MujocoPolicy if w["kind"] == "mujoco" else D.DiscretePolicy
         policy = cls(w["n_in"], w["n_act"], seed=TABLE_SEED, h1=w["h1"], h2=w["h2"], device=local,

@@ -47,3 +47,19 @@ def test_b200_arm_has_no_cpu_fallback():
         return          # on a GPU box the arm runs; the refusal is what is checked here
     out = _run(["--steps", "1", "--warmup", "1"])
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_precision_flag_maps_to_policy_levels():
+    """--precision -> dfd_policy_desc.precision: the tensor paths are opt-out for IMPALA, opt-in below 32 observations per
+    member for the MuJoCo MLPs, and never taken by the Discrete / Atari kernels (exact fp32 only)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.forward_precision("mujoco", "auto", 128) == (True, 2)
+    assert bench.forward_precision("mujoco", "auto", 1) == (False, 2)
+    assert bench.forward_precision("mujoco", "tf32", 1) == (True, 1)
+    assert bench.forward_precision("mujoco", "fp32", 128)[0] is False
+    assert bench.forward_precision("impala", "auto", 1) == (True, 1)
+    assert bench.forward_precision("impala", "fp32", 1) == (False, 1)
+    for kind in ("discrete", "atari"):
+        for prec in ("auto", "fp32", "tf32", "tf32a"):
+            assert bench.forward_precision(kind, prec, 128) == (False, 0)
