@@ -19,15 +19,16 @@ def affine_transform(value, from_min, from_max, to_min, to_max):
 
 
 class DSGD(Optimizer):
+    """Hyper-parameters of the normalised-gradient step theta -= lr * sqrt(P) * lr_scale * g / ||g||.  The attribute
+    names (`lr`, `coef`, `lr_scale`, `min_scale`, `max_scale`, `steps`) are the ones the reference learner and drivers
+    read (dynamic_sgd.py:7-16, finite_differences.py:51-52)."""
+
     def __init__(self, params, lr, min_scale=0.23, max_scale=1.0):
         super().__init__(params, {"lr": lr})
-        self.lr = lr
-        self.min_scale = min_scale
-        self.max_scale = max_scale
-        self.coef = 1
+        self.lr, self.min_scale, self.max_scale = lr, min_scale, max_scale
         self.lr_scale = 1
         self.steps = 0
-        self._compute_coef()
+        self.coef = np.sqrt(sum(p.numel() for group in self.param_groups for p in group["params"]))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -46,13 +47,6 @@ class DSGD(Optimizer):
 
     def adjust_lr(self, omega):
         self.lr_scale = affine_transform(omega.omega, omega.min_omega, omega.max_omega, self.min_scale, self.max_scale)
-
-    def _compute_coef(self):
-        d = 0
-        for group in self.param_groups:
-            for p in group["params"]:
-                d += p.numel()
-        self.coef = np.sqrt(d)
 
 
 def is_dsgd(opt):

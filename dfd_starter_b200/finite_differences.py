@@ -189,6 +189,13 @@ class FiniteDifferences(object):
         all_rewards: with a process group, the rewards of ALL ranks' accepted returns (the
         standardisation is global); gathered here when omitted."""
         epochs = np.asarray(epochs, dtype=np.int64)
+        idx = np.asarray(idx, dtype=np.int64)
+        sign = np.asarray(sign, dtype=np.int8)
+        rewards = np.asarray(rewards, dtype=np.float64)
+        if self.paired and epochs.shape[0]:
+            sel = self._pair_order(idx, sign)
+            if sel is not None:
+                epochs, idx, sign, rewards = epochs[sel], idx[sel], sign[sel], rewards[sel]
         n_in = epochs.shape[0]
         # finite_differences.py:80-85: a return is usable iff its epoch is still in the distance map
         hist_row = np.full(n_in, -2, dtype=np.int32)
@@ -209,9 +216,24 @@ class FiniteDifferences(object):
                 keep = np.concatenate([pk, pk])
         if policy_reward is None:
             policy_reward = 0
-        idx = np.asarray(idx, dtype=np.int64)[keep]
-        sign = np.asarray(sign, dtype=np.int8)[keep]
-        rewards = np.asarray(rewards, dtype=np.float64)[keep]
+        # keys come off the wire (FDReturn.encoded_noise): a slice that does not lie inside the table would be an
+        # out-of-bounds read on the device.  The reference fails on the short slice (shape mismatch in :88-89); here the
+        # offending returns are dropped and counted like too-old ones
+        size = int(getattr(self.table, "size", 0) or 0)
+        if size and n_in:
+            in_table = (idx >= 0) & (idx + self.P <= size)
+            n_oob = int((keep & ~in_table).sum())
+            if n_oob:
+                print("FINITE DIFFERENCE LEARNER RECEIVED %d RETURN(S) WHOSE NOISE KEY IS OUTSIDE THE TABLE" % n_oob)
+                self.discarded_returns += n_oob
+                keep = keep & in_table
+                if self.paired:
+                    R = n_in // 2
+                    pk = keep[:R] & keep[R:2 * R]
+                    keep = np.concatenate([pk, pk, np.zeros(n_in - 2 * R, dtype=bool)])
+        idx = idx[keep]
+        sign = sign[keep]
+        rewards = rewards[keep]
         hist_row = hist_row[keep]
         n = idx.shape[0]
         pg = self.process_group
@@ -272,6 +294,28 @@ class FiniteDifferences(object):
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=pg)     # the one parameter-sized exchange
         return self._apply_update()
+
+    @staticmethod
+    def _pair_order(idx, sign):
+        """paired=True promises the device kernels the layout [R plus-members | R minus-members] of the same R table
+        rows (they pair entry r with r + R and read the row pointer from entry r only).  Returns None when the batch
+        already has it, else the selection that establishes it: eval members (sign 0) are dropped, as the drivers drop
+        them before `step` (run_sequential.py:137-147), and complete +/- pairs in any other order - concatenated RPC
+        chunks [+A -A +B -B], LIFO pops (server.py:80) - are regrouped, plus members kept in arrival order.  A batch
+        that does not consist of complete pairs is refused rather than mispaired silently."""
+        n = idx.shape[0]
+        R = n // 2
+        if n % 2 == 0 and (sign[:R] == 1).all() and (sign[R:] == -1).all() and np.array_equal(idx[:R], idx[R:]):
+            return None
+        pos, neg = np.flatnonzero(sign == 1), np.flatnonzero(sign == -1)
+        pos = pos[np.argsort(idx[pos], kind="stable")]
+        neg = neg[np.argsort(idx[neg], kind="stable")]
+        if pos.shape[0] != neg.shape[0] or not np.array_equal(idx[pos], idx[neg]):
+            raise _lib.DfdError("paired=True needs complete antithetic pairs (a '+i' and a '-i' return per table row); the "
+                                "%d plus / %d minus members received do not pair up - build the learner with paired=False "
+                                "for one-sided or mixed batches" % (pos.shape[0], neg.shape[0]))
+        by_arrival = np.argsort(pos, kind="stable")
+        return np.concatenate([pos[by_arrival], neg[by_arrival]])
 
     def _fused_scratch_for(self, n, paired):
         """Zero-filled scratch of the one-kernel step for this batch shape, or None when the shape is not served."""
@@ -395,15 +439,24 @@ class FiniteDifferences(object):
             if self._host_policy and self.sync_policy:
                 self.policy.set_trainable_flat(self._theta_host.numpy())
         else:
-            # any other torch optimizer: it owns the update rule and runs where the policy's parameters live
-            # (finite_differences.py:54-57); the device keeps the history / distance rows
-            flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32).copy()
+            # any other torch optimizer: it owns the update rule (finite_differences.py:54-57); the device keeps the
+            # history / distance rows
             self.gradient_optimizer.zero_grad()
-            self.policy.set_grad_from_flat(-self.gradient_memory)
-            self.gradient_optimizer.step()
-            new_flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32)
-            update_size = float(np.linalg.norm(flat - new_flat))
-            self.theta.copy_(torch.from_numpy(new_flat.copy()))
+            if not self._host_policy:
+                # device policy: its parameters() is ONE flat nn.Parameter aliasing theta, so the optimizer updates the
+                # vector the kernels read, on the device, with no host round trip
+                before = self.theta.clone()
+                self.policy.set_grad_from_flat(-self.grad)                       # policy.py:63-70
+                self.gradient_optimizer.step()
+                update_size = float(torch.linalg.vector_norm(before - self.theta.detach()))
+            else:
+                flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32).copy()
+                with torch.enable_grad():
+                    self.policy.set_grad_from_flat(-self.gradient_memory)
+                self.gradient_optimizer.step()
+                new_flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32)
+                update_size = float(np.linalg.norm(flat - new_flat))
+                self.theta.copy_(torch.from_numpy(new_flat.copy()))
             zero = torch.zeros_like(self.grad)
             _lib.check(self.lib.dfd_dsgd_step(
                 self.ctx.handle, ptr(self.theta), ptr(zero), self.P, 0.0, 0.0, ptr(self.hist), ptr(self.dist),

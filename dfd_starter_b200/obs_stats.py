@@ -14,74 +14,87 @@ from .device import ptr
 
 
 class WelfordRunningStat(object):
+    """Running (count, mean, sum of squared deviations) of observations behind the reference's interface
+    (utils/math_helpers.py:7-101; attribute and method names are what workers, drivers and `FDState.obs_stats` use).
+
+    Everything funnels into two primitives: `_absorb` folds raw observations in one at a time (Welford's recurrence,
+    evaluated in the accumulator's dtype and in the reference's operation order, so fp32 results are bit-identical to
+    its `update`), and `_merge` combines with another accumulator's moments (Chan's pairwise formula, the reference's
+    `increment_from_obs_stats_update`).  `running_variance` keeps the reference's name although it holds M2, the sum of
+    squared deviations - the variance is M2 / (count - 1)."""
+
     def __init__(self, shape):
-        self.ones = np.ones(shape=shape, dtype=np.float32)
-        self.zeros = np.zeros(shape=shape, dtype=np.float32)
-        self.running_mean = np.zeros(shape=shape, dtype=np.float32)
-        self.running_variance = np.zeros(shape=shape, dtype=np.float32)
-        self.count = 0
         self.shape = shape
+        self.count = 0
+        self.running_mean = np.zeros(shape, dtype=np.float32)
+        self.running_variance = np.zeros(shape, dtype=np.float32)
+
+    # ---- primitives ------------------------------------------------------------------------------------------
+    def _absorb(self, observations):
+        mean, m2 = self.running_mean, self.running_variance
+        for x in observations:
+            seen = self.count
+            self.count = seen + 1
+            dev = np.reshape(x - mean, mean.shape)              # deviation from the mean BEFORE this observation
+            shift = np.reshape(dev / self.count, mean.shape)
+            mean += shift
+            m2 += dev * shift * seen
+
+    def _merge(self, mean_b, m2_b, n_b):
+        if n_b == 0:
+            return
+        n_a, mean_a = self.count, self.running_mean
+        n = n_a + n_b
+        gap = mean_b - mean_a
+        self.running_variance = self.running_variance + m2_b + gap * gap * n_a * n_b / n
+        self.running_mean = (n_a * mean_a + n_b * mean_b) / n
+        self.count = n
+
+    def _split(self, flat):
+        """[mean | M2 | count] (the `serialize` layout) -> the three parts, mean / M2 still flat."""
+        k = int(np.prod(self.shape))
+        return flat[:k], flat[k:-1], flat[-1]
+
+    # ---- the reference's surface -----------------------------------------------------------------------------
+    def update(self, sample):
+        self._absorb((sample["frame"] if isinstance(sample, dict) else sample,))
 
     def increment(self, samples, num):
-        if num > 1:
-            for i in range(num):
-                self.update(samples[i])
-        else:
-            self.update(samples)
-
-    def update(self, sample):
-        if type(sample) == dict:
-            sample = sample["frame"]
-        current_count = self.count
-        self.count += 1
-        delta = (sample - self.running_mean).reshape(self.running_mean.shape)
-        delta_n = (delta / self.count).reshape(self.running_mean.shape)
-        self.running_mean += delta_n
-        self.running_variance += delta * delta_n * current_count
+        self._absorb([samples[i] for i in range(num)] if num > 1 else (samples,))
 
     def reset(self):
         self.__init__(self.shape)
 
     @property
     def mean(self):
-        return self.zeros if self.count < 2 else self.running_mean
+        return self.running_mean if self.count >= 2 else np.zeros(self.shape, dtype=np.float32)
 
     @property
     def std(self):
         if self.count < 2:
-            return self.ones
+            return np.ones(self.shape, dtype=np.float32)
         var = self.running_variance / (self.count - 1)
-        var = np.where(var == 0, 1.0, var)         # a constant feature normalises to zero instead of dividing by zero
-        return np.sqrt(var)
+        # a constant feature gets variance 1, so (x - mean) / std maps it to zero instead of dividing by zero
+        return np.sqrt(np.where(var == 0, 1.0, var))
 
     def increment_from_obs_stats_update(self, obs_stats_update):
-        """math_helpers.py:68-87: pairwise merge of (mean, M2, count)."""
+        """Fold in what a worker shipped as `FDReturn.obs_stats_update` (math_helpers.py:68-87)."""
         if len(obs_stats_update) == 0:
             return
-        n = int(np.prod(self.shape))
-        other_mean = np.asarray(obs_stats_update[:n], dtype=np.float32).reshape(self.running_mean.shape)
-        other_var = np.asarray(obs_stats_update[n:-1], dtype=np.float32).reshape(self.running_variance.shape)
-        other_count = obs_stats_update[-1]
-        if other_count == 0:
-            return
-        count = self.count + other_count
-        mean_delta = other_mean - self.running_mean
-        mean_delta_squared = mean_delta * mean_delta
-        combined_mean = (self.count * self.running_mean + other_count * other_mean) / count
-        combined_variance = self.running_variance + other_var + mean_delta_squared * self.count * other_count / count
-        self.running_mean = combined_mean
-        self.running_variance = combined_variance
-        self.count = count
+        mean_b, m2_b, n_b = self._split(obs_stats_update)
+        as_f32 = lambda v: np.asarray(v, dtype=np.float32).reshape(self.running_mean.shape)   # noqa: E731
+        self._merge(as_f32(mean_b), as_f32(m2_b), n_b)
 
     def serialize(self):
         return self.running_mean.ravel().tolist() + self.running_variance.ravel().tolist() + [self.count]
 
     def deserialize(self, other):
-        self.reset()
-        n = int(np.prod(self.shape))
-        self.running_mean = np.reshape(other[:n], self.shape)
-        self.running_variance = np.reshape(other[n:-1], self.shape)
-        self.count = other[-1]
+        """Adopt serialized moments as they are: the arrays take the dtype numpy infers from `other` (float64 for the
+        lists `FDState.obs_stats` carries - which is why a worker that loaded them normalises in fp64, worker.py:43)."""
+        mean, m2, n = self._split(other)
+        self.running_mean = np.reshape(mean, self.shape)
+        self.running_variance = np.reshape(m2, self.shape)
+        self.count = n
 
 
 def normalize_obs(ctx, obs, mean, std, clip=10.0, out=None):

@@ -121,12 +121,32 @@ def build_layout(kind, n_in, n_act, h1=64, h2=64):
 # initial parameters: torch default init drawn in registration order, then the
 # reference's normc re-initialisation of Sequential layers (policy.py:88-115)
 # ----------------------------------------------------------------------------
-def _default_init(layout):
-    """Draw torch's default initialisation for every tensor, consuming the global
-    torch RNG in registration order exactly as constructing the modules would."""
+def _construction_order(kind, layout):
+    """Entries in the order the reference CONSTRUCTS the modules (= the order torch's default init consumes the global
+    RNG).  For every policy but IMPALA that is the registration order.  ImpalaCNN builds stage by stage - feat_convs[s],
+    then the stage's two residual blocks (impala.py:62-107) - and only afterwards wraps the three lists in ModuleLists
+    (:109-111), so its draws run feat0, res1_0, res2_0, feat1, ... while parameters() lists feat0..2, res1_0..2, res2_0..2."""
+    ents = layout.entries
+    if kind != "impala":
+        return list(ents)
+    order, taken = [], set()
+    for s in range(3):
+        for blk in ("feat_convs", "resnet1", "resnet2"):
+            prefix = "model.0.%s.%d." % (blk, s)
+            for i, e in enumerate(ents):
+                if e["name"].startswith(prefix):
+                    order.append(e)
+                    taken.add(i)
+    order += [e for i, e in enumerate(ents) if i not in taken]      # fc, core, policy: constructed last, in this order
+    return order
+
+
+def _default_init(layout, kind=None):
+    """Draw torch's default initialisation for every tensor, consuming the global torch RNG in the order the reference's
+    constructor creates the modules (see _construction_order); values land at their state_dict offsets."""
     theta = np.zeros(layout.num_params, np.float32)
     buf = np.zeros(layout.num_buffers, np.float32)
-    ents = layout.entries
+    ents = _construction_order(kind, layout)
     i = 0
     while i < len(ents):
         e = ents[i]
@@ -188,7 +208,7 @@ def initial_parameters(kind, n_in, n_act, seed=124, h1=64, h2=64):
     torch default init from the global torch RNG, then normc from RandomState(seed)
     (IMPALA: normc finds no layer with a weight in `self.model`, policy.py:94-100)."""
     layout = build_layout(kind, n_in, n_act, h1, h2)
-    theta, buf = _default_init(layout)
+    theta, buf = _default_init(layout, kind)
     if kind != "impala":
         _normc(layout, theta, np.random.RandomState(seed))
     return theta, buf
@@ -219,6 +239,8 @@ class Policy(object):
         self._one_idx = torch.zeros(1, dtype=torch.int64, device=dev)
         self._one_sign = torch.zeros(1, dtype=torch.int8, device=dev)
         self._table = None
+        self._flat_param = None
+        self._entry = {e["name"]: e for e in self.layout.entries}
 
     # ---- flat parameter access (policy.py:36-61) -------------------------------
     def get_trainable_flat(self):
@@ -242,6 +264,52 @@ class Policy(object):
 
     def reset(self):
         pass
+
+    # ---- optimizer-facing surface (policy.py:63-84): ONE flat parameter that aliases theta ----------
+    def parameters(self):
+        """What a stock torch optimizer is built from (`torch.optim.Adam(policy.parameters())`, as the drivers build
+        theirs from the reference nn.Module): a single flat `nn.Parameter` sharing theta's device storage, so the
+        optimizer's in-place update IS the update of the vector every kernel reads."""
+        if self._flat_param is None:
+            self._flat_param = nn.Parameter(self.theta, requires_grad=True)
+        return [self._flat_param]
+
+    def set_grad_from_flat(self, gradient):
+        """policy.py:63-70: hand a flat gradient (host array or device tensor, any float dtype) to the optimizer; it is
+        cast to fp32 and ACCUMULATED into .grad the way `p.backward(grad)` does."""
+        p = self.parameters()[0]
+        g = torch.as_tensor(gradient).to(device=self.theta.device, dtype=torch.float32).reshape(-1)
+        if g.numel() != self.num_params:
+            raise ValueError("set_grad_from_flat: %d values for %d parameters" % (g.numel(), self.num_params))
+        p.grad = g.clone() if p.grad is None else p.grad.add_(g)
+
+    def get_grad_as_flat(self):
+        """policy.py:72-83 (float64 host vector; zeros where no gradient has been set)."""
+        p = self._flat_param
+        if p is None or p.grad is None:
+            return np.zeros(self.num_params)
+        return p.grad.double().cpu().numpy()
+
+    # ---- train-mode pass of the UNPERTURBED policy (compute_vbn, policy.py:31-34) ---------------------
+    def _tensor(self, name):
+        e = self._entry[name]
+        src = self.theta if e["param"] else self.buffers
+        return src[e["off"]:e["off"] + e["numel"]].view(e["shape"])
+
+    def _norm_train(self, x, name):
+        """nn.BatchNorm*d.forward in training mode: normalise with the batch statistics and move the shared running
+        statistics towards them (momentum 0.1, unbiased variance), in place in `self.buffers`."""
+        y = nn.functional.batch_norm(x, self._tensor(name + ".running_mean"), self._tensor(name + ".running_var"),
+                                     self._tensor(name + ".weight"), self._tensor(name + ".bias"), True, 0.1, 1e-5)
+        self._tensor(name + ".num_batches_tracked").add_(1)
+        return y
+
+    def _dense(self, x, name):
+        return nn.functional.linear(x, self._tensor(name + ".weight"), self._tensor(name + ".bias"))
+
+    def _conv(self, x, name, stride=1, padding=0):
+        return nn.functional.conv2d(x, self._tensor(name + ".weight"), self._tensor(name + ".bias"), stride=stride,
+                                    padding=padding)
 
     # ---- batched forward ---------------------------------------------------------
     def bind_table(self, noise_source):
@@ -324,33 +392,16 @@ class DiscretePolicy(Policy):
     def get_strategy(self, x):
         return self.forward(x).cpu().numpy()
 
+    @torch.no_grad()
     def compute_vbn(self, buffer):
-        """policy.py:31-34: a train-mode forward of the UNPERTURBED policy refreshes the
-        shared BN running statistics (momentum 0.1, unbiased variance).  Once per epoch,
-        off the hot path; plain torch ops on the device."""
-        x = torch.as_tensor(np.asarray(buffer), dtype=torch.float32).reshape(-1, int(np.prod(self.input_shape)))
-        x = x.to(self.ctx.device)
-        L = {e["name"]: e for e in self.layout.entries}
-
-        def par(n):
-            e = L[n]
-            return self.theta[e["off"]:e["off"] + e["numel"]].view(e["shape"])
-
-        def bufv(n):
-            e = L[n]
-            return self.buffers[e["off"]:e["off"] + e["numel"]]
-
-        for bn, lin, act in (("model.0", "model.1", True), ("model.3", "model.4", True), ("model.6", "model.7", False)):
-            mean = x.mean(0)
-            var_b = x.var(0, unbiased=False)
-            n = x.shape[0]
-            bufv(bn + ".running_mean").mul_(0.9).add_(0.1 * mean)
-            bufv(bn + ".running_var").mul_(0.9).add_(0.1 * var_b * (n / max(n - 1, 1)))
-            bufv(bn + ".num_batches_tracked").add_(1)
-            x = (x - mean) / torch.sqrt(var_b + 1e-5) * par(bn + ".weight") + par(bn + ".bias")
-            x = torch.nn.functional.linear(x, par(lin + ".weight"), par(lin + ".bias"))
-            if act:
-                x = torch.relu(x)
+        """policy.py:31-34: a train-mode forward of the UNPERTURBED policy refreshes the shared BN running statistics
+        (momentum 0.1, unbiased variance).  Once per epoch, off the hot path: plain torch ops on the device over views
+        of theta / the buffer vector."""
+        x = torch.as_tensor(np.asarray(buffer) if not torch.is_tensor(buffer) else buffer, dtype=torch.float32)
+        x = x.reshape(-1, int(np.prod(self.input_shape))).to(self.ctx.device)
+        x = torch.relu(self._dense(self._norm_train(x, "model.0"), "model.1"))
+        x = torch.relu(self._dense(self._norm_train(x, "model.3"), "model.4"))
+        self._dense(self._norm_train(x, "model.6"), "model.7")
 
 
 class AtariPolicy(DiscretePolicy):
@@ -364,8 +415,16 @@ class AtariPolicy(DiscretePolicy):
     def _obs_shape(self):
         return (4, 84, 84)
 
+    @torch.no_grad()
     def compute_vbn(self, buffer):
-        raise NotImplementedError("AtariPolicy.compute_vbn: refresh BN statistics with set_buffers()")
+        """policy.py:31-34 over atari.py:35-51: conv0 -> BN1 -> ReLU -> conv3 -> BN4 -> ReLU -> flatten -> L7 -> BN8 in
+        training mode on the unperturbed parameters; `buffer`: frames (N,4,84,84) in [0,1] (tensor or array)."""
+        x = torch.as_tensor(np.asarray(buffer) if not torch.is_tensor(buffer) else buffer, dtype=torch.float32)
+        x = x.reshape((-1,) + self._obs_shape()).to(self.ctx.device)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            x = torch.relu(self._norm_train(self._conv(x, "model.0", stride=4), "model.1"))
+            x = torch.relu(self._norm_train(self._conv(x, "model.3", stride=2), "model.4"))
+        self._norm_train(self._dense(x.flatten(1), "model.7"), "model.8")
 
 
 class ImpalaPolicy(DiscretePolicy):
@@ -418,8 +477,47 @@ class ImpalaPolicy(DiscretePolicy):
         self.state = (h1, c1)
         return probs[0]
 
+    @torch.no_grad()
     def compute_vbn(self, buffer):
-        raise NotImplementedError("ImpalaPolicy.compute_vbn: refresh BN statistics with set_buffers()")
+        """impala.py:13-17: `buffer` is a list of the dicts the environment wrapper emits (frame (1,1,3,64,64) 0..255,
+        reward (1,1), done (1,1)); they are stacked into one batch of N single-step sequences and run through the
+        UNPERTURBED network in training mode (:136-186), which refreshes the running statistics of all 17 BatchNorm
+        layers.  Like the reference, the pass also advances the carried LSTM state (by N steps, see below)."""
+        dev = self.ctx.device
+        frame = torch.cat([torch.as_tensor(b["frame"]).float().reshape(-1, 3, 64, 64) for b in buffer]).to(dev)
+        reward = torch.cat([torch.as_tensor(b["reward"]).float().reshape(-1) for b in buffer]).to(dev)
+        done = torch.cat([torch.as_tensor(b["done"]).reshape(-1) for b in buffer]).to(dev)
+        n = frame.shape[0]
+        x = frame / 255.0
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            for s in range(3):
+                fc = "model.0.feat_convs.%d" % s
+                x = nn.functional.max_pool2d(self._conv(self._norm_train(x, fc + ".0"), fc + ".1", padding=1), 3, 2, 1)
+                for blk in ("resnet1", "resnet2"):
+                    b = "model.0.%s.%d" % (blk, s)
+                    y = self._conv(torch.relu(self._norm_train(x, b + ".0")), b + ".2", padding=1)
+                    y = self._conv(torch.relu(self._norm_train(y, b + ".3")), b + ".5", padding=1)
+                    x = x + y
+        x = torch.relu(x).reshape(n, -1)
+        x = torch.relu(self._dense(self._norm_train(x, "model.0.fc.0"), "model.0.fc.1"))
+        core_in = torch.cat([x, reward.clamp(-1, 1).reshape(n, 1)], dim=-1)
+        w_ih, b_ih = self._tensor("model.0.core.weight_ih_l0"), self._tensor("model.0.core.bias_ih_l0")
+        w_hh, b_hh = self._tensor("model.0.core.weight_hh_l0"), self._tensor("model.0.core.bias_hh_l0")
+        # the stacked batch is (B = N, T = 1); the LSTM is batch_first and is handed inp.unsqueeze(0) = (1, N, 257)
+        # (impala.py:166-173), so the N entries run through it as ONE sequence of N steps from the carried state, and
+        # only the first entry's `done` flag is applied (zip over T = 1 items, :166)
+        keep = 0.0 if bool(done.reshape(-1)[0]) else 1.0
+        h = self.state[0].reshape(1, 256) * keep
+        c = self.state[1].reshape(1, 256) * keep
+        x_part = nn.functional.linear(core_in, w_ih, b_ih)
+        outs = []
+        for t in range(n):
+            gi, gf, gg, go = (x_part[t:t + 1] + nn.functional.linear(h, w_hh, b_hh)).chunk(4, dim=-1)
+            c = torch.sigmoid(gf) * c + torch.sigmoid(gi) * torch.tanh(gg)
+            h = torch.sigmoid(go) * torch.tanh(c)
+            outs.append(h)
+        self._norm_train(torch.cat(outs), "model.0.policy.0")
+        self.state = (h.reshape(1, 1, 256).contiguous(), c.reshape(1, 1, 256).contiguous())
 
 
 POLICY_CLASSES = {"mujoco": MujocoPolicy, "discrete": DiscretePolicy, "atari": AtariPolicy, "impala": ImpalaPolicy}

@@ -7,7 +7,7 @@ import torch
 
 
 def smoke():
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    root = os.path.dirname(os.path.abspath(__file__))
     if root not in sys.path:
         sys.path.insert(0, root)
     from oracle import dfd_oracle as O          # the checker (test infrastructure)

@@ -622,7 +622,104 @@ def gen_obs_stats():
                         back_mean=np.asarray(back.mean, dtype=np.float64), back_std=np.asarray(back.std, dtype=np.float64))
 
 
+# ---------------------------------------------------------------- round 2: compute_vbn, non-DSGD optimizer, default init
+def gen_vbn():
+    """policy.py:31-34 / impala.py:13-17: train-mode forward of the unperturbed policy refreshes every BatchNorm's
+    running statistics.  Records the buffers before / after for Atari (tensor batch) and IMPALA (list of dicts)."""
+    rec = {}
+    torch.manual_seed(124)
+    pol = AtariPolicy((84, 84), 6, seed=124)
+    L = O.atari_layout(6)
+    pol.set_trainable_flat(O.synthetic_theta(L, 21))
+    load_buffers(pol, L, O.synthetic_buffers(L, 22))
+    x = torch.rand(6, 4, 84, 84, generator=torch.Generator().manual_seed(41))
+    with torch.no_grad():
+        pol.compute_vbn(x)
+        pol.compute_vbn(x[:3])
+    assert not pol.training
+    rec.update(atari_theta_seed=21, atari_buffer_seed=22, atari_obs_seed=41,
+               atari_serialized_after=np.asarray(pol.serialize(), dtype=np.float32))
+    torch.manual_seed(124)
+    pol = ImpalaPolicy((3, 64, 64), 15, seed=124)
+    L = O.impala_layout(15)
+    pol.set_trainable_flat(O.synthetic_theta(L, 31))
+    load_buffers(pol, L, O.synthetic_buffers(L, 32))
+    g = torch.Generator().manual_seed(42)
+    n = 4
+    frames = torch.randint(0, 256, (n, 1, 1, 3, 64, 64), generator=g).float()
+    rewards = torch.tensor([0.5, -3.0, 2.0, 0.0]).view(n, 1, 1)
+    dones = torch.tensor([False, True, False, False]).view(n, 1, 1)
+    buf = [{"frame": frames[i], "reward": rewards[i], "done": dones[i]} for i in range(n)]
+    pol.reset()
+    with torch.no_grad():
+        pol.compute_vbn(buf)
+    rec.update(impala_state_h=pol.model[0].state[0].reshape(-1).numpy().copy(),
+               impala_state_c=pol.model[0].state[1].reshape(-1).numpy().copy())
+    rec.update(impala_theta_seed=31, impala_buffer_seed=32, impala_frame_seed=42, impala_reward=rewards.view(-1).numpy(),
+               impala_done=dones.view(-1).numpy(), impala_serialized_after=np.asarray(pol.serialize(), dtype=np.float32))
+    # keep the fixture small: only the buffer values (state_dict order) are compared
+    for k, LL in (("atari", O.atari_layout(6)), ("impala", O.impala_layout(15))):
+        full = rec.pop(k + "_serialized_after")
+        off, vals = 0, []
+        for e in LL.entries:
+            if e.kind == "buffer":
+                vals.append(full[off:off + e.numel])
+            off += e.numel
+        rec[k + "_buffers_after"] = np.concatenate(vals)
+    np.savez_compressed(os.path.join(HERE, "vbn.npz"), **rec)
+
+
+def gen_adam_steps():
+    """finite_differences.py:54-57 with a stock torch optimizer (not DSGD): policy.set_grad_from_flat(-g)
+    (policy.py:63-70) then optimizer.step().  4 steps of the unmodified learner with torch.optim.Adam."""
+    import io
+    import contextlib
+    torch.manual_seed(124)
+    pol = MujocoPolicy(17, 6, seed=124)
+    P = pol.num_params
+    table = SharedNoiseTable(1_000_000, P, 123)
+    opt = torch.optim.Adam(pol.parameters(), lr=0.01)
+    fd = FiniteDifferences(pol, opt, _Omega(0.3), table, noise_std=0.02, batch_size=16, ent_coef=0.0, max_delayed_return=3)
+    rrng = np.random.RandomState(7)
+    rec = {"theta0": pol.get_trainable_flat().copy(), "H": 3, "sigma": 0.02, "lr": 0.01, "table_size": 1_000_000,
+           "table_seed": 123, "n_steps": 4}
+    for s in range(4):
+        keys = [table.sample()[0] for _ in range(16)]
+        rewards = (rrng.randn(16) * 2.0 + 1.0).tolist()
+        epochs = [fd.epoch] * 16 if s < 2 else [fd.epoch - (i % 3) for i in range(16)]
+        with torch.enable_grad(), contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step([mkret(e, k, r) for e, k, r in zip(epochs, keys, rewards)], 0.0, 0.0, 0.0)
+        rec["s%d_keys" % s] = np.array(keys)
+        rec["s%d_epochs" % s] = np.array(epochs)
+        rec["s%d_rewards" % s] = np.array(rewards)
+        rec["s%d_grad" % s] = fd.gradient_memory.copy()
+        rec["s%d_theta" % s] = pol.get_trainable_flat().copy()
+        rec["s%d_update" % s] = float(upd)
+    np.savez_compressed(os.path.join(HERE, "fd_steps_adam.npz"), **rec)
+
+
+def gen_default_init():
+    """Initial parameter vectors of the reference constructors under torch.manual_seed(124) (IMPALA: modules are
+    CONSTRUCTED stage by stage - impala.py:62-107 - but registered list by list, :109-111)."""
+    rec = {}
+    for name, ctor in (("impala", lambda: ImpalaPolicy((3, 64, 64), 15, seed=124)),
+                       ("atari", lambda: AtariPolicy((84, 84), 6, seed=124))):
+        torch.manual_seed(124)
+        th = ctor().get_trainable_flat()
+        rec[name + "_sha256"] = sha(th)
+        rec[name + "_head"] = th[:8].copy()
+        rec[name + "_probe_idx"] = np.linspace(0, th.shape[0] - 1, 64).astype(np.int64)
+        rec[name + "_probe"] = th[rec[name + "_probe_idx"]].copy()
+    np.savez(os.path.join(HERE, "default_init.npz"), **rec)
+
+
 def main():
+    only = sys.argv[1:]
+    if only:       # regenerate just the named fixtures: python make_golden.py vbn adam_steps default_init
+        for name in only:
+            globals()["gen_" + name]()
+        print("golden fixtures written to", HERE, only)
+        return
     with open(os.path.join(HERE, "noise.json"), "w") as f:
         json.dump({"tables": gen_noise(), "worker": gen_worker_draws()}, f, indent=1)
     gen_mujoco()
@@ -635,6 +732,9 @@ def main():
     gen_wire()
     gen_strategy()
     gen_obs_stats()
+    gen_vbn()
+    gen_adam_steps()
+    gen_default_init()
     print("golden fixtures written to", HERE)
 
 

@@ -1,0 +1,359 @@
+"""Round-2 GPU parity tests (-m gpu): the holes VERDICT r1 named.
+
+* the streaming tcgen05 forward (wide nets, C3) with MANY work items per CTA: ring wrap across members, the TMEM
+  hand-off between consecutive members, antithetic pairs on neighbouring CTAs and unrelated indices;
+* `compute_vbn` of the CNN policies on the device against buffers the reference's own `compute_vbn` produced;
+* the non-DSGD optimizer branch (`set_grad_from_flat` + a stock torch optimizer) against unmodified reference steps;
+* host-side validation of wire-supplied keys and of the paired layout;
+* the loop body of the reference's server driver (run_server.py:110-201) executed with the import swap only."""
+import contextlib
+import io
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dfd_oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as G
+    G.build()
+    import dfd_starter_b200 as D
+    return D
+
+
+class Omega(object):
+    def __init__(self, w=0.3):
+        self.omega, self.min_omega, self.max_omega = w, 0.0, 1.0
+
+
+def rel_max(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+# ---------------------------------------------------------------- a7: wide-net tensor path, many members per CTA
+@pytest.mark.parametrize("E,M,layout", [(128, 640, "pairs"), (200, 604, "pairs"), (128, 601, "unrelated"),
+                                        (16, 1500, "pairs"), (200, 298, "mixed")])
+def test_humanoid_stream_kernel_many_members(D, E, M, layout):
+    """C3 shape 376-256-256-17 through `mlp_forward_stream_kernel` with 2-10 work items per persistent CTA
+    (grid = min(148, work items)): every member against the exact fp32 path (stated tolerance of the tf32 path: max-abs
+    2e-3, mean-abs 3e-4, as tests/test_gpu_tensor_core.py), a subset against the CPU oracle, and run-to-run bit identity."""
+    n_in, h, n_act = 376, 256, 17
+    L = O.mujoco_layout(n_in, n_act, h, h)
+    P = L.num_params
+    table = D.SharedNoiseTable(4_000_000, P, 123, device=0)
+    pol = D.MujocoPolicy(n_in, n_act, seed=5, h1=h, h2=h, device=0, precision=1).bind_table(table)
+    exact = D.MujocoPolicy(n_in, n_act, seed=5, h1=h, h2=h, device=0, precision=0).bind_table(table)
+    theta = O.synthetic_theta(L, 5)
+    pol.set_trainable_flat(theta)
+    exact.set_trainable_flat(theta)
+    rng = np.random.RandomState(E + M)
+    if layout == "pairs":                       # [plus | minus] of the same rows: what the bench and the Worker submit
+        half = rng.randint(0, 4_000_000 - P, size=M // 2).astype(np.int64)
+        idx = np.concatenate([half, half])
+        sign = np.concatenate([np.ones(M // 2), -np.ones(M // 2)]).astype(np.int8)
+    elif layout == "unrelated":                 # odd count, every member its own row, eval members (sign 0) mixed in
+        idx = rng.randint(0, 4_000_000 - P, size=M).astype(np.int64)
+        sign = rng.choice([-1, 0, 1], size=M).astype(np.int8)
+    else:                                       # pairs whose twins are NOT M/2 apart + all table alignments
+        idx = (rng.randint(0, 1_000_000, size=M) * 4 + np.arange(M) % 4).astype(np.int64) % (4_000_000 - P)
+        idx[1::2] = idx[0::2][:len(idx[1::2])]
+        sign = np.where(np.arange(M) % 2 == 0, 1, -1).astype(np.int8)
+    obs = rng.randn(M, E, n_in).astype(np.float32)
+    args = (torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(), 0.02)
+    out_t = pol.forward_members(*args)
+    out = out_t.cpu().numpy()
+    ref = exact.forward_members(*args).cpu().numpy()
+    err = np.abs(out - ref)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() <= 2e-3 and err.mean() <= 3e-4, (err.max(), err.mean(), worst)
+    per_member = err.reshape(M, -1).max(1)      # no single member (a lost ring slot, a stale TMEM region) may stand out
+    assert per_member.max() <= 2e-3 and np.isfinite(out).all()
+    for m in (0, 1, M // 2, M - 1, int(rng.randint(M))):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
+        mean, std = O.mujoco_forward(L, th, obs[m])
+        np.testing.assert_allclose(ref[m], np.concatenate([mean, std], -1), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(out[m], np.concatenate([mean, std], -1), rtol=0, atol=2e-3)
+    assert torch.equal(pol.forward_members(*args), out_t)          # deterministic across launches
+
+
+# ---------------------------------------------------------------- a9 / a10: compute_vbn on the device
+def test_atari_compute_vbn_golden(D, golden_dir):
+    g = np.load(os.path.join(golden_dir, "vbn.npz"))
+    L = O.atari_layout(6)
+    pol = D.AtariPolicy((84, 84), 6, seed=124, device=0)
+    pol.set_trainable_flat(O.synthetic_theta(L, int(g["atari_theta_seed"])))
+    pol.set_buffers(O.synthetic_buffers(L, int(g["atari_buffer_seed"])))
+    x = torch.rand(6, 4, 84, 84, generator=torch.Generator().manual_seed(int(g["atari_obs_seed"])))
+    pol.compute_vbn(x)
+    pol.compute_vbn(x[:3])
+    got, ref = pol.buffers.cpu().numpy(), g["atari_buffers_after"]
+    assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3)) < 1e-4
+    # and the refreshed statistics are what the eval-mode kernel normalises with from now on
+    table = D.SharedNoiseTable(1_000_000, L.num_params, 123, device=0)
+    pol.bind_table(table)
+    probs = pol.forward(x[:1]).cpu().numpy()
+    want = O.atari_forward(L, pol.get_trainable_flat(), ref, x[:1].numpy())
+    np.testing.assert_allclose(probs.reshape(-1), want.reshape(-1), atol=1e-5)
+
+
+def test_impala_compute_vbn_golden(D, golden_dir):
+    g = np.load(os.path.join(golden_dir, "vbn.npz"))
+    L = O.impala_layout(15)
+    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0)
+    pol.set_trainable_flat(O.synthetic_theta(L, int(g["impala_theta_seed"])))
+    pol.set_buffers(O.synthetic_buffers(L, int(g["impala_buffer_seed"])))
+    frames = torch.randint(0, 256, (4, 1, 1, 3, 64, 64), generator=torch.Generator().manual_seed(int(g["impala_frame_seed"]))).float()
+    buf = [{"frame": frames[i], "reward": torch.tensor(g["impala_reward"][i]).view(1, 1),
+            "done": torch.tensor(g["impala_done"][i]).view(1, 1)} for i in range(4)]
+    pol.reset()
+    pol.compute_vbn(buf)
+    got, ref = pol.buffers.cpu().numpy(), g["impala_buffers_after"]
+    assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3)) < 2e-4
+    np.testing.assert_allclose(pol.state[0].reshape(-1).cpu().numpy(), g["impala_state_h"], atol=1e-5)
+    np.testing.assert_allclose(pol.state[1].reshape(-1).cpu().numpy(), g["impala_state_c"], atol=1e-5)
+
+
+# ---------------------------------------------------------------- a18: set_grad_from_flat + a stock torch optimizer
+@pytest.mark.parametrize("policy_kind", ["device", "host"])
+def test_adam_steps_golden(D, golden_dir, policy_kind):
+    """finite_differences.py:54-57 with torch.optim.Adam: 4 steps of the UNMODIFIED reference learner (2 fd_return, 2
+    with delayed epochs) replayed through this learner - with this package's device policy (flat nn.Parameter aliasing
+    theta) and with a reference-style host nn.Module policy."""
+    g = np.load(os.path.join(golden_dir, "fd_steps_adam.npz"))
+    table = D.SharedNoiseTable(int(g["table_size"]), 6092, int(g["table_seed"]), device=0)
+    if policy_kind == "device":
+        pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+        pol.set_trainable_flat(g["theta0"])
+    else:
+        class HostModule(torch.nn.Module):          # the reference Policy's flat surface on a host nn.Module
+            def __init__(self, theta):
+                super().__init__()
+                self.w = torch.nn.Parameter(torch.from_numpy(np.array(theta, np.float32)))
+                self.num_params = self.w.numel()
+
+            def get_trainable_flat(self):
+                return self.w.detach().numpy().copy()
+
+            def set_trainable_flat(self, flat):
+                with torch.no_grad():
+                    self.w.copy_(torch.as_tensor(np.asarray(flat), dtype=torch.float32))
+
+            def set_grad_from_flat(self, gradient):
+                self.w.backward(torch.as_tensor(gradient, dtype=torch.float32))
+        pol = HostModule(g["theta0"])
+    opt = torch.optim.Adam(pol.parameters(), lr=float(g["lr"]))
+    fd = D.FiniteDifferences(pol, opt, Omega(0.3), table, noise_std=float(g["sigma"]), batch_size=16,
+                             max_delayed_return=int(g["H"]))
+    assert not fd.using_dsgd
+    for s in range(int(g["n_steps"])):
+        batch = []
+        for e, k, r in zip(g["s%d_epochs" % s], g["s%d_keys" % s], g["s%d_rewards" % s]):
+            ret = D.FDReturn()
+            ret.epoch, ret.encoded_noise, ret.reward = int(e), str(k), float(r)
+            batch.append(ret)
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step(batch, 0.0, 0.0, 0.0)
+        assert rel_max(fd.gradient_memory, g["s%d_grad" % s]) <= 1e-5, s
+        # Adam's first steps are +-lr per element whatever the gradient scale: atol on theta, rel 1e-4 on the norm
+        assert np.max(np.abs(pol.get_trainable_flat() - g["s%d_theta" % s])) <= 5e-6, s
+        assert abs(upd - float(g["s%d_update" % s])) <= 1e-4 * float(g["s%d_update" % s]), s
+    assert fd.epoch == int(g["n_steps"])
+
+
+# ---------------------------------------------------------------- keys off the wire, paired layout
+def test_out_of_table_keys_are_discarded_not_read(D):
+    P = 6092
+    table = D.SharedNoiseTable(1_000_000, P, 123, device=0)
+    theta = O.synthetic_theta(O.mujoco_layout(17, 6), 1)
+    oracle_table = O.NoiseTableOracle(1_000_000, P, 123)
+
+    def learner():
+        pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+        pol.set_trainable_flat(theta)
+        return D.FiniteDifferences(pol, D.DSGD([torch.nn.Parameter(torch.zeros(P))], lr=0.01), Omega(), table,
+                                   noise_std=0.02, batch_size=32, max_delayed_return=4)
+    rng = np.random.RandomState(3)
+    good = [(0, str(int(i)), float(r)) for i, r in zip(table.sample_indices(12), rng.randn(12))]
+    bad = [(0, str(1_000_000 - P + 1), 5.0), (0, str(10 ** 12), -2.0), (0, str(1_000_000 - 1), 1.0)]
+    fd, ofd = learner(), O.FiniteDifferencesOracle(theta, oracle_table, 0.02, 0.01, max_delayed_return=4, omega=0.3)
+
+    def rets(rows):
+        out = []
+        for e, k, r in rows:
+            ret = D.FDReturn()
+            ret.epoch, ret.encoded_noise, ret.reward = e, k, r
+            out.append(ret)
+        return out
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        upd = fd.step(rets(good[:5] + bad[:2] + good[5:] + bad[2:]), 0.1, 0.0, 0.0)
+    assert "OUTSIDE THE TABLE" in log.getvalue() and fd.discarded_returns == 3
+    oupd = ofd.step([O.Ret(*r) for r in good], 0.1)            # the oracle on the in-table returns only
+    assert rel_max(fd.gradient_memory, ofd.gradient_memory) <= 1e-5 and abs(upd - oupd) <= 1e-5 * oupd
+    # the last valid slice (idx + P == size) is still accepted
+    fd2 = learner()
+    assert fd2.step(rets([(0, str(1_000_000 - P), 1.0), (0, "17", -1.0)]), 0.0) > 0 and fd2.discarded_returns == 0
+
+
+def test_paired_learner_regroups_or_refuses(D):
+    P = 6092
+    table = D.SharedNoiseTable(1_000_000, P, 123, device=0)
+    theta = O.synthetic_theta(O.mujoco_layout(17, 6), 2)
+
+    def learner():
+        pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+        pol.set_trainable_flat(theta)
+        return D.FiniteDifferences(pol, D.DSGD([torch.nn.Parameter(torch.zeros(P))], lr=0.01), Omega(), table,
+                                   noise_std=0.02, batch_size=64, max_delayed_return=4, paired=True)
+    rng = np.random.RandomState(5)
+    R = 24
+    idx = table.sample_indices(R)
+    idx[7] = idx[3]                                             # a table row drawn twice is legal
+    rp, rm = rng.randn(R), rng.randn(R)
+    ep = np.zeros(2 * R, np.int64)
+    canon = learner()
+    canon.step_arrays(ep, np.concatenate([idx, idx]), np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8),
+                      np.concatenate([rp, rm]), 0.0)
+    g0 = canon.gradient_memory
+    # (1) interleaved chunks [+A -A +B -B ...] with eval members (sign 0) in between, as Worker.evaluate / RPC chunks give
+    i2 = np.empty(2 * R + 3, np.int64)
+    s2 = np.empty(2 * R + 3, np.int8)
+    r2 = np.empty(2 * R + 3)
+    i2[:3], s2[:3], r2[:3] = 0, 0, 9.0
+    i2[3::2], s2[3::2], r2[3::2] = idx, 1, rp
+    i2[4::2], s2[4::2], r2[4::2] = idx, -1, rm
+    inter = learner()
+    inter.step_arrays(np.zeros(2 * R + 3, np.int64), i2, s2, r2, 0.0)
+    assert rel_max(inter.gradient_memory, g0) <= 2e-6
+    # (2) reversed arrival (LIFO pops): same pairs, other order -> same gradient up to summation order
+    rev = learner()
+    rev.step_arrays(ep, np.concatenate([idx, idx])[::-1].copy(), np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)[::-1].copy(),
+                    np.concatenate([rp, rm])[::-1].copy(), 0.0)
+    assert rel_max(rev.gradient_memory, g0) <= 2e-6
+    # (3) an unmatched member is refused, not mispaired
+    bad = learner()
+    from dfd_starter_b200._lib import DfdError
+    with pytest.raises(DfdError):
+        bad.step_arrays(np.zeros(4, np.int64), np.array([5, 9, 5, 11]), np.array([1, 1, -1, -1], np.int8), np.ones(4), 0.0)
+    assert bad.epoch == 0
+
+
+# ---------------------------------------------------------------- boundary: the server driver's loop body
+def test_server_train_loop_body_three_epochs(D):
+    """run_server.py:110-201 (`ServerRunner.train`) with ONLY the INTEGRATION.md import swap: the statements below are
+    the driver's, in its order, with its variable names; what differs is where the classes come from.  A client thread
+    plays run_client.py:31-96 (poll state -> worker.update -> collect -> submit).  Checked: three learner epochs happen,
+    the policy the clients load is the learner's, BN statistics refresh every epoch, and the parameters after three
+    epochs equal the CPU oracle's fed the very same returns."""
+    from dfd_starter_b200 import (SharedNoiseTable, FiniteDifferences, FDState, DSGD, DiscretePolicy, GRPCWorker,
+                                  RPCClient, Worker, SyntheticAgent, WelfordRunningStat)
+    random_seed, noise_std, batch_size, max_delayed_return, eval_prob = 124, 0.02, 24, 10, 0.1
+    torch.manual_seed(random_seed)
+    policy = DiscretePolicy(2, 9, seed=random_seed, device=0)                       # run_server.py:78
+    noise_source = SharedNoiseTable(1_000_000, policy.num_params, random_seed=random_seed)
+    omega = Omega(0.0)
+    opt = DSGD(policy.parameters(), lr=0.01)                                        # :81
+    learner = FiniteDifferences(policy, opt, omega, noise_source, noise_std=noise_std, batch_size=batch_size,
+                                ent_coef=0.0, max_delayed_return=max_delayed_return)   # :82-86
+    global_obs_stats = WelfordRunningStat(policy.input_shape)
+    vbn_buffer = torch.rand(32, 2, generator=torch.Generator().manual_seed(9))
+    current_state = FDState()
+    current_state.strategy_frames, current_state.strategy_history = [], []
+    current_state.policy_params = policy.serialize()
+    current_state.obs_stats = global_obs_stats.serialize()
+    current_state.epoch = learner.epoch
+    current_state.experiment_id = 77
+    current_state.cfg = {"env_id": "synthetic", "noise_std": noise_std, "random_seed": random_seed, "eval_prob": eval_prob}
+    worker = GRPCWorker(current_state)                                              # :108
+    worker.update(current_state)
+    worker.start(address="127.0.0.1", port=0)                                       # :127 (port 0: any free port)
+    port = worker.grpc_server.bound_port
+
+    # ---- the client side: run_client.py:31-96 with this package's batched Worker
+    stop = threading.Event()
+    shipped = []
+    gpu = threading.Lock()      # one context per device, not re-entrant (include/dfd_b200.h): learner and client take turns
+
+    def client_main():
+        cpol = DiscretePolicy(2, 9, seed=1, device=0)
+        ctable = SharedNoiseTable(1_000_000, cpol.num_params, random_seed=random_seed)     # shared table seed (App. D)
+        cworker = Worker(cpol, SyntheticAgent(cpol, 4, seed=3), ctable, None, sigma=noise_std, eval_prob=eval_prob,
+                         random_seed=random_seed + 1)
+        client = RPCClient()
+        client.connect(address="127.0.0.1", port=port)
+        while not stop.is_set():
+            flag = client.get_server_state()
+            with gpu:
+                if flag in (client.NEW_STATE_FLAG, client.NEW_EXPERIMENT_FLAG):
+                    cworker.update(client.current_state)
+                if cworker.epoch < 0:
+                    continue
+                rets = list(cworker.collect_returns(8))
+            shipped.append(cworker.epoch)
+            client.submit_returns(rets)
+            stop.wait(0.002)
+        client.disconnect()
+    th = threading.Thread(target=client_main, daemon=True)
+    th.start()
+
+    policy_reward = policy_entropy = policy_novelty = None
+    fed = []                # what the learner was given, for the oracle replay
+    thetas = [policy.get_trainable_flat().copy()]
+    bn_before = policy.buffers.clone()
+    try:
+        while learner.epoch < 3:                                                    # :129 (timestep limit -> 3 epochs)
+            ret_rewards, ret_novelties, non_eval_returns, any_eval = [], [], [], False
+            returns, timesteps, n_delayed, n_discarded = worker.collect_returns(
+                batch_size=batch_size, current_epoch=learner.epoch, max_delayed_return=max_delayed_return)   # :135-137
+            learner.discarded_returns += n_discarded
+            for ret in returns:                                                     # :142-159
+                global_obs_stats.increment_from_obs_stats_update(ret.obs_stats_update)
+                if ret.is_eval:
+                    any_eval = True
+                    if policy_reward is None:
+                        policy_reward, policy_entropy, policy_novelty = ret.reward, ret.entropy, ret.novelty
+                    else:
+                        policy_reward = policy_reward * 0.9 + ret.reward * 0.1
+                        policy_entropy = policy_entropy * 0.9 + ret.entropy * 0.1
+                        policy_novelty = policy_novelty * 0.9 + ret.novelty * 0.1
+                else:
+                    non_eval_returns.append(ret)
+                    ret_rewards.append(ret.reward)
+                    ret_novelties.append(ret.novelty)
+            fed.append(([(int(r.epoch), str(r.encoded_noise), float(r.reward)) for r in non_eval_returns], policy_reward))
+            with gpu:
+                update_magnitude = learner.step(non_eval_returns, policy_reward, policy_novelty, policy_entropy)   # :167
+                if vbn_buffer is not None:
+                    policy.compute_vbn(vbn_buffer)                                  # :169-170
+                thetas.append(policy.get_trainable_flat().copy())
+                current_state.policy_params = policy.serialize()                    # :192-197
+            assert update_magnitude > 0 and len(ret_rewards) != 0
+            current_state.epoch = learner.epoch
+            current_state.obs_stats = global_obs_stats.serialize()
+            worker.update(current_state)
+    finally:
+        stop.set()
+        th.join(timeout=20)
+        worker.stop()
+    assert learner.epoch == 3 and max(shipped) >= 2            # the clients followed the learner's epochs
+    assert not torch.equal(policy.buffers, bn_before)          # compute_vbn refreshed the shared statistics
+    nbt = [e for e in policy.layout.entries if e["name"].endswith("num_batches_tracked")]
+    assert all(float(policy.buffers[e["off"]]) == 3.0 for e in nbt)
+    # the same returns through the CPU oracle learner
+    otable = O.NoiseTableOracle(1_000_000, policy.num_params, random_seed)
+    ofd = O.FiniteDifferencesOracle(thetas[0], otable, noise_std, 0.01, max_delayed_return=max_delayed_return, omega=0.0)
+    for k, (rows, base) in enumerate(fed):
+        ofd.step([O.Ret(*r) for r in rows], base)
+        assert np.max(np.abs(ofd.theta - thetas[k + 1])) <= 2e-6, k
+    # what a client would load next is the learner's policy, buffers included
+    probe = DiscretePolicy(2, 9, seed=2, device=0)
+    probe.deserialize(current_state.policy_params)
+    assert torch.equal(probe.theta, policy.theta) and torch.equal(probe.buffers, policy.buffers)

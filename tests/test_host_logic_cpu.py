@@ -168,3 +168,100 @@ def test_welford_running_stat_follows_the_reference(golden_dir):
     assert np.array_equal(np.asarray(back.std, dtype=np.float64), g["back_std"])
     fresh = WelfordRunningStat(K)
     assert np.array_equal(fresh.mean, np.zeros(K)) and np.array_equal(fresh.std, np.ones(K))     # count < 2
+
+
+# ---------------------------------------------------------------- round 2: compute_vbn, default init order, flat-gradient surface
+class _CpuCtx(object):
+    device = torch.device("cpu")
+
+
+def _policy_shell(cls, kind, n_act, theta, buf, in_shape):
+    """A policy object without a device context: the HOST logic of compute_vbn / set_grad_from_flat is plain torch over
+    views of theta / the buffer vector and can be checked here; everything that launches a kernel still needs the GPU."""
+    p = object.__new__(cls)
+    p.layout = P.build_layout(kind, 0 if kind in ("atari", "impala") else in_shape, n_act)
+    p.num_params = p.layout.num_params
+    p.theta, p.buffers = torch.from_numpy(np.array(theta, np.float32)), torch.from_numpy(np.array(buf, np.float32))
+    p._entry = {e["name"]: e for e in p.layout.entries}
+    p._flat_param, p.ctx, p.input_shape = None, _CpuCtx(), in_shape
+    return p
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3)))
+
+
+def test_compute_vbn_atari_and_impala_follow_the_reference(golden_dir):
+    """policy.py:31-34, impala.py:13-17: buffers after the reference's own compute_vbn (tests/golden/make_golden.py
+    gen_vbn) vs the train-mode pass of policies.py on the same synthetic theta / buffers / inputs."""
+    from oracle import dfd_oracle as O
+    g = np.load(os.path.join(golden_dir, "vbn.npz"))
+    L = O.atari_layout(6)
+    a = _policy_shell(P.AtariPolicy, "atari", 6, O.synthetic_theta(L, 21), O.synthetic_buffers(L, 22), (4, 84, 84))
+    x = torch.rand(6, 4, 84, 84, generator=torch.Generator().manual_seed(int(g["atari_obs_seed"])))
+    a.compute_vbn(x)
+    a.compute_vbn(x[:3].numpy())                       # arrays are accepted as well; num_batches_tracked counts calls
+    assert _rel(a.buffers.numpy(), g["atari_buffers_after"]) < 1e-4
+    nbt = [e for e in a.layout.entries if e["name"].endswith("num_batches_tracked")]
+    assert all(a.buffers[e["off"]] == g["atari_buffers_after"][e["off"]] for e in nbt)
+
+    L = O.impala_layout(15)
+    p = _policy_shell(P.ImpalaPolicy, "impala", 15, O.synthetic_theta(L, 31), O.synthetic_buffers(L, 32), (3, 64, 64))
+    p.reset()
+    frames = torch.randint(0, 256, (4, 1, 1, 3, 64, 64), generator=torch.Generator().manual_seed(int(g["impala_frame_seed"]))).float()
+    buf = [{"frame": frames[i], "reward": torch.tensor(g["impala_reward"][i]).view(1, 1),
+            "done": torch.tensor(g["impala_done"][i]).view(1, 1)} for i in range(4)]
+    p.compute_vbn(buf)
+    assert _rel(p.buffers.numpy(), g["impala_buffers_after"]) < 1e-4
+    # the pass also advances the carried LSTM state by the 4 stacked entries (impala.py:166-173,184)
+    np.testing.assert_allclose(p.state[0].reshape(-1).numpy(), g["impala_state_h"], atol=2e-6)
+    np.testing.assert_allclose(p.state[1].reshape(-1).numpy(), g["impala_state_c"], atol=2e-6)
+
+
+def test_default_init_follows_construction_order(golden_dir):
+    """ImpalaCNN constructs its modules stage by stage but registers them list by list; the initial theta
+    must equal the reference constructor's under the same torch seed (sha256 of the whole vector)."""
+    import hashlib
+    g = np.load(os.path.join(golden_dir, "default_init.npz"))
+    for kind, n_act in (("impala", 15), ("atari", 6)):
+        torch.manual_seed(124)
+        th, _ = P.initial_parameters(kind, 0, n_act, 124)
+        assert np.array_equal(th[g[kind + "_probe_idx"]], g[kind + "_probe"]), kind
+        assert hashlib.sha256(th.tobytes()).hexdigest() == str(g[kind + "_sha256"]), kind
+
+
+def test_flat_gradient_surface_drives_a_torch_optimizer():
+    """policy.py:63-84: set_grad_from_flat accumulates like p.backward(grad); parameters() is one flat nn.Parameter
+    that shares theta's storage, so a stock optimizer's step IS the theta update."""
+    th = np.linspace(-1, 1, 6092).astype(np.float32)
+    p = _policy_shell(P.MujocoPolicy, "mujoco", 6, th, np.zeros(0), 17)
+    assert not p.get_grad_as_flat().any()
+    opt = torch.optim.SGD(p.parameters(), lr=0.5)
+    g = np.random.RandomState(0).randn(6092)
+    p.set_grad_from_flat(g)
+    p.set_grad_from_flat(g)                          # accumulates
+    np.testing.assert_allclose(p.get_grad_as_flat(), 2 * g.astype(np.float32), rtol=1e-6)
+    opt.step()
+    np.testing.assert_allclose(p.theta.numpy(), th - g.astype(np.float32), atol=1e-6)
+    opt.zero_grad()
+    assert not p.get_grad_as_flat().any()
+    with pytest.raises(ValueError):
+        p.set_grad_from_flat(g[:10])
+
+
+def test_pair_order_validates_the_paired_layout():
+    """paired=True must not trust the [plus | minus] layout blindly."""
+    from dfd_starter_b200.finite_differences import FiniteDifferences
+    from dfd_starter_b200._lib import DfdError
+    po = FiniteDifferences._pair_order
+    idx = np.array([7, 3, 9, 7, 3, 9])
+    assert po(idx, np.array([1, 1, 1, -1, -1, -1], np.int8)) is None                 # canonical: untouched
+    # interleaved RPC chunks + an eval member (sign 0): regrouped, plus members in arrival order
+    sel = po(np.array([0, 7, 7, 3, 3]), np.array([0, 1, -1, -1, 1], np.int8))
+    assert sel.tolist() == [1, 4, 2, 3]
+    # a row drawn twice pairs up with itself in any consistent way
+    sel = po(np.array([5, 5, 5, 5]), np.array([1, -1, -1, 1], np.int8))
+    assert sorted(sel[:2].tolist()) == [0, 3] and sorted(sel[2:].tolist()) == [1, 2]
+    for bad_idx, bad_sign in (([5, 9, 5, 11], [1, 1, -1, -1]), ([5, 5, 5], [1, -1, 1]), ([5, 6], [1, 1])):
+        with pytest.raises(DfdError):
+            po(np.array(bad_idx), np.array(bad_sign, np.int8))
