@@ -46,10 +46,37 @@ WORKLOADS = {
     "C1": dict(kind="discrete", n_in=2, h1=64, h2=64, n_act=9, pairs=20, E=128,
                desc="C1 simple_trap-shaped discrete MLP 2-64-64-9, 20 antithetic pairs, fd_return"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-# `ncu --set full` capture of this workload (profiles/r01/SUMMARY.md); None where no capture exists
-NCU_TRAFFIC = {("C2", "policy_forward"): 42.45e6 + 0.52e6, ("C3", "policy_forward"): 1.1775e9 + 28.3e6,
-               ("C4", "policy_forward"): 1.2648e9 + 5.2e6, ("C5", "policy_forward"): 976.7e6 + 10.3e6, ("C2", "fd_reduce"): 24.55e6, ("C3", "fd_reduce"): 570.2e6 + 7.3e6}
+# which committed `ncu --set full` capture (profiles/rNN/<name>_raw_metrics.csv, newest round first) holds the dominant
+# kernel of a (workload, kernel) pair; roofline.traffic is READ from it at run time (dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_CAPTURE = {("C2", "policy_forward"): "prof_fwd_c2", ("C3", "policy_forward"): "prof_fwd_c3",
+               ("C4", "policy_forward"): "prof_fwd_c4", ("C5", "policy_forward"): "prof_fwd_c5",
+               ("C2", "fd_reduce"): "prof_reduce_c2", ("C3", "fd_reduce"): "prof_reduce_c3",
+               ("C5", "fd_reduce"): "prof_reduce_c5", ("cold", "fd_reduce"): "prof_reduce_cold"}
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_traffic(workload, kernel):
+    """(bytes per launch, capture path) from the newest committed capture of this kernel, or (None, None)."""
+    name = NCU_CAPTURE.get((workload, kernel))
+    prof = os.path.join(ROOT, "profiles")
+    if name is None or not os.path.isdir(prof):
+        return None, None
+    for rnd in sorted((d for d in os.listdir(prof) if os.path.isdir(os.path.join(prof, d))), reverse=True):
+        path = os.path.join(prof, rnd, name + "_raw_metrics.csv")
+        if not os.path.exists(path):
+            continue
+        tot, seen = 0.0, 0
+        with open(path) as f:
+            for line in f:
+                c = line.rstrip("\n").split(",")
+                if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[1] in _UNIT:
+                    tot += float(c[2]) * _UNIT[c[1]]
+                    seen += 1
+        if seen == 2:
+            return tot, "profiles/%s/%s_raw_metrics.csv" % (rnd, name)
+    return None, None
+
+
 TABLE_SIZE = 25_000_000
 TABLE_SEED = 124
 SIGMA = 0.02
@@ -80,7 +107,11 @@ def parse_args():
                     help="N > 1: gradient exchange as one NVLink peer-memory kernel (default) or NCCL collectives")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true",
+                    help="default C2 run only: skip the C3 / C4 / C5 workloads and the E = 1 / 16 / fp32 operating points")
     ap.add_argument("--cpu-sample-members", type=int, default=0)
+    ap.add_argument("--reference-port", action="store_true",
+                    help="--impl reference: time the oracle port even when the reference itself is importable")
     return ap.parse_args()
 
 
@@ -90,6 +121,7 @@ def workload(args):
         w["E"] = args.obs_per_member
     if args.pairs:
         w["pairs"] = args.pairs
+    w["name"] = args.workload
     w["members"] = 2 * w["pairs"]
     w["out_width"] = 2 * w["n_act"] if w["kind"] == "mujoco" else w["n_act"]
     return w
@@ -161,7 +193,7 @@ def run_reference(args, w, as_baseline=False):
               target=np.tanh(rng.randn(w["out_width"])).astype(np.float32) * 0.5)
     import multiprocessing as mp
     steps, warm = (args.steps, args.warmup) if not as_baseline else (2, 1)
-    steps = max(1, min(steps, 5))     # each step is already seconds of CPU work
+    steps = max(1, min(steps, 5))     # each step is already seconds of CPU work (the count actually run is printed)
     warm = max(0, min(warm, 1))
     times = []
     for it in range(warm + steps):
@@ -201,17 +233,191 @@ def run_reference(args, w, as_baseline=False):
                   "estimator: %d of %d returns (FiniteDifferences.step restatement, numpy BLAS threads), scaled linearly"
                   % (sample, M, E, cores, M / sample, n_fd, M))
     return dict(value=value, unit="env-steps/s", cores=cores, kind="port", sample=sample_txt,
-                ms_per_step=step_s * 1e3, fd_estimates_per_s=1.0 / t_fd, forward_s=t_fwd, estimator_s=t_fd)
+                ms_per_step=step_s * 1e3, fd_estimates_per_s=1.0 / t_fd, forward_s=t_fwd, estimator_s=t_fd, steps_run=steps)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm proper: the UNMODIFIED reference, imported from baseline/_ref (or $DFD_REFERENCE)
+# ----------------------------------------------------------------------------------------------
+def reference_root():
+    """Where an importable copy of the unmodified reference lives: $DFD_REFERENCE, else baseline/_ref (installed once
+    with pip --target from the read-only checkout, git-ignored, travels to the GPU box).  None -> the oracle port."""
+    for cand in (os.environ.get("DFD_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.exists(os.path.join(cand, "learner", "finite_differences.py")):
+            return cand
+    return None
+
+
+_R = {}
+
+
+def _real_member_chunk(task):
+    """worker/worker.py:26-32 for a chunk of members, in a forked single-threaded client process: new_flat = flat +
+    sigma * eps -> set_trainable_flat -> policy.forward(obs) -> set_trainable_flat(flat)."""
+    import torch
+    members, flat = task
+    pol, table, idx, sign, obs, kind, target = (_R[k] for k in ("policy", "table", "idx", "sign", "obs", "kind", "target"))
+    out_r = []
+    with torch.no_grad():
+        for m in members:
+            eps = table.decode(str(int(idx[m])))
+            new_flat = flat + SIGMA * (eps if sign[m] > 0 else -eps)
+            pol.set_trainable_flat(new_flat)
+            if kind == "mujoco":
+                mean, std = pol.forward(obs)
+                out = np.concatenate([mean.numpy(), std.numpy()], -1)
+            elif kind == "impala":
+                pol.reset()
+                outs = []
+                for e in range(obs.shape[0]):           # E independent single-step environments (impala.py:136-186)
+                    pol.reset()
+                    outs.append(pol.forward({"frame": obs[e:e + 1].view(1, 1, 3, 64, 64), "reward": torch.zeros(1, 1),
+                                             "done": torch.zeros(1, 1, dtype=torch.bool)}).reshape(-1).numpy())
+                out = np.stack(outs)
+            else:
+                out = pol.forward(obs).numpy()
+            pol.set_trainable_flat(flat)
+            out_r.append(float(-np.mean((out - target) ** 2)))
+    return out_r
+
+
+def run_reference_real(args, w, ref_root, as_baseline=False):
+    """--impl reference when the reference itself is importable: its own SharedNoiseTable, policy classes,
+    FiniteDifferences.step and DSGD, unmodified, on the host cores.  Per step: (1) the worker loop of worker.py:26-32 over
+    a bounded sample of the members on `cores` forked single-threaded processes (run_client.py:15), each member's E
+    observations in one `policy.forward` call; (2) the unmodified learner step on a bounded number of returns; both
+    scaled linearly to the full population (stated in `sample`)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden", "_shim"))      # `gym` is absent from the image
+    sys.path.insert(0, ref_root)
+    from utils import SharedNoiseTable                    # noqa: E402  (reference)
+    from utils import torch_helpers
+    from policies import MujocoPolicy, DiscretePolicy, AtariPolicy, ImpalaPolicy
+    from learner import FiniteDifferences, FDReturn
+    from dsgd import DSGD
+    import torch.nn as nn
+    torch.set_num_threads(1)
+    cores = len(os.sched_getaffinity(0))
+    torch.manual_seed(TABLE_SEED)
+    kind = w["kind"]
+    if kind == "mujoco":
+        h1, h2 = w["h1"], w["h2"]
+
+        class _Widths(MujocoPolicy):
+            """hidden widths as parameters (the reference hard-codes 64 x 64, mujoco.py:33-34; BASELINE config 3 names
+            256 x 256); the 64 x 64 default builds the stock model"""
+            def _build_model(self):
+                self.model = nn.Sequential(nn.Linear(self.input_shape, h1), nn.Tanh(), nn.Linear(h1, h2), nn.Tanh(),
+                                           nn.Linear(h2, self.output_shape * 2), torch_helpers.MapContinuousToAction())
+        policy = MujocoPolicy(w["n_in"], w["n_act"], seed=TABLE_SEED) if (h1, h2) == (64, 64) else _Widths(w["n_in"], w["n_act"], seed=TABLE_SEED)
+    elif kind == "discrete":
+        policy = DiscretePolicy(w["n_in"], w["n_act"], seed=TABLE_SEED)
+    elif kind == "atari":
+        policy = AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED)
+    else:
+        policy = ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED)
+    P = policy.num_params
+
+    class SignedTable(SharedNoiseTable):
+        """antithetic keys '+i' / '-i' (the extension the B200 arm's batch uses) on the reference's own table"""
+        def decode(self, key):
+            key = str(key)
+            if key[0] == "-":
+                return -super().decode(key[1:])
+            return super().decode(key[1:] if key[0] == "+" else key)
+    table = SignedTable(args.table_size, P, TABLE_SEED)
+
+    class Omega(object):
+        omega, min_omega, max_omega = 0.0, 0.0, 1.0
+    opt = DSGD(policy.parameters(), lr=LR)
+    learner = FiniteDifferences(policy, opt, Omega(), table, noise_std=SIGMA, batch_size=w["members"], ent_coef=0.0,
+                                max_delayed_return=H)
+    M, E, R = w["members"], w["E"], w["pairs"]
+    rng = np.random.RandomState(0)
+    if kind == "atari":
+        obs = torch.from_numpy(rng.rand(E, 4, 84, 84).astype(np.float32))
+    elif kind == "impala":
+        obs = torch.from_numpy(np.floor(rng.rand(E, 3, 64, 64) * 255.0).astype(np.float32))
+    else:
+        obs = torch.from_numpy(rng.randn(E, w["n_in"]).astype(np.float32))
+    target = np.tanh(rng.randn(w["out_width"])).astype(np.float32) * 0.5
+    # bounded sample: about a second of member evaluations and about a second of estimator per step
+    per_member_s = {"mujoco": 2.5e-4 + 4e-9 * P, "discrete": 4e-4, "atari": 3e-3, "impala": 1.2e-2}[kind] * max(1.0, E / 16.0)
+    sample = args.cpu_sample_members or int(min(M, max(cores * 4, min(cores * 32, cores * 1.0 / per_member_s))))
+    n_fd = min(M, max(64, int(2.0e8 // P) // 2 * 2))
+    steps, warm = (args.steps, args.warmup) if not as_baseline else (2, 1)
+    warm = min(warm, 2)
+    import multiprocessing as mp
+    _R.update(policy=policy, table=table, obs=obs, kind=kind, target=target)
+    times = []
+    t_budget = time.perf_counter() + 240.0
+    done_steps = 0
+    import io
+    import contextlib
+    for it in range(warm + steps):
+        pairs_idx = np.array([int(table.sample()[0]) for _ in range(R)], dtype=np.int64)
+        idx = np.concatenate([pairs_idx, pairs_idx])
+        sign = np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)
+        _R.update(idx=idx, sign=sign)
+        flat = policy.get_trainable_flat().copy()
+        members = list(range(0, M, max(1, M // sample)))[:sample]
+        n_tasks = max(1, min(len(members), cores * 2))
+        tasks = [(members[i::n_tasks], flat) for i in range(n_tasks)]
+        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None      # forked after _R holds this step's indices
+        t0 = time.perf_counter()
+        if pool is not None:
+            chunks = pool.map(_real_member_chunk, tasks, chunksize=1)
+            pool.close()
+        else:
+            chunks = [_real_member_chunk(t) for t in tasks]
+        t_fwd = (time.perf_counter() - t0) * (M / len(members))
+        rewards = rng.randn(M)
+        got = [r for c in chunks for r in c]
+        rewards[:len(got)] = got
+        sel = np.concatenate([np.arange(n_fd // 2), R + np.arange(n_fd // 2)])
+        batch = []
+        for i, sgn, r in zip(idx[sel], sign[sel], rewards[sel]):
+            ret = FDReturn()
+            ret.epoch, ret.encoded_noise, ret.reward = learner.epoch, ("+%d" if sgn > 0 else "-%d") % i, float(r)
+            batch.append(ret)
+        t1 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            learner.step(batch, 0.0, 0.0, 0.0)                 # unmodified finite_differences.py:24-64 + DSGD.step
+        t_fd = (time.perf_counter() - t1) * (M / n_fd)
+        if it >= warm:
+            times.append((t_fwd, t_fd))
+            done_steps += 1
+        if time.perf_counter() > t_budget and done_steps >= 1:
+            break
+    t_fwd = float(np.mean([t[0] for t in times]))
+    t_fd = float(np.mean([t[1] for t in times]))
+    step_s = t_fwd + t_fd
+    sample_txt = ("unmodified reference from %s. forward: worker.py:26-32 loop over %d of %d members x %d obs per step on %d "
+                  "forked processes x 1 torch thread, scaled x%.1f; estimator: FiniteDifferences.step + DSGD on %d of %d "
+                  "returns (numpy BLAS threads), scaled linearly; %d timed steps"
+                  % (os.path.relpath(ref_root, ROOT), len(members), M, E, cores, M / len(members), n_fd, M, done_steps))
+    return dict(value=M * E / step_s, unit="env-steps/s", cores=cores, kind="reference", sample=sample_txt,
+                ms_per_step=step_s * 1e3, fd_estimates_per_s=1.0 / t_fd, forward_s=t_fwd, estimator_s=t_fd,
+                steps_run=done_steps)
 
 
 def reference_main(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = run_reference(args, w)
+    ref_root = None if args.reference_port else reference_root()
+    if ref_root is not None:
+        try:
+            r = run_reference_real(args, w, ref_root)
+        except Exception as e:          # an unimportable copy: say so and time the port instead
+            sys.stderr.write("bench: reference at %s could not be run (%s: %s); timing the oracle port\n" % (ref_root, type(e).__name__, e))
+            r = run_reference(args, w)
+    else:
+        r = run_reference(args, w)
     line = {
         "impl": "reference", "metric": "perturbed-policy env-steps/sec", "value": r["value"], "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_run": r.get("steps_run"),
+        "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench_config(args, w),
         "fd_estimates_per_s": r["fd_estimates_per_s"],
@@ -285,17 +491,23 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------
-def b200_main(args, w):
+class Env(object):
+    """What every workload of one bench process shares: rank layout, process group, device context, measured peaks."""
+    pass
+
+
+def b200_env(args):
     import torch
     import torch.distributed as dist
-    import ctypes as C
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    env = Env()
+    rank = env.rank = int(os.environ.get("RANK", "0"))
+    world = env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = env.local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
-    pg = None
+    env.affinity = bind_rank_to_cores(local, world)
+    env.pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on the C-level stdout when the communicator is created: point fd 1 at stderr
@@ -311,26 +523,75 @@ def b200_main(args, w):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-        pg = dist.group.WORLD
+        env.pg = dist.group.WORLD
     import __graft_entry__ as G
     if rank == 0:
         G.build()
     if world > 1:
         dist.barrier()
-    import dfd_starter_b200 as D
-    from dfd_starter_b200 import _lib
-    from dfd_starter_b200.device import get_context, ptr
-    ctx = get_context(local)
-    lib = ctx.lib
-    dev = ctx.device
+    from dfd_starter_b200.device import get_context
+    env.ctx = get_context(local)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    env.hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    env.peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    return env
 
+
+def bind_rank_to_cores(local, world):
+    """N > 1: give every rank its own slice of the host cores (preferring the cores of the GPU's NUMA node), so eight
+    Python chains + their pinned-memory pages do not migrate over each other.  Pinned buffers are allocated AFTER this,
+    i.e. first-touched on the rank's own node.  Returns a short description for the JSON line."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        if world <= 1 or len(avail) < 2 * world:
+            return {"bound": False, "cores_available": len(avail)}
+        import torch
+        node_cpus = None
+        try:
+            bus = torch.cuda.get_device_properties(local).pci_bus_id
+            dom = torch.cuda.get_device_properties(local).pci_domain_id
+            dev_id = torch.cuda.get_device_properties(local).pci_device_id
+            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dev_id)
+            if os.path.exists(path):
+                cpus = []
+                for part in open(path).read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus += list(range(int(lo), int(hi or lo) + 1))
+                node_cpus = [c for c in cpus if c in avail]
+        except Exception:
+            node_cpus = None
+        per = len(avail) // world
+        mine = avail[local * per:(local + 1) * per]
+        if node_cpus and len(node_cpus) >= per:
+            # ranks whose GPUs share a node split that node's cores between them
+            sharers = max(1, world // max(1, len(avail) // max(len(node_cpus), 1)))
+            k = local % sharers
+            per_n = max(1, len(node_cpus) // sharers)
+            cand = node_cpus[k * per_n:(k + 1) * per_n]
+            if cand:
+                mine = cand
+        os.sched_setaffinity(0, mine)
+        return {"bound": True, "cores": len(mine), "first_core": mine[0], "numa_local": bool(node_cpus)}
+    except Exception as e:       # never fatal
+        return {"bound": False, "error": str(e)}
+
+
+def run_workload(env, args, w, full=True):
+    """One workload on this process group: device-resident steps (value), per-kernel timings and roofline, the untimed
+    parity step, e2e through the reference-facing objects.  full=False (the other named configs riding in the same JSON
+    line): fewer e2e steps, no clock sampling, no at-scale / cold reduction runs, no CPU baseline."""
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import dfd_starter_b200 as D
+    from dfd_starter_b200 import _lib
+    from dfd_starter_b200.device import ptr
+    rank, world, local, pg, ctx = env.rank, env.world, env.local, env.pg, env.ctx
+    lib, dev, hbm_peak, peak_src = ctx.lib, ctx.device, env.hbm_peak, env.peak_src
     M, E, R = w["members"], w["E"], w["pairs"]
     torch.manual_seed(TABLE_SEED)
     use_tc, tc_level = forward_precision(w["kind"], args.precision, E)
@@ -371,7 +632,7 @@ def b200_main(args, w):
     idx_sets = [table.sample_indices(R) for _ in range(CYC)]
     idx_host = torch.stack([torch.from_numpy(np.concatenate([i, i])) for i in idx_sets]).pin_memory()
     sign_host = torch.from_numpy(np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)).pin_memory()
-    n_obs_buf = CYC if M * E * w["n_in"] * 4 * CYC < (8 << 30) else 3
+    n_obs_buf = (CYC if M * E * w["n_in"] * 4 * CYC < (8 << 30) else 3) if full else min(3, CYC)
     if w["kind"] in ("atari", "impala"):
         obs_host = torch.rand((n_obs_buf, M, E) + obs_shape, generator=g)
         if is_impala:
@@ -423,6 +684,16 @@ def b200_main(args, w):
     for k in range(n_warm):
         device_step(k)
     torch.cuda.synchronize()
+    # ---------------- untimed parity step: this step's gradient against the fp64 closed form of the UNSHARDED batch ----
+    parity = None
+    if not args.profile_mode:
+        try:
+            parity = parity_step(env, w, table, learner, n_warm % CYC, idx_sets, hist_row_d, reward_d,
+                                 lambda: device_step(n_warm))
+        except Exception as e:       # reported, never fatal for the headline
+            parity = {"error": "%s: %s" % (type(e).__name__, e)}
+        n_warm += 1
+        torch.cuda.synchronize()
     graphs = None
     launches_per_graph = LAUNCHES_PER_STEP
     if use_graph:
@@ -456,7 +727,7 @@ def b200_main(args, w):
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and full:
         sampler.start()
         time.sleep(0.3)
     launches0 = ctx.launch_count()
@@ -481,20 +752,17 @@ def b200_main(args, w):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     if args.profile_mode:
-        if rank == 0:
-            print(json.dumps({"profile_mode": True, "ms_per_step": ms_step, "launches": launches_plain}), flush=True)
-        _finish(world)
-        return
+        return {"profile_mode": True, "ms_per_step": ms_step, "launches": launches_plain}
     # keep the same step running ~1.5 s so nvidia-smi (100 ms period) sees the clocks under this load
     t_load0 = time.perf_counter()
     kk = 0
-    while time.perf_counter() - t_load0 < 1.5:
+    while full and time.perf_counter() - t_load0 < 1.5:
         for _ in range(50):
             run_step(n_warm + args.steps + kk)
             kk += 1
         torch.cuda.synchronize()
     t_load1 = time.perf_counter()
-    clocks = sampler.stop(t_wall0, t_load1) if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_load1) if (rank == 0 and full) else None
     n_done = n_warm + args.steps + kk
 
     # ---------------- per-kernel durations (CUDA events on the launch stream, same inputs, back to back) ----
@@ -580,17 +848,20 @@ def b200_main(args, w):
     dk = kernels[dominant]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": dk["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": dk["achieved_GBps"] / hbm_peak,
-                "traffic": NCU_TRAFFIC.get((args.workload, dominant)) if (E == WORKLOADS[args.workload]["E"] and not args.pairs) else None,
-                "traffic_source": "profiles/r01/SUMMARY.md (ncu --set full, one launch)", "peak_source": peak_src,
+                "traffic": None, "traffic_source": None, "peak_source": peak_src,
                 "share_of_step": dk["us"] / (ms_step * 1e3),
                 "fd_reduce": {"achieved": kernels["fd_reduce"]["achieved_GBps"], "frac": kernels["fd_reduce"]["achieved_GBps"] / hbm_peak,
                               "us": us_reduce, "algorithmic_bytes": red_bytes}}
 
+    if E == WORKLOADS[w["name"]]["E"] and not args.pairs and use_tc == forward_precision(w["kind"], "auto", E)[0]:
+        roofline["traffic"], roofline["traffic_source"] = ncu_traffic(w["name"], dominant)
+        if roofline["traffic"] is not None:
+            roofline["traffic_source"] += " (ncu --set full, one launch: dram__bytes_read.sum + dram__bytes_write.sum)"
     # ---------------- the reduction at a size where HBM, not launch latency, is the bound ----------------------
     # The default workload's reduction streams 25 MB (3.8 us of HBM time): it is latency bound.  The same kernel entry
     # point on the per-GPU reduction of BASELINE config 3 (1024 table rows x 171 042 parameters, 700 MB per launch, row
     # sets rotated so a launch never finds its rows in L2) shows what it does when bandwidth is the limit.
-    if rank == 0 and not args.profile_mode and args.table_size > 171042 + 1024:
+    if rank == 0 and full and args.table_size > 171042 + 1024:
         try:
             Pb, Rb, NSET = 171042, 1024, 6
             dt_ = table.device_table
@@ -616,6 +887,42 @@ def b200_main(args, w):
             del big_sets, gb, sb
         except Exception as e:      # reported, never fatal for the headline
             roofline["fd_reduce_at_scale"] = {"error": str(e)}
+
+    # ---------------- the reduction on rows that CANNOT be L2-resident ----------------------------------------------
+    # Rows of the 25 M-entry table overlap (1024 rows x 684 KB drawn from 100 MB), so L2 serves part of every launch above.
+    # Here every row is its own disjoint slice of a multi-GB buffer and consecutive launches walk through NSET different
+    # row sets (>= 3.5 GB apart): each launch streams its algorithmic bytes from DRAM, nothing else.
+    if rank == 0 and full:
+        def reduce_cold(Pb, Rb, NSET):
+            Pb4 = (Pb + 3) // 4 * 4
+            cold = torch.randn(NSET * Rb * Pb4, device=dev)
+            gb = torch.empty(Pb, device=dev)
+            sb = ctx.zeros_bytes(lib.dfd_fd_reduce_scratch_bytes(ctx.handle, Pb, Rb))
+            sets = []
+            for c in range(NSET):
+                rp = (cold.data_ptr() + 4 * Pb4 * (c * Rb + torch.arange(Rb, dtype=torch.int64))).to(dev)
+                rc = torch.randn(Rb, device=dev)
+                sets.append((rp, rc, _lib.DfdFdRows(rp.data_ptr(), rc.data_ptr(), Rb)))
+
+            def k(r):
+                _lib.check(lib.dfd_fd_reduce(ctx.handle, C.byref(sets[r % NSET][2]), Rb, Pb, ptr(gb), aligned_ptr(sb),
+                                             sb.numel() - 256, ctx.stream))
+            us = min(time_calls(k, 3 * NSET) for _ in range(3))
+            # correctness of this launch shape against torch on the same rows (fp32 matmul, relative to the result's scale)
+            k(0)
+            want = sets[0][1].double() @ cold[:Rb * Pb4].view(Rb, Pb4)[:, :Pb].double()
+            err = float((gb.double() - want).abs().max() / want.abs().max())
+            nbytes = Rb * Pb * 4 + Pb * 4
+            tr, src = ncu_traffic("cold", "fd_reduce") if Pb == 171042 else (None, None)
+            return {"rows": Rb, "n_params": Pb, "algorithmic_bytes": nbytes, "us": us, "achieved": nbytes / us * 1e-3,
+                    "frac": nbytes / us * 1e-3 / hbm_peak, "unit": "GB/s", "row_sets_cycled": NSET,
+                    "buffer_GB": NSET * Rb * Pb4 * 4 / 1e9, "rel_err_vs_fp64_matvec": err, "traffic": tr, "traffic_source": src}
+        for key, shape in (("C3_size", (171042, 1024, 6)), ("C5_size", (1158709, 256, 4))):
+            try:
+                roofline.setdefault("fd_reduce_cold", {})[key] = reduce_cold(*shape)
+            except Exception as e:
+                roofline.setdefault("fd_reduce_cold", {})[key] = {"error": str(e)}
+            torch.cuda.empty_cache()
 
     # ---------------- e2e through the reference-facing objects, host buffers ---------------------------
     e2e = None
@@ -738,7 +1045,7 @@ def b200_main(args, w):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             return dt
-        n_e2e = max(3, min(args.steps, 30))
+        n_e2e = max(3, min(args.steps, 30 if full else 10))
         # a pinned page reaches full DMA speed only after the device has read it a few times (first reads of fresh pinned
         # memory ran at 34-47 GB/s on this box, 54.8 GB/s from the third pass on: scripts/h2d_probe.py); a long-running
         # worker reuses its staging buffers, so the staging buffers are read through before the timed loops
@@ -747,14 +1054,23 @@ def b200_main(args, w):
                 agent.bufs[0].copy_(obs_host[b], non_blocking=True)
         torch.cuda.synchronize()
         # the bound of the end-to-end step: its observations crossing PCIe (measured here, same buffers, copy engine)
+        # N > 1: every rank copies at the same moment (barrier first), so this is the CONCURRENT host->device rate - the
+        # floor the sharded end-to-end step can reach on this host - and the slowest rank's rate is reported beside it
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
         ea.record()
         for b in range(8):
             agent.bufs[0].copy_(obs_host[b % n_obs_buf], non_blocking=True)
         eb.record()
         torch.cuda.synchronize()
         h2d_gbps = obs_host[0].numel() * 4 * 8 / (ea.elapsed_time(eb) * 1e-3) / 1e9
-        dt_serial = e2e_run(n_done, False)
+        h2d_gbps_min = h2d_gbps
+        if world > 1:
+            t = torch.tensor([h2d_gbps], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            h2d_gbps_min = float(t.item())
+        dt_serial = e2e_run(n_done, False) if full else None
         if TRACE is not None:
             del TRACE[:]
         dt = e2e_run(n_done + 3 + n_e2e, True)
@@ -773,38 +1089,185 @@ def b200_main(args, w):
         d2h = M * 8 + 4 + P * 4
         e2e = {"value": M * E * world * n_e2e / dt, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / n_e2e * 1e3, "steps": n_e2e,
-               "serial_ms_per_step": dt_serial / n_e2e * 1e3,
-               "pcie": {"h2d_GBps_measured": h2d_gbps, "floor_ms_per_step": h2d / (h2d_gbps * 1e9) * 1e3,
-                        "frac_of_floor": (h2d / (h2d_gbps * 1e9)) / (dt / n_e2e)},
+               "serial_ms_per_step": None if dt_serial is None else dt_serial / n_e2e * 1e3,
+               "pcie": {"h2d_GBps_measured": h2d_gbps, "h2d_GBps_slowest_rank_all_ranks_copying": h2d_gbps_min,
+                        "floor_ms_per_step": h2d / (h2d_gbps_min * 1e9) * 1e3,
+                        "frac_of_floor": (h2d / (h2d_gbps_min * 1e9)) / (dt / n_e2e)},
                "api": "Worker.evaluate -> ReturnBatch (sequence of FDReturn) -> FiniteDifferences.step (host observations, host "
                       "returns, theta mirrored to host); observations double-buffered: step k+1's pinned host->device copy is "
                       "issued on a copy stream while step k's returns are read back and the learner steps "
                       "(serial_ms_per_step: the same loop with the copy in front of each forward)"}
 
+    # release what the workload held (graphs keep their memory pool alive) before the next one starts
+    if xchg is not None and not full:
+        try:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            xchg.close()
+        except Exception:
+            pass
+    value = M * E * world / (ms_step * 1e-3)
+    dtype = ("fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
+             if w["kind"] == "impala" else
+             "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6")) \
+        if use_tc else "f32"
+    return {"value": value, "ms_per_step": ms_step, "dtype": dtype, "fd_estimates_per_s": 1e3 / ms_step,
+            "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
+            "roofline": roofline, "kernels": kernels, "e2e": e2e, "parity": parity,
+            "gpu_launches": int(launches_plain if graphs is None else args.steps * launches_per_graph), "clocks": clocks,
+            "E": E, "R": R}
+
+
+def parity_step(env, w, table, learner, c, idx_sets, hist_row_d, reward_d, run_one_step):
+    """One UNTIMED step whose gradient is compared with an independent fp64 evaluation of
+    learner/finite_differences.py:40-49,80-112 over the UNSHARDED batch (all ranks' members):
+        g = sum_i w_i * lam_i / ||lam_i||^2,  lam_i = fp32(s_i * sigma * eps_i) [+ dist_row(e_i)],  w = standardize(R - b)
+    written here in numpy (bench.py never calls the oracle on the GPU arm).  Every rank's indices, rewards and epoch
+    rows are gathered; rank 0 evaluates the closed form - on every coordinate for short parameter vectors, on a fixed
+    sample of 16 384 coordinates (plus both ends) for long ones, the row norms always over the full rows - and all
+    ranks' gradients are compared bit for bit."""
+    import torch
+    import torch.distributed as dist
+    rank, world, pg = env.rank, env.world, env.pg
+    dev = env.ctx.device
+    P, R = learner.P, w["pairs"]
+    fd_state = hist_row_d is not None
+    dist_before = learner.dist[:, :P].clone() if fd_state else None
+    run_one_step()
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    grad = learner.grad.clone()
+    rew = reward_d.clone()
+    idx_local = torch.from_numpy(np.ascontiguousarray(idx_sets[c])).to(dev)
+    hr = hist_row_d.clone() if fd_state else None
+    digest = (grad.view(torch.int32).to(torch.int64) * torch.arange(1, P + 1, device=dev)).sum().reshape(1)
+    if world > 1:
+        def gather(t):
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t.contiguous(), group=pg)
+            return out
+        idx_all, rew_all, dig_all = gather(idx_local), gather(rew), gather(digest)
+        hr_all = gather(hr) if fd_state else None
+    else:
+        idx_all, rew_all, dig_all, hr_all = [idx_local], [rew], [digest], ([hr] if fd_state else None)
+    identical = all(int(d.item()) == int(dig_all[0].item()) for d in dig_all)
     if rank != 0:
-        _xchg_profile(ctx, rank)
+        return None
+    t0 = time.perf_counter()
+    tab = table._table
+    sig32 = np.float32(SIGMA)
+    g_dev = grad.double().cpu().numpy()
+    full_cols = P <= 200_000
+    cols = np.arange(P) if full_cols else np.unique(np.concatenate([
+        np.arange(256), np.arange(P - 256, P), np.random.RandomState(5).randint(0, P, size=16384)]))
+    rewards = np.concatenate([r.cpu().numpy() for r in rew_all])          # rank-major, each [plus | minus]
+    x = rewards - 0.0                                                    # baseline b = 0 in the bench step
+    s = x.std()
+    wts = x if s == 0 else (x - x.mean()) / s
+    g = np.zeros(cols.shape[0])
+    drows = dist_before.cpu().numpy() if fd_state else None
+    for r in range(world):
+        ix = idx_all[r].cpu().numpy()
+        wr = wts[r * 2 * R:(r + 1) * 2 * R]
+        hrow = hr_all[r].cpu().numpy() if fd_state else None
+        for j in range(R):
+            eps = tab[ix[j]:ix[j] + P]
+            lam_p = eps * sig32                                           # fp32 product, as finite_differences.py:89
+            if not fd_state:
+                # both members of the pair share ||lam||^2; lam- = -lam+
+                n2 = float(np.dot(lam_p.astype(np.float64), lam_p.astype(np.float64)))
+                g += ((wr[j] - wr[R + j]) / n2) * lam_p[cols]
+                continue
+            for member, sgn in ((j, 1.0), (R + j, -1.0)):
+                lam = lam_p if sgn > 0 else -lam_p
+                if hrow[member] >= 0:
+                    lam = lam + drows[hrow[member]]                       # fp32 add (:89)
+                l64 = lam.astype(np.float64)
+                g += (wr[member] / float(np.dot(l64, l64))) * l64[cols]
+    ref_max = float(np.max(np.abs(g)))
+    rel = float(np.max(np.abs(g_dev[cols] - g)) / ref_max) if ref_max > 0 else float("nan")
+    cos = float(np.dot(g_dev[cols], g) / (np.linalg.norm(g_dev[cols]) * np.linalg.norm(g) + 1e-300))
+    return {"grad_rel_max": rel, "cosine": cos, "ranks_bit_identical": bool(identical), "ranks": world,
+            "returns_checked": int(2 * R * world), "coordinates_checked": int(cols.shape[0]), "of": int(P),
+            "tolerance": 1e-5, "ok": bool(rel <= 1e-5 and identical),
+            "reference": "fp64 closed form of finite_differences.py:40-49,80-112 over the unsharded batch, evaluated in "
+                         "bench.py (numpy) on rank 0", "seconds": time.perf_counter() - t0}
+
+
+SUB_WORKLOADS = ("C3", "C4", "C5")
+C2_POINTS = (("E1", dict(obs_per_member=1)), ("E16", dict(obs_per_member=16)), ("E128_fp32", dict(precision="fp32")))
+
+
+def _brief(res, w, world):
+    """What a non-headline workload contributes to the JSON line."""
+    rl = res["roofline"]
+    out = {"workload": w["desc"], "obs_per_member": res["E"], "pairs_per_gpu": res["R"], "ms_per_step": res["ms_per_step"],
+           "value": res["value"], "unit": "env-steps/s", "fd_estimates_per_s": res["fd_estimates_per_s"], "dtype": res["dtype"],
+           "forward_us": res["kernels"]["policy_forward"]["us"], "reduce_us": res["kernels"]["fd_reduce"]["us"],
+           "kernels": res["kernels"],
+           "roofline": {k: rl.get(k) for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "share_of_step",
+                                               "fd_reduce")},
+           "parity": res["parity"], "launch_mode": res["launch_mode"]}
+    if res["e2e"] is not None:
+        out["e2e"] = {k: res["e2e"].get(k) for k in ("value", "unit", "ms_per_step", "steps", "h2d_bytes_per_step",
+                                                     "d2h_bytes_per_step", "pcie")}
+    return out
+
+
+def b200_main(args, w):
+    import copy
+    import gc
+    import torch
+    env = b200_env(args)
+    rank, world = env.rank, env.world
+    res = run_workload(env, args, w, full=True)
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps(res), flush=True)
         _finish(world)
         return
-    value = M * E * world / (ms_step * 1e-3)
-    line = {
-        "metric": "perturbed-policy env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": ("fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
-                                       if w["kind"] == "impala" else
-                                       "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"))
-        if use_tc else "f32",
-        "data": "synthetic", "config": bench_config(args, w),
-        "fd_estimates_per_s": 1e3 / ms_step,
-        "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
-        "roofline": roofline, "kernels": kernels, "e2e": e2e,
-        "gpu_launches": int(launches_plain if graphs is None else args.steps * launches_per_graph),
-        "clocks": clocks,
-    }
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "perturbed-policy env-steps/sec", "value": res["value"], "unit": "env-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": res["dtype"], "data": "synthetic", "config": bench_config(args, w),
+            "fd_estimates_per_s": res["fd_estimates_per_s"], "launch_mode": res["launch_mode"], "roofline": res["roofline"],
+            "kernels": res["kernels"], "e2e": res["e2e"], "parity": res["parity"], "gpu_launches": res["gpu_launches"],
+            "clocks": res["clocks"], "host": {"affinity": env.affinity},
+        }
+    # ---------------- the other named configs and operating points, same process group, same JSON line ----------------
+    default_run = args.workload == "C2" and not args.obs_per_member and not args.pairs and args.precision == "auto"
+    if default_run and not args.no_workloads:
+        extra = []
+        extra += [("operating_points", name, "C2", ov) for name, ov in C2_POINTS]
+        extra += [("workloads", name, name, {}) for name in SUB_WORKLOADS]
+        for group, name, wl, ov in extra:
+            gc.collect()
+            torch.cuda.empty_cache()
+            a2 = copy.copy(args)
+            a2.workload, a2.obs_per_member, a2.pairs = wl, ov.get("obs_per_member", 0), 0
+            a2.precision = ov.get("precision", "auto")
+            w2 = workload(a2)
+            t0 = time.perf_counter()
+            try:
+                r2 = run_workload(env, a2, w2, full=False)
+                entry = _brief(r2, w2, world) if rank == 0 else None
+            except Exception as e:          # a failed side workload is reported, the headline stands
+                entry = {"error": "%s: %s" % (type(e).__name__, e)}
+            if rank == 0:
+                entry["bench_seconds"] = time.perf_counter() - t0
+                line.setdefault(group, {})[name] = entry
+    if rank != 0:
+        _xchg_profile(env.ctx, rank)
+        _finish(world)
+        return
     if not args.no_cpu_baseline and world == 1:
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
-                   "--obs-per-member", str(E), "--pairs", str(R), "--table-size", str(args.table_size), "--steps", "2",
-                   "--warmup", "1"]
+                   "--obs-per-member", str(res["E"]), "--pairs", str(res["R"]), "--table-size", str(args.table_size),
+                   "--steps", "2", "--warmup", "1"]
             outp = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
                                   env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
             ref = json.loads(outp.stdout.strip().splitlines()[-1])
@@ -814,7 +1277,7 @@ def b200_main(args, w):
             line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port",
                                     "sample": "failed: %s" % e}
     print(json.dumps(line), flush=True)
-    _xchg_profile(ctx, rank)
+    _xchg_profile(env.ctx, rank)
     _finish(world)
 
 

@@ -79,9 +79,11 @@ class PeerExchange(object):
                    "dfd_xchg_allreduce")
 
     def close(self):
+        """Unmap the peers' mailboxes, then - once EVERY rank has unmapped (barrier) - free this rank's own."""
         for p in self._peers:
             self.lib.dfd_xchg_mailbox_close(self.ctx.handle, p)
         self._peers = []
         if self._mine:
+            dist.barrier(group=self.group)
             self.lib.dfd_xchg_mailbox_destroy(self.ctx.handle, self._mine)
             self._mine = None

@@ -56,3 +56,74 @@ def smoke():
     assert np.max(np.abs(policy.get_trainable_flat() - ofd.theta)) < 1e-6
     print("smoke ok: forward max-abs < 1e-5, gradient rel-max %.2e, update %.6f (oracle %.6f), launches %d"
           % (rel, upd, oupd, policy.ctx.launch_count()))
+    _smoke_tensor_paths(O, D)
+
+
+def _smoke_tensor_paths(O, D):
+    """Small launches of the tcgen05 / TMA kernels the bench spends its time in, each checked against the oracle, so the
+    driver's kernel list of smoke() names them: resident-weight MLP forward (mlp_forward_ws_kernel), streaming MLP
+    forward (mlp_forward_stream_kernel), TMA-fed wide-row reduction (fd_reduce_tma_kernel, through one learner step of
+    a Humanoid-sized policy), one-kernel learner step (fd_tail_kernel), IMPALA forward with tensor-core convolutions."""
+    sigma = 0.02
+    rng = np.random.RandomState(11)
+
+    def mlp(n_in, h, n_act, M, E, precision, atol, table):
+        L = O.mujoco_layout(n_in, n_act, h, h)
+        pol = D.MujocoPolicy(n_in, n_act, seed=3, h1=h, h2=h, device=0, precision=precision).bind_table(table)
+        theta = O.synthetic_theta(L, 3)
+        pol.set_trainable_flat(theta)
+        half = rng.randint(0, table.size - L.num_params, size=M // 2).astype(np.int64)
+        idx, sign = np.concatenate([half, half]), np.concatenate([np.ones(M // 2), -np.ones(M // 2)]).astype(np.int8)
+        obs = rng.randn(M, E, n_in).astype(np.float32)
+        out = pol.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(),
+                                  sigma).cpu().numpy()
+        worst = 0.0
+        for m in (0, M // 2, M - 1):
+            th = O.perturb(theta, sigma, table._table[idx[m]:idx[m] + L.num_params], int(sign[m]))
+            mean, std = O.mujoco_forward(L, th, obs[m])
+            worst = max(worst, float(np.max(np.abs(out[m] - np.concatenate([mean, std], -1)))))
+        assert worst <= atol, ("tensor-path forward mismatch", n_in, h, worst)
+        return pol, theta, worst
+
+    t_small = D.SharedNoiseTable(1_000_000, 6092, 123, device=0)
+    _, _, e_ws = mlp(17, 64, 6, 16, 128, 2, 4e-3, t_small)                       # mlp_forward_ws_kernel
+    t_wide = D.SharedNoiseTable(2_000_000, 171042, 123, device=0)
+    pol, theta, e_st = mlp(376, 256, 17, 300, 128, 1, 2e-3, t_wide)              # mlp_forward_stream_kernel, 2 items per CTA
+
+    # one learner step at Humanoid width: prepare + fd_reduce_tma_kernel + DSGD, against the fp64 closed form
+    class Omega(object):
+        omega, min_omega, max_omega = 0.0, 0.0, 1.0
+    P, R = 171042, 48
+    opt = D.DSGD([torch.nn.Parameter(torch.zeros(P))], lr=0.01)
+    fd = D.FiniteDifferences(pol, opt, Omega(), t_wide, noise_std=sigma, batch_size=2 * R, max_delayed_return=2, paired=True)
+    idx = t_wide.sample_indices(R)
+    rew = rng.randn(2 * R)
+    sign = np.concatenate([np.ones(R), -np.ones(R)]).astype(np.int8)
+    fd.step_arrays(np.zeros(2 * R, np.int64), np.concatenate([idx, idx]), sign, rew, 0.0)
+    ref = O.fd_gradient_closed_form(t_wide._table, np.concatenate([idx, idx]), sign, rew, sigma, P)
+    e_red = float(np.max(np.abs(fd.gradient_memory - ref)) / np.max(np.abs(ref)))
+    assert e_red <= 1e-5, ("wide reduction mismatch", e_red)
+
+    # IMPALA, tensor-core convolutions, one antithetic pair
+    L = O.impala_layout(15)
+    t_imp = D.SharedNoiseTable(2_000_000, L.num_params, 123, device=0)
+    ipol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=1).bind_table(t_imp)
+    th, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
+    ipol.set_trainable_flat(th)
+    ipol.set_buffers(buf)
+    i0 = int(rng.randint(0, 2_000_000 - L.num_params))
+    idx, sign = np.array([i0, i0], np.int64), np.array([1, -1], np.int8)
+    frames = rng.randint(0, 256, size=(2, 1, 3, 64, 64)).astype(np.float32)
+    zero = np.zeros((2, 1, 256), np.float32)
+    probs, h1, c1 = ipol.forward_members_impala(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(),
+                                                torch.from_numpy(frames).cuda(), torch.zeros(2, 1).cuda(),
+                                                torch.zeros(2, 1, dtype=torch.bool).cuda(), torch.from_numpy(zero).cuda(),
+                                                torch.from_numpy(zero).cuda(), sigma)
+    e_imp = 0.0
+    for m in range(2):
+        thm = O.perturb(th, sigma, t_imp._table[i0:i0 + L.num_params], int(sign[m]))
+        rp, _, _ = O.impala_forward(L, thm, buf, frames[m], np.zeros(1, np.float32), np.zeros(1, bool), zero[m], zero[m])
+        e_imp = max(e_imp, float(np.abs(probs[m].cpu().numpy() - rp).max()))
+    assert e_imp <= 2e-3, ("impala tensor-core forward mismatch", e_imp)
+    print("smoke ok (tensor / TMA paths): ws forward %.1e, stream forward %.1e, wide reduction rel %.1e, impala probs %.1e, "
+          "launches %d" % (e_ws, e_st, e_red, e_imp, pol.ctx.launch_count()))
