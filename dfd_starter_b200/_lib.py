@@ -20,6 +20,7 @@ SYMBOLS = [
     "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
     "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused", "dfd_wire_count_returns", "dfd_wire_decode_returns",
     "dfd_strategy_distances", "dfd_host_stage", "dfd_normalize_obs", "dfd_member_obs_stats",
+    "dfd_table_scaled16_bytes", "dfd_table_build_scaled16", "dfd_table_drop_scaled16", "dfd_policy_direct_supported",
 ]
 
 
@@ -72,6 +73,10 @@ def load():
     proto("dfd_table_replica_stride", i64, [i64])
     proto("dfd_table_scratch_bytes", sz, [i64])
     proto("dfd_table_build", i32, [vp, vp, i64, vp, i64, vp, vp, sz, vp])
+    proto("dfd_table_scaled16_bytes", sz, [i64, i64])
+    proto("dfd_table_build_scaled16", i32, [vp, P(DfdTable), f32, i64, vp, sz, vp])
+    proto("dfd_table_drop_scaled16", i32, [vp])
+    proto("dfd_policy_direct_supported", i32, [P(DfdPolicyDesc)])
     proto("dfd_perturb_members", i32, [vp, P(DfdTable), vp, i64, vp, vp, i32, f32, vp, i64, vp])
     proto("dfd_policy_num_params", i64, [P(DfdPolicyDesc)])
     proto("dfd_policy_num_buffers", i64, [P(DfdPolicyDesc)])

@@ -12,6 +12,14 @@ struct dfd_ctx {
     int device;
     int sm_count;
     int64_t launches;
+    // sigma-scaled fp16 mirror of a noise table + fp16 scratch for theta (caller-owned memory registered by
+    // dfd_table_build_scaled16; csrc/mlp_forward_direct.cu)
+    const float* scaled_src;      // table->replicas the mirror was built from
+    float scaled_sigma;
+    void* scaled16;               // 8 replicas x scaled16_stride halves
+    int64_t scaled16_stride;
+    void* theta16;                // theta16_cap halves
+    int64_t theta16_cap;
 };
 
 void dfd_set_error(const char* fmt, ...);

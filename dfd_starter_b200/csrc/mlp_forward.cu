@@ -359,6 +359,9 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
                             const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
                             int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
 
+int dfd_mlp_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                                const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
+                                int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
 int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                                 const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
                                 int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
@@ -386,6 +389,10 @@ extern "C" int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
         const int rc = dfd_mlp_forward_ws_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member, out,
                                                desc->precision == 2 ? 1 : 0, st);
         if (rc >= 0) return rc;
+        // wide nets with a sigma-scaled fp16 mirror of the table registered: weights straight from the table by TMA
+        const int rd = dfd_mlp_forward_direct_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member,
+                                                   out, desc->precision == 2 ? 1 : 0, st);
+        if (rd >= 0) return rd;
         const int rs = dfd_mlp_forward_stream_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member,
                                                    out, desc->precision == 2 ? 1 : 0, st);
         if (rs >= 0) return rs;

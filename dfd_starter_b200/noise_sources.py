@@ -154,6 +154,25 @@ class DeviceTable(object):
     def ref(self):
         return C.byref(self.c)
 
+    def ensure_scaled16(self, sigma, n_params):
+        """Register the sigma-scaled fp16 mirror of this table with the context (include/dfd_b200.h:
+        dfd_table_build_scaled16) unless the context already holds one for this table, this sigma and at least
+        n_params parameters.  One-off cost: a pass over the table and 16 bytes per table entry; call it outside CUDA-graph
+        capture (the first eager forward does)."""
+        ctx = self.ctx
+        sig = float(np.float32(sigma))
+        have = getattr(ctx, "_scaled16", None)
+        if have is not None and have[0] == self.replicas.data_ptr() and have[1] == sig and have[2] >= int(n_params):
+            return
+        lib = ctx.lib
+        nbytes = int(lib.dfd_table_scaled16_bytes(self.size, int(n_params)))
+        ctx._scaled16 = None
+        _lib.check(lib.dfd_table_drop_scaled16(ctx.handle), "dfd_table_drop_scaled16")
+        buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=ctx.device)
+        _lib.check(lib.dfd_table_build_scaled16(ctx.handle, self.ref(), sig, int(n_params), aligned_ptr(buf), nbytes,
+                                                ctx.stream), "dfd_table_build_scaled16")
+        ctx._scaled16 = (self.replicas.data_ptr(), sig, int(n_params), buf)
+
 
 def parse_key(key):
     """'123' -> (123, +1); '+123' -> (123, +1); '-123' -> (123, -1)."""

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DFD_ABI_VERSION 1
+#define DFD_ABI_VERSION 2
 
 typedef struct dfd_ctx dfd_ctx;
 typedef void* dfd_stream; /* cudaStream_t */
@@ -64,6 +64,20 @@ size_t dfd_table_scratch_bytes(int64_t size);
 int dfd_table_build(dfd_ctx* ctx, const float* table_dev, int64_t size, float* replicas, int64_t replica_stride,
                     double* prefix_sq, void* scratch, size_t scratch_bytes, dfd_stream stream);
 
+/* sigma-scaled fp16 mirror of the table for the "direct-from-table" forward of wide MuJoCo MLPs
+ * (csrc/mlp_forward_direct.cu): a Linear layer is linear in its weights, x.(theta + s*sigma*eps)^T =
+ * x.theta^T + s*(x.(sigma*eps)^T), so a member's weight tiles are never built - both terms are tcgen05 MMAs whose B
+ * operands come by TMA from (i) an fp16 copy of theta and (ii) this mirror: eight element-shifted replicas of
+ * fp16(fl32(sigma*table[j])) (the first rounding is worker.py:28's own) so that any table[idx+off:...] slice starts
+ * 16-byte aligned.  buf: CALLER-owned device memory of dfd_table_scaled16_bytes(size, n_params) bytes, 256-byte aligned,
+ * which also carries the fp16 theta scratch for policies of up to n_params parameters; it must stay alive until
+ * dfd_table_drop_scaled16 / dfd_ctx_destroy.  One mirror per context (one table, one sigma); dfd_policy_forward uses it
+ * when `table` and `sigma` match and dfd_policy_direct_supported(desc), and the streaming kernel otherwise. */
+size_t dfd_table_scaled16_bytes(int64_t size, int64_t n_params);
+int dfd_table_build_scaled16(dfd_ctx* ctx, const dfd_table* table, float sigma, int64_t n_params, void* buf, size_t bytes,
+                             dfd_stream stream);
+int dfd_table_drop_scaled16(dfd_ctx* ctx);
+
 /* ---- perturbation: worker/worker.py:28  new_flat = flat + sigma * eps ---- */
 /* out[m, :] = theta + sign[m]*sigma*table[idx[m] : idx[m]+P], fp32, product
  * rounded then sum rounded (no FMA) so the result is bit-identical to numpy.
@@ -89,6 +103,8 @@ typedef struct dfd_policy_desc {
 } dfd_policy_desc;
 
 int64_t dfd_policy_num_params(const dfd_policy_desc* desc);
+/* 1 when the direct-from-table tensor path serves this MuJoCo shape (n_in % 8 == 0, hidden widths 128 or 256, 2A <= 48) */
+int dfd_policy_direct_supported(const dfd_policy_desc* desc);
 int64_t dfd_policy_num_buffers(const dfd_policy_desc* desc);
 int64_t dfd_policy_out_width(const dfd_policy_desc* desc);
 

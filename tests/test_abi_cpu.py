@@ -31,7 +31,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_pure_helpers(lib):
     from dfd_starter_b200._lib import DfdPolicyDesc
-    assert lib.dfd_abi_version() == 1
+    assert lib.dfd_abi_version() == 2
     assert lib.dfd_table_replica_stride(25_000_000) % 32 == 0
     assert lib.dfd_table_replica_stride(25_000_000) >= 25_000_064
     for kind, n_in, h1, h2, a, P, B, W in [(0, 17, 64, 64, 6, 6092, 0, 12), (0, 376, 256, 256, 17, 171042, 0, 34),
