@@ -320,6 +320,10 @@ __global__ void __launch_bounds__(AT_LAUNCH, 1) atari_forward_kernel(const float
 
 }  // namespace
 
+int dfd_atari_forward_tc_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                              const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
+                              const float* obs, int obs_per_member, float* out, cudaStream_t st);
+
 int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                            const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
                            const float* obs, int obs_per_member, float* out, cudaStream_t st) {
@@ -328,6 +332,11 @@ int dfd_atari_forward_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_
     DFD_CHECK_ARG((((uintptr_t)obs) & 15) == 0 && (((uintptr_t)theta) & 15) == 0,
                   "dfd_policy_forward: Atari obs / theta must be 16-byte aligned");
     DFD_CHECK_ARG(dfd_policy_num_params(desc) < table->size, "dfd_policy_forward: num_params >= table size");
+    if (desc->precision >= 1) {       // tensor path (csrc/cnn_forward_tc.cu) when the scaled table mirror is registered
+        const int rt = dfd_atari_forward_tc_impl(ctx, desc, table, theta, bn_buffers, idx, sign, n_members, sigma, obs,
+                                                 obs_per_member, out, st);
+        if (rt >= 0) return rt;
+    }
     const int tiles = (obs_per_member + AT_ET - 1) / AT_ET;
     DFD_CHECK_ARG((int64_t)n_members * tiles < 2147483647LL, "dfd_policy_forward: grid too large");
     const size_t smem = (size_t)(FRAME + 4096 + 32 + A0N + AT_ET * A1N + AT_ET * 256 + AT_ET * 32) * sizeof(float);

@@ -24,9 +24,7 @@
 //   warps 12-15   observation tile fp32 -> fp16 into the swizzled A-operand slots of layer 0
 // TMEM (512 columns):  [0,256) layer-0 accumulator, later [0,128) layer-1 accumulator (outputs 128..255) and [128,256) the
 // layer-2 A operand;  [256,384) layer-1 A operand;  [384,512) layer-1 accumulator (outputs 0..127), later the head accumulator.
-#include "tc_common.cuh"
-#include <cuda.h>
-#include <cuda_fp16.h>
+#include "direct_common.cuh"
 
 namespace {
 
@@ -61,84 +59,6 @@ __device__ __forceinline__ void dr_item(const DrParams& p, int work, int& m, int
     const int M = p.n_work / p.tiles;
     m = p.pair_order ? ((mm & 1) ? (M >> 1) + (mm >> 1) : (mm >> 1)) : mm;
 }
-__device__ __forceinline__ void dr_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok, spins = 0;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(bar), "r"(parity), "r"(200000u) : "memory");
-        if (!ok && ++spins > (1u << 22)) __trap();      // a lost arrival must fault, not hang the GPU
-    } while (!ok);
-}
-__device__ __forceinline__ void dr_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void dr_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dr_tma_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-                 "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void dr_tma_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
-                 "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
-}
-// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, M = 128; bit 13 negates A
-__device__ __forceinline__ uint32_t dr_idesc(int n, int negate_a) {
-    return (1u << 4) | (negate_a ? (1u << 13) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-__device__ __forceinline__ void dr_umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void dr_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void dr_tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void dr_tmem_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
-        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-// two floats -> packed halves, `lo` in the low 16 bits (the even k of the pair)
-__device__ __forceinline__ uint32_t dr_pack(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-template <bool APPROX>
-__device__ __forceinline__ float dr_tanh(float x) {
-    if (APPROX) {
-        float y;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-        return y;
-    } else {
-        return tanh_fast(x);
-    }
-}
-
-__global__ void theta_to_f16_kernel(const float* __restrict__ theta, __half* __restrict__ out, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = __float2half_rn(theta[i]);
-}
-
 // replica_s[j] = fp16(fl32(sigma * table[j + s])), s = 0..7: the first rounding is the reference's own (worker.py:28 rounds
 // sigma*eps to fp32 before the add), the second is the operand precision of this path
 __global__ void table_scaled16_kernel(const float* __restrict__ replica0, int64_t size, float sigma, __half* __restrict__ out,
@@ -155,7 +75,8 @@ template <bool APPROX>
 __global__ void __launch_bounds__(DR_THREADS, 1)
 mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps, const float* __restrict__ replicas, int64_t stride,
                           const float* __restrict__ theta, const int64_t* __restrict__ idx, const int8_t* __restrict__ sign,
-                          const float* __restrict__ obs, float* __restrict__ out) {
+                          const float* __restrict__ obs, float* __restrict__ out, long long* __restrict__ prof) {
+#define DR_TL(cond, slot) do { if (prof && (cond) && u == 3) prof[(size_t)blockIdx.x * 32 + (slot)] = clock64(); } while (0)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[DB_COUNT];
     __shared__ uint32_t tmem_base_s;
@@ -233,6 +154,9 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                                 if (we == 1 && sg == 0) continue;           // unperturbed member: no E term
                                 const int slot = g % p.ns;
                                 dr_wait(DR_BAR(DB_EMPTY + slot), (uint32_t)((g / p.ns) & 1) ^ 1u);
+                                DR_TL(l == 0 && a == 0 && b == 0 && we == 0, 16);
+                                DR_TL(l == 1 && a == 0 && b == 0 && we == 0, 17);
+                                DR_TL(l == 2 && a == 0 && we == 0, 18);
                                 dr_expect_tx(DR_BAR(DB_FULL + slot), bytes);
                                 const uint32_t dst = ring0 + (uint32_t)slot * DR_TILE;
                                 if (we == 0) dr_tma_2d(dst, &maps.w[l], c * DR_KC, h * 128, DR_BAR(DB_FULL + slot));
@@ -254,10 +178,12 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
             const int sg = (int)sign[m];
             const uint32_t id_w128 = dr_idesc(128, 0), id_e128 = dr_idesc(128, sg < 0);
             // ---- layer 0: A = observation tile in shared memory ----
+            DR_TL(lane == 0, 0);
 #pragma unroll 1
             for (int c = 0; c < nc0; ++c, ++xg) {
                 const int xs = xg % p.nx;
                 dr_wait(DR_BAR(DB_XFULL + xs), (uint32_t)((xg / p.nx) & 1));
+                DR_TL(lane == 0 && c == 0, 7);
                 const uint64_t adesc = make_desc_sw128(xring0 + (uint32_t)xs * DR_TILE);
 #pragma unroll 1
                 for (int h = 0; h < nh1; ++h)
@@ -278,6 +204,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                 umma_commit_elect(DR_BAR(DB_XEMPTY + xs));
             }
             umma_commit_elect(DR_BAR(DB_D0FULL));
+            DR_TL(lane == 0, 1);
             // ---- layer 1: A = layer-0 activations in TMEM, one complete K loop per 128-wide output half ----
 #pragma unroll 1
             for (int h = 0; h < nh2; ++h) {
@@ -288,6 +215,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                         dr_wait(DR_BAR(DB_A1READY + 2 * c), ph);
                         dr_wait(DR_BAR(DB_A1READY + 2 * c + 1), ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        DR_TL(lane == 0 && c == 0, 2);
                     }
 #pragma unroll 1
                     for (int we = 0; we < 2; ++we) {
@@ -305,6 +233,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                     }
                 }
                 umma_commit_elect(DR_BAR(DB_D1FULL + h));
+                DR_TL(lane == 0, 3 + h);
             }
             // ---- head: A = layer-1 activations in TMEM ----
             {
@@ -314,6 +243,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                     dr_wait(DR_BAR(DB_A2READY + 2 * c), ph);
                     dr_wait(DR_BAR(DB_A2READY + 2 * c + 1), ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    DR_TL(lane == 0 && c == 0, 5);
 #pragma unroll 1
                     for (int we = 0; we < 2; ++we) {
                         if (we == 1 && sg == 0) continue;
@@ -330,6 +260,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                     }
                 }
                 umma_commit_elect(DR_BAR(DB_DHFULL));
+                DR_TL(lane == 0, 6);
             }
             __syncwarp();
             ph ^= 1u;
@@ -392,6 +323,8 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) dr_arrive(DR_BAR(DB_XFULL + xs));
+                DR_TL(cw == 0 && lane == 0 && c == 0, 20);
+                DR_TL(cw == 0 && lane == 0 && c == nc0 - 1, 21);
             }
         }
     } else if (warp >= DR_EPI_WARP0) {
@@ -409,8 +342,10 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
             const float* bs = bias_s + bb * 768;
             dr_wait(DR_BAR(DB_BFULL + bb), (uint32_t)((u >> 1) & 1));
             // ---- layer 0 accumulator -> layer-1 A operand ----
+            DR_TL(ew == 0 && lane == 0, 19);
             dr_wait(DR_BAR(DB_D0FULL), ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            DR_TL(ew == 0 && lane == 0, 8);
 #pragma unroll 1
             for (int j = set; j < p.N1 / 32; j += 2) {
                 uint32_t r[32], o[16];
@@ -427,11 +362,13 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                 __syncwarp();
                 if (lane == 0) dr_arrive(DR_BAR(DB_A1READY + j));
             }
+            DR_TL(ew == 0 && lane == 0, 9);
             // ---- layer 1 accumulator (two halves) -> layer-2 A operand ----
 #pragma unroll 1
             for (int h = 0; h < nh2; ++h) {
                 dr_wait(DR_BAR(DB_D1FULL + h), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                DR_TL(ew == 0 && lane == 0, 10 + 2 * h);
                 const uint32_t d = h == 0 ? tD1a : tD1b;
 #pragma unroll 1
                 for (int jj = set; jj < 4; jj += 2) {
@@ -450,11 +387,13 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                     __syncwarp();
                     if (lane == 0) dr_arrive(DR_BAR(DB_A2READY + j));
                 }
+                DR_TL(ew == 0 && lane == 0, 11 + 2 * h);
             }
             // ---- head (set 0 only): accumulator -> mean | std rows, staged and bulk-stored ----
             if (set == 0) {
                 dr_wait(DR_BAR(DB_DHFULL), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                DR_TL(ew == 0 && lane == 0, 14);
                 float* o = out + ((int64_t)m * p.E + e0i + gt) * p.nout;
                 float* og = out + ((int64_t)m * p.E + e0i) * p.nout;
                 const uint32_t obytes = (uint32_t)(ne * p.nout) * 4u;
@@ -491,6 +430,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
                 }
             }
             __syncwarp();
+            DR_TL(ew == 0 && lane == 0, 15);
             if (lane == 0) dr_arrive(DR_BAR(DB_BEMPTY + bb));
             ph ^= 1u;
         }
@@ -503,23 +443,7 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     }
 #undef DR_BAR
-}
-
-typedef CUresult (*dr_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-dr_encode_fn dr_encoder() {
-    static dr_encode_fn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        encode = (dr_encode_fn)fn;
-    }
-    return encode;
+#undef DR_TL
 }
 
 }  // namespace
@@ -596,48 +520,41 @@ int dfd_mlp_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const
     p.nx = getenv("DFD_DR_NX") ? atoi(getenv("DFD_DR_NX")) : 2;
     if (p.ns < 2 || p.ns > DR_NS_MAX) p.ns = DR_NS_MAX;
     if (p.nx < 1 || p.nx > DR_NX_MAX) p.nx = 2;
-    dr_encode_fn encode = dr_encoder();
-    DFD_CHECK_ARG(encode != nullptr, "direct MLP path: cuTensorMapEncodeTiled not available");
-    __half* th16 = (__half*)ctx->theta16;
     DrMaps maps;
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int l = 0; l < 3; ++l) {
-        const cuuint32_t rows = l == 2 ? (cuuint32_t)p.N3 : 128u;
-        {
-            const cuuint64_t dims[2] = {(cuuint64_t)in_[l], (cuuint64_t)outr[l]};
-            const cuuint64_t strides[1] = {(cuuint64_t)in_[l] * 2};
-            const cuuint32_t box[2] = {(cuuint32_t)DR_KC, rows};
-            DFD_CHECK_ARG(encode(&maps.w[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, th16 + p.w_off[l], dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS,
-                          "direct MLP path: cuTensorMapEncodeTiled failed for the layer-%d weights", l);
-        }
-        {
-            // a member's [n_out x k_in] matrix starts at element s = idx + w_off of the table: replica s & 7, start s >> 3
-            const int64_t s16 = ctx->scaled16_stride;
-            const cuuint64_t starts = (cuuint64_t)((s16 - (int64_t)in_[l] * outr[l]) / 8);
-            const cuuint64_t dims[4] = {(cuuint64_t)in_[l], starts, (cuuint64_t)outr[l], 8};
-            const cuuint64_t strides[3] = {16, (cuuint64_t)in_[l] * 2, (cuuint64_t)s16 * 2};
-            const cuuint32_t box[4] = {(cuuint32_t)DR_KC, 1, rows, 1};
-            DFD_CHECK_ARG(encode(&maps.e[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ctx->scaled16, dims, strides, box, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS,
-                          "direct MLP path: cuTensorMapEncodeTiled failed for the layer-%d table rows", l);
-        }
+        const int rows = l == 2 ? p.N3 : 128;
+        DFD_CHECK_ARG(dr_map_w(&maps.w[l], ctx, p.w_off[l], in_[l], outr[l], rows) == 0,
+                      "direct MLP path: cuTensorMapEncodeTiled failed for the layer-%d weights", l);
+        DFD_CHECK_ARG(dr_map_e(&maps.e[l], ctx, in_[l], outr[l], rows) == 0,
+                      "direct MLP path: cuTensorMapEncodeTiled failed for the layer-%d table rows", l);
     }
-    theta_to_f16_kernel<<<(int)((p.P + 1023) / 1024), 256, 0, st>>>(theta, th16, p.P);
-    DFD_LAUNCHED(ctx);
+    if (dr_theta16(ctx, theta, p.P, st)) return 3;
     const size_t smem = (size_t)(p.ns + p.nx) * DR_TILE + (2 * 768 + 128 * (size_t)nout) * sizeof(float) + 1024;
     DFD_CHECK_ARG(smem <= 227 * 1024, "direct MLP path: %zu bytes of shared memory", smem);
     int grid = ctx->sm_count;
     if (grid > p.n_work) grid = p.n_work;
+    long long* prof = nullptr;
+    if (getenv("DFD_DR_PROF")) { cudaMalloc(&prof, (size_t)grid * 32 * 8); cudaMemset(prof, 0, (size_t)grid * 32 * 8); }
     if (approx_tanh) {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_direct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_direct_kernel<true><<<grid, DR_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out);
+        mlp_forward_direct_kernel<true><<<grid, DR_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     } else {
         DFD_CUDA(cudaFuncSetAttribute(mlp_forward_direct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_forward_direct_kernel<false><<<grid, DR_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out);
+        mlp_forward_direct_kernel<false><<<grid, DR_THREADS, smem, st>>>(p, maps, table->replicas, table->replica_stride, theta, idx, sign, obs, out, prof);
     }
     DFD_LAUNCHED(ctx);
+    if (prof) {
+        cudaStreamSynchronize(st);
+        static long long h[32];
+        for (int cta = 7; cta < grid; cta += 60) {
+            cudaMemcpy(h, prof + 32 * cta, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[0];
+            fprintf(stderr, "[direct timeline] CTA %d unit 3 (cycles from L0 start) MMA: x0 ready %lld L0 issued %lld | a1 first %lld L1h0 issued %lld L1h1 issued %lld | a2 first %lld head issued %lld || "
+                    "EPI: enter %lld d0full %lld epi0 done %lld | d1a %lld done %lld | d1b %lld done %lld | dh %lld end %lld || TMA: L0 first %lld L1 first %lld head first %lld || CVT: first %lld last %lld\n",
+                    cta, h[7]-t0, h[1]-t0, h[2]-t0, h[3]-t0, h[4]-t0, h[5]-t0, h[6]-t0, h[19]-t0, h[8]-t0, h[9]-t0, h[10]-t0, h[11]-t0, h[12]-t0, h[13]-t0, h[14]-t0, h[15]-t0,
+                    h[16]-t0, h[17]-t0, h[18]-t0, h[20]-t0, h[21]-t0);
+        }
+        cudaFree(prof);
+    }
     return 0;
 }

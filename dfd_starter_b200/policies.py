@@ -333,8 +333,8 @@ class Policy(object):
         if out is None:
             out = torch.empty(M, E, self.out_width, dtype=torch.float32, device=self.ctx.device)
         obs = obs.contiguous()
-        if (self.desc.precision >= 1 and self.kind == "mujoco" and hasattr(table, "ensure_scaled16")
-                and self.ctx.lib.dfd_policy_direct_supported(C.byref(self.desc))
+        if (self.desc.precision >= 1 and hasattr(table, "ensure_scaled16")
+                and (self.kind == "atari" or (self.kind == "mujoco" and self.ctx.lib.dfd_policy_direct_supported(C.byref(self.desc))))
                 and not torch.cuda.is_current_stream_capturing()):
             table.ensure_scaled16(sigma, self.num_params)       # wide MLPs: weight tiles straight from the table by TMA
         _lib.check(self.ctx.lib.dfd_policy_forward(

@@ -1,0 +1,114 @@
+"""GPU parity tests (-m gpu) of the "direct-from-table" tensor paths: a layer that is linear in its weights is evaluated as
+x.theta^T + s*(x.(sigma*eps)^T) with both weight operands arriving by TMA (fp16 copy of theta; sigma-scaled fp16 mirror of
+the noise table) - csrc/mlp_forward_direct.cu, csrc/cnn_forward_tc.cu.  The checker is the CPU oracle / the exact fp32 path;
+the stated tolerance of these paths is 2e-3 on outputs that are probabilities or tanh-bounded (fp16 operands carry tf32's
+10-bit mantissa; fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dfd_oracle as O  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as G
+    G.build()
+    import dfd_starter_b200 as D
+    return D
+
+
+def _atari(D, precision, table, theta, buf):
+    pol = D.AtariPolicy((84, 84), 6, seed=124, device=0, precision=precision).bind_table(table)
+    pol.set_trainable_flat(theta)
+    pol.set_buffers(buf)
+    return pol
+
+
+@pytest.mark.parametrize("M,E,layout", [(4, 1, "pairs"), (4, 2, "pairs"), (6, 8, "pairs"), (4, 2, "unrelated"), (3, 1, "odd"),
+                                        (3, 5, "odd"), (2, 16, "odd16"), (40, 1, "pairs")])
+def test_atari_tensor_path_vs_oracle(D, M, E, layout):
+    """policies/atari.py:35-51 through atari_forward_tc_kernel: pair CTAs with a shared table row (all eight table
+    alignments occur), pairs of unrelated members (eval member with sign 0 among them), one CTA per member for odd member
+    counts, up to 16 (member, observation) columns; against the CPU oracle per member and the exact fp32 kernel."""
+    L = O.atari_layout(6)
+    P = L.num_params
+    table = D.SharedNoiseTable(2_000_000, P, 123, device=0)
+    theta, buf = O.synthetic_theta(L, 51), O.synthetic_buffers(L, 52)
+    tc, exact = _atari(D, 1, table, theta, buf), _atari(D, 0, table, theta, buf)
+    rng = np.random.RandomState(100 * M + E)
+    if layout == "pairs":
+        half = (rng.randint(0, (2_000_000 - P) // 8, size=M // 2) * 8 + np.arange(M // 2) % 8).astype(np.int64)
+        idx = np.concatenate([half, half])
+        sign = np.concatenate([np.ones(M // 2), -np.ones(M // 2)]).astype(np.int8)
+    elif layout == "unrelated":
+        idx = rng.randint(0, 2_000_000 - P, size=M).astype(np.int64)
+        sign = np.array([1, 0, -1, 1], dtype=np.int8)
+    else:
+        idx = rng.randint(0, 2_000_000 - P, size=M).astype(np.int64)
+        sign = np.array([1, -1, 0], dtype=np.int8)[:M]
+    obs = rng.rand(M, E, 4, 84, 84).astype(np.float32)
+    args = (torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(), 0.02)
+    out = tc.forward_members(*args).cpu().numpy()
+    ref = exact.forward_members(*args).cpu().numpy()
+    assert np.isfinite(out).all()
+    np.testing.assert_allclose(out.sum(-1), 1.0, atol=1e-5)
+    err = np.abs(out - ref)
+    assert err.max() <= 2e-3, (err.max(), np.unravel_index(np.argmax(err), err.shape))
+    assert err.max() > 0.0                         # the tensor path did run (the exact kernel would match itself bit for bit)
+    for m in sorted(set([0, M // 2, M - 1])):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
+        np.testing.assert_allclose(out[m], O.atari_forward(L, th, buf, obs[m]), rtol=0, atol=2e-3)
+    out2 = tc.forward_members(*args).cpu().numpy()
+    assert np.array_equal(out, out2)               # deterministic
+
+
+def test_atari_tensor_path_golden(D, golden_dir):
+    """The reference's own outputs (tests/golden/atari_c4.npz, produced by the unmodified AtariPolicy) at the tensor path's
+    stated tolerance."""
+    import os
+    g = np.load(os.path.join(golden_dir, "atari_c4.npz"))
+    L = O.atari_layout(6)
+    table = D.SharedNoiseTable(int(g["table_size"]), L.num_params, int(g["table_seed"]), device=0)
+    pol = _atari(D, 1, table, O.synthetic_theta(L, int(g["theta_seed"])), O.synthetic_buffers(L, int(g["buffer_seed"])))
+    obs = torch.rand(3, 2, 4, 84, 84, generator=torch.Generator().manual_seed(int(g["obs_seed"])))
+    out = pol.forward_members(torch.from_numpy(g["idx"].astype(np.int64)).cuda(),
+                              torch.from_numpy(g["sign"].astype(np.int8)).cuda(), obs.cuda(), float(g["sigma"])).cpu().numpy()
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=2e-3)
+
+
+def test_direct_and_streaming_wide_mlp_agree(D, monkeypatch):
+    """C3 shape: the direct-from-table kernel and the streaming (weights built in shared memory) kernel are two tensor
+    paths of the same forward; both within 2e-3 of the exact fp32 path, on pairs and on unrelated / unperturbed members."""
+    n_in, h, n_act, M, E = 376, 256, 17, 302, 130
+    L = O.mujoco_layout(n_in, n_act, h, h)
+    P = L.num_params
+    table = D.SharedNoiseTable(3_000_000, P, 123, device=0)
+    theta = O.synthetic_theta(L, 7)
+    pols = {}
+    for name, prec in (("tensor", 1), ("exact", 0)):
+        pols[name] = D.MujocoPolicy(n_in, n_act, seed=5, h1=h, h2=h, device=0, precision=prec).bind_table(table)
+        pols[name].set_trainable_flat(theta)
+    rng = np.random.RandomState(3)
+    idx = rng.randint(0, 3_000_000 - P, size=M).astype(np.int64)
+    idx[M // 2:] = idx[:M // 2]
+    sign = np.concatenate([np.ones(M // 2), -np.ones(M // 2)]).astype(np.int8)
+    sign[5] = 0
+    idx[M - 1] = 17                                # an unrelated last member
+    obs = rng.randn(M, E, n_in).astype(np.float32)
+    args = (torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(), 0.02)
+    direct = pols["tensor"].forward_members(*args).cpu().numpy()
+    monkeypatch.setenv("DFD_TC_NO_DIRECT", "1")
+    stream = pols["tensor"].forward_members(*args).cpu().numpy()
+    monkeypatch.delenv("DFD_TC_NO_DIRECT")
+    ref = pols["exact"].forward_members(*args).cpu().numpy()
+    assert np.abs(direct - ref).max() <= 2e-3 and np.abs(stream - ref).max() <= 2e-3
+    assert not np.array_equal(direct, stream)      # two different kernels ran
+    for m in (0, 5, M // 2, M - 1):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
+        mean, std = O.mujoco_forward(L, th, obs[m])
+        np.testing.assert_allclose(direct[m], np.concatenate([mean, std], -1), rtol=0, atol=2e-3)
