@@ -130,11 +130,12 @@ def workload(args):
 def forward_precision(kind, precision, E):
     """--precision -> (tensor path on?, dfd_policy_desc.precision level).  MuJoCo MLPs: tcgen05 tf32 (level 1: accurate
     tanh, level 2: tanh.approx) when asked for, or by default from 32 observations per member; IMPALA: tensor-core
-    convolutions (level 1) unless fp32 is asked for; Discrete / Atari: the exact fp32 kernels only."""
+    convolutions (level 1) unless fp32 is asked for; Atari: tcgen05 convolutions and first Linear with TMA-fed weight tiles
+    (level 1) unless fp32 is asked for; Discrete: the exact fp32 kernels only."""
     if kind == "mujoco":
         on = precision in ("tf32", "tf32a") or (precision == "auto" and E >= 32)
         return on, (1 if precision == "tf32" else 2)
-    if kind == "impala":
+    if kind in ("impala", "atari"):
         return precision != "fp32", 1
     return False, 0
 
@@ -601,7 +602,7 @@ def run_workload(env, args, w, full=True):
                      precision=tc_level if use_tc else 0)
         obs_shape = (w["n_in"],)
     elif w["kind"] == "atari":
-        policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local)
+        policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local, precision=1 if use_tc else 0)
         obs_shape = (4, 84, 84)
     else:
         policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local, precision=1 if use_tc else 0)
@@ -1108,10 +1109,19 @@ def run_workload(env, args, w, full=True):
         except Exception:
             pass
     value = M * E * world / (ms_step * 1e-3)
-    dtype = ("fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
-             if w["kind"] == "impala" else
-             "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % ("tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6")) \
-        if use_tc else "f32"
+    tanh_txt = "tanh.approx.f32" if tc_level == 2 else "tanh to 1e-6"
+    if not use_tc:
+        dtype = "f32"
+    elif w["kind"] == "impala":
+        dtype = "fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
+    elif w["kind"] == "atari":
+        dtype = ("fp16 operands (tcgen05 kind::f16, 10-bit mantissa as tf32; weight tiles by TMA from an fp16 copy of theta and "
+                 "the sigma-scaled fp16 table mirror), fp32 accumulate, fp32 BatchNorm folds and head; f32 estimator")
+    elif lib.dfd_policy_direct_supported(C.byref(policy.desc)):
+        dtype = ("fp16 forward operands (tcgen05 kind::f16, 10-bit mantissa as tf32; weight tiles by TMA from an fp16 copy of "
+                 "theta and the sigma-scaled fp16 table mirror), fp32 accumulate, fp32 biases, %s; f32 estimator" % tanh_txt)
+    else:
+        dtype = "tf32 forward operands, fp32 accumulate, %s; f32 estimator" % tanh_txt
     return {"value": value, "ms_per_step": ms_step, "dtype": dtype, "fd_estimates_per_s": 1e3 / ms_step,
             "launch_mode": "cuda-graph replay (one graph per history-ring position)" if graphs is not None else "plain launches",
             "roofline": roofline, "kernels": kernels, "e2e": e2e, "parity": parity,

@@ -20,6 +20,7 @@
 //   * the dense tail (Linear 2048 -> 256, LSTM 513 -> 1024) streams 8.4 MB of theta and eps per pair: every warp keeps
 //     256 B (Linear) / 272 B (LSTM, two gate rows at a time) of loads in flight per lane.
 #include "common.cuh"
+#include "impala_layout.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -30,18 +31,6 @@ constexpr int MAP_TC = 18560; // the same map padded for the tensor-core path: 1
 constexpr int BAND = 9248;    // conv-row band for the pooled stages: 9 rows x (64 x 16 | 32 x 32), 32 x 16 x 16; staging of a
                               // layer's weights (32 rows x 289)
 constexpr int WMAX = 9216;    // largest conv weight block (32 x 32 x 3 x 3)
-
-struct ConvP { int g, be, w, b, bm, bv, cin, cout; };
-struct ImpalaP {
-    ConvP feat[3];
-    ConvP res[2][3][2];
-    int fc_g, fc_be, fc_w, fc_b, fc_bm, fc_bv;
-    int wih, whh, bih, bhh;
-    int pol_g, pol_be, pol_w, pol_b, pol_bm, pol_bv;
-    int A;
-    int64_t P;
-    int seq_w[16], seq_n[16];     // conv weight segments in execution order (L2 prefetch of the next layer)
-};
 
 struct Ctx {
     const float* theta;
@@ -840,56 +829,6 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
         }
     }
     stamp();                    // 12: end
-}
-
-ImpalaP make_impala(int A) {
-    ImpalaP L = {};
-    int off = 0, boff = 0;
-    const int cin_[3] = {3, 16, 32}, cout_[3] = {16, 32, 32};
-    auto conv = [&](ConvP& p, int cin, int cout) {
-        p.cin = cin; p.cout = cout;
-        p.g = off; off += cin;
-        p.be = off; off += cin;
-        p.bm = boff; boff += cin;
-        p.bv = boff; boff += cin;
-        boff += 1;   // num_batches_tracked
-        p.w = off; off += cout * cin * 9;
-        p.b = off; off += cout;
-    };
-    for (int s = 0; s < 3; ++s) conv(L.feat[s], cin_[s], cout_[s]);
-    for (int blk = 0; blk < 2; ++blk)
-        for (int s = 0; s < 3; ++s) {
-            conv(L.res[blk][s][0], cout_[s], cout_[s]);
-            conv(L.res[blk][s][1], cout_[s], cout_[s]);
-        }
-    L.fc_g = off; off += 2048;
-    L.fc_be = off; off += 2048;
-    L.fc_bm = boff; boff += 2048;
-    L.fc_bv = boff; boff += 2048;
-    boff += 1;
-    L.fc_w = off; off += 256 * 2048;
-    L.fc_b = off; off += 256;
-    L.wih = off; off += 1024 * 257;
-    L.whh = off; off += 1024 * 256;
-    L.bih = off; off += 1024;
-    L.bhh = off; off += 1024;
-    L.pol_g = off; off += 256;
-    L.pol_be = off; off += 256;
-    L.pol_bm = boff; boff += 256;
-    L.pol_bv = boff; boff += 256;
-    boff += 1;
-    L.pol_w = off; off += A * 256;
-    L.pol_b = off; off += A;
-    L.A = A;
-    L.P = off;
-    int n = 0;
-    auto seq = [&](const ConvP& p) { L.seq_w[n] = p.w; L.seq_n[n] = p.cout * p.cin * 9; ++n; };
-    for (int s = 0; s < 3; ++s) {
-        seq(L.feat[s]);
-        for (int blk = 0; blk < 2; ++blk) { seq(L.res[blk][s][0]); seq(L.res[blk][s][1]); }
-    }
-    L.seq_w[15] = 0; L.seq_n[15] = 0;
-    return L;
 }
 
 }  // namespace

@@ -60,9 +60,10 @@ def test_precision_flag_maps_to_policy_levels():
     assert bench.forward_precision("mujoco", "fp32", 128)[0] is False
     assert bench.forward_precision("impala", "auto", 1) == (True, 1)
     assert bench.forward_precision("impala", "fp32", 1) == (False, 1)
-    for kind in ("discrete", "atari"):
-        for prec in ("auto", "fp32", "tf32", "tf32a"):
-            assert bench.forward_precision(kind, prec, 128) == (False, 0)
+    assert bench.forward_precision("atari", "auto", 1) == (True, 1)
+    assert bench.forward_precision("atari", "fp32", 1) == (False, 1)
+    for prec in ("auto", "fp32", "tf32", "tf32a"):
+        assert bench.forward_precision("discrete", prec, 128) == (False, 0)
 
 
 def test_reference_arm_runs_the_reference_itself_when_it_is_importable():
