@@ -833,6 +833,12 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
 
 }  // namespace
 
+int dfd_impala_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                                   const float* bn_buffers, const int64_t* idx, const int8_t* sign, int n_members, float sigma,
+                                   const float* frame, const float* reward, const uint8_t* done, const float* h_in,
+                                   const float* c_in, int obs_per_member, float* probs, float* h_out, float* c_out,
+                                   cudaStream_t st);
+
 extern "C" size_t dfd_impala_scratch_bytes(int n_members, int obs_per_member) {
     (void)n_members;
     (void)obs_per_member;
@@ -856,6 +862,11 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     DFD_CHECK_ARG(L.P == dfd_policy_num_params(desc) && L.P < table->size, "dfd_impala_forward: parameter count mismatch");
     DFD_CHECK_ARG((((uintptr_t)theta) & 15) == 0, "dfd_impala_forward: theta must be 16-byte aligned");
     DFD_CHECK_ARG((int64_t)n_members * obs_per_member < 2147483647LL, "dfd_impala_forward: grid too large");
+    if (desc->precision >= 2) {       // tcgen05 trunk + TMA-fed dense tail (csrc/impala_forward_tc.cu) when the scaled table mirror is registered
+        const int rd = dfd_impala_forward_direct_impl(ctx, desc, table, theta, bn_buffers, idx, sign, n_members, sigma, frame, reward,
+                                                      done, h_in, c_in, obs_per_member, probs, h_out, c_out, (cudaStream_t)stream);
+        if (rd >= 0) return rd;
+    }
     const bool tc = desc->precision >= 1;
     const size_t smem = (size_t)(2 * (tc ? MAP_TC : MAP) + BAND + WMAX + 96 + 2048) * sizeof(float);
     // 2: one CTA per (antithetic pair, env) - members j and j + M/2 of [plus | minus] batches; 1: CTA per (member, env),

@@ -463,6 +463,9 @@ class ImpalaPolicy(DiscretePolicy):
         h, c = h.contiguous(), c.contiguous()
         probs = torch.empty(M, E, self.out_width, device=dev)
         h1, c1 = torch.empty_like(h), torch.empty_like(c)
+        if (self.desc.precision >= 2 and hasattr(self._table, "ensure_scaled16")
+                and not torch.cuda.is_current_stream_capturing()):
+            self._table.ensure_scaled16(sigma, self.num_params)     # tcgen05 trunk + TMA-fed dense tail
         _lib.check(self.ctx.lib.dfd_impala_forward(
             self.ctx.handle, C.byref(self.desc), self._table.ref(), ptr(self.theta), ptr(self.buffers), ptr(idx),
             ptr(sign), M, float(sigma), ptr(frame), ptr(reward), ptr(done8), ptr(h), ptr(c), E, ptr(probs), ptr(h1),

@@ -96,10 +96,15 @@ typedef struct dfd_policy_desc {
     int n_in;      /* MLPs: observation width K                                            */
     int h1, h2;    /* MLPs: hidden widths (reference: 64, 64; mujoco.py:33-34)             */
     int n_act;     /* actions A (MuJoCo head emits 2A: mean | std)                         */
-    int precision; /* 0 = fp32 CUDA cores (exact path), 1 = tensor cores (MuJoCo MLPs: tf32 tcgen05;
-                      IMPALA: mma convolutions with fp16 operands - tf32's 10-bit mantissa - and fp32
-                      accumulate, fp32 dense tail),
-                      2 = MuJoCo: tf32 tcgen05 + single-instruction tanh.approx (2^-11 relative)  */
+    int precision; /* 0 = fp32 CUDA cores (exact path);
+                      1 = tensor cores.  MuJoCo 64x64 nets: tf32 tcgen05, weights resident; wide MuJoCo nets and Atari:
+                          fp16-operand tcgen05 with TMA-fed weight tiles when the scaled table mirror is registered
+                          (dfd_table_build_scaled16), else tf32 tcgen05 with weights built in shared memory (MuJoCo) /
+                          the exact kernel (Atari); IMPALA: mma.sync convolutions with fp16 operands, fp32 dense tail;
+                      2 = MuJoCo: as 1 + single-instruction tanh.approx (2^-11 relative); IMPALA: tcgen05 trunk
+                          (accumulators and the residual stream in TMEM) + TMA-fed tcgen05 dense tail when the scaled
+                          mirror is registered, else as 1.  fp16 operands carry tf32's 10-bit mantissa; accumulation
+                          is fp32 everywhere.  */
 } dfd_policy_desc;
 
 int64_t dfd_policy_num_params(const dfd_policy_desc* desc);

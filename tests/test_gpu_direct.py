@@ -112,3 +112,50 @@ def test_direct_and_streaming_wide_mlp_agree(D, monkeypatch):
         th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
         mean, std = O.mujoco_forward(L, th, obs[m])
         np.testing.assert_allclose(direct[m], np.concatenate([mean, std], -1), rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("shared,M,E", [(True, 4, 2), (False, 4, 2), (False, 3, 1), (True, 40, 1)])
+def test_impala_tcgen05_path_vs_oracle(D, shared, M, E):
+    """policies/impala.py:136-186 through impala_direct_kernel (precision level 2): tcgen05 trunk with the residual stream in
+    TMEM, TMA-fed swap-AB dense tail (class-mapped LSTM rows).  Pair CTAs with a shared table row, pairs of unrelated
+    members (an unperturbed eval member among them), odd member counts (one CTA per member); non-zero incoming state, one
+    finished environment, rewards outside [-1, 1].  Stated tolerance of the tensor paths: 2e-3 on the action
+    probabilities, 1e-2 on the carried LSTM state (15 convolutions deep), against the CPU oracle for every member."""
+    L = O.impala_layout(15)
+    P = L.num_params
+    table = D.SharedNoiseTable(2_500_000, P, 123, device=0)
+    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=2).bind_table(table)
+    theta, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
+    pol.set_trainable_flat(theta)
+    pol.set_buffers(buf)
+    rng = np.random.RandomState(7 * M + shared)
+    half = (rng.randint(0, (2_500_000 - P) // 8, size=M // 2) * 8 + np.arange(M // 2) % 8).astype(np.int64)
+    idx = np.concatenate([half, half]) if shared else rng.randint(0, 2_500_000 - P, size=M).astype(np.int64)
+    sign = (np.concatenate([np.ones(M // 2), -np.ones(M // 2)]) if shared else np.array([1, 0, -1, 1][:M])).astype(np.int8)
+    frames = rng.randint(0, 256, size=(M, E, 3, 64, 64)).astype(np.float32)
+    reward = rng.uniform(-2, 2, size=(M, E)).astype(np.float32)
+    done = np.zeros((M, E), bool)
+    done[1, 0] = True
+    h0 = (0.3 * rng.randn(M, E, 256)).astype(np.float32)
+    c0 = (0.3 * rng.randn(M, E, 256)).astype(np.float32)
+    args = (torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(frames).cuda(),
+            torch.from_numpy(reward).cuda(), torch.from_numpy(done).cuda(), torch.from_numpy(h0).cuda(),
+            torch.from_numpy(c0).cuda(), 0.02)
+    probs, h1, c1 = [t.cpu().numpy() for t in pol.forward_members_impala(*args)]
+    assert np.isfinite(probs).all() and np.isfinite(h1).all() and np.isfinite(c1).all()
+    err = [0.0, 0.0, 0.0]
+    check = range(M) if M <= 8 else (0, 1, 7, M // 2, M // 2 + 7, M - 1)
+    for m in check:
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
+        rp, rh, rc = O.impala_forward(L, th, buf, frames[m], reward[m], done[m], h0[m], c0[m])
+        err = [max(err[0], np.abs(probs[m] - rp).max()), max(err[1], np.abs(h1[m] - rh).max()), max(err[2], np.abs(c1[m] - rc).max())]
+    print("impala tcgen05 max-abs errors: probs %.2e h %.2e c %.2e" % tuple(err))
+    assert err[0] <= 2e-3 and err[1] <= 1e-2 and err[2] <= 1e-2, err
+    again = [t.cpu().numpy() for t in pol.forward_members_impala(*args)]
+    assert np.array_equal(probs, again[0]) and np.array_equal(h1, again[1])      # deterministic
+    # the mma.sync path (level 1) is a different kernel with the same contract
+    pol1 = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=1).bind_table(table)
+    pol1.set_trainable_flat(theta)
+    pol1.set_buffers(buf)
+    p1 = pol1.forward_members_impala(*args)[0].cpu().numpy()
+    assert np.abs(p1 - probs).max() <= 4e-3 and not np.array_equal(p1, probs)
