@@ -135,7 +135,9 @@ def forward_precision(kind, precision, E):
     if kind == "mujoco":
         on = precision in ("tf32", "tf32a") or (precision == "auto" and E >= 32)
         return on, (1 if precision == "tf32" else 2)
-    if kind in ("impala", "atari"):
+    if kind == "impala":
+        return precision != "fp32", 2       # level 2: mma.sync trunk + TMA-fed tcgen05 dense tail
+    if kind == "atari":
         return precision != "fp32", 1
     return False, 0
 
@@ -605,7 +607,7 @@ def run_workload(env, args, w, full=True):
         policy = D.AtariPolicy((84, 84), w["n_act"], seed=TABLE_SEED, device=local, precision=1 if use_tc else 0)
         obs_shape = (4, 84, 84)
     else:
-        policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local, precision=1 if use_tc else 0)
+        policy = D.ImpalaPolicy((3, 64, 64), w["n_act"], seed=TABLE_SEED, device=local, precision=tc_level if use_tc else 0)
         obs_shape = (3, 64, 64)
     is_impala = w["kind"] == "impala"
     P = policy.num_params
@@ -1113,7 +1115,9 @@ def run_workload(env, args, w, full=True):
     if not use_tc:
         dtype = "f32"
     elif w["kind"] == "impala":
-        dtype = "fp16 convolution operands (mma.sync m16n8k16, 10-bit mantissa as tf32), fp32 accumulate, fp32 dense tail; f32 estimator"
+        dtype = ("fp16 operands (10-bit mantissa as tf32), fp32 accumulate: convolutions on mma.sync m16n8k16, dense tail (Linear + LSTM) on "
+                 "tcgen05 kind::f16 with weight tiles by TMA from an fp16 repack of theta and the sigma-scaled fp16 table mirror; "
+                 "fp32 BatchNorm folds, LSTM cell and head; f32 estimator")
     elif w["kind"] == "atari":
         dtype = ("fp16 operands (tcgen05 kind::f16, 10-bit mantissa as tf32; weight tiles by TMA from an fp16 copy of theta and "
                  "the sigma-scaled fp16 table mirror), fp32 accumulate, fp32 BatchNorm folds and head; f32 estimator")

@@ -19,8 +19,7 @@
 //     the NEXT layer's eps segment is prefetched into L2 while the current layer computes;
 //   * the dense tail (Linear 2048 -> 256, LSTM 513 -> 1024) streams 8.4 MB of theta and eps per pair: every warp keeps
 //     256 B (Linear) / 272 B (LSTM, two gate rows at a time) of loads in flight per lane.
-#include "common.cuh"
-#include "impala_layout.cuh"
+#include "impala_tail.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -495,7 +494,6 @@ __device__ __forceinline__ void conv_first_mma(const float* __restrict__ in_o, c
 // Dense tail for the NM members of this CTA (NM = 2: the two members of an antithetic pair, whose eps row is streamed ONCE).
 // fc[q]: BN'd flattened trunk output of member q (2048); st: per-member scratch (core 260 | h0 256 | gates 1024 | hn 256 |
 // logits 32 = ST floats).
-constexpr int ST = 260 + 256 + 1024 + 256 + 32;
 template <int NM>
 __device__ __forceinline__ void dense_tail(const ImpalaP& L, const float* __restrict__ theta, const float* __restrict__ row,
                                            const float* __restrict__ bnbuf, const float (&sg)[2], const int (&inst)[2],
@@ -653,9 +651,12 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
                                                                        const float* __restrict__ c_in, int E,
                                                                        float* __restrict__ probs, float* __restrict__ h_out,
                                                                        float* __restrict__ c_out, int n_members, int pair_order,
-                                                                       long long* __restrict__ prof) {
+                                                                       long long* __restrict__ prof,
+                                                                       const __grid_constant__ ItMaps maps, int tail_tc) {
     constexpr int MAPF = TC ? MAP_TC : MAP;
     extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t tbars[TB_COUNT];      // dense tail on tcgen05 / TMA (impala_tail.cuh), tail_tc != 0
+    __shared__ uint32_t tmem_base_s;
     float* bufA = sm;
     float* bufB = bufA + MAPF;
     float* band = bufB + MAPF;
@@ -666,6 +667,19 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
     float* fc0 = bias + 32;        // 2048: BN'd trunk output of the CTA's first member (the second one's goes to `band`)
 
     const int tid = threadIdx.x;
+    if (tail_tc) {
+        if (tid == 0) {
+            for (int i = 0; i < TB_COUNT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tbars[i])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if ((tid >> 5) == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     int stamp_i = 0;
     // DFD_IMPALA_PROF=1: cycle stamps of CTA 7 at the phase boundaries (all stamps follow a CTA barrier)
     auto stamp = [&]() {
@@ -817,7 +831,29 @@ __global__ void __launch_bounds__(IM_THREADS, 1) impala_forward_kernel(ImpalaP L
     __syncthreads();            // trunks done: the map buffers are dead and hold the dense tail's scratch from here on
     stamp_i = 11;
     stamp();                    // 11: trunks done
-    if (nmem == 2 && rows[0] == rows[1]) {
+    if (tail_tc) {
+        // TMA-fed tcgen05 dense tail: warps 0-14 are the workers, lane 0 of warp 15 streams the weight tiles
+        const uint32_t sraw = smem_u32(sm), s0 = (sraw + 1023u) & ~1023u;
+        uint8_t* smb = reinterpret_cast<uint8_t*>(sm) + (s0 - sraw);
+        constexpr int XT_OFF = TL_HT + 5120, FCIN_OFF = XT_OFF + TL_XT_BYTES;
+        __half* fcin = reinterpret_cast<__half*>(smb + FCIN_OFF);
+        for (int i = tid; i < nmem * 2048; i += IM_THREADS) fcin[i] = __float2half_rn(fcs[i >> 11][i & 2047]);
+        __syncthreads();
+        TailArgs ta;
+        ta.theta = theta; ta.bnbuf = bnbuf; ta.reward = reward; ta.done = done; ta.h_in = h_in; ta.c_in = c_in;
+        ta.probs = probs; ta.h_out = h_out; ta.c_out = c_out; ta.sigma = sigma; ta.nmem = nmem;
+        ta.nE = (nmem == 2 && rows[0] != rows[1]) ? 2 : 1;
+        for (int i = 0; i < 2; ++i) { ta.inst[i] = inst[i]; ta.sgi[i] = (int)sign[ms[i]]; ta.ids[i] = idx[ms[i]]; ta.rows[i] = rows[i]; }
+        const uint32_t tb0 = smem_u32(&tbars[0]);
+        if (tid < 480) tl_dense_tail_workers<480, XT_OFF>(L, ta, smb, s0, fcin, tb0, tmem_base_s, 0u);
+        else if (tid == 480) tl_dense_tail_producer(L, maps, ta, s0, tb0);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if ((tid >> 5) == 1) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(512u) : "memory");
+        }
+    } else if (nmem == 2 && rows[0] == rows[1]) {
         dense_tail<2>(L, theta, rows[0], bnbuf, sgs, inst, fcs, bufA, reward, done, h_in, c_in, probs, h_out, c_out);
     } else {
         for (int mem = 0; mem < nmem; ++mem) {
@@ -862,7 +898,7 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     DFD_CHECK_ARG(L.P == dfd_policy_num_params(desc) && L.P < table->size, "dfd_impala_forward: parameter count mismatch");
     DFD_CHECK_ARG((((uintptr_t)theta) & 15) == 0, "dfd_impala_forward: theta must be 16-byte aligned");
     DFD_CHECK_ARG((int64_t)n_members * obs_per_member < 2147483647LL, "dfd_impala_forward: grid too large");
-    if (desc->precision >= 2) {       // tcgen05 trunk + TMA-fed dense tail (csrc/impala_forward_tc.cu) when the scaled table mirror is registered
+    if (desc->precision >= 3) {       // tcgen05 trunk + TMA-fed dense tail (csrc/impala_forward_tc.cu) when the scaled table mirror is registered
         const int rd = dfd_impala_forward_direct_impl(ctx, desc, table, theta, bn_buffers, idx, sign, n_members, sigma, frame, reward,
                                                       done, h_in, c_in, obs_per_member, probs, h_out, c_out, (cudaStream_t)stream);
         if (rd >= 0) return rd;
@@ -876,16 +912,26 @@ extern "C" int dfd_impala_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     const int grid = (mode == 2 ? n_members / 2 : n_members) * obs_per_member;
     long long* prof = nullptr;
     if (getenv("DFD_IMPALA_PROF")) { cudaMalloc(&prof, 32 * 8); cudaMemset(prof, 0, 32 * 8); }   // 0..12 phases, 16..27 fine stamps
+    // level 2: the dense tail (90 % of the parameters) as TMA-fed tcgen05 GEMMs (impala_tail.cuh) when the sigma-scaled
+    // fp16 mirror of this table is registered with the context
+    ItMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int tail_tc = 0;
+    if (desc->precision >= 2 && !getenv("DFD_TC_NO_DIRECT") && ctx->scaled16 && ctx->scaled_src == table->replicas &&
+        ctx->scaled_sigma == sigma && ctx->theta16_cap >= 1048576) {
+        if (tl_prepare(ctx, L, theta, &maps, (cudaStream_t)stream)) return 3;
+        tail_tc = 1;
+    }
     if (tc) {
         DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         impala_forward_kernel<true><<<grid, IM_THREADS, smem, (cudaStream_t)stream>>>(
             L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
-            obs_per_member, probs, h_out, c_out, n_members, mode, prof);
+            obs_per_member, probs, h_out, c_out, n_members, mode, prof, maps, tail_tc);
     } else {
         DFD_CUDA(cudaFuncSetAttribute(impala_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         impala_forward_kernel<false><<<grid, IM_THREADS, smem, (cudaStream_t)stream>>>(
             L, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign, sigma, frame, reward, done, h_in, c_in,
-            obs_per_member, probs, h_out, c_out, n_members, mode, prof);
+            obs_per_member, probs, h_out, c_out, n_members, mode, prof, maps, tail_tc);
     }
     DFD_LAUNCHED(ctx);
     if (prof) {

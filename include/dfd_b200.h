@@ -101,10 +101,12 @@ typedef struct dfd_policy_desc {
                           fp16-operand tcgen05 with TMA-fed weight tiles when the scaled table mirror is registered
                           (dfd_table_build_scaled16), else tf32 tcgen05 with weights built in shared memory (MuJoCo) /
                           the exact kernel (Atari); IMPALA: mma.sync convolutions with fp16 operands, fp32 dense tail;
-                      2 = MuJoCo: as 1 + single-instruction tanh.approx (2^-11 relative); IMPALA: tcgen05 trunk
-                          (accumulators and the residual stream in TMEM) + TMA-fed tcgen05 dense tail when the scaled
-                          mirror is registered, else as 1.  fp16 operands carry tf32's 10-bit mantissa; accumulation
-                          is fp32 everywhere.  */
+                      2 = MuJoCo: as 1 + single-instruction tanh.approx (2^-11 relative); IMPALA: as 1 with the dense
+                          tail (Linear 2048->256 + LSTM, 90 % of the parameters) as TMA-fed tcgen05 GEMMs when the
+                          scaled mirror is registered (csrc/impala_tail.cuh);
+                      3 = IMPALA: tcgen05 trunk as well (implicit GEMMs over channel-last fp16 operand maps, the
+                          residual stream in TMEM; csrc/impala_forward_tc.cu) - parity-tested, not yet the fastest.
+                      fp16 operands carry tf32's 10-bit mantissa; accumulation is fp32 everywhere.  */
 } dfd_policy_desc;
 
 int64_t dfd_policy_num_params(const dfd_policy_desc* desc);

@@ -114,17 +114,19 @@ def test_direct_and_streaming_wide_mlp_agree(D, monkeypatch):
         np.testing.assert_allclose(direct[m], np.concatenate([mean, std], -1), rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("level", [2, 3])
 @pytest.mark.parametrize("shared,M,E", [(True, 4, 2), (False, 4, 2), (False, 3, 1), (True, 40, 1)])
-def test_impala_tcgen05_path_vs_oracle(D, shared, M, E):
-    """policies/impala.py:136-186 through impala_direct_kernel (precision level 2): tcgen05 trunk with the residual stream in
-    TMEM, TMA-fed swap-AB dense tail (class-mapped LSTM rows).  Pair CTAs with a shared table row, pairs of unrelated
+def test_impala_tcgen05_path_vs_oracle(D, shared, M, E, level):
+    """policies/impala.py:136-186 at precision level 2 (mma.sync trunk + TMA-fed tcgen05 swap-AB dense tail with class-mapped
+    LSTM rows, csrc/impala_tail.cuh inside impala_forward_kernel) and level 3 (impala_direct_kernel: tcgen05 trunk with the
+    residual stream in TMEM + the same tail).  Pair CTAs with a shared table row, pairs of unrelated
     members (an unperturbed eval member among them), odd member counts (one CTA per member); non-zero incoming state, one
     finished environment, rewards outside [-1, 1].  Stated tolerance of the tensor paths: 2e-3 on the action
     probabilities, 1e-2 on the carried LSTM state (15 convolutions deep), against the CPU oracle for every member."""
     L = O.impala_layout(15)
     P = L.num_params
     table = D.SharedNoiseTable(2_500_000, P, 123, device=0)
-    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=2).bind_table(table)
+    pol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=level).bind_table(table)
     theta, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
     pol.set_trainable_flat(theta)
     pol.set_buffers(buf)
@@ -149,7 +151,7 @@ def test_impala_tcgen05_path_vs_oracle(D, shared, M, E):
         th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
         rp, rh, rc = O.impala_forward(L, th, buf, frames[m], reward[m], done[m], h0[m], c0[m])
         err = [max(err[0], np.abs(probs[m] - rp).max()), max(err[1], np.abs(h1[m] - rh).max()), max(err[2], np.abs(c1[m] - rc).max())]
-    print("impala tcgen05 max-abs errors: probs %.2e h %.2e c %.2e" % tuple(err))
+    print("impala level %d max-abs errors: probs %.2e h %.2e c %.2e" % ((level,) + tuple(err)))
     assert err[0] <= 2e-3 and err[1] <= 1e-2 and err[2] <= 1e-2, err
     again = [t.cpu().numpy() for t in pol.forward_members_impala(*args)]
     assert np.array_equal(probs, again[0]) and np.array_equal(h1, again[1])      # deterministic
