@@ -613,19 +613,25 @@ def run_workload(env, args, w, full=True):
     P = policy.num_params
     table = D.SharedNoiseTable(args.table_size, P, TABLE_SEED, device=local)
     policy.bind_table(table)
+    if is_impala and use_tc:
+        # the bench calls dfd_impala_forward directly: register the sigma-scaled fp16 table mirror the level-2 dense tail
+        # streams its weight tiles from (ImpalaPolicy.forward_members_impala does this on first use)
+        table.device_table.ensure_scaled16(SIGMA, P)
 
     class Omega(object):
         omega, min_omega, max_omega = 0.0, 0.0, 1.0
     opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
     opt.coef = np.sqrt(P)
-    # sharded population: fd_return workloads exchange through ONE peer-memory kernel per step (dist.PeerExchange);
-    # fd_state (IMPALA, delayed returns) keeps the rewards all-gather + NCCL all_reduce
+    # sharded population: the exchange runs over NVLink peer memory (dist.PeerExchange), no NCCL call on the step
     xchg = None
-    if world > 1 and not is_impala and args.exchange == "peer":
+    if world > 1 and args.exchange == "peer":
         from dfd_starter_b200.dist import PeerExchange
         xchg = PeerExchange(ctx, P, pg)
+    # fd_state (IMPALA, delayed returns): the per-return norms are rank-local, so the standardisation cannot be deferred:
+    # rewards gathered over peer memory, then the gradient summed over peer memory ("general" mode, two peer kernels)
     learner = D.FiniteDifferences(policy, opt, Omega(), table, noise_std=SIGMA, batch_size=M, max_delayed_return=H,
-                                  paired=True, process_group=pg, peer_exchange=xchg)
+                                  paired=True, process_group=pg, peer_exchange=xchg,
+                                  exchange_mode="general" if (is_impala and xchg is not None) else "fd_return")
 
     CYC = H  # graphs / index sets / observation buffers cycle with the history ring
     g = torch.Generator().manual_seed(1234 + rank)

@@ -20,7 +20,7 @@ SYMBOLS = [
     "dfd_xchg_mailbox_close", "dfd_xchg_mailbox_destroy", "dfd_xchg_allreduce",
     "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused", "dfd_wire_count_returns", "dfd_wire_decode_returns",
     "dfd_strategy_distances", "dfd_host_stage", "dfd_normalize_obs", "dfd_member_obs_stats",
-    "dfd_table_scaled16_bytes", "dfd_table_build_scaled16", "dfd_table_drop_scaled16", "dfd_policy_direct_supported",
+    "dfd_xchg_gather_f64", "dfd_table_scaled16_bytes", "dfd_table_build_scaled16", "dfd_table_drop_scaled16", "dfd_policy_direct_supported",
 ]
 
 
@@ -100,6 +100,7 @@ def load():
     proto("dfd_xchg_mailbox_close", i32, [vp, vp])
     proto("dfd_xchg_mailbox_destroy", i32, [vp, vp])
     proto("dfd_xchg_allreduce", i32, [vp, vp, i32, i32, i64, vp, vp, vp, vp])
+    proto("dfd_xchg_gather_f64", i32, [vp, vp, i32, i32, i64, vp, i32, vp, vp])
     proto("dfd_fd_step_fused_scratch_bytes", sz, [vp, i64, i32, i32])
     proto("dfd_fd_step_fused", i32, [vp, P(DfdTable), i64, vp, vp, vp, i32, i32, f64, f32, vp, vp, f64, f64, vp, vp, i64,
                                      i32, i32, vp, vp, i32, i32, vp, sz, vp])

@@ -167,6 +167,49 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
     }
 }
 
+// All-gather of a short fp64 vector (the rewards of every rank's returns: the standardisation of fd_state batches needs
+// the mean / std over ALL ranks' returns before the coefficients can be formed, learner/finite_differences.py:40-43) with
+// the same mailbox protocol and step counter: push n doubles into slot [parity][rank] of every peer, publish, wait for all
+// ranks, copy the world slots in rank order to dst[world][n].  One CTA; n * 8 bytes must fit a slot.
+__global__ void __launch_bounds__(XCHG_THREADS) xchg_gather_kernel(char* const* __restrict__ mailboxes, int rank, int world,
+                                                                   int64_t P, const double* __restrict__ src, int n,
+                                                                   double* __restrict__ dst) {
+    char* const mine = mailboxes[rank];
+    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(mine + 8);
+    const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(step_ctr);
+    const int par = (int)(step & 1ull);
+    const size_t slot = xchg_slot_bytes(P);
+    const size_t slots0 = XCHG_HDR + XCHG_FLAGS + (size_t)par * world * slot;
+    const size_t my_slot_off = slots0 + (size_t)rank * slot;
+    for (int i = threadIdx.x; i < n; i += XCHG_THREADS) {
+        const double v = src[i];
+        for (int w = 0; w < world; ++w) {
+            const int d = (rank + w) % world;
+            *reinterpret_cast<double*>(mailboxes[d] + my_slot_off + 8 * (size_t)i) = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        unsigned long long* f = reinterpret_cast<unsigned long long*>(mailboxes[threadIdx.x] + XCHG_HDR) + par * XCHG_MAX_WORLD + rank;
+        st_release_sys(f, step + 1ull);
+    }
+    if (threadIdx.x == 0) *step_ctr = step + 1ull;
+    if (threadIdx.x < world) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCHG_HDR) + par * XCHG_MAX_WORLD + threadIdx.x;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < step + 1ull) {
+            if (++spins > (1u << 26)) __trap();    // a missing peer must fault, not hang the GPU
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < world * n; i += XCHG_THREADS) {
+        const int w = i / n, j = i - w * n;
+        dst[i] = __ldcg(reinterpret_cast<const double*>(mine + slots0 + (size_t)w * slot) + j);
+    }
+}
+
 }  // namespace
 
 static unsigned long long* g_xchg_prof = nullptr;
@@ -225,6 +268,18 @@ extern "C" int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank
     unsigned long long* prof = g_xchg_prof;
     xchg_allreduce_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params,
                                                                            grad_partial, stats5, grad_out, prof);
+    DFD_LAUNCHED(ctx);
+    return 0;
+}
+
+extern "C" int dfd_xchg_gather_f64(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params, const double* src,
+                                   int n, double* dst, dfd_stream stream) {
+    DFD_CHECK_ARG(ctx && mailboxes && src && dst, "dfd_xchg_gather_f64: NULL argument");
+    DFD_CHECK_ARG(world >= 1 && world <= XCHG_MAX_WORLD && rank >= 0 && rank < world, "dfd_xchg_gather_f64: rank %d / world %d", rank, world);
+    DFD_CHECK_ARG(n >= 0 && (size_t)n * 8 + 256 <= xchg_slot_bytes(n_params),
+                  "dfd_xchg_gather_f64: %d doubles do not fit a mailbox slot of a %lld-parameter exchange", n, (long long)n_params);
+    if (n == 0) return 0;
+    xchg_gather_kernel<<<1, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params, src, n, dst);
     DFD_LAUNCHED(ctx);
     return 0;
 }

@@ -78,6 +78,14 @@ class PeerExchange(object):
                                                ptr(grad_partial), ptr(stats5), ptr(grad_out), self.ctx.stream),
                    "dfd_xchg_allreduce")
 
+    def gather_f64(self, src, n, dst):
+        """dst[world, n] = every rank's src[:n] (float64 device tensors), over the same mailboxes: the rewards all-gather of
+        fd_state batches without NCCL.  Every rank must call it with the same n."""
+        from . import _lib
+        from .device import ptr
+        _lib.check(self.lib.dfd_xchg_gather_f64(self.ctx.handle, ptr(self.table), self.rank, self.world, self.P, ptr(src),
+                                                int(n), ptr(dst), self.ctx.stream), "dfd_xchg_gather_f64")
+
     def close(self):
         """Unmap the peers' mailboxes, then - once EVERY rank has unmapped (barrier) - free this rank's own."""
         for p in self._peers:

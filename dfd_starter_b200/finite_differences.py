@@ -60,7 +60,7 @@ class _Staging(object):
 class FiniteDifferences(object):
     def __init__(self, policy, gradient_optimizer, omega, noise_source, noise_std=0.1, batch_size=100, ent_coef=0.0,
                  max_delayed_return=10, paired=False, process_group=None, device=None, sync_policy=True,
-                 peer_exchange=None, fused_step=True):
+                 peer_exchange=None, fused_step=True, exchange_mode="fd_return"):
         self.max_delayed_return = max_delayed_return
         self.ent_coef = ent_coef
         self.noise_std = noise_std
@@ -73,6 +73,15 @@ class FiniteDifferences(object):
         # dist.PeerExchange: the exchange runs as one peer-memory kernel instead of NCCL calls whenever the batch
         # is antithetic pairs of the current epoch (otherwise: rewards all-gather + NCCL all_reduce)
         self.peer_exchange = peer_exchange
+        # every rank must take the same exchange path every step, so the mode is fixed per learner:
+        #   "fd_return": antithetic pairs of the current epoch only - standardisation deferred, ONE peer-memory kernel;
+        #   "general":   any accepted batch (delayed epochs = fd_state mode, one-sided members): rewards gathered over
+        #                peer memory, coefficients with the statistics of all ranks' returns, partial gradients summed
+        #                over peer memory (two peer kernels per step, no NCCL on the device-resident step)
+        if exchange_mode not in ("fd_return", "general"):
+            raise _lib.DfdError("exchange_mode must be 'fd_return' or 'general'")
+        self.exchange_mode = exchange_mode
+        self._gathered = None
         # short parameter vectors: prepare + reduce [+ exchange] + DSGD run as ONE kernel (csrc/fd_tail.cu)
         self.fused_step = fused_step
         self._fused_scratch = {}
@@ -240,7 +249,8 @@ class FiniteDifferences(object):
         if pg is None and n == 0:
             return 0                                             # :30-31, no update, epoch unchanged
         stats = None
-        if pg is not None and self.peer_exchange is not None:
+        general_peer = pg is not None and self.peer_exchange is not None and self.exchange_mode == "general"
+        if pg is not None and self.peer_exchange is not None and not general_peer:
             # the mode is fixed per learner (every rank must take the same path every step): a learner built
             # with a PeerExchange only accepts what the one-kernel exchange can express
             if not (self.paired and n % 2 == 0 and bool((hist_row == -1).all())):
@@ -290,7 +300,11 @@ class FiniteDifferences(object):
                 aligned_ptr(self._red_scratch), self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
         else:
             self.grad.zero_()
-        if pg is not None:
+        if general_peer:                        # partial gradients are already standardised: stats with count 0 = identity scale
+            self._grad_partial[:self.P].copy_(self.grad)
+            self._stats5.zero_()
+            self.peer_exchange.allreduce(self._grad_partial, self._stats5, self.grad)
+        elif pg is not None:
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=pg)     # the one parameter-sized exchange
         return self._apply_update()
@@ -369,7 +383,16 @@ class FiniteDifferences(object):
         else:
             n_hist = len(self._dist_epoch) and (max(self._dist_epoch.values()) + 1)
         paired = 1 if (self.paired and n % 2 == 0) else 0
-        if self.process_group is not None and self.peer_exchange is not None:
+        general_peer = self.process_group is not None and self.peer_exchange is not None and self.exchange_mode == "general"
+        if general_peer:
+            # rewards of every rank over peer memory (every rank submits the same n), then the ordinary prepare with the
+            # statistics of all returns
+            world = self.peer_exchange.world
+            if self._gathered is None or self._gathered.shape[0] < world * n:
+                self._gathered = torch.empty(world * max(n, 16), dtype=torch.float64, device=self.ctx.device)
+            self.peer_exchange.gather_f64(reward_d, n, self._gathered)
+            stats_d = self._gathered[:world * n]
+        if self.process_group is not None and self.peer_exchange is not None and not general_peer:
             if not (paired and n_hist == 0 and stats_d is None):
                 raise _lib.DfdError("a learner with peer_exchange takes antithetic pairs of the current epoch only")
             scratch = self._fused_scratch_for(n, 1)
@@ -392,9 +415,12 @@ class FiniteDifferences(object):
             self._prep_scratch.numel() - 256, st), "dfd_fd_prepare")
         n_rows = (n // 2 if paired else n) + int(n_hist)
         _lib.check(self.lib.dfd_fd_reduce(
-            self.ctx.handle, C.byref(self._rows), n_rows, self.P, ptr(self.grad), aligned_ptr(self._red_scratch),
-            self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
-        if self.process_group is not None:
+            self.ctx.handle, C.byref(self._rows), n_rows, self.P, ptr(self._grad_partial if general_peer else self.grad),
+            aligned_ptr(self._red_scratch), self._red_scratch.numel() - 256, st), "dfd_fd_reduce")
+        if general_peer:
+            self._stats5.zero_()                # count 0: the partial gradients are already standardised
+            self.peer_exchange.allreduce(self._grad_partial, self._stats5, self.grad)
+        elif self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.process_group)
         self._apply_update(sync=False)

@@ -221,6 +221,14 @@ int dfd_xchg_mailbox_close(dfd_ctx* ctx, void* peer_mailbox);
 int dfd_xchg_mailbox_destroy(dfd_ctx* ctx, void* mailbox);
 int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params,
                        const float* grad_partial, const double* stats5, float* grad_out, dfd_stream stream);
+/* All-gather of n doubles per rank (every rank the SAME n) over the same mailboxes and step counter: dst[world][n] in rank
+ * order.  The sharded learner's fd_state batches (returns from older epochs: per-return norms are rank-local, the
+ * standardisation of finite_differences.py:40-43 is not deferrable) gather the rewards with this call, form the
+ * coefficients with the statistics of ALL ranks' returns (dfd_fd_prepare, stats_reward = dst), reduce, and sum the
+ * partial gradients with dfd_xchg_allreduce(stats5 = five zeros: count 0 means "already standardised").  n * 8 + 256 bytes
+ * must fit a slot of the n_params-sized mailbox; n == 0 on every rank is a no-op.  No NCCL call on the step. */
+int dfd_xchg_gather_f64(dfd_ctx* ctx, void* const* mailboxes, int rank, int world, int64_t n_params, const double* src,
+                        int n, double* dst, dfd_stream stream);
 
 /* ---- the whole step after the returns are known, as ONE kernel (short parameter vectors) ---------------
  * dfd_fd_step_fused = dfd_fd_prepare + dfd_fd_reduce [+ dfd_xchg_allreduce] + dfd_dsgd_step for fd_return-mode

@@ -43,6 +43,67 @@ def make_learner(xchg):
                                     process_group=dist.group.WORLD, peer_exchange=xchg)
 
 
+if SHAPE == "state":
+    # fd_state batches (returns from older epochs) through the "general" peer mode: rewards gathered over peer memory /
+    # the process group, coefficients with the statistics of ALL ranks' returns, partial gradients summed over peer memory.
+    # host path (step_arrays) against the CPU oracle of the unsharded batch; device-resident path (step_device) against
+    # the host path; ranks bit-identical.
+    H = 3
+    xchg = PeerExchange(ctx, P, dist.group.WORLD)
+
+    def mk():
+        table = D.SharedNoiseTable(1_000_000, P, 123, device=local)
+        pol = D.MujocoPolicy(P_IN, ACT, seed=3, h1=HID, h2=HID, device=local).bind_table(table)
+        pol.set_trainable_flat(theta0)
+        opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
+        opt.coef = np.sqrt(P)
+        return pol, D.FiniteDifferences(pol, opt, Omega(), table, noise_std=SIG, batch_size=2 * PAIRS, paired=True,
+                                        max_delayed_return=H, process_group=dist.group.WORLD, peer_exchange=xchg,
+                                        exchange_mode="general")
+    pol_a, fa = mk()
+    pol_d, fdv = mk()
+    ref = O.FiniteDifferencesOracle(theta0.copy(), noise, SIG, LR, max_delayed_return=H, omega=0.0)
+    rng = np.random.RandomState(11)
+    lo, hi = shard_pairs(PAIRS, rank, world)
+    assert (hi - lo) * world == PAIRS
+    worst = 0.0
+    for step in range(6):
+        idx = rng.randint(0, 1_000_000 - P, size=PAIRS).astype(np.int64)
+        rp, rm = rng.randn(PAIRS) * 2.0, rng.randn(PAIRS) * 2.0 + 0.3
+        back = rng.randint(0, min(step, H) + 1, size=PAIRS)          # epochs in the accepted window, the same for + and -
+        ep = ref.epoch - back
+        e2 = np.concatenate([ep[lo:hi], ep[lo:hi]]).astype(np.int64)
+        i2 = np.concatenate([idx[lo:hi], idx[lo:hi]])
+        s2 = np.concatenate([np.ones(hi - lo), -np.ones(hi - lo)]).astype(np.int8)
+        r2 = np.concatenate([rp[lo:hi], rm[lo:hi]])
+        # device-resident step first (it needs the history rows of the CURRENT state)
+        hist_row = np.array([-1 if e == fdv.epoch else fdv._dist_epoch[int(e)] for e in e2], dtype=np.int32)
+        fdv.step_device(torch.from_numpy(i2).cuda(), torch.from_numpy(s2).cuda(), torch.from_numpy(r2).cuda(), 2 * (hi - lo), 0.1,
+                        hist_row_d=torch.from_numpy(hist_row).cuda())
+        u_a = fa.step_arrays(e2, i2, s2, r2, 0.1)
+        batch = [O.Ret(int(e), "+%d" % i, float(r)) for e, i, r in zip(ep, idx, rp)] + \
+                [O.Ret(int(e), "-%d" % i, float(r)) for e, i, r in zip(ep, idx, rm)]
+        u_o = ref.step(batch, 0.1)
+        rel = np.abs(fa.gradient_memory - ref.gradient_memory).max() / np.abs(ref.gradient_memory).max()
+        worst = max(worst, rel)
+        assert rel <= 1e-5, (step, rel)
+        assert abs(u_a - u_o) <= 1e-6 * max(1.0, abs(u_o)), (u_a, u_o)
+        assert np.abs(pol_a.get_trainable_flat() - ref.theta).max() <= 2e-6
+        g_d = fdv.grad.cpu().numpy()
+        rel_d = np.abs(g_d - fa.gradient_memory).max() / np.abs(fa.gradient_memory).max()
+        assert rel_d <= 1e-6, (step, rel_d)
+        assert np.abs(pol_d.get_trainable_flat() - pol_a.get_trainable_flat()).max() <= 1e-6
+        t = pol_a.theta.clone()
+        ts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        assert all(torch.equal(ts[0], x) for x in ts), "ranks diverged"
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print("xchg ok: %d ranks, fd_state general mode, worst gradient rel-max vs oracle %.2e" % (world, worst), flush=True)
+    sys.stdout.flush()
+    os._exit(0)
+
 xchg = PeerExchange(ctx, P, dist.group.WORLD)
 pol_f, fused = make_learner(xchg)
 pol_n, nccl = make_learner(None)

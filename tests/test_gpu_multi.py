@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("shape", ["", "odd", "wide"])
+@pytest.mark.parametrize("shape", ["", "odd", "wide", "state"])
 def test_peer_exchange_matches_nccl_and_oracle(shape):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
