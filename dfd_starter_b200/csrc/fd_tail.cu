@@ -31,6 +31,17 @@ constexpr int TL_MAX_WORLD = 16;
 constexpr size_t TL_XHDR = 256, TL_XFLAGS = 2 * TL_MAX_WORLD * 8;   // mailbox layout of xchg_allreduce.cu
 
 __host__ __device__ inline size_t tl_slot_bytes(int64_t P) { return (size_t)((P + 3) / 4 * 4) * 4 + 256; }
+// low-latency region of the mailbox (after the flag-protocol slots): every value travels as an 8-byte packet
+// {fp32 bits | step number}, so a packet is its own "ready" flag: no system-scope fence, no separate flag store, no grid-wide
+// ticket on the exchange path - one NVLink store latency between a finished tile and the peers that combine it
+__host__ __device__ inline size_t tl_ll_slot_bytes(int64_t P) { return P <= (int64_t)TL_MAXTILES * 128 ? (size_t)((P + 3) / 4 * 4 + 16) * 8 : 0; }
+__host__ __device__ inline size_t tl_ll_base(int64_t P, int world) { return TL_XHDR + TL_XFLAGS + 2 * (size_t)world * tl_slot_bytes(P); }
+__device__ __forceinline__ void tl_st_ll2(char* p, uint32_t a, uint32_t b, uint32_t flag) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(flag), "r"(b), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void tl_ld_ll2(const char* p, uint32_t& a, uint32_t& fa, uint32_t& b, uint32_t& fb) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(p) : "memory");
+}
 
 struct TailParams {
     const float* replicas; int64_t stride; const double* prefix; int64_t P;
@@ -199,55 +210,41 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
         }
     }
     if (p.world > 1) {
-        // ---- exchange: push the tile (and, from tile 0, the statistics) to every peer, publish, wait, combine ---
+        // ---- exchange over the low-latency packets: push the tile (and, from tile 0, the statistics) to every peer,
+        //      poll the world slots of this tile in rank order, combine ---
         const int par = (int)(xstep & 1ull);
-        const size_t slot = tl_slot_bytes(p.P);
+        const uint32_t flag = (uint32_t)(xstep + 1ull);
         const int64_t n4 = (p.P + 3) / 4;
-        const size_t my_off = TL_XHDR + TL_XFLAGS + ((size_t)par * p.world + p.rank) * slot;
+        const size_t ll_slot = tl_ll_slot_bytes(p.P);
+        const size_t ll0 = tl_ll_base(p.P, p.world) + (size_t)par * p.world * ll_slot;
+        const size_t my_off = ll0 + (size_t)p.rank * ll_slot;
         if (tid < 32 && colc < p.P) {
             for (int w = 0; w < p.world; ++w) {
-                const int dst = (p.rank + w) % p.world;
-                *reinterpret_cast<float4*>(p.mailboxes[dst] + my_off + 4 * (size_t)colc) = g;
+                char* dst = p.mailboxes[(p.rank + w) % p.world] + my_off + 8 * (size_t)colc;
+                tl_st_ll2(dst, __float_as_uint(g.x), __float_as_uint(g.y), flag);
+                tl_st_ll2(dst + 16, __float_as_uint(g.z), __float_as_uint(g.w), flag);
             }
         }
         if (tile == 0 && tid >= 32 && tid < 37) {
-            const double sv = stats_s[tid - 32];
+            const unsigned long long sv = (unsigned long long)__double_as_longlong(stats_s[tid - 32]);
             for (int w = 0; w < p.world; ++w)
-                *reinterpret_cast<double*>(p.mailboxes[w] + my_off + 16 * (size_t)n4 + 8 * (tid - 32)) = sv;
+                tl_st_ll2(p.mailboxes[w] + my_off + 8 * (size_t)(4 * n4) + 16 * (tid - 32), (uint32_t)sv, (uint32_t)(sv >> 32), flag);
         }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            ticket_s = atomicAdd(p.glob + 0, 1u);
-        }
-        __syncthreads();
-        if (ticket_s == (unsigned)(p.tiles - 1)) {       // last finisher to have pushed: publish this rank's step
-            if (tid == 0) __threadfence_system();
-            __syncthreads();
-            if (tid < p.world) {
-                unsigned long long* f = reinterpret_cast<unsigned long long*>(p.mailboxes[tid] + TL_XHDR) + par * TL_MAX_WORLD + p.rank;
-                tl_st_release_sys(f, xstep + 1ull);
-            }
-            if (tid == 0) {
-                p.glob[0] = 0u;
-                *reinterpret_cast<unsigned long long*>(p.mailboxes[p.rank] + 8) = xstep + 1ull;
-            }
-        }
-        char* const mine = p.mailboxes[p.rank];
-        if (tid < p.world) {
-            const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + TL_XHDR) + par * TL_MAX_WORLD + tid;
-            unsigned spins = 0;
-            while (tl_ld_acquire_sys(f) < xstep + 1ull)
-                if (++spins > (1u << 26)) __trap();      // a missing peer must fault, not hang the GPU
-        }
-        __syncthreads();
-        const size_t slots0 = TL_XHDR + TL_XFLAGS + (size_t)par * p.world * slot;
+        const char* mine = p.mailboxes[p.rank];
         if (tid < 32) {
             double sv[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
             if (tid < p.world) {
-                const double* st = reinterpret_cast<const double*>(mine + slots0 + (size_t)tid * slot + 16 * (size_t)n4);
+                const char* st = mine + ll0 + (size_t)tid * ll_slot + 8 * (size_t)(4 * n4);
 #pragma unroll
-                for (int k = 0; k < 5; ++k) sv[k] = __ldcg(st + k);
+                for (int k = 0; k < 5; ++k) {
+                    uint32_t lo, flo, hi, fhi;
+                    unsigned spins = 0;
+                    do {
+                        tl_ld_ll2(st + 16 * k, lo, flo, hi, fhi);
+                        if (++spins > (1u << 26)) __trap();          // a missing peer must fault, not hang the GPU
+                    } while (flo != flag || fhi != flag);
+                    sv[k] = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                }
             }
             double ts = 0.0, tss = 0.0, tn = 0.0, tmn = 1e300, tmx = -1e300;
             for (int w = 0; w < p.world; ++w) {
@@ -265,9 +262,16 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
             const float invf = (float)inv;
             g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (colc < p.P) {
-                for (int w = 0; w < p.world; ++w) {
-                    const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + slots0 + (size_t)w * slot + 4 * (size_t)colc));
-                    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+                for (int w = 0; w < p.world; ++w) {          // rank order: bitwise identical sums on every rank
+                    const char* src = mine + ll0 + (size_t)w * ll_slot + 8 * (size_t)colc;
+                    uint32_t a, fa, b2, fb, c, fc, d, fd;
+                    unsigned spins = 0;
+                    do {
+                        tl_ld_ll2(src, a, fa, b2, fb);
+                        tl_ld_ll2(src + 16, c, fc, d, fd);
+                        if (++spins > (1u << 26)) __trap();
+                    } while (fa != flag || fb != flag || fc != flag || fd != flag);
+                    g.x += __uint_as_float(a); g.y += __uint_as_float(b2); g.z += __uint_as_float(c); g.w += __uint_as_float(d);
                 }
             }
             g.x *= invf; g.y *= invf; g.z *= invf; g.w *= invf;
@@ -350,6 +354,7 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
             *p.update_size = (float)sqrt(t);
             p.glob[1] = 0u;      // every finisher is past the meeting point (it arrived here after it)
             p.glob[2] = 0u;
+            if (p.world > 1) *reinterpret_cast<unsigned long long*>(p.mailboxes[p.rank] + 8) = xstep + 1ull;   // one exchange step done
         }
     }
 }

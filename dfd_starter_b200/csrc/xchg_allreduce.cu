@@ -216,7 +216,10 @@ static unsigned long long* g_xchg_prof = nullptr;
 
 extern "C" size_t dfd_xchg_mailbox_bytes(int64_t n_params, int world) {
     if (n_params <= 0 || world <= 0 || world > XCHG_MAX_WORLD) return 0;
-    return XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params);
+    // flag-protocol slots, then (short parameter vectors only) the low-latency packet region of the one-kernel step
+    // (csrc/fd_tail.cu: tl_ll_slot_bytes - 8 bytes per value + 16 packets of statistics)
+    const size_t ll_slot = n_params <= 32768 ? (size_t)((n_params + 3) / 4 * 4 + 16) * 8 : 0;
+    return XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params) + 2 * (size_t)world * ll_slot;
 }
 
 extern "C" int dfd_xchg_mailbox_create(dfd_ctx* ctx, size_t bytes, void** mailbox, unsigned char* ipc_handle64) {
