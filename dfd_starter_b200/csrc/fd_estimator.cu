@@ -9,6 +9,7 @@
 // returns from older epochs only, eps_i . d_e dot products (a first pass over
 // just those rows).  The reduction is HBM-bound: rows*P*4 bytes in, P*4 out.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 // ---------------------------------------------------------------------------
@@ -31,7 +32,8 @@ __global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __res
                                                               const int64_t* __restrict__ idx,
                                                               const int32_t* __restrict__ hist_row, int n_returns, int R_pairs,
                                                               const float* __restrict__ dist, int64_t dist_stride,
-                                                              int64_t P, double* __restrict__ out) {
+                                                              int64_t P, double* __restrict__ out,
+                                                              const __half* __restrict__ mirror, int64_t mstride, double inv_sigma) {
     __shared__ double sh[2][DOT_THREADS / 32];
     const int y = blockIdx.y;
     const int RB = R_pairs > 0 ? R_pairs : n_returns;
@@ -53,6 +55,51 @@ __global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __res
     const int64_t c0 = (int64_t)blockIdx.x * DOT_CHUNK;
     const int64_t c1 = min(c0 + (int64_t)DOT_CHUNK, P);
     double acc0 = 0.0, acc1 = 0.0;
+    if (mirror != nullptr && y < RB) {
+        // the table row from the sigma-scaled fp16 mirror (dfd_table_build_scaled16: half the bytes of the fp32 row; the dot
+        // enters ||lambda||^2 as a ~1e-3 correction, so the 2^-11 operand rounding moves the coefficient by ~1e-7
+        // relative): 8 halves per 16-byte load against two float4 of the distance row (L2-resident)
+        const int64_t id = idx[y];
+        const __half* a16 = mirror + (id & 7) * mstride + (id & ~(int64_t)7);
+        const int64_t v8 = c0 + ((c1 - c0) & ~(int64_t)7);
+        constexpr int U8 = 4;
+        for (int64_t cb = c0 + 8 * threadIdx.x; cb < v8; cb += 8 * DOT_THREADS * U8) {
+            uint4 x[U8];
+#pragma unroll
+            for (int u = 0; u < U8; ++u) {
+                const int64_t c = cb + (int64_t)u * 8 * DOT_THREADS;
+                x[u] = make_uint4(0, 0, 0, 0);
+                if (c < v8) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[u].x), "=r"(x[u].y), "=r"(x[u].z), "=r"(x[u].w) : "l"(a16 + c));
+            }
+#pragma unroll
+            for (int u = 0; u < U8; ++u) {
+                const int64_t c = cb + (int64_t)u * 8 * DOT_THREADS;
+                if (c < v8) {
+                    const float2 e0 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].x)), e1 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].y));
+                    const float2 e2 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].z)), e3 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].w));
+                    const float4 ya = *reinterpret_cast<const float4*>(b0 + c), yb = *reinterpret_cast<const float4*>(b0 + c + 4);
+                    float s = e0.x * ya.x;
+                    s = fmaf(e0.y, ya.y, s); s = fmaf(e1.x, ya.z, s); s = fmaf(e1.y, ya.w, s);
+                    s = fmaf(e2.x, yb.x, s); s = fmaf(e2.y, yb.y, s); s = fmaf(e3.x, yb.z, s); s = fmaf(e3.y, yb.w, s);
+                    acc0 += (double)s;
+                    if (b1) {
+                        const float4 za = *reinterpret_cast<const float4*>(b1 + c), zb = *reinterpret_cast<const float4*>(b1 + c + 4);
+                        float s1 = e0.x * za.x;
+                        s1 = fmaf(e0.y, za.y, s1); s1 = fmaf(e1.x, za.z, s1); s1 = fmaf(e1.y, za.w, s1);
+                        s1 = fmaf(e2.x, zb.x, s1); s1 = fmaf(e2.y, zb.y, s1); s1 = fmaf(e3.x, zb.z, s1); s1 = fmaf(e3.y, zb.w, s1);
+                        acc1 += (double)s1;
+                    }
+                }
+            }
+        }
+        for (int64_t c = v8 + threadIdx.x; c < c1; c += DOT_THREADS) {
+            const double e = (double)__half2float(a16[c]);
+            acc0 += e * (double)b0[c];
+            if (b1) acc1 += e * (double)b1[c];
+        }
+        acc0 *= inv_sigma;
+        acc1 *= inv_sigma;
+    } else {
     // all bases are 16-byte aligned (replica rows by construction, dist rows because dist_stride % 4 == 0)
     const int64_t v1 = c0 + ((c1 - c0) & ~(int64_t)3);
     constexpr int U = 4;
@@ -87,6 +134,7 @@ __global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __res
     for (int64_t c = v1 + threadIdx.x; c < c1; c += DOT_THREADS) {
         acc0 += (double)a[c] * (double)b0[c];
         if (b1) acc1 += (double)a[c] * (double)b1[c];
+    }
     }
     acc0 = warp_sum(acc0);
     acc1 = warp_sum(acc1);
@@ -265,8 +313,12 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
     if (n_hist > 0) {
         DFD_CUDA(cudaMemsetAsync(dots, 0, (size_t)(n_returns + 2 * n_hist) * sizeof(double), st));
         dim3 grid((unsigned)((n_params + DOT_CHUNK - 1) / DOT_CHUNK), (unsigned)((paired ? R : n_returns) + n_hist));
+        // with the sigma-scaled fp16 mirror of this table registered (dfd_table_build_scaled16) the pass reads half the bytes
+        const bool m16 = ctx->scaled16 && ctx->scaled_src == table->replicas && ctx->scaled_sigma == sigma && sigma != 0.f &&
+                         !getenv("DFD_DOTS_FP32");
         fd_dots_kernel<<<grid, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
-                                                     paired ? R : 0, dist, dist_stride, n_params, dots);
+                                                     paired ? R : 0, dist, dist_stride, n_params, dots,
+                                                     m16 ? (const __half*)ctx->scaled16 : nullptr, ctx->scaled16_stride, 1.0 / (double)sigma);
         DFD_LAUNCHED(ctx);
     }
     fd_coef_kernel<<<(R + COEF_THREADS - 1) / COEF_THREADS, COEF_THREADS, 0, st>>>(

@@ -359,7 +359,7 @@ __device__ __noinline__ void conv3x3_mma(const float* __restrict__ in_o, const f
                 sh[q] = sh_in[cb + tig + 4 * q];
             }
             const uint32_t* wb = wpk + ((((cb >> 4) * 9) * 4 + tig) * cout << 1);
-#pragma unroll
+#pragma unroll 1   // filter-row loop rolled: a third of the code per layer shape
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {

@@ -41,7 +41,7 @@ for rep in sorted(f for f in os.listdir(os.path.join(ROOT, "gpurun_out")) if f.e
     st = sorted(((float(d[k]), k.split("stalled_")[1].split("_per")[0]) for k in hdr
                  if "issue_stalled" in k and "per_issue_active" in k and d.get(k) not in (None, "")), reverse=True)[:5]
     lines.append("\nTop warp stall reasons (warps per issue-active cycle): " + ", ".join("%s %.2f" % (n, v) for v, n in st) + "\n")
-for ll in ("launches_c2.csv", "launches_c3.csv", "launches_c5.csv"):
+for ll in ("launches_c2.csv", "launches_c3.csv", "launches_c4.csv", "launches_c5.csv"):
     p = os.path.join(ROOT, "gpurun_out", ll)
     if not os.path.exists(p):
         continue

@@ -161,3 +161,58 @@ def test_impala_tcgen05_path_vs_oracle(D, shared, M, E, level):
     pol1.set_buffers(buf)
     p1 = pol1.forward_members_impala(*args)[0].cpu().numpy()
     assert np.abs(p1 - probs).max() <= 4e-3 and not np.array_equal(p1, probs)
+
+
+class _HostPolicy(object):
+    def __init__(self, theta):
+        self.theta_h = np.array(theta, dtype=np.float32)
+        self.num_params = len(theta)
+
+    def get_trainable_flat(self):
+        return self.theta_h.copy()
+
+    def set_trainable_flat(self, flat):
+        self.theta_h = np.array(flat, dtype=np.float32)
+
+
+class _Omega(object):
+    omega, min_omega, max_omega = 0.3, 0.0, 1.0
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_fd_state_dots_from_the_fp16_mirror(D, paired):
+    """With the sigma-scaled fp16 mirror of the table registered, the eps . d pass of fd_state batches
+    (learner/finite_differences.py:87-89,107) reads the mirror - half the bytes.  The dot enters ||lambda||^2 as a small
+    correction, so the estimator stays within its 1e-5 gradient tolerance of the oracle: 10 steps, H = 5; one-sided members with
+    delayed, too-old and current returns, and antithetic pairs from delayed epochs."""
+    import contextlib
+    import io
+    rng = np.random.RandomState(9)
+    P, N, H, sigma = 30498, 64, 5, 0.05
+    table = D.SharedNoiseTable(2_000_000, P, 123, device=0)
+    table.device_table.ensure_scaled16(sigma, P)
+    theta = (rng.randn(P) * 0.1).astype(np.float32)
+    opt = D.DSGD([torch.nn.Parameter(torch.zeros(P))], lr=0.05)
+    fd = D.FiniteDifferences(_HostPolicy(theta), opt, _Omega(), table, noise_std=sigma, batch_size=N, max_delayed_return=H,
+                             paired=paired)
+    ofd = O.FiniteDifferencesOracle(theta, O.NoiseTableOracle(2_000_000, P, 123), sigma, 0.05, max_delayed_return=H, omega=0.3)
+    for s in range(10):
+        if paired:
+            i = rng.randint(0, 2_000_000 - P, size=N // 2).astype(np.int64)
+            idx, sign = np.concatenate([i, i]), np.concatenate([np.ones(N // 2), -np.ones(N // 2)]).astype(np.int8)
+            keys = ["+%d" % v for v in i] + ["-%d" % v for v in i]
+        else:
+            idx, sign = rng.randint(0, 2_000_000 - P, size=N).astype(np.int64), np.ones(N, dtype=np.int8)
+            keys = [str(int(v)) for v in idx]
+        rewards = rng.randn(N) * 2.0
+        if paired:          # the two members of a pair were evaluated against one FDState: same epoch, inside the window
+            eh = fd.epoch - rng.randint(0, min(s, H) + 1, size=N // 2)
+            epochs = np.concatenate([eh, eh])
+        else:               # one-sided members: any epoch, some one epoch too old (discarded)
+            epochs = fd.epoch - rng.randint(0, H + 2, size=N)
+        with contextlib.redirect_stdout(io.StringIO()):
+            upd = fd.step_arrays(epochs, idx, sign, rewards, 0.5)
+            oupd = ofd.step([O.Ret(int(e), k, float(r)) for e, k, r in zip(epochs, keys, rewards)], 0.5)
+        rel = float(np.max(np.abs(fd.gradient_memory - ofd.gradient_memory)) / np.max(np.abs(ofd.gradient_memory)))
+        assert rel <= 1e-5, (s, rel)
+        assert abs(upd - oupd) <= 1e-5 * oupd
