@@ -62,8 +62,10 @@ def smoke():
 def _smoke_tensor_paths(O, D):
     """Small launches of the tcgen05 / TMA kernels the bench spends its time in, each checked against the oracle, so the
     driver's kernel list of smoke() names them: resident-weight MLP forward (mlp_forward_ws_kernel), streaming MLP
-    forward (mlp_forward_stream_kernel), TMA-fed wide-row reduction (fd_reduce_tma_kernel, through one learner step of
-    a Humanoid-sized policy), one-kernel learner step (fd_tail_kernel), IMPALA forward with tensor-core convolutions."""
+    forward with TMA-fed weight tiles straight from the table mirror (mlp_forward_direct_kernel) and with weights built in
+    shared memory (mlp_forward_stream_kernel), TMA-fed wide-row reduction (fd_reduce_tma_kernel, through one learner step
+    of a Humanoid-sized policy), one-kernel learner step (fd_tail_kernel), Atari forward on tcgen05 (atari_forward_tc_kernel),
+    IMPALA forward with tensor-core convolutions and the TMA-fed tcgen05 dense tail (impala_forward_kernel, level 2)."""
     sigma = 0.02
     rng = np.random.RandomState(11)
 
@@ -88,7 +90,10 @@ def _smoke_tensor_paths(O, D):
     t_small = D.SharedNoiseTable(1_000_000, 6092, 123, device=0)
     _, _, e_ws = mlp(17, 64, 6, 16, 128, 2, 4e-3, t_small)                       # mlp_forward_ws_kernel
     t_wide = D.SharedNoiseTable(2_000_000, 171042, 123, device=0)
-    pol, theta, e_st = mlp(376, 256, 17, 300, 128, 1, 2e-3, t_wide)              # mlp_forward_stream_kernel, 2 items per CTA
+    pol, theta, e_dr = mlp(376, 256, 17, 300, 128, 1, 2e-3, t_wide)              # mlp_forward_direct_kernel, 2 items per CTA
+    os.environ["DFD_TC_NO_DIRECT"] = "1"
+    _, _, e_st = mlp(376, 256, 17, 300, 128, 1, 2e-3, t_wide)                    # mlp_forward_stream_kernel
+    del os.environ["DFD_TC_NO_DIRECT"]
 
     # one learner step at Humanoid width: prepare + fd_reduce_tma_kernel + DSGD, against the fp64 closed form
     class Omega(object):
@@ -104,10 +109,27 @@ def _smoke_tensor_paths(O, D):
     e_red = float(np.max(np.abs(fd.gradient_memory - ref)) / np.max(np.abs(ref)))
     assert e_red <= 1e-5, ("wide reduction mismatch", e_red)
 
-    # IMPALA, tensor-core convolutions, one antithetic pair
+    # Atari on tcgen05: implicit-GEMM convolutions + TMA-fed swap-AB first Linear, one antithetic pair
+    La = O.atari_layout(6)
+    t_at = D.SharedNoiseTable(2_000_000, La.num_params, 123, device=0)
+    apol = D.AtariPolicy((84, 84), 6, seed=124, device=0, precision=1).bind_table(t_at)
+    tha, bufa = O.synthetic_theta(La, 51), O.synthetic_buffers(La, 52)
+    apol.set_trainable_flat(tha)
+    apol.set_buffers(bufa)
+    ia = int(rng.randint(0, 2_000_000 - La.num_params))
+    aobs = rng.rand(2, 1, 4, 84, 84).astype(np.float32)
+    aout = apol.forward_members(torch.tensor([ia, ia]).cuda(), torch.tensor([1, -1], dtype=torch.int8).cuda(),
+                                torch.from_numpy(aobs).cuda(), sigma).cpu().numpy()
+    e_at = 0.0
+    for m, sg in enumerate((1, -1)):
+        thm = O.perturb(tha, sigma, t_at._table[ia:ia + La.num_params], sg)
+        e_at = max(e_at, float(np.abs(aout[m] - O.atari_forward(La, thm, bufa, aobs[m])).max()))
+    assert e_at <= 2e-3, ("atari tensor-path forward mismatch", e_at)
+
+    # IMPALA, tensor-core convolutions + TMA-fed tcgen05 dense tail (level 2), one antithetic pair
     L = O.impala_layout(15)
     t_imp = D.SharedNoiseTable(2_000_000, L.num_params, 123, device=0)
-    ipol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=1).bind_table(t_imp)
+    ipol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=2).bind_table(t_imp)
     th, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
     ipol.set_trainable_flat(th)
     ipol.set_buffers(buf)
@@ -125,5 +147,5 @@ def _smoke_tensor_paths(O, D):
         rp, _, _ = O.impala_forward(L, thm, buf, frames[m], np.zeros(1, np.float32), np.zeros(1, bool), zero[m], zero[m])
         e_imp = max(e_imp, float(np.abs(probs[m].cpu().numpy() - rp).max()))
     assert e_imp <= 2e-3, ("impala tensor-core forward mismatch", e_imp)
-    print("smoke ok (tensor / TMA paths): ws forward %.1e, stream forward %.1e, wide reduction rel %.1e, impala probs %.1e, "
-          "launches %d" % (e_ws, e_st, e_red, e_imp, pol.ctx.launch_count()))
+    print("smoke ok (tensor / TMA paths): ws forward %.1e, direct forward %.1e, stream forward %.1e, wide reduction rel %.1e, "
+          "atari probs %.1e, impala probs %.1e, launches %d" % (e_ws, e_dr, e_st, e_red, e_at, e_imp, pol.ctx.launch_count()))
