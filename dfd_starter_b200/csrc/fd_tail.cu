@@ -83,6 +83,7 @@ __device__ __forceinline__ unsigned tl_ld_volatile(const unsigned* p) {
 
 __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams p) {
     __shared__ float4 sm[TL_WARPS][32];
+    __shared__ float4 xsm[TL_MAX_WORLD][32];      // sharded: the world's packets of this tile, one row per rank
     __shared__ const float* ptr_s[TL_MAXROWS];
     __shared__ float coef_s[TL_MAXROWS];
     __shared__ double sh[TL_WARPS];
@@ -231,6 +232,27 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
                 tl_st_ll2(p.mailboxes[w] + my_off + 8 * (size_t)(4 * n4) + 16 * (tid - 32), (uint32_t)sv, (uint32_t)(sv >> 32), flag);
         }
         const char* mine = p.mailboxes[p.rank];
+        // every warp polls the packets of its own ranks (w, w + 8, ...), so the peers' latencies overlap instead of adding up;
+        // the sum below still runs in rank order
+        {
+            const int64_t cl = (int64_t)tile * 128 + 4 * lane;
+            for (int w = warp; w < p.world; w += TL_WARPS) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cl < p.P) {
+                    const char* src = mine + ll0 + (size_t)w * ll_slot + 8 * (size_t)cl;
+                    uint32_t a, fa, b2, fb, c, fc, d, fd;
+                    unsigned spins = 0;
+                    do {
+                        tl_ld_ll2(src, a, fa, b2, fb);
+                        tl_ld_ll2(src + 16, c, fc, d, fd);
+                        if (++spins > (1u << 26)) __trap();          // a missing peer must fault, not hang the GPU
+                    } while (fa != flag || fb != flag || fc != flag || fd != flag);
+                    t = make_float4(__uint_as_float(a), __uint_as_float(b2), __uint_as_float(c), __uint_as_float(d));
+                }
+                xsm[w][lane] = t;
+            }
+        }
+        __syncthreads();
         if (tid < 32) {
             double sv[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
             if (tid < p.world) {
@@ -263,15 +285,8 @@ __global__ void __launch_bounds__(TL_THREADS, 3) fd_tail_kernel(const TailParams
             g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (colc < p.P) {
                 for (int w = 0; w < p.world; ++w) {          // rank order: bitwise identical sums on every rank
-                    const char* src = mine + ll0 + (size_t)w * ll_slot + 8 * (size_t)colc;
-                    uint32_t a, fa, b2, fb, c, fc, d, fd;
-                    unsigned spins = 0;
-                    do {
-                        tl_ld_ll2(src, a, fa, b2, fb);
-                        tl_ld_ll2(src + 16, c, fc, d, fd);
-                        if (++spins > (1u << 26)) __trap();
-                    } while (fa != flag || fb != flag || fc != flag || fd != flag);
-                    g.x += __uint_as_float(a); g.y += __uint_as_float(b2); g.z += __uint_as_float(c); g.w += __uint_as_float(d);
+                    const float4 t = xsm[w][tid];
+                    g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
                 }
             }
             g.x *= invf; g.y *= invf; g.z *= invf; g.w *= invf;

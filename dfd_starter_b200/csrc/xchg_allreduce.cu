@@ -167,6 +167,136 @@ __global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_kernel(char* cons
     }
 }
 
+// Two-phase form for LONG parameter vectors on many ranks: the one-phase kernel above pushes every rank's whole partial to
+// every peer (world * P floats leave each GPU - fine at 24 KB, 37 MB per rank at C5 size on 8 GPUs).  Here rank r OWNS slice
+// r of the vector: (1) reduce-scatter - every rank pushes slice d of its partial to rank d only (and its 5 statistics to
+// everybody), (2) the owner sums the world contributions of its slice in rank order, applies 1 / std and pushes the reduced
+// slice to every peer's result region, (3) all-gather - every rank copies the other slices out of its own result region.
+// ~2 P floats leave each GPU instead of world * P; two flag rounds instead of one.  Same determinism: every element is
+// summed by exactly one rank, in rank order, and every rank receives those bits.
+__global__ void __launch_bounds__(XCHG_THREADS) xchg_allreduce_rs_kernel(char* const* __restrict__ mailboxes, int rank, int world, int64_t P,
+                                                                         const float* __restrict__ grad_partial,
+                                                                         const double* __restrict__ stats5, float* __restrict__ grad_out,
+                                                                         size_t off2) {
+    __shared__ unsigned ticket_s;
+    __shared__ double inv_sd_s;
+    char* const mine = mailboxes[rank];
+    unsigned* bar_ctr = reinterpret_cast<unsigned*>(mine);
+    unsigned* bar_ctr2 = reinterpret_cast<unsigned*>(mine + 4);
+    unsigned long long* step_ctr = reinterpret_cast<unsigned long long*>(mine + 8);
+    const unsigned long long step = *reinterpret_cast<volatile unsigned long long*>(step_ctr);
+    const int par = (int)(step & 1ull);
+    const size_t slot = xchg_slot_bytes(P);
+    const int64_t n4 = (P + 3) / 4;
+    const int64_t per = (n4 + world - 1) / world;
+    const size_t slots0 = XCHG_HDR + XCHG_FLAGS + (size_t)par * world * slot;
+    const size_t my_slot_off = slots0 + (size_t)rank * slot;
+    const size_t res_off = off2 + XCHG_FLAGS + (size_t)par * slot;
+    const int64_t gstride = (int64_t)gridDim.x * XCHG_THREADS, g0 = (int64_t)blockIdx.x * XCHG_THREADS + threadIdx.x;
+    // ---- 1. reduce-scatter push: element i goes to its owner only ----
+    for (int64_t i = g0; i < n4; i += gstride) {
+        float4 v;
+        if (4 * i + 3 < P) v = *reinterpret_cast<const float4*>(grad_partial + 4 * i);
+        else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < 4 && 4 * i + k < P; ++k) t[k] = grad_partial[4 * i + k];
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(mailboxes[(int)(i / per)] + my_slot_off + 16 * (size_t)i) = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 5) {
+        const double sv = stats5[threadIdx.x];
+        for (int w = 0; w < world; ++w) *reinterpret_cast<double*>(mailboxes[w] + my_slot_off + 16 * (size_t)n4 + 8 * threadIdx.x) = sv;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        ticket_s = atomicAdd(bar_ctr, 1u);
+    }
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {
+        if (threadIdx.x == 0) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<unsigned long long*>(mailboxes[threadIdx.x] + XCHG_HDR) + par * XCHG_MAX_WORLD + rank, step + 1ull);
+        if (threadIdx.x == 0) *bar_ctr = 0u;
+    }
+    if (threadIdx.x < world) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + XCHG_HDR) + par * XCHG_MAX_WORLD + threadIdx.x;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < step + 1ull)
+            if (++spins > (1u << 26)) __trap();    // a missing peer must fault, not hang the GPU
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {        // standardize_arr over the whole population (utils/math_helpers.py:127-134), as in the one-phase kernel
+        double v[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+        if (threadIdx.x < world) {
+            const double* st = reinterpret_cast<const double*>(mine + slots0 + (size_t)threadIdx.x * slot + 16 * (size_t)n4);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) v[k] = __ldcg(st + k);
+        }
+        double s = 0.0, ss = 0.0, n = 0.0, mn = 1e300, mx = -1e300;
+        for (int w = 0; w < world; ++w) {
+            const double a0 = __shfl_sync(0xffffffffu, v[0], w), a1 = __shfl_sync(0xffffffffu, v[1], w);
+            const double a2 = __shfl_sync(0xffffffffu, v[2], w), a3 = __shfl_sync(0xffffffffu, v[3], w);
+            const double a4 = __shfl_sync(0xffffffffu, v[4], w);
+            if (a2 > 0.0) { s += a0; ss += a1; n += a2; mn = fmin(mn, a3); mx = fmax(mx, a4); }
+        }
+        double inv = 1.0;
+        if (n > 0.0 && mn != mx) {
+            const double mean = s / n;
+            const double var = fmax(ss / n - mean * mean, 0.0);
+            if (var > 0.0) inv = 1.0 / sqrt(var);
+        }
+        if (threadIdx.x == 0) inv_sd_s = inv;
+    }
+    __syncthreads();
+    const float inv_sd = (float)inv_sd_s;
+    // ---- 2. the owner reduces its slice in rank order and hands it to every peer ----
+    const int64_t lo = (int64_t)rank * per, hi = min(lo + per, n4);
+    for (int64_t i = lo + g0; i < hi; i += gstride) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < world; ++w) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(mine + slots0 + (size_t)w * slot + 16 * (size_t)i));
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+        g.x *= inv_sd; g.y *= inv_sd; g.z *= inv_sd; g.w *= inv_sd;
+        const float t[4] = {g.x, g.y, g.z, g.w};
+        for (int k = 0; k < 4 && 4 * i + k < P; ++k) grad_out[4 * i + k] = t[k];
+        for (int w = 1; w < world; ++w) *reinterpret_cast<float4*>(mailboxes[(rank + w) % world] + res_off + 16 * (size_t)i) = g;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        ticket_s = atomicAdd(bar_ctr2, 1u);
+    }
+    __syncthreads();
+    if (ticket_s == gridDim.x - 1) {
+        if (threadIdx.x == 0) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world)
+            st_release_sys(reinterpret_cast<unsigned long long*>(mailboxes[threadIdx.x] + off2) + par * XCHG_MAX_WORLD + rank, step + 1ull);
+        if (threadIdx.x == 0) {
+            *bar_ctr2 = 0u;
+            *step_ctr = step + 1ull;
+        }
+    }
+    // ---- 3. all-gather: the other owners' slices out of this rank's result region ----
+    if (threadIdx.x < world) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + off2) + par * XCHG_MAX_WORLD + threadIdx.x;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < step + 1ull)
+            if (++spins > (1u << 26)) __trap();
+    }
+    __syncthreads();
+    for (int64_t i = g0; i < n4; i += gstride) {
+        if (i >= lo && i < hi) continue;
+        const float4 g = __ldcg(reinterpret_cast<const float4*>(mine + res_off + 16 * (size_t)i));
+        const float t[4] = {g.x, g.y, g.z, g.w};
+        for (int k = 0; k < 4 && 4 * i + k < P; ++k) grad_out[4 * i + k] = t[k];
+    }
+}
+
 // All-gather of a short fp64 vector (the rewards of every rank's returns: the standardisation of fd_state batches needs
 // the mean / std over ALL ranks' returns before the coefficients can be formed, learner/finite_differences.py:40-43) with
 // the same mailbox protocol and step counter: push n doubles into slot [parity][rank] of every peer, publish, wait for all
@@ -219,7 +349,9 @@ extern "C" size_t dfd_xchg_mailbox_bytes(int64_t n_params, int world) {
     // flag-protocol slots, then (short parameter vectors only) the low-latency packet region of the one-kernel step
     // (csrc/fd_tail.cu: tl_ll_slot_bytes - 8 bytes per value + 16 packets of statistics)
     const size_t ll_slot = n_params <= 32768 ? (size_t)((n_params + 3) / 4 * 4 + 16) * 8 : 0;
-    return XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params) + 2 * (size_t)world * ll_slot;
+    // long vectors: second flag array + result region (2 parities) of the two-phase kernel
+    const size_t rs = n_params > 32768 ? XCHG_FLAGS + 2 * xchg_slot_bytes(n_params) : 0;
+    return XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params) + 2 * (size_t)world * ll_slot + rs;
 }
 
 extern "C" int dfd_xchg_mailbox_create(dfd_ctx* ctx, size_t bytes, void** mailbox, unsigned char* ipc_handle64) {
@@ -269,6 +401,14 @@ extern "C" int dfd_xchg_allreduce(dfd_ctx* ctx, void* const* mailboxes, int rank
         cudaMemset(g_xchg_prof, 0, 64);
     }
     unsigned long long* prof = g_xchg_prof;
+    static const bool one_phase = getenv("DFD_XCHG_ONEPHASE") != nullptr;
+    if (world >= 4 && n_params >= 65536 && !one_phase) {      // long vectors on many ranks: reduce-scatter + all-gather
+        const size_t off2 = XCHG_HDR + XCHG_FLAGS + 2 * (size_t)world * xchg_slot_bytes(n_params);
+        xchg_allreduce_rs_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params,
+                                                                                  grad_partial, stats5, grad_out, off2);
+        DFD_LAUNCHED(ctx);
+        return 0;
+    }
     xchg_allreduce_kernel<<<grid, XCHG_THREADS, 0, (cudaStream_t)stream>>>((char* const*)mailboxes, rank, world, n_params,
                                                                            grad_partial, stats5, grad_out, prof);
     DFD_LAUNCHED(ctx);
