@@ -362,6 +362,9 @@ int dfd_mlp_forward_ws_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd
 int dfd_mlp_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                                 const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
                                 int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
+int dfd_mlp_forward_ws16_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
+                              const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
+                              int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
 int dfd_mlp_forward_stream_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, const dfd_table* table, const float* theta,
                                 const int64_t* idx, const int8_t* sign, int n_members, float sigma, const float* obs,
                                 int obs_per_member, float* out, int approx_tanh, cudaStream_t st);
@@ -386,6 +389,10 @@ extern "C" int dfd_policy_forward(dfd_ctx* ctx, const dfd_policy_desc* desc, con
     if (desc->precision >= 1 && desc->kind == DFD_POLICY_MUJOCO) {
         // 64x64 nets: warp-specialised resident-weight kernel; wide nets: warp-specialised streaming kernel;
         // anything else: the generic tcgen05 kernel
+        // 64x64 nets with the table mirror registered: resident theta image + eps tiles straight from the table by TMA
+        const int r6 = dfd_mlp_forward_ws16_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member, out,
+                                                 desc->precision == 2 ? 1 : 0, st);
+        if (r6 >= 0) return r6;
         const int rc = dfd_mlp_forward_ws_impl(ctx, desc, table, theta, idx, sign, n_members, sigma, obs, obs_per_member, out,
                                                desc->precision == 2 ? 1 : 0, st);
         if (rc >= 0) return rc;

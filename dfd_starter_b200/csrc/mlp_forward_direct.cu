@@ -450,12 +450,18 @@ mlp_forward_direct_kernel(const DrParams p, const __grid_constant__ DrMaps maps,
 
 static inline int64_t dr_stride16(int64_t size) { return (size + 64 + 63) / 64 * 64; }
 
+// fp16 theta scratch: at least 16 384 halves (the resident theta image of the 64 x 64 kernel needs 9 216 whatever P is)
+static inline int64_t dr_theta16_cap(int64_t n_params) { return n_params > 16384 ? n_params : 16384; }
+
 extern "C" size_t dfd_table_scaled16_bytes(int64_t size, int64_t n_params) {
-    return (size_t)8 * (size_t)dr_stride16(size) * 2 + dfd_align_up((size_t)n_params * 2, 256) + 256;
+    return (size_t)8 * (size_t)dr_stride16(size) * 2 + dfd_align_up((size_t)dr_theta16_cap(n_params) * 2, 256) + 256;
 }
+
+int dfd_ws16_supported(const dfd_policy_desc* desc);
 
 extern "C" int dfd_policy_direct_supported(const dfd_policy_desc* desc) {
     if (!desc || desc->kind != DFD_POLICY_MUJOCO) return 0;
+    if (dfd_ws16_supported(desc)) return 1;
     const int K0 = desc->n_in, N1 = desc->h1, N2 = desc->h2, nout = 2 * desc->n_act;
     // whole 16-byte groups of halves along K in every layer (row pitch and layer offsets of the TMA maps), hidden widths in
     // whole 128-column accumulator halves, head within one MMA
@@ -475,7 +481,7 @@ extern "C" int dfd_table_build_scaled16(dfd_ctx* ctx, const dfd_table* table, fl
     ctx->scaled16 = buf;
     ctx->scaled16_stride = s16;
     ctx->theta16 = (char*)buf + (size_t)8 * (size_t)s16 * 2;
-    ctx->theta16_cap = n_params;
+    ctx->theta16_cap = dr_theta16_cap(n_params);
     return 0;
 }
 

@@ -216,3 +216,46 @@ def test_fd_state_dots_from_the_fp16_mirror(D, paired):
         rel = float(np.max(np.abs(fd.gradient_memory - ofd.gradient_memory)) / np.max(np.abs(ofd.gradient_memory)))
         assert rel <= 1e-5, (s, rel)
         assert abs(upd - oupd) <= 1e-5 * oupd
+
+
+def test_resident_theta_direct_kernel_for_64x64_nets():
+    """mlp_forward_ws16_kernel (opt-in: DFD_WS16=1): C2 shape 17-64-64-6 with the 17-wide first-layer rows fetched as eight
+    class boxes (rows 8q + c) straight from the table mirror, theta image resident, four items in flight.  Runs in a
+    subprocess because the switch is read once per process; checked against the CPU oracle per member (pairs, unrelated and
+    unperturbed members, ragged observation counts)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import dfd_starter_b200 as D
+from oracle import dfd_oracle as O
+L = O.mujoco_layout(17, 6, 64, 64); P = L.num_params
+table = D.SharedNoiseTable(1_000_000, P, 123, device=0)
+theta = O.synthetic_theta(L, 3)
+rng = np.random.RandomState(1)
+for M, E, prec, tol in ((600, 128, 1, 2e-3), (301, 200, 2, 4e-3)):
+    pol = D.MujocoPolicy(17, 6, seed=3, device=0, precision=prec).bind_table(table)
+    pol.set_trainable_flat(theta)
+    idx = rng.randint(0, 1_000_000 - P, size=M).astype(np.int64)
+    if M %% 2 == 0:
+        idx[M // 2:] = idx[:M // 2]
+    sign = np.where(np.arange(M) < M // 2, 1, -1).astype(np.int8)
+    sign[3] = 0
+    obs = rng.randn(M, E, 17).astype(np.float32)
+    out = pol.forward_members(torch.from_numpy(idx).cuda(), torch.from_numpy(sign).cuda(), torch.from_numpy(obs).cuda(), 0.02).cpu().numpy()
+    assert pol.ctx._scaled16 is not None
+    worst = 0.0
+    for m in (0, 3, M // 2, M - 1, 17):
+        th = theta if sign[m] == 0 else O.perturb(theta, 0.02, table._table[idx[m]:idx[m] + P], int(sign[m]))
+        mean, std = O.mujoco_forward(L, th, obs[m])
+        worst = max(worst, float(np.abs(out[m] - np.concatenate([mean, std], -1)).max()))
+    assert worst <= tol, worst
+    assert np.isfinite(out).all()
+print("ws16 ok")
+''' % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=280, cwd=root,
+                         env=dict(os.environ, DFD_WS16="1"))
+    assert out.returncode == 0 and "ws16 ok" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
