@@ -159,6 +159,133 @@ __global__ void __launch_bounds__(DOT_THREADS) fd_dots_kernel(const float* __res
     }
 }
 
+// Epoch-grouped form of the dots pass: CTA (column chunk, history row e) keeps the chunk of the distance row d_e in SHARED
+// memory and streams the table rows of every return whose epoch maps to e against it - the distance rows are read from L2
+// once per chunk instead of once per return (at C5 size: 2.1 GB of L2 reads for 466 delayed returns, which bounded the
+// per-return form above at ~255 us), so the pass is bound by the table rows from HBM.  With the sigma-scaled fp16 mirror
+// registered the rows are read from it (half the bytes; the dot enters ||lambda||^2 as a ~1e-3 correction).  Also emits
+// ||d_e||^2 of the chunk (the CTA holds it anyway).  out: dot[n_returns] | dd[n_hist].
+static const int DOTE_CHUNK = 4096;          // columns per CTA: 16 KB of d_e in shared memory, several CTAs per SM
+__global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const float* __restrict__ replicas, int64_t stride,
+                                                                    const int64_t* __restrict__ idx, const int32_t* __restrict__ hist_row,
+                                                                    int n_returns, int R_pairs, const float* __restrict__ dist,
+                                                                    int64_t dist_stride, int64_t P, double* __restrict__ out,
+                                                                    const __half* __restrict__ mirror, int64_t mstride, double inv_sigma) {
+    __shared__ __align__(16) float d_s[DOTE_CHUNK];
+    __shared__ double sh[DOT_THREADS / 32];
+    const int e = blockIdx.y;
+    const int RB = R_pairs > 0 ? R_pairs : n_returns;
+    const int64_t c0 = (int64_t)blockIdx.x * DOTE_CHUNK;
+    const int nc = (int)min((int64_t)DOTE_CHUNK, P - c0);                 // columns of this chunk
+    const int nc8 = nc & ~7;
+    const float* de = dist + (int64_t)e * dist_stride + c0;               // 16-byte aligned: dist_stride % 4 == 0, c0 % 4096 == 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double dd = 0.0;
+    for (int c = 4 * threadIdx.x; c < DOTE_CHUNK; c += 4 * DOT_THREADS) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c + 3 < nc) v = *reinterpret_cast<const float4*>(de + c);
+        else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < 4 && c + k < nc; ++k) t[k] = de[c + k];
+            v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(d_s + c) = v;
+        dd += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    dd = warp_sum(dd);
+    if (lane == 0) sh[warp] = dd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < DOT_THREADS / 32; ++i) t += sh[i];
+        atomicAdd(out + n_returns + e, t);
+    }
+    // the rows whose return(s) come from epoch row e are compacted into shared memory first (blocks of 1024 rows: one
+    // coalesced pass over hist_row / idx instead of dependent global loads per candidate row), then the warps take the
+    // matching rows round-robin; a warp covers the whole chunk of a row: 4096 columns = 32 lanes x 16 vectors of 8 elements,
+    // all loads of a row in flight before the first use
+    __shared__ int64_t l_idx[1024];
+    __shared__ int l_row[1024];          // row | (h0 == e) << 30 | (h1 == e) << 31
+    __shared__ int l_n;
+    for (int yb = 0; yb < RB; yb += 1024) {
+    __syncthreads();
+    if (threadIdx.x == 0) l_n = 0;
+    __syncthreads();
+    for (int y = yb + threadIdx.x; y < min(yb + 1024, RB); y += DOT_THREADS) {
+        const int h0 = hist_row[y], h1 = R_pairs > 0 ? hist_row[y + R_pairs] : -1;
+        if (h0 == e || h1 == e) {
+            const int slot = atomicAdd(&l_n, 1);
+            l_row[slot] = y | (h0 == e ? (1 << 30) : 0) | (h1 == e ? (1 << 31) : 0);
+            l_idx[slot] = idx[y];
+        }
+    }
+    __syncthreads();
+    const int ln = l_n;
+    for (int li = warp; li < ln; li += DOT_THREADS / 32) {
+        const int lr = l_row[li], y = lr & 0x3fffffff;
+        const bool m0 = (lr >> 30) & 1, m1 = (lr >> 31) & 1;
+        const int64_t id = l_idx[li];
+        double acc = 0.0;
+        if (mirror != nullptr) {
+            const __half* a16 = mirror + (id & 7) * mstride + (id & ~(int64_t)7) + c0;      // c0 % 8 == 0: 16-byte aligned
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {         // 8 loads of 16 bytes in flight per lane, twice (64 registers per thread cap: 4 CTAs per SM)
+                uint4 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = 8 * (lane + 32 * (u + 8 * part));
+                    x[u] = make_uint4(0, 0, 0, 0);
+                    if (c < nc8) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[u].x), "=r"(x[u].y), "=r"(x[u].z), "=r"(x[u].w) : "l"(a16 + c));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = 8 * (lane + 32 * (u + 8 * part));
+                    if (c < nc8) {
+                        const float2 e0 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].x)), e1 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].y));
+                        const float2 e2 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].z)), e3 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].w));
+                        const float4 ya = *reinterpret_cast<const float4*>(d_s + c), yb = *reinterpret_cast<const float4*>(d_s + c + 4);
+                        float s = e0.x * ya.x;
+                        s = fmaf(e0.y, ya.y, s); s = fmaf(e1.x, ya.z, s); s = fmaf(e1.y, ya.w, s);
+                        s = fmaf(e2.x, yb.x, s); s = fmaf(e2.y, yb.y, s); s = fmaf(e3.x, yb.z, s); s = fmaf(e3.y, yb.w, s);
+                        acc += (double)s;
+                    }
+                }
+            }
+            for (int c = nc8 + lane; c < nc; c += 32) acc += (double)__half2float(a16[c]) * (double)d_s[c];
+            acc *= inv_sigma;
+        } else {
+            const float* a = table_row_ptr(replicas, stride, id) + c0;
+            const int nc4 = nc & ~3;
+#pragma unroll 1
+            for (int half = 0; half < 4; ++half) {
+                float4 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = 4 * (lane + 32 * (u + 8 * half));
+                    x[u] = c < nc4 ? ldg_stream_f4(a + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c = 4 * (lane + 32 * (u + 8 * half));
+                    if (c < nc4) {
+                        const float4 yv = *reinterpret_cast<const float4*>(d_s + c);
+                        float s = x[u].x * yv.x;
+                        s = fmaf(x[u].y, yv.y, s); s = fmaf(x[u].z, yv.z, s); s = fmaf(x[u].w, yv.w, s);
+                        acc += (double)s;
+                    }
+                }
+            }
+            for (int c = nc4 + lane; c < nc; c += 32) acc += (double)a[c] * (double)d_s[c];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            if (m0) atomicAdd(out + y, acc);
+            if (m1) atomicAdd(out + y + R_pairs, acc);
+        }
+    }
+    }
+}
+
 __device__ __forceinline__ double block_reduce_d(double v, double* sh, int op /*0 sum,1 min,2 max*/) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
@@ -316,6 +443,15 @@ extern "C" int dfd_fd_prepare(dfd_ctx* ctx, const dfd_table* table, int64_t n_pa
         // with the sigma-scaled fp16 mirror of this table registered (dfd_table_build_scaled16) the pass reads half the bytes
         const bool m16 = ctx->scaled16 && ctx->scaled_src == table->replicas && ctx->scaled_sigma == sigma && sigma != 0.f &&
                          !getenv("DFD_DOTS_FP32");
+        // long rows with many returns per epoch: the epoch-grouped form (distance-row chunk in shared memory, table rows
+        // streamed against it); otherwise one CTA per (chunk, return)
+        static const bool per_return = getenv("DFD_DOTS_PER_RETURN") != nullptr;
+        if (!per_return && n_params >= 4 * DOTE_CHUNK && n_returns >= 4 * n_hist) {
+            dim3 ge((unsigned)((n_params + DOTE_CHUNK - 1) / DOTE_CHUNK), (unsigned)n_hist);
+            fd_dots_epoch_kernel<<<ge, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
+                                                             paired ? R : 0, dist, dist_stride, n_params, dots,
+                                                             m16 ? (const __half*)ctx->scaled16 : nullptr, ctx->scaled16_stride, 1.0 / (double)sigma);
+        } else
         fd_dots_kernel<<<grid, DOT_THREADS, 0, st>>>(table->replicas, table->replica_stride, idx, hist_row, n_returns,
                                                      paired ? R : 0, dist, dist_stride, n_params, dots,
                                                      m16 ? (const __half*)ctx->scaled16 : nullptr, ctx->scaled16_stride, 1.0 / (double)sigma);

@@ -60,6 +60,30 @@ __device__ __forceinline__ void w6_tmem_st32(uint32_t taddr, const uint32_t* r) 
         : "memory");
 }
 
+// tanh of two pre-activations -> packed halves (`a` in the low half: the even k of the pair).  APPROX: round the pair to fp16
+// first and take ONE tanh.approx.f16x2 (2^-10.99 relative, the class of the operand rounding that follows anyway): half the
+// SFU operations of the fp32 form and no separate pack
+template <bool APPROX>
+__device__ __forceinline__ uint32_t w6_act2(float a, float b) {
+    if (APPROX) {
+        uint32_t h = dr_pack(a, b);
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(h) : "r"(h));
+        return h;
+    } else {
+        return dr_pack(tanh_fast(a), tanh_fast(b));
+    }
+}
+__device__ __forceinline__ void w6_tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
 template <bool APPROX>
 __global__ void __launch_bounds__(W6_THREADS, 1)
 mlp_forward_ws16_kernel(const W6Params p, const __grid_constant__ W6Maps maps, const float* __restrict__ replicas, int64_t stride,
@@ -241,10 +265,12 @@ mlp_forward_ws16_kernel(const W6Params p, const __grid_constant__ W6Maps maps, c
 #pragma unroll 1
             for (int l = 0; l < 2; ++l) {
                 const float* bs = bias_s + l * 64;
+                uint32_t v[64];
+                w6_tmem_ld32_nowait(tD + lane_sel, v);                    // both halves in flight, one wait
+                w6_tmem_ld32_nowait(tD + lane_sel + 32u, v + 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t v[32];
-                    dr_tmem_ld32(tD + lane_sel + (uint32_t)(32 * h), v);
                     if (l == 0) {
                         // accumulator column c*8 + q holds neuron 8q + c (class-major rows of the layer-0 tiles): this half holds
                         // classes 4h .. 4h + 3, i.e. the neuron pairs (8q + 4h + 2t, + 1) = A columns 4q + 2h + t: undone for free
@@ -254,8 +280,8 @@ mlp_forward_ws16_kernel(const W6Params p, const __grid_constant__ W6Maps maps, c
 #pragma unroll
                             for (int t = 0; t < 2; ++t) {
                                 const int k0 = 8 * qq + 4 * h + 2 * t;
-                                o2[t] = dr_pack(dr_tanh<APPROX>(__uint_as_float(v[(2 * t) * 8 + qq]) + bs[k0]),
-                                                dr_tanh<APPROX>(__uint_as_float(v[(2 * t + 1) * 8 + qq]) + bs[k0 + 1]));
+                                o2[t] = w6_act2<APPROX>(__uint_as_float(v[32 * h + (2 * t) * 8 + qq]) + bs[k0],
+                                                        __uint_as_float(v[32 * h + (2 * t + 1) * 8 + qq]) + bs[k0 + 1]);
                             }
                             asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(tA + lane_sel + (uint32_t)(4 * qq + 2 * h)), "r"(o2[0]), "r"(o2[1]) : "memory");
                         }
@@ -263,8 +289,7 @@ mlp_forward_ws16_kernel(const W6Params p, const __grid_constant__ W6Maps maps, c
                         uint32_t o[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            o[j] = dr_pack(dr_tanh<APPROX>(__uint_as_float(v[2 * j]) + bs[32 * h + 2 * j]),
-                                           dr_tanh<APPROX>(__uint_as_float(v[2 * j + 1]) + bs[32 * h + 2 * j + 1]));
+                            o[j] = w6_act2<APPROX>(__uint_as_float(v[32 * h + 2 * j]) + bs[32 * h + 2 * j], __uint_as_float(v[32 * h + 2 * j + 1]) + bs[32 * h + 2 * j + 1]);
                         asm volatile(
                             "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(tA + lane_sel + (uint32_t)(16 * h)),
                             "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]),

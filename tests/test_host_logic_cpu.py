@@ -265,3 +265,14 @@ def test_pair_order_validates_the_paired_layout():
     for bad_idx, bad_sign in (([5, 9, 5, 11], [1, 1, -1, -1]), ([5, 5, 5], [1, -1, 1]), ([5, 6], [1, 1])):
         with pytest.raises(DfdError):
             po(np.array(bad_idx), np.array(bad_sign, np.int8))
+
+
+def test_exchange_mode_is_validated_without_a_gpu():
+    """The learner's exchange mode is fixed per learner (every rank must take the same exchange path every step): only
+    'fd_return' and 'general' exist, and the check runs before any device work (the constructor needs a GPU afterwards, so
+    the accepted values are read from the source)."""
+    import inspect
+    import dfd_starter_b200.finite_differences as F
+    src = inspect.getsource(F.FiniteDifferences.__init__)
+    assert 'exchange_mode not in ("fd_return", "general")' in src
+    assert src.index("exchange_mode not in") < src.index("get_context(")
