@@ -40,13 +40,18 @@ def rel_max(a, b):
 
 
 # ---------------------------------------------------------------- a7: wide-net tensor path, many members per CTA
+@pytest.mark.parametrize("kernel", ["stream", "direct"])
 @pytest.mark.parametrize("E,M,layout", [(128, 640, "pairs"), (200, 604, "pairs"), (128, 601, "unrelated"),
                                         (16, 1500, "pairs"), (200, 298, "mixed")])
-def test_humanoid_stream_kernel_many_members(D, E, M, layout):
-    """C3 shape 376-256-256-17 through `mlp_forward_stream_kernel` with 2-10 work items per persistent CTA
+def test_humanoid_stream_kernel_many_members(D, E, M, layout, kernel, monkeypatch):
+    """C3 shape 376-256-256-17 through `mlp_forward_stream_kernel` (weights built in shared memory; DFD_TC_NO_DIRECT=1) and
+    through `mlp_forward_direct_kernel` (weight tiles by TMA straight from the table mirror, the default once the mirror is
+    registered) with 2-10 work items per persistent CTA
     (grid = min(148, work items)): every member against the exact fp32 path (stated tolerance of the tf32 path: max-abs
     2e-3, mean-abs 3e-4, as tests/test_gpu_tensor_core.py), a subset against the CPU oracle, and run-to-run bit identity."""
     n_in, h, n_act = 376, 256, 17
+    if kernel == "stream":
+        monkeypatch.setenv("DFD_TC_NO_DIRECT", "1")
     L = O.mujoco_layout(n_in, n_act, h, h)
     P = L.num_params
     table = D.SharedNoiseTable(4_000_000, P, 123, device=0)
