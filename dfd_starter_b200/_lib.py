@@ -21,6 +21,7 @@ SYMBOLS = [
     "dfd_fd_step_fused_scratch_bytes", "dfd_fd_step_fused", "dfd_wire_count_returns", "dfd_wire_decode_returns",
     "dfd_strategy_distances", "dfd_host_stage", "dfd_normalize_obs", "dfd_member_obs_stats",
     "dfd_xchg_gather_f64", "dfd_table_scaled16_bytes", "dfd_table_build_scaled16", "dfd_table_drop_scaled16", "dfd_policy_direct_supported",
+    "dfd_rng_scratch_bytes", "dfd_rng_normal_rows",
 ]
 
 
@@ -107,6 +108,8 @@ def load():
     proto("dfd_strategy_distances", i32, [vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp])
     proto("dfd_normalize_obs", i32, [vp, vp, i64, i32, vp, vp, i32, f32, vp, vp])
     proto("dfd_member_obs_stats", i32, [vp, vp, vp, i32, i32, i32, vp, vp])
+    proto("dfd_rng_scratch_bytes", sz, [i32, i64, i64, f64])
+    proto("dfd_rng_normal_rows", i32, [vp, vp, i32, i64, i64, vp, f64, vp, vp, vp, i64, vp, vp, i32, i32, f64, vp, sz, vp])
     proto("dfd_host_stage", i32, [vp, vp, vp, sz, vp])
     proto("dfd_wire_count_returns", i64, [C.c_char_p, sz])
     proto("dfd_wire_decode_returns", i64, [C.c_char_p, sz, i32, i64, P(DfdReturnSoa)])

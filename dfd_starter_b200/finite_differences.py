@@ -92,7 +92,7 @@ class FiniteDifferences(object):
         self.lib = self.ctx.lib
         dev = self.ctx.device
         # a shared table lives on the device for the whole run; other noise sources (RNGNoiseSource, SimpleNoiseSource:
-        # utils/noise_sources.py:4-33) are decoded on the host per batch and staged as a RowTable
+        # utils/noise_sources.py:4-33) are staged per batch as a RowTable - drawn on the device (RNGNoiseSource) or on the host
         self.table = noise_source.device_table if hasattr(noise_source, "device_table") else None
         P = int(policy.num_params)
         self.P = P
@@ -181,10 +181,18 @@ class FiniteDifferences(object):
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
         ok = np.array([(e == self.epoch) or (e in self._dist_epoch) for e in epochs], dtype=bool)
-        rows = [np.asarray(self.noise_source.decode(r.encoded_noise), dtype=np.float32) for r, k in zip(batch, ok) if k]
-        if not rows:
+        if not ok.any():
             return self.step_arrays(epochs, np.zeros(len(batch), np.int64), np.ones(len(batch), np.int8), rewards, policy_reward)
-        rt = RowTable(self.ctx, np.stack(rows))
+        if getattr(self.noise_source, "device_rows", False):
+            # RNGNoiseSource: the accepted returns' vectors are redrawn from their keys ON THE DEVICE, bit-identical to
+            # decode() (csrc/rng_normal.cu), straight into the row table; the source's generator ends where the last
+            # decode() would have left it
+            rt = RowTable(self.ctx, shape=(int(ok.sum()), self.P))
+            self.noise_source.decode_rows(self.ctx, [r.encoded_noise for r, k in zip(batch, ok) if k], rt.raw, rt.Ps)
+            rt.build()
+        else:
+            rt = RowTable(self.ctx, np.stack([np.asarray(self.noise_source.decode(r.encoded_noise), dtype=np.float32)
+                                              for r, k in zip(batch, ok) if k]))
         idx = np.zeros(len(batch), dtype=np.int64)
         idx[ok] = rt.idx
         self.table = rt

@@ -76,30 +76,140 @@ class SharedNoiseTable(object):
         return self.to_device()
 
 
+# arguments on which glibc's two builds of log1p (plain / -mfma, csrc/rng_normal_core.h) round differently:
+# (u, log1p(-u) of the plain build, log1p(-u) of the fused build)
+_LOG1P_PROBES = (
+    ("0x1.cea9fc931f76cp-3", "-0x1.0636846356c73p-2", "-0x1.0636846356c74p-2"),
+    ("0x1.59f5ba805f9c0p-5", "-0x1.617a3c45aff1ap-5", "-0x1.617a3c45aff1bp-5"),
+    ("0x1.3965b6984e77ep-2", "-0x1.76207f9db2642p-2", "-0x1.76207f9db2641p-2"),
+    ("0x1.a840cb21997efp-1", "-0x1.c38cdbde6e899p+0", "-0x1.c38cdbde6e898p+0"),
+)
+
+
+def libm_log1p_fused():
+    """Which build of log1p this process's libm resolved to (numpy's ziggurat tail calls it): 1 = the FMA build,
+    0 = the plain one.  Anything else is a libm the device restatement was not pinned against: raise."""
+    import math
+    got = [math.log1p(-float.fromhex(u)).hex() for u, _, _ in _LOG1P_PROBES]
+    if got == [f for _, _, f in _LOG1P_PROBES]:
+        return 1
+    if got == [p for _, p, _ in _LOG1P_PROBES]:
+        return 0
+    raise _lib.DfdError("this libm's log1p matches neither glibc build the device generator was pinned against "
+                        "(%s): RNGNoiseSource(device=False) draws on the host" % ", ".join(got))
+
+
+def pcg64_advance(state, inc, words):
+    """State of numpy's PCG64 `words` 64-bit outputs after (state, inc)."""
+    bg = np.random.PCG64()
+    bg.state = {"bit_generator": "PCG64", "state": {"state": int(state), "inc": int(inc)}, "has_uint32": 0, "uinteger": 0}
+    bg.advance(int(words))
+    return int(bg.state["state"]["state"])
+
+
+class RngStatusError(_lib.DfdError):
+    """The device generator declined to decide a draw (status word of dfd_rng_normal_rows)."""
+
+    def __init__(self, status):
+        _lib.DfdError.__init__(self, "dfd_rng_normal_rows status 0x%x: a wedge comparison within 64 ulps of exp() "
+                               "(or a tail loop beyond 60 rounds) is not decided on the device" % status)
+        self.status = status
+
+
+def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_stride=None, theta=None, sigma=0.0,
+                       dest_row=None, want_f64=False, force_serial=False, margin=0.0):
+    """dfd_rng_normal_rows (include/dfd_b200.h): numpy's Generator(PCG64).standard_normal drawn on the device, bit-exact.
+    streams: [n, 2] Python ints or an [n, 4] uint64 array {state_lo, state_hi, inc_lo, inc_hi}.
+    Returns (rows fp32 device tensor [rows, row_stride] or None, rows_f64 or None, row_words int64 [n, rows_per_stream + 1],
+    status).  Retries with a larger word budget on DFD_RNG_SHORT; raises RngStatusError on an undecided draw."""
+    lib = ctx.lib
+    if not (isinstance(streams, np.ndarray) and streams.dtype == np.uint64):
+        m64 = (1 << 64) - 1
+        streams = np.array([[int(s) & m64, int(s) >> 64, int(i) & m64, int(i) >> 64] for s, i in streams], dtype=np.uint64)
+    streams = np.ascontiguousarray(streams.reshape(-1, 4))
+    n = streams.shape[0]
+    n_rows = n * int(rows_per_stream)
+    row_stride = int(row_stride or n_params)
+    fused = libm_log1p_fused()
+    with torch.cuda.device(ctx.device):
+        d_streams = torch.from_numpy(streams.view(np.int64)).to(ctx.device)
+        if out is None:
+            n_out = n_rows if dest_row is None else int(np.max(dest_row)) + 1
+            out = torch.empty(n_out * row_stride, dtype=torch.float32, device=ctx.device)
+        out64 = torch.empty(out.numel(), dtype=torch.float64, device=ctx.device) if want_f64 else None
+        d_dest = None if dest_row is None else torch.from_numpy(np.ascontiguousarray(dest_row, dtype=np.int32)).to(ctx.device)
+        d_words = torch.zeros(n * (int(rows_per_stream) + 1), dtype=torch.int64, device=ctx.device)
+        d_status = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+        for margin in ((margin or 1.04), 1.25, 2.0, 8.0):
+            nbytes = int(lib.dfd_rng_scratch_bytes(n, int(rows_per_stream), int(n_params), float(margin)))
+            scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=ctx.device)
+            _lib.check(lib.dfd_rng_normal_rows(ctx.handle, ptr(d_streams), n, int(rows_per_stream), int(n_params), ptr(theta),
+                                               float(sigma), ptr(d_dest), ptr(out), ptr(out64), row_stride, ptr(d_words),
+                                               ptr(d_status), fused, 1 if force_serial else 0, float(margin),
+                                               aligned_ptr(scratch), nbytes, ctx.stream), "dfd_rng_normal_rows")
+            status = int(d_status.item()) & 0xffffffff
+            del scratch
+            if not status & 4:
+                break
+        else:
+            raise _lib.DfdError("dfd_rng_normal_rows: word budget still short at 8 words per normal")
+        if status & 3:
+            raise RngStatusError(status)
+        words = d_words.cpu().numpy().reshape(n, int(rows_per_stream) + 1)
+    return out, out64, words, status
+
+
 class RNGNoiseSource(object):
     """utils/noise_sources.py:4-20 restated for numpy >= 2 (the reference reads `rng.__getstate__()['state']`, which
     newer numpy no longer lays out that way; the PCG64 words themselves are the same).  The key is the generator's
     `state,inc` BEFORE the draw, the noise is `standard_normal(P)` in fp64; `decode` rewinds the SAME generator to the
     key and redraws (so, as in the reference, it also moves the stream `sample()` continues from).
-    Noise is generated on the host; the learner and the worker stage the vectors on the device per batch
-    (`RowTable`).  In-kernel PCG64 + ziggurat generation is SURVEY.md §8(f) row N4."""
 
-    def __init__(self, n_params, random_seed=123):
+    `sample` / `decode` are the reference's per-member host calls.  The batched worker and the learner do not call them:
+    `sample_rows` / `decode_rows` draw the rows of a whole batch on the device (csrc/rng_normal.cu, bit-identical to
+    numpy: SURVEY.md §8(f) row N4) and leave this object's generator where the per-member calls would have left it.
+    device=False keeps the host path (`Worker` / `FiniteDifferences` then stage host-drawn rows)."""
+
+    def __init__(self, n_params, random_seed=123, device=True):
         self.rng = np.random.default_rng(np.random.SeedSequence(random_seed))
         self.n_params = n_params
+        self.device_rows = bool(device)
+
+    def _state(self):
+        st = self.rng.bit_generator.state["state"]
+        return int(st["state"]), int(st["inc"])
+
+    def _set_state(self, state, inc):
+        self.rng.bit_generator.state = {"bit_generator": "PCG64", "state": {"state": int(state), "inc": int(inc)},
+                                        "has_uint32": 0, "uinteger": 0}
 
     def sample(self):
-        st = self.rng.bit_generator.state["state"]
-        state = "{},{}".format(st["state"], st["inc"])
+        state = "{},{}".format(*self._state())
         noise = self.rng.standard_normal(size=self.n_params)
         return state, noise
 
     def decode(self, state):
         state_data = str(state).split(",")
-        self.rng.bit_generator.state = {"bit_generator": "PCG64",
-                                        "state": {"state": int(state_data[0]), "inc": int(state_data[1])},
-                                        "has_uint32": 0, "uinteger": 0}
+        self._set_state(state_data[0], state_data[1])
         return self.rng.standard_normal(size=self.n_params)
+
+    # ---- batched device forms ------------------------------------------------
+    def sample_rows(self, ctx, n, out, row_stride, dest_row=None, theta=None, sigma=0.0):
+        """n successive `sample()` calls: returns their keys; row j goes to row dest_row[j] of `out` (fp32 device
+        buffer, row_stride apart) as fp32(eps) or, with theta, as fp32(fp64(theta) + sigma * eps) (worker.py:28)."""
+        s0, inc = self._state()
+        _, _, words, _ = device_normal_rows(ctx, [(s0, inc)], n, self.n_params, out=out, row_stride=row_stride, theta=theta,
+                                            sigma=sigma, dest_row=dest_row)
+        keys = ["{},{}".format(pcg64_advance(s0, inc, w), inc) for w in words[0, :n]]
+        self._set_state(pcg64_advance(s0, inc, words[0, n]), inc)
+        return keys
+
+    def decode_rows(self, ctx, keys, out, row_stride):
+        """`decode(key)` for every key, in order: row j of `out` = fp32(noise_j)."""
+        streams = [tuple(int(v) for v in str(k).split(",")) for k in keys]
+        _, _, words, _ = device_normal_rows(ctx, streams, 1, self.n_params, out=out, row_stride=row_stride)
+        s, inc = streams[-1]
+        self._set_state(pcg64_advance(s, inc, words[-1, 1]), inc)    # where the last decode() leaves the generator
 
 
 class SimpleNoiseSource(object):
@@ -118,29 +228,46 @@ class SimpleNoiseSource(object):
 
 
 class RowTable(object):
-    """N host vectors staged as a throw-away device table: row j lives at entries [j*Ps, j*Ps + P) with Ps = P rounded
+    """N vectors staged as a throw-away device table: row j lives at entries [j*Ps, j*Ps + P) with Ps = P rounded
     up to 4, so every row starts 16-byte aligned in replica 0 and all kernels (forward, prepare, reduce, one-kernel
-    step) run unchanged with idx[j] = j*Ps.  Used for noise sources that are not a shared table."""
+    step) run unchanged with idx[j] = j*Ps.  Used for noise sources that are not a shared table.
+    rows: host array [n, P] - or shape=(n, P): `raw` is left zeroed for a device producer (RNGNoiseSource.sample_rows /
+    decode_rows write rows at stride Ps), which then calls build()."""
 
-    def __init__(self, ctx, rows):
-        rows = np.ascontiguousarray(rows, dtype=np.float32)
-        n, P = rows.shape
+    def __init__(self, ctx, rows=None, shape=None):
+        self.ctx = ctx
+        if rows is not None:
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+            n, P = rows.shape
+        else:
+            n, P = int(shape[0]), int(shape[1])
+        self.n, self.P = n, P
         self.Ps = (P + 3) // 4 * 4
-        size = n * self.Ps + self.Ps + 8          # strictly larger than any row end; the tail is zero
-        host = np.zeros(size, dtype=np.float32)
-        host[:n * self.Ps].reshape(n, self.Ps)[:, :P] = rows
-        lib = ctx.lib
+        self.size = n * self.Ps + self.Ps + 8     # strictly larger than any row end; the tail is zero
+        with torch.cuda.device(ctx.device):
+            if rows is not None:
+                host = np.zeros(self.size, dtype=np.float32)
+                host[:n * self.Ps].reshape(n, self.Ps)[:, :P] = rows
+                self.raw = torch.from_numpy(host).to(ctx.device)
+            else:
+                self.raw = torch.zeros(self.size, dtype=torch.float32, device=ctx.device)
+        self.idx = np.arange(n, dtype=np.int64) * self.Ps
+        self.table = None
+        if rows is not None:
+            self.build()
+
+    def build(self):
+        ctx, lib, size = self.ctx, self.ctx.lib, self.size
         stride = int(lib.dfd_table_replica_stride(size))
         with torch.cuda.device(ctx.device):
-            raw = torch.from_numpy(host).to(ctx.device)
             replicas = torch.empty(4 * stride, dtype=torch.float32, device=ctx.device)
             prefix = torch.empty(size + 1, dtype=torch.float64, device=ctx.device)
             scratch = ctx.zeros_bytes(lib.dfd_table_scratch_bytes(size))
-            _lib.check(lib.dfd_table_build(ctx.handle, ptr(raw), size, ptr(replicas), stride, ptr(prefix),
+            _lib.check(lib.dfd_table_build(ctx.handle, ptr(self.raw), size, ptr(replicas), stride, ptr(prefix),
                                            aligned_ptr(scratch), scratch.numel() - 256, ctx.stream), "dfd_table_build")
-        self._keep = (raw, scratch)               # stream-ordered: freed with the object
+        self._keep = (self.raw, scratch)          # stream-ordered: freed with the object
         self.table = DeviceTable(ctx, replicas, stride, prefix, size)
-        self.idx = np.arange(n, dtype=np.int64) * self.Ps
+        return self
 
     def ref(self):
         return self.table.ref()

@@ -73,6 +73,8 @@ class Worker(object):
         device as a RowTable and evaluated in ONE batched launch against theta = 0 (0 + 1 * x == x bit for bit).
         Same two draws per member, in the same order, as the reference loop."""
         from .noise_sources import RowTable
+        if getattr(self.noise_source, "device_rows", False):
+            return self._collect_returns_device_rng(n)
         flat = np.asarray(self.policy.get_trainable_flat(), dtype=np.float32)
         rows = np.empty((n, flat.shape[0]), dtype=np.float32)
         keys, is_eval = [], np.zeros(n, dtype=bool)
@@ -88,6 +90,35 @@ class Worker(object):
         ctx = self.policy.ctx
         rt = RowTable(ctx, rows)
         view = _RowPolicyView(self.policy, rt, torch.zeros(flat.shape[0], dtype=torch.float32, device=ctx.device))
+        res = self.agent.collect_returns(view, rt.idx, np.ones(n, dtype=np.int8), 1.0)
+        return ReturnBatch(self.epoch, rt.idx, np.ones(n, dtype=np.int8), res["reward"], res["entropy"], res["timesteps"],
+                           is_eval, states=res.get("states"), keys=keys)
+
+    @torch.no_grad()
+    def _collect_returns_device_rng(self, n):
+        """`RNGNoiseSource` with the rows drawn on the device (csrc/rng_normal.cu): the same draws in the same order as
+        the loop of worker/worker.py:19-38 - the eval coin of member j comes from the worker's own generator, the
+        noise of the non-eval members from ONE pass over the noise source's PCG64 stream (their keys are the stream
+        states at the row boundaries) - and the same members: fp32(fp64(flat) + sigma * eps) built in-kernel, eval
+        members = flat.  Evaluated in one batched launch against theta = 0 like the host-drawn form."""
+        from .noise_sources import RowTable
+        ctx = self.policy.ctx
+        theta = self.policy.theta
+        P = int(theta.numel())
+        is_eval = np.array([self.rng.uniform(0, 1) < self.eval_prob for _ in range(n)], dtype=bool)
+        train = np.nonzero(~is_eval)[0]
+        rt = RowTable(ctx, shape=(n, P))
+        rows = rt.raw[:n * rt.Ps].view(n, rt.Ps)
+        keys = ["0"] * n
+        if len(train):
+            drawn = self.noise_source.sample_rows(ctx, len(train), rt.raw, rt.Ps, dest_row=train, theta=theta,
+                                                  sigma=float(self.sigma))
+            for j, k in zip(train, drawn):
+                keys[j] = k
+        if is_eval.any():
+            rows[torch.from_numpy(np.nonzero(is_eval)[0]).to(ctx.device), :P] = theta
+        rt.build()
+        view = _RowPolicyView(self.policy, rt, torch.zeros(P, dtype=torch.float32, device=ctx.device))
         res = self.agent.collect_returns(view, rt.idx, np.ones(n, dtype=np.int8), 1.0)
         return ReturnBatch(self.epoch, rt.idx, np.ones(n, dtype=np.int8), res["reward"], res["entropy"], res["timesteps"],
                            is_eval, states=res.get("states"), keys=keys)

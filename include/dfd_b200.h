@@ -334,6 +334,42 @@ int64_t dfd_wire_decode_returns(const uint8_t* host_buf, size_t len, int is_arra
 int dfd_strategy_distances(dfd_ctx* ctx, const float* a, int n_a, const float* b, int n_b, int n_frames, int width,
                            int kind, double* dists, double* row_min, int exclude_diagonal, dfd_stream stream);
 
+/* ---- RNGNoiseSource drawn on the device: utils/noise_sources.py:4-20 ------ */
+/* The reference's default noise source (run_sequential.py:89, run_server.py:78, run_client.py:123): the key of a
+ * member is the "state,inc" of a numpy PCG64 and its noise is Generator.standard_normal(n_params) drawn from that state
+ * (sample :10-13 on the worker, decode :15-20 once per return on the learner, finite_differences.py:87).  This call
+ * draws the rows of a whole batch, bit-identical to numpy's 256-layer ziggurat over PCG64 (csrc/rng_normal_core.h has
+ * the algorithm and how parity is pinned):
+ *   streams       device, n_streams x {state_lo, state_hi, inc_lo, inc_hi}: the PCG64 state each stream starts from;
+ *   every stream yields rows_per_stream consecutive rows of n_params normals (learner: one stream per return,
+ *                 rows_per_stream = 1; worker: ONE stream whose rows are its consecutive sample() calls);
+ *   row r of the launch (stream * rows_per_stream + row) goes to row dest_row[r] (device, nullable = r) of
+ *                 rows_out (fp32, nullable) and / or rows_out_f64 (the raw normals, nullable), row_stride elements apart:
+ *                 theta == NULL: rows_out = fp32(eps)                       (np.asarray(decode(key), float32))
+ *                 theta != NULL: rows_out = fp32(fp64(theta) + sigma * eps) (worker.py:28 + policy.py:40-42: product
+ *                                and sum rounded separately in fp64, then the fp32 cast of set_trainable_flat);
+ *   row_words     device, n_streams x (rows_per_stream + 1) int64: 64-bit words the stream has consumed when row r
+ *                 begins (entry rows_per_stream: when the last row ends) - the host advances the key by that count to
+ *                 name the next row's key and to leave its generator where numpy would have left it;
+ *   status        device, one word, 0 when every normal is exact; DFD_RNG_UNCERTAIN: a wedge comparison fell within
+ *                 64 ulps of exp() (not decided on the device: libdevice's exp and glibc's may round differently; about
+ *                 1e-14 per normal); DFD_RNG_SHORT: the word budget (margin x normals + 1024; < 1 selects 1.04, the
+ *                 mean is 1.022) ended early - call again with a larger margin; DFD_RNG_SERIAL (informational): a
+ *                 stream's chunk entries were resolved by the serial pass;
+ *   log1p_fused   which of glibc's two log1p builds the host's numpy calls in the ziggurat tail (1: the -mfma build
+ *                 that x86-64 CPUs with FMA select; probe: a few arguments on which the two differ);
+ *   force_serial  != 0 resolves every stream serially (tests);
+ *   scratch       256-byte aligned, dfd_rng_scratch_bytes(n_streams, rows_per_stream, n_params, margin) bytes. */
+#define DFD_RNG_UNCERTAIN 1u
+#define DFD_RNG_TAILCAP 2u
+#define DFD_RNG_SHORT 4u
+#define DFD_RNG_SERIAL 8u
+size_t dfd_rng_scratch_bytes(int n_streams, int64_t rows_per_stream, int64_t n_params, double margin);
+int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_streams, int64_t rows_per_stream, int64_t n_params,
+                        const float* theta, double sigma, const int32_t* dest_row, float* rows_out, double* rows_out_f64,
+                        int64_t row_stride, int64_t* row_words, uint32_t* status, int log1p_fused, int force_serial,
+                        double margin, void* scratch, size_t scratch_bytes, dfd_stream stream);
+
 /* ---- synthetic return (bench / tests only) ------------------------------- */
 /* Stand-in for the environment, which is outside this path (worker/agent.py is
  * out of scope): reward[m] = -mean_{e,j}(out[m,e,j]-target[j])^2 (fp64). */
