@@ -1219,6 +1219,80 @@ SUB_WORKLOADS = ("C3", "C4", "C5")
 C2_POINTS = (("E1", dict(obs_per_member=1)), ("E16", dict(obs_per_member=16)), ("E128_fp32", dict(precision="fp32")))
 
 
+def rng_noise_source_point(env, full=True):
+    """The reference drivers' DEFAULT noise source (run_sequential.py:89, run_server.py:78, run_client.py:123:
+    RNGNoiseSource - numpy PCG64 keys, standard_normal(P) per member on the worker and again per return on the learner).
+    Measured here: (1) one batch of member rows drawn on the device (RNGNoiseSource.sample_rows -> dfd_rng_normal_rows,
+    bit-identical to numpy, tests/test_gpu_rng.py) at the C2 and C3 row shapes, CUDA events around the public call,
+    next to numpy's rate on this host for the same draws (bounded sample); (2) the reference's own worker -> learner step
+    (Worker.collect_returns(n) -> FiniteDifferences.step) with that noise source at the C2 shape, rows drawn on the
+    device vs on the host."""
+    import numpy as np
+    import torch
+    import dfd_starter_b200 as D
+    ctx, dev = env.ctx, env.ctx.device
+    out = {"source": "RNGNoiseSource (numpy Generator(PCG64).standard_normal, bit-exact on the device)", "rows": {}}
+    for name, P, rows in (("C2", 6092, 2048), ("C3", 171042, 2048 if full else 128)):
+        Ps = (P + 3) // 4 * 4
+        src = D.RNGNoiseSource(P, TABLE_SEED)
+        theta = torch.zeros(P, dtype=torch.float32, device=dev)
+        buf = torch.empty(rows * Ps, dtype=torch.float32, device=dev)
+        src.sample_rows(ctx, 4, buf, Ps, theta=theta, sigma=SIGMA)                     # warm-up
+        times = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            src.sample_rows(ctx, rows, buf, Ps, theta=theta, sigma=SIGMA)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        ms = sorted(times)[1]
+        n_cpu = min(rows * P, 4_000_000)
+        g = np.random.default_rng(1)
+        t0 = time.perf_counter()
+        g.standard_normal(n_cpu)
+        cpu_rate = n_cpu / (time.perf_counter() - t0)
+        out["rows"][name] = {"rows": rows, "n_params": P, "normals": rows * P, "ms": ms, "normals_per_s": rows * P / ms * 1e3,
+                             "rows_written_GBps": rows * P * 4 / ms * 1e-6, "numpy_normals_per_s_1core": cpu_rate,
+                             "numpy_ms_extrapolated": rows * P / cpu_rate * 1e3}
+        del buf
+    # the reference's worker -> learner step with this noise source (C2 shape, 128 observations per member)
+    wl = WORKLOADS["C2"]
+    n, E = 2 * wl["pairs"], wl["E"]
+    steps = {}
+    for mode in ("device", "host"):
+        policy = D.MujocoPolicy(wl["n_in"], wl["n_act"], seed=TABLE_SEED, h1=wl["h1"], h2=wl["h2"], device=ctx.device_index, precision=0)
+        P = policy.num_params
+        src = D.RNGNoiseSource(P, TABLE_SEED, device=(mode == "device"))
+        agent = D.SyntheticAgent(policy, E, seed=1)
+
+        class Omega(object):
+            omega, min_omega, max_omega = 0.0, 0.0, 1.0
+        opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=LR)
+        opt.coef = np.sqrt(P)
+        learner = D.FiniteDifferences(policy, opt, Omega(), src, noise_std=SIGMA, batch_size=n, max_delayed_return=3)
+        worker = D.Worker(policy, agent, src, None, sigma=SIGMA, eval_prob=0.0, random_seed=TABLE_SEED)
+        n_steps = 5 if mode == "device" else 2
+        import contextlib
+        import io
+        for k in range(1 + n_steps):
+            if k == 1:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            worker.epoch = learner.epoch
+            rets = worker.collect_returns(n)
+            with contextlib.redirect_stdout(io.StringIO()):
+                learner.step([r for r in rets if not r.is_eval], 0.0, 0.0, 0.0)
+        torch.cuda.synchronize()
+        steps[mode] = (time.perf_counter() - t0) / n_steps * 1e3
+    out["worker_learner_step_C2"] = {"members": n, "obs_per_member": E, "ms_per_step_rows_on_device": steps["device"],
+                                     "ms_per_step_rows_on_host": steps["host"],
+                                     "env_steps_per_s_rows_on_device": n * E / steps["device"] * 1e3,
+                                     "note": "per-return FDReturn objects as in the reference loop; exact fp32 forward"}
+    return out
+
+
 def _brief(res, w, world):
     """What a non-headline workload contributes to the JSON line."""
     rl = res["roofline"]
@@ -1283,6 +1357,15 @@ def b200_main(args, w):
         _xchg_profile(env.ctx, rank)
         _finish(world)
         return
+    if default_run and not args.no_workloads and world == 1:
+        gc.collect()
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        try:
+            line["noise_sources"] = {"rng": rng_noise_source_point(env)}
+        except Exception as e:
+            line["noise_sources"] = {"rng": {"error": "%s: %s" % (type(e).__name__, e)}}
+        line["noise_sources"]["rng"]["bench_seconds"] = time.perf_counter() - t0
     if not args.no_cpu_baseline and world == 1:
         try:
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,

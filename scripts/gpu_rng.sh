@@ -1,0 +1,7 @@
+#!/bin/bash
+# device RNGNoiseSource: its own tests + every existing test that drives the learner / worker with that noise source
+mkdir -p gpurun_out
+T=${1:-rng}
+timeout 900 python -m pytest tests/test_gpu_rng.py -q -x -s --timeout 600 > gpurun_out/${T}_rng.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_rng.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -q -k "noise_sources or server_train" --timeout 600 > gpurun_out/${T}_users.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_users.log
+tail -15 gpurun_out/${T}_rng.log; tail -15 gpurun_out/${T}_users.log

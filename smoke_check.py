@@ -149,3 +149,21 @@ def _smoke_tensor_paths(O, D):
     assert e_imp <= 2e-3, ("impala tensor-core forward mismatch", e_imp)
     print("smoke ok (tensor / TMA paths): ws forward %.1e, direct forward %.1e, stream forward %.1e, wide reduction rel %.1e, "
           "atari probs %.1e, impala probs %.1e, launches %d" % (e_ws, e_dr, e_st, e_red, e_at, e_imp, pol.ctx.launch_count()))
+    _smoke_rng_rows(D)
+
+
+def _smoke_rng_rows(D):
+    """RNGNoiseSource rows drawn on the device (csrc/rng_normal.cu) against numpy's own generator: bit-identical."""
+    import numpy as np
+    import torch
+    from dfd_starter_b200.device import get_context
+    ctx = get_context(0)
+    P, n = 6092, 6
+    src, ref = D.RNGNoiseSource(P, 7), D.RNGNoiseSource(P, 7, device=False)
+    out = torch.zeros(n * P, dtype=torch.float32, device=ctx.device)
+    keys = src.sample_rows(ctx, n, out, P)
+    got = out.cpu().numpy().reshape(n, P)
+    for j in range(n):
+        key, eps = ref.sample()
+        assert keys[j] == key and np.array_equal(got[j].view(np.uint32), eps.astype(np.float32).view(np.uint32)), ("rng row", j)
+    print("smoke ok (device RNGNoiseSource): %d rows x %d normals bit-identical to numpy, keys equal" % (n, P))
