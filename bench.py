@@ -1219,7 +1219,7 @@ SUB_WORKLOADS = ("C3", "C4", "C5")
 C2_POINTS = (("E1", dict(obs_per_member=1)), ("E16", dict(obs_per_member=16)), ("E128_fp32", dict(precision="fp32")))
 
 
-def rng_noise_source_point(env, full=True):
+def rng_noise_source_point(ctx, full=True, rows_only=False):
     """The reference drivers' DEFAULT noise source (run_sequential.py:89, run_server.py:78, run_client.py:123:
     RNGNoiseSource - numpy PCG64 keys, standard_normal(P) per member on the worker and again per return on the learner).
     Measured here: (1) one batch of member rows drawn on the device (RNGNoiseSource.sample_rows -> dfd_rng_normal_rows,
@@ -1230,7 +1230,7 @@ def rng_noise_source_point(env, full=True):
     import numpy as np
     import torch
     import dfd_starter_b200 as D
-    ctx, dev = env.ctx, env.ctx.device
+    dev = ctx.device
     out = {"source": "RNGNoiseSource (numpy Generator(PCG64).standard_normal, bit-exact on the device)", "rows": {}}
     for name, P, rows in (("C2", 6092, 2048), ("C3", 171042, 2048 if full else 128)):
         Ps = (P + 3) // 4 * 4
@@ -1257,6 +1257,8 @@ def rng_noise_source_point(env, full=True):
                              "rows_written_GBps": rows * P * 4 / ms * 1e-6, "numpy_normals_per_s_1core": cpu_rate,
                              "numpy_ms_extrapolated": rows * P / cpu_rate * 1e3}
         del buf
+    if rows_only:
+        return out
     # the reference's worker -> learner step with this noise source (C2 shape, 128 observations per member)
     wl = WORKLOADS["C2"]
     n, E = 2 * wl["pairs"], wl["E"]
@@ -1362,7 +1364,7 @@ def b200_main(args, w):
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
         try:
-            line["noise_sources"] = {"rng": rng_noise_source_point(env)}
+            line["noise_sources"] = {"rng": rng_noise_source_point(env.ctx)}
         except Exception as e:
             line["noise_sources"] = {"rng": {"error": "%s: %s" % (type(e).__name__, e)}}
         line["noise_sources"]["rng"]["bench_seconds"] = time.perf_counter() - t0

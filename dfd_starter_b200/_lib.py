@@ -109,7 +109,7 @@ def load():
     proto("dfd_normalize_obs", i32, [vp, vp, i64, i32, vp, vp, i32, f32, vp, vp])
     proto("dfd_member_obs_stats", i32, [vp, vp, vp, i32, i32, i32, vp, vp])
     proto("dfd_rng_scratch_bytes", sz, [i32, i64, i64, f64])
-    proto("dfd_rng_normal_rows", i32, [vp, vp, i32, i64, i64, vp, f64, vp, vp, vp, i64, vp, vp, i32, i32, f64, vp, sz, vp])
+    proto("dfd_rng_normal_rows", i32, [vp, vp, i32, i64, i64, vp, f64, vp, vp, vp, i64, vp, vp, vp, i32, i32, f64, vp, sz, vp])
     proto("dfd_host_stage", i32, [vp, vp, vp, sz, vp])
     proto("dfd_wire_count_returns", i64, [C.c_char_p, sz])
     proto("dfd_wire_decode_returns", i64, [C.c_char_p, sz, i32, i64, P(DfdReturnSoa)])

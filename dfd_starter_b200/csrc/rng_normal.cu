@@ -30,6 +30,7 @@ constexpr int RNG_JUMP_BITS = 48;       // chunk index bits served by the jump t
 __device__ const uint64_t g_zig_ki[256] = ZIG_KI_INIT;
 __device__ const uint64_t g_zig_wi[256] = ZIG_WI_BITS_INIT;
 __device__ const uint64_t g_zig_fi[256] = ZIG_FI_BITS_INIT;
+__device__ const uint64_t g_exp_tab[256] = EXP_TAB_INIT;   // wedge tests only (1.2 % of the attempts): read through L1
 
 // state after n steps = A^n * s + G_n * inc (mod 2^128) with G_n = 1 + A + ... + A^(n-1): both universal, so the
 // jump to chunk c is one (multiply, multiply, add) per set bit of c.  Entries j: n = RNGN_CHUNK * 2^j.
@@ -55,7 +56,7 @@ struct RngArgs {
     int32_t* blocksum;         // n_streams x n_blocks
     int64_t* blockoff;         // n_streams x n_blocks
     unsigned* status;
-    int log1p_fused;
+    int libm_fused;
     int force_serial;
 };
 
@@ -69,7 +70,8 @@ __device__ __forceinline__ void load_tables(uint64_t* sm, rngn_tables& t, int fu
     t.ki = sm;
     t.wi = reinterpret_cast<const double*>(sm + 256);
     t.fi = reinterpret_cast<const double*>(sm + 512);
-    t.log1p_fused = fused;
+    t.exp_tab = g_exp_tab;
+    t.libm_fused = fused;
 }
 
 __device__ __forceinline__ void stream_state(const uint64_t* streams, int s, rngn_u128& st, rngn_u128& inc) {
@@ -89,7 +91,7 @@ __device__ __forceinline__ rngn_u128 jump_to_chunk(rngn_u128 s, rngn_u128 inc, i
 __global__ void __launch_bounds__(RNG_BLOCK) rng_table_kernel(RngArgs a) {
     __shared__ uint64_t sm[768];
     rngn_tables t;
-    load_tables(sm, t, a.log1p_fused);
+    load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.y;
     const int64_t c = (int64_t)blockIdx.x * RNG_BLOCK + threadIdx.x;
     if (c >= a.n_chunks) return;
@@ -109,7 +111,7 @@ __device__ __forceinline__ void store_entry(const RngArgs& a, int64_t at, int e,
 __global__ void __launch_bounds__(RNG_BLOCK) rng_resolve_kernel(RngArgs a) {
     __shared__ uint64_t sm[768];
     rngn_tables t;
-    load_tables(sm, t, a.log1p_fused);
+    load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.y;
     const int64_t c = (int64_t)blockIdx.x * RNG_BLOCK + threadIdx.x;
     if (c >= a.n_chunks) return;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_resolve_kernel(RngArgs a) {
 __global__ void __launch_bounds__(32) rng_serial_kernel(RngArgs a) {
     __shared__ uint64_t sm[768];
     rngn_tables t;
-    load_tables(sm, t, a.log1p_fused);
+    load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.x * 32 + threadIdx.x;
     if (s >= a.n_streams || !(a.fail[s] || a.force_serial)) return;
     rngn_u128 st, inc;
@@ -223,6 +225,7 @@ struct EmitArgs {
     double* rows_out_f64;      // nullable
     int64_t row_stride;
     int64_t* row_words;        // n_streams x (rows_per_stream + 1)
+    uint64_t* row_state;       // nullable: n_streams x (rows_per_stream + 1) x {lo, hi}
 };
 
 struct StageSink {
@@ -231,10 +234,16 @@ struct StageSink {
     int64_t next_row_end;      // index of the next normal that ends a row
     int64_t n_params;
     int64_t* row_words;
-    __device__ __forceinline__ void operator()(int64_t g, double v, int64_t words_after) {
+    uint64_t* row_state;
+    __device__ __forceinline__ void operator()(int64_t g, double v, int64_t words_after, rngn_u128 st) {
         stage[g - g0] = v;
         if (g == next_row_end) {
-            row_words[(g + 1) / n_params] = words_after;
+            const int64_t r = (g + 1) / n_params;
+            row_words[r] = words_after;
+            if (row_state) {
+                row_state[2 * r] = st.lo;
+                row_state[2 * r + 1] = st.hi;
+            }
             next_row_end += n_params;
         }
     }
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
     uint64_t* sm = reinterpret_cast<uint64_t*>(smem_raw);
     double* stage = reinterpret_cast<double*>(sm + 768);             // RNG_BLOCK * RNGN_CHUNK doubles
     rngn_tables t;
-    load_tables(sm, t, a.log1p_fused);
+    load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.y;
     const int64_t c = (int64_t)blockIdx.x * RNG_BLOCK + threadIdx.x;
     const int64_t at = (int64_t)s * a.n_chunks + c;
@@ -254,7 +263,13 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
     int tot;
     const int pre = block_exclusive_scan(k, &tot);
     if (g0 >= a.n_draws) return;                                     // uniform per CTA
-    if (blockIdx.x == 0 && threadIdx.x == 0) o.row_words[(int64_t)s * (a.rows_per_stream + 1)] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        o.row_words[(int64_t)s * (a.rows_per_stream + 1)] = 0;
+        if (o.row_state) {
+            o.row_state[2 * (int64_t)s * (a.rows_per_stream + 1)] = a.streams[4 * s];
+            o.row_state[2 * (int64_t)s * (a.rows_per_stream + 1) + 1] = a.streams[4 * s + 1];
+        }
+    }
     if (c < a.n_chunks && k > 0) {
         int e = a.entry[at];
         if (e == 255) e = a.entry_big[at];
@@ -267,6 +282,7 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
         sink.n_params = a.n_params;
         sink.next_row_end = (first_g / a.n_params + 1) * a.n_params - 1;
         sink.row_words = o.row_words + (int64_t)s * (a.rows_per_stream + 1);
+        sink.row_state = o.row_state ? o.row_state + 2 * (int64_t)s * (a.rows_per_stream + 1) : nullptr;
         unsigned status = 0;
         rngn_emit_chunk(jump_to_chunk(st, inc, c), inc, t, c, e, first_g, a.n_draws, &status, sink);
         // status bits were already reported by the table / resolve kernels for the same attempts
@@ -355,7 +371,7 @@ extern "C" size_t dfd_rng_scratch_bytes(int n_streams, int64_t rows_per_stream, 
 extern "C" int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_streams, int64_t rows_per_stream,
                                    int64_t n_params, const float* theta, double sigma, const int32_t* dest_row,
                                    float* rows_out, double* rows_out_f64, int64_t row_stride, int64_t* row_words,
-                                   uint32_t* status, int log1p_fused, int force_serial, double margin, void* scratch,
+                                   uint64_t* row_state, uint32_t* status, int libm_fused, int force_serial, double margin, void* scratch,
                                    size_t scratch_bytes, dfd_stream stream) {
     DFD_CHECK_ARG(ctx && streams && row_words && status && scratch, "dfd_rng_normal_rows: null argument");
     DFD_CHECK_ARG(n_streams > 0 && n_streams <= 65535, "dfd_rng_normal_rows: n_streams %d not in 1..65535", n_streams);
@@ -386,7 +402,7 @@ extern "C" int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_
     a.blocksum = reinterpret_cast<int32_t*>(base + L.off_bsum);
     a.blockoff = reinterpret_cast<int64_t*>(base + L.off_boff);
     a.status = status;
-    a.log1p_fused = log1p_fused;
+    a.libm_fused = libm_fused;
     a.force_serial = force_serial;
     EmitArgs o;
     o.theta = theta;
@@ -396,6 +412,7 @@ extern "C" int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_
     o.rows_out_f64 = rows_out_f64;
     o.row_stride = row_stride;
     o.row_words = row_words;
+    o.row_state = row_state;
     DFD_CUDA(cudaMemsetAsync(status, 0, sizeof(uint32_t), st));
     DFD_CUDA(cudaMemsetAsync(a.fail, 0, (size_t)n_streams * sizeof(int), st));
     const dim3 grid((unsigned)L.n_blocks, (unsigned)n_streams);

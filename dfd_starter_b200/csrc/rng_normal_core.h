@@ -17,9 +17,9 @@
  * The same source compiles for the device (nvcc) and for the host (g++, tests/native/rng_core_host.cpp: the CPU test
  * that pins this file against numpy itself).  Every floating-point operation is a single IEEE double operation in the
  * order of numpy's C source: on the device the explicit _rn intrinsics keep nvcc from contracting a*b+c into an FMA.
- * log1p is glibc's (fdlibm-derived sysdeps/ieee754/dbl-64/s_log1p.c) operation sequence restated - a chain of IEEE
- * operations, hence bit-identical on both sides; exp only decides a comparison (wedge test), so the device's own exp is
- * used and a comparison closer than RNGN_EXP_GUARD ulps raises the `uncertain` flag instead of guessing. */
+ * The two libm calls of the algorithm - log1p in the tail, exp in the wedge test - are glibc's own operation sequences
+ * restated (rngn_log1p_neg, rngn_exp_neg): chains of IEEE operations and table look-ups, hence bit-identical on both
+ * sides, so no draw is ever "close enough": every comparison is decided exactly as numpy decides it. */
 #ifndef DFD_RNG_NORMAL_CORE_H
 #define DFD_RNG_NORMAL_CORE_H
 
@@ -53,11 +53,9 @@
 #define RNGN_CHUNK 32            /* words per chunk (one thread of the table / emit kernels); <= 32 (bit masks).  The
                                     CPU test also builds this file with tiny chunks to stress the entry resolution */
 #endif
-#define RNGN_EXP_GUARD 64.0      /* wedge comparisons closer than this many ulps of exp() are not decided on the device */
 #define RNGN_TAIL_CAP 60         /* a tail loop longer than this (probability < 1e-60) is reported, not followed */
 
 /* status bits (device word, OR-ed) */
-#define RNGN_ST_UNCERTAIN 1u     /* a wedge comparison fell inside the exp guard band */
 #define RNGN_ST_TAILCAP 2u       /* tail loop cap hit */
 #define RNGN_ST_SHORT 4u         /* the word budget ended before n_draws normals were produced */
 #define RNGN_ST_SERIAL 8u        /* (informational) the chunk entries were resolved by the serial fallback */
@@ -151,7 +149,7 @@ RNGN_HD double rngn_with_hi32(double d, int32_t hi) {
  * compiled with -mfma -mavx2 in which gcc contracted thirteen multiply-adds into FMAs.  Which roundings were fused is a
  * property of that binary (read off libm.so.6's `__log1p_fma`; pinned by tests/test_rng_core_cpu.py against
  * math.log1p on this machine, and against the plain build through GLIBC_TUNABLES=glibc.cpu.hwcaps=-FMA): `fused`
- * selects it, and the host probes which build its libm uses (noise_sources.libm_log1p_fused).
+ * selects it, and the host probes which build its libm uses (noise_sources.libm_fused).
  * Only the branches reachable from x = -u, u in [0, 1) a multiple of 2^-53, are kept. */
 RNGN_HD double rngn_log1p_neg(double x, int fused) {
     const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
@@ -232,12 +230,46 @@ RNGN_HD double rngn_log1p_neg(double x, int fused) {
     return RNGN_SUB(RNGN_MUL(kd, ln2_hi), RNGN_SUB(RNGN_SUB(hfsq, RNGN_ADD(v, RNGN_ADD(RNGN_MUL(kd, ln2_lo), c))), f));
 }
 
+/* exp(x) for x in [-8, 0]: glibc 2.39's dbl-64 exp (sysdeps/ieee754/dbl-64/e_exp.c - Szabolcs Nagy's table-driven
+ * algorithm from ARM's optimized routines: k = round(x * 128/ln2) through the 1.5 * 2^52 shift, r = x - k * ln2/128 in two
+ * pieces, 2^(k/128) from a 128-entry table (tab), degree-5 polynomial), in the operation order of the two builds glibc
+ * selects from by CPU: `fused` = the -mfma build (read off libm.so.6's `__exp_fma`: seven FMAs), else the plain build.
+ * Only what x = -0.5 * v * v, |v| < 3.66, reaches: the main path and the |x| < 2^-54 shortcut. */
+RNGN_HD double rngn_exp_neg(double x, int fused, const uint64_t* tab) {
+    const double InvLn2N = 0x1.71547652b82fep7, Shift = 0x1.8p52, NegLn2hiN = -0x1.62e42fefa0000p-8,
+                 NegLn2loN = -0x1.cf79abc9e3b3ap-47, C2 = 0x1.ffffffffffdbdp-2, C3 = 0x1.555555555543cp-3,
+                 C4 = 0x1.55555cf172b91p-5, C5 = 0x1.1111167a4d017p-7;
+    uint32_t abstop = (uint32_t)(rngn_double_to_bits(x) >> 52) & 0x7ff;
+    if (abstop < 0x3c9) return RNGN_ADD(1.0, x);             /* |x| < 2^-54 */
+    double kd, r, r2, tmp, scale;
+    uint64_t ki, idx, sbits;
+    kd = fused ? RNGN_FMA(x, InvLn2N, Shift) : RNGN_ADD(RNGN_MUL(InvLn2N, x), Shift);
+    ki = rngn_double_to_bits(kd);
+    kd = RNGN_SUB(kd, Shift);
+    if (fused) r = RNGN_FMA(kd, NegLn2loN, RNGN_FMA(kd, NegLn2hiN, x));
+    else r = RNGN_ADD(RNGN_ADD(x, RNGN_MUL(kd, NegLn2hiN)), RNGN_MUL(kd, NegLn2loN));
+    idx = 2 * (ki & 127);
+    sbits = tab[idx + 1] + (ki << 45);
+    r2 = RNGN_MUL(r, r);
+    if (fused) {
+        tmp = RNGN_FMA(RNGN_MUL(r2, r2), RNGN_FMA(r, C5, C4),
+                       RNGN_FMA(RNGN_FMA(r, C3, C2), r2, RNGN_ADD(r, rngn_bits_to_double(tab[idx]))));
+        scale = rngn_bits_to_double(sbits);
+        return RNGN_FMA(scale, tmp, scale);
+    }
+    tmp = RNGN_ADD(RNGN_ADD(RNGN_ADD(rngn_bits_to_double(tab[idx]), r), RNGN_MUL(r2, RNGN_ADD(C2, RNGN_MUL(r, C3)))),
+                   RNGN_MUL(RNGN_MUL(r2, r2), RNGN_ADD(C4, RNGN_MUL(r, C5))));
+    scale = rngn_bits_to_double(sbits);
+    return RNGN_ADD(scale, RNGN_MUL(scale, tmp));
+}
+
 /* the ziggurat tables as seen by the simulation: pointers so that the device can keep them in shared memory */
 typedef struct rngn_tables {
     const uint64_t* ki;
     const double* wi;
     const double* fi;
-    int log1p_fused;   /* which of glibc's two log1p builds the host's numpy calls (rngn_log1p_neg) */
+    const uint64_t* exp_tab;   /* glibc's __exp_data.tab */
+    int libm_fused;    /* which of glibc's two builds of log1p / exp the host's numpy calls (1 = -mfma) */
 } rngn_tables;
 
 typedef struct rngn_attempt {
@@ -272,8 +304,8 @@ RNGN_HD rngn_attempt rngn_attempt_at(rngn_u128* s, rngn_u128 inc, const rngn_tab
     if (rabs < t.ki[idx]) return a;
     if (idx == 0) {
         for (int it = 0;; ++it) {
-            double xx = RNGN_MUL(-RNGN_NOR_INV_R, rngn_log1p_neg(-rngn_next_double(s, inc), t.log1p_fused));
-            double yy = -rngn_log1p_neg(-rngn_next_double(s, inc), t.log1p_fused);
+            double xx = RNGN_MUL(-RNGN_NOR_INV_R, rngn_log1p_neg(-rngn_next_double(s, inc), t.libm_fused));
+            double yy = -rngn_log1p_neg(-rngn_next_double(s, inc), t.libm_fused);
             a.len += 2;
             if (RNGN_ADD(yy, yy) > RNGN_MUL(xx, xx)) {
                 a.val = ((rabs >> 8) & 0x1) ? -RNGN_ADD(RNGN_NOR_R, xx) : RNGN_ADD(RNGN_NOR_R, xx);
@@ -289,10 +321,7 @@ RNGN_HD rngn_attempt rngn_attempt_at(rngn_u128* s, rngn_u128 inc, const rngn_tab
     double u = rngn_next_double(s, inc);
     a.len = 2;
     double lhs = RNGN_ADD(RNGN_MUL(RNGN_SUB(t.fi[idx - 1], t.fi[idx]), u), t.fi[idx]);
-    double rhs = exp(RNGN_MUL(RNGN_MUL(-0.5, x), x));
-    /* exp is not the same code on both sides (glibc vs libdevice, each within an ulp): refuse knife edges */
-    double gap = fabs(RNGN_SUB(lhs, rhs));
-    if (gap <= RNGN_MUL(RNGN_MUL(rhs, 2.220446049250313e-16), RNGN_EXP_GUARD)) *status |= RNGN_ST_UNCERTAIN;
+    double rhs = rngn_exp_neg(RNGN_MUL(RNGN_MUL(-0.5, x), x), t.libm_fused, t.exp_tab);
     a.out = lhs < rhs ? 1 : 0;
     return a;
 }
@@ -388,8 +417,9 @@ RNGN_HD void rngn_resolve_serial(const rngn_rec* rec, int64_t n_chunks, rngn_u12
     }
 }
 
-/* step 3: replay chunk c from its entry and hand every normal to sink(g, value, words_after) - g = index of the normal
- * in its stream, words_after = stream words consumed once this normal has been returned (the next normal's key) */
+/* step 3: replay chunk c from its entry and hand every normal to sink(g, value, words_after, state_after) - g = index
+ * of the normal in its stream, words_after / state_after = stream words consumed / generator state once this normal has
+ * been returned (the next normal's key) */
 template <typename Sink>
 RNGN_HD void rngn_emit_chunk(rngn_u128 s_chunk, rngn_u128 inc, const rngn_tables t, int64_t c, int entry, int64_t first_g,
                              int64_t n_draws, unsigned* status, Sink& sink) {
@@ -402,7 +432,7 @@ RNGN_HD void rngn_emit_chunk(rngn_u128 s_chunk, rngn_u128 inc, const rngn_tables
         rngn_attempt a = rngn_attempt_at(&s, inc, t, status);
         pos += a.len;
         if (a.out) {
-            sink(g, a.val, c * RNGN_CHUNK + pos);
+            sink(g, a.val, c * RNGN_CHUNK + pos, s);
             ++g;
         }
     }

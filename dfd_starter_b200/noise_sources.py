@@ -86,16 +86,27 @@ _LOG1P_PROBES = (
 )
 
 
-def libm_log1p_fused():
-    """Which build of log1p this process's libm resolved to (numpy's ziggurat tail calls it): 1 = the FMA build,
-    0 = the plain one.  Anything else is a libm the device restatement was not pinned against: raise."""
+# the same for exp: (x, exp(x) of the plain build, exp(x) of the fused build)
+_EXP_PROBES = (
+    ("-0x1.558f2e05ccc8ap-3", "0x1.b159cfd428588p-1", "0x1.b159cfd428587p-1"),
+    ("-0x1.b1d883ba3443dp+1", "0x1.144d3b88dd75ap-5", "0x1.144d3b88dd759p-5"),
+    ("-0x1.0371da37ef5a9p-3", "0x1.c3143d528ab2ap-1", "0x1.c3143d528ab2bp-1"),
+    ("-0x1.a47b45f17bd8cp-1", "0x1.c26ff070c5ac8p-2", "0x1.c26ff070c5ac9p-2"),
+)
+
+
+def libm_fused():
+    """Which builds of log1p and exp this process's libm resolved to (numpy's ziggurat calls them in the tail and in the
+    wedge test): 1 = glibc's -mfma builds, 0 = the plain ones.  Anything else - or a mixed answer - is a libm the device
+    restatement was not pinned against: raise rather than draw normals that might differ from numpy's."""
     import math
-    got = [math.log1p(-float.fromhex(u)).hex() for u, _, _ in _LOG1P_PROBES]
-    if got == [f for _, _, f in _LOG1P_PROBES]:
+    got = [math.log1p(-float.fromhex(u)).hex() for u, _, _ in _LOG1P_PROBES] + \
+          [math.exp(float.fromhex(x)).hex() for x, _, _ in _EXP_PROBES]
+    if got == [f for _, _, f in _LOG1P_PROBES + _EXP_PROBES]:
         return 1
-    if got == [p for _, p, _ in _LOG1P_PROBES]:
+    if got == [p for _, p, _ in _LOG1P_PROBES + _EXP_PROBES]:
         return 0
-    raise _lib.DfdError("this libm's log1p matches neither glibc build the device generator was pinned against "
+    raise _lib.DfdError("this libm's log1p / exp match neither glibc build the device generator was pinned against "
                         "(%s): RNGNoiseSource(device=False) draws on the host" % ", ".join(got))
 
 
@@ -107,21 +118,11 @@ def pcg64_advance(state, inc, words):
     return int(bg.state["state"]["state"])
 
 
-class RngStatusError(_lib.DfdError):
-    """The device generator declined to decide a draw (status word of dfd_rng_normal_rows)."""
-
-    def __init__(self, status):
-        _lib.DfdError.__init__(self, "dfd_rng_normal_rows status 0x%x: a wedge comparison within 64 ulps of exp() "
-                               "(or a tail loop beyond 60 rounds) is not decided on the device" % status)
-        self.status = status
-
-
 def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_stride=None, theta=None, sigma=0.0,
                        dest_row=None, want_f64=False, force_serial=False, margin=0.0):
     """dfd_rng_normal_rows (include/dfd_b200.h): numpy's Generator(PCG64).standard_normal drawn on the device, bit-exact.
     streams: [n, 2] Python ints or an [n, 4] uint64 array {state_lo, state_hi, inc_lo, inc_hi}.
-    Returns (rows fp32 device tensor [rows, row_stride] or None, rows_f64 or None, row_words int64 [n, rows_per_stream + 1],
-    status).  Retries with a larger word budget on DFD_RNG_SHORT; raises RngStatusError on an undecided draw."""
+    Returns (rows fp32 device tensor [rows, row_stride] or None, rows_f64 or None, RowMarks, status).  Retries with a larger word budget on DFD_RNG_SHORT."""
     lib = ctx.lib
     if not (isinstance(streams, np.ndarray) and streams.dtype == np.uint64):
         m64 = (1 << 64) - 1
@@ -130,7 +131,7 @@ def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_st
     n = streams.shape[0]
     n_rows = n * int(rows_per_stream)
     row_stride = int(row_stride or n_params)
-    fused = libm_log1p_fused()
+    fused = libm_fused()
     with torch.cuda.device(ctx.device):
         d_streams = torch.from_numpy(streams.view(np.int64)).to(ctx.device)
         if out is None:
@@ -139,13 +140,14 @@ def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_st
         out64 = torch.empty(out.numel(), dtype=torch.float64, device=ctx.device) if want_f64 else None
         d_dest = None if dest_row is None else torch.from_numpy(np.ascontiguousarray(dest_row, dtype=np.int32)).to(ctx.device)
         d_words = torch.zeros(n * (int(rows_per_stream) + 1), dtype=torch.int64, device=ctx.device)
+        d_states = torch.zeros(2 * n * (int(rows_per_stream) + 1), dtype=torch.int64, device=ctx.device)
         d_status = torch.zeros(1, dtype=torch.int32, device=ctx.device)
         for margin in ((margin or 1.04), 1.25, 2.0, 8.0):
             nbytes = int(lib.dfd_rng_scratch_bytes(n, int(rows_per_stream), int(n_params), float(margin)))
             scratch = torch.empty(nbytes + 256, dtype=torch.uint8, device=ctx.device)
             _lib.check(lib.dfd_rng_normal_rows(ctx.handle, ptr(d_streams), n, int(rows_per_stream), int(n_params), ptr(theta),
                                                float(sigma), ptr(d_dest), ptr(out), ptr(out64), row_stride, ptr(d_words),
-                                               ptr(d_status), fused, 1 if force_serial else 0, float(margin),
+                                               ptr(d_states), ptr(d_status), fused, 1 if force_serial else 0, float(margin),
                                                aligned_ptr(scratch), nbytes, ctx.stream), "dfd_rng_normal_rows")
             status = int(d_status.item()) & 0xffffffff
             del scratch
@@ -153,10 +155,25 @@ def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_st
                 break
         else:
             raise _lib.DfdError("dfd_rng_normal_rows: word budget still short at 8 words per normal")
-        if status & 3:
-            raise RngStatusError(status)
+        if status & 2:
+            raise _lib.DfdError("dfd_rng_normal_rows: a ziggurat tail loop ran past 60 rounds (status 0x%x)" % status)
         words = d_words.cpu().numpy().reshape(n, int(rows_per_stream) + 1)
-    return out, out64, words, status
+        states = d_states.cpu().numpy().view(np.uint64).reshape(n, int(rows_per_stream) + 1, 2)
+    return out, out64, RowMarks(words, states), status
+
+
+class RowMarks(object):
+    """Where the rows of a device draw begin in their streams: `words[s, r]` 64-bit words consumed, `state(s, r)` the
+    PCG64 state there (row r's key; r = rows_per_stream: where the stream stands after the last row)."""
+
+    def __init__(self, words, states):
+        self.words, self._states = words, states
+
+    def state(self, s, r):
+        return int(self._states[s, r, 0]) | (int(self._states[s, r, 1]) << 64)
+
+    def __getitem__(self, i):
+        return self.words[i]
 
 
 class RNGNoiseSource(object):
@@ -198,18 +215,17 @@ class RNGNoiseSource(object):
         """n successive `sample()` calls: returns their keys; row j goes to row dest_row[j] of `out` (fp32 device
         buffer, row_stride apart) as fp32(eps) or, with theta, as fp32(fp64(theta) + sigma * eps) (worker.py:28)."""
         s0, inc = self._state()
-        _, _, words, _ = device_normal_rows(ctx, [(s0, inc)], n, self.n_params, out=out, row_stride=row_stride, theta=theta,
+        _, _, marks, _ = device_normal_rows(ctx, [(s0, inc)], n, self.n_params, out=out, row_stride=row_stride, theta=theta,
                                             sigma=sigma, dest_row=dest_row)
-        keys = ["{},{}".format(pcg64_advance(s0, inc, w), inc) for w in words[0, :n]]
-        self._set_state(pcg64_advance(s0, inc, words[0, n]), inc)
+        keys = ["{},{}".format(marks.state(0, r), inc) for r in range(n)]
+        self._set_state(marks.state(0, n), inc)
         return keys
 
     def decode_rows(self, ctx, keys, out, row_stride):
         """`decode(key)` for every key, in order: row j of `out` = fp32(noise_j)."""
         streams = [tuple(int(v) for v in str(k).split(",")) for k in keys]
-        _, _, words, _ = device_normal_rows(ctx, streams, 1, self.n_params, out=out, row_stride=row_stride)
-        s, inc = streams[-1]
-        self._set_state(pcg64_advance(s, inc, words[-1, 1]), inc)    # where the last decode() leaves the generator
+        _, _, marks, _ = device_normal_rows(ctx, streams, 1, self.n_params, out=out, row_stride=row_stride)
+        self._set_state(marks.state(len(streams) - 1, 1), streams[-1][1])    # where the last decode() leaves the generator
 
 
 class SimpleNoiseSource(object):

@@ -351,23 +351,25 @@ int dfd_strategy_distances(dfd_ctx* ctx, const float* a, int n_a, const float* b
  *   row_words     device, n_streams x (rows_per_stream + 1) int64: 64-bit words the stream has consumed when row r
  *                 begins (entry rows_per_stream: when the last row ends) - the host advances the key by that count to
  *                 name the next row's key and to leave its generator where numpy would have left it;
- *   status        device, one word, 0 when every normal is exact; DFD_RNG_UNCERTAIN: a wedge comparison fell within
- *                 64 ulps of exp() (not decided on the device: libdevice's exp and glibc's may round differently; about
- *                 1e-14 per normal); DFD_RNG_SHORT: the word budget (margin x normals + 1024; < 1 selects 1.04, the
- *                 mean is 1.022) ended early - call again with a larger margin; DFD_RNG_SERIAL (informational): a
- *                 stream's chunk entries were resolved by the serial pass;
- *   log1p_fused   which of glibc's two log1p builds the host's numpy calls in the ziggurat tail (1: the -mfma build
- *                 that x86-64 CPUs with FMA select; probe: a few arguments on which the two differ);
+ *   row_state     device, nullable, n_streams x (rows_per_stream + 1) x {lo, hi}: the PCG64 state at the same points
+ *                 (the "state" half of row r's key, ready to print);
+ *   status        device, one word, 0 = done.  DFD_RNG_SHORT: the word budget (margin x normals + 1024; < 1 selects
+ *                 1.04, the mean is 1.022) ended early - call again with a larger margin; DFD_RNG_TAILCAP: a tail loop
+ *                 ran past 60 rounds (probability < 1e-60; reported, not followed); DFD_RNG_SERIAL (informational): a
+ *                 stream's chunk entries were resolved by the serial pass.  There is no "approximately equal" case:
+ *                 the two libm calls of numpy's ziggurat (log1p, exp) are restated operation by operation;
+ *   libm_fused    which of glibc's two builds of log1p / exp the host's numpy calls (1: the -mfma builds that x86-64
+ *                 CPUs with FMA + AVX2 select; the host probes a few arguments on which the builds differ);
  *   force_serial  != 0 resolves every stream serially (tests);
  *   scratch       256-byte aligned, dfd_rng_scratch_bytes(n_streams, rows_per_stream, n_params, margin) bytes. */
-#define DFD_RNG_UNCERTAIN 1u
 #define DFD_RNG_TAILCAP 2u
 #define DFD_RNG_SHORT 4u
 #define DFD_RNG_SERIAL 8u
 size_t dfd_rng_scratch_bytes(int n_streams, int64_t rows_per_stream, int64_t n_params, double margin);
 int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_streams, int64_t rows_per_stream, int64_t n_params,
                         const float* theta, double sigma, const int32_t* dest_row, float* rows_out, double* rows_out_f64,
-                        int64_t row_stride, int64_t* row_words, uint32_t* status, int log1p_fused, int force_serial,
+                        int64_t row_stride, int64_t* row_words, uint64_t* row_state, uint32_t* status, int libm_fused,
+                        int force_serial,
                         double margin, void* scratch, size_t scratch_bytes, dfd_stream stream);
 
 /* ---- synthetic return (bench / tests only) ------------------------------- */

@@ -54,6 +54,7 @@ def test_one_stream_rows_are_numpys(D, n_rows, P, force_serial):
     assert np.array_equal(_bits(got64), _bits(ref))
     assert np.array_equal(_bits(got32), _bits(ref.astype(np.float32)))
     assert [pcg64_advance(s, inc, w) for w in words[0]] == keys
+    assert [words.state(0, r) for r in range(n_rows + 1)] == keys
 
 
 def test_many_streams_decode_form(D):
@@ -75,8 +76,8 @@ def test_many_streams_decode_form(D):
     got = out64.cpu().numpy().reshape(-1, P + 3)
     for j in range(n):
         assert np.array_equal(_bits(got[dest[j], :P]), _bits(ref[j])), j
-        assert pcg64_advance(streams[j][0], streams[j][1], words[j, 1]) == ends[j]
-        assert words[j, 0] == 0
+        assert pcg64_advance(streams[j][0], streams[j][1], words[j][1]) == ends[j]
+        assert words[j][0] == 0 and words.state(j, 0) == streams[j][0] and words.state(j, 1) == ends[j]
 
 
 def test_worker_members_built_in_kernel(D):

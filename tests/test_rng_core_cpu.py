@@ -31,9 +31,9 @@ def _build(tmp, chunk=None):
 
 @pytest.fixture(scope="module")
 def core(tmp_path_factory):
-    from dfd_starter_b200.noise_sources import libm_log1p_fused
+    from dfd_starter_b200.noise_sources import libm_fused
     L = _build(str(tmp_path_factory.mktemp("rngcore")))
-    L.rngn_host_set_fused(libm_log1p_fused())
+    L.rngn_host_set_fused(libm_fused())
     return L
 
 
@@ -50,8 +50,14 @@ def _chunked(L, s, inc, n, P, force_serial=0):
     cw = L.rngn_host_chunk_words()
     nc = (int(n * 1.04) + 1024 + cw - 1) // cw
     out, rows, failed = np.zeros(n), np.zeros(n // P + 1, dtype=np.int64), C.c_int(0)
+    states = np.zeros((n // P + 1, 2), dtype=np.uint64)
     st = L.rngn_host_chunked(*_split(s), *_split(inc), i64(n), i64(P), i64(nc), force_serial, out.ctypes.data_as(C.c_void_p),
-                             rows.ctypes.data_as(C.c_void_p), C.byref(failed))
+                             rows.ctypes.data_as(C.c_void_p), states.ctypes.data_as(C.c_void_p), C.byref(failed))
+    # the state handed out at a row boundary must be the stream advanced by the word count handed out with it
+    for w, (lo, hi) in zip(rows, states):
+        adv = (u64 * 2)()
+        L.rngn_host_advance(*_split(s), *_split(inc), u64(int(w)), adv)
+        assert (int(adv[0]), int(adv[1])) == (int(lo), int(hi))
     return st, out, rows, failed.value
 
 
@@ -104,9 +110,9 @@ def test_chunk_form_is_numpys(core, seed, n_rows, P):
 def test_entry_resolution_under_stress(tmp_path):
     """4-word chunks make multi-word attempts straddle chunk boundaries all the time: speculated entries fail to verify
     for some streams and the serial resolver takes over - the output must not change."""
-    from dfd_starter_b200.noise_sources import libm_log1p_fused
+    from dfd_starter_b200.noise_sources import libm_fused
     L = _build(str(tmp_path), chunk=4)
-    L.rngn_host_set_fused(libm_log1p_fused())
+    L.rngn_host_set_fused(libm_fused())
     seeds = np.random.default_rng(42).integers(0, 2 ** 62, 1500)
     n_failed = 0
     for sd in seeds:
@@ -124,8 +130,9 @@ def test_short_word_budget_is_reported(core):
     g = np.random.default_rng(1)
     s, inc = _state(g)
     out, rows, failed = np.zeros(700), np.zeros(2, dtype=np.int64), C.c_int(0)
+    states = np.zeros((2, 2), dtype=np.uint64)
     st = core.rngn_host_chunked(*_split(s), *_split(inc), i64(700), i64(700), i64(22), 0, out.ctypes.data_as(C.c_void_p),
-                                rows.ctypes.data_as(C.c_void_p), C.byref(failed))
+                                rows.ctypes.data_as(C.c_void_p), states.ctypes.data_as(C.c_void_p), C.byref(failed))
     assert st & 4
 
 
@@ -134,9 +141,10 @@ import ctypes as C, math, struct, sys
 import numpy as np
 L = C.CDLL(sys.argv[1]); fused = int(sys.argv[2])
 L.rngn_host_log1p_neg.restype = C.c_double; L.rngn_host_log1p_neg.argtypes = [C.c_double, C.c_int]
+L.rngn_host_exp_neg.restype = C.c_double; L.rngn_host_exp_neg.argtypes = [C.c_double, C.c_int]
 sys.path.insert(0, sys.argv[3])
-from dfd_starter_b200.noise_sources import libm_log1p_fused
-assert libm_log1p_fused() == fused, "probe disagrees"
+from dfd_starter_b200.noise_sources import libm_fused
+assert libm_fused() == fused, "probe disagrees"
 r = np.random.default_rng(1)
 us = [r.integers(0, 2 ** 53, 400000, dtype=np.uint64) * 2.0 ** -53,
       r.integers(1, 2 ** 30, 5000, dtype=np.uint64) * 2.0 ** -53, r.integers(1, 2 ** 24, 5000, dtype=np.uint64) * 2.0 ** -53,
@@ -149,24 +157,28 @@ for hi in (0x3fd2bec2, 0x3fd2bec3, 0x3fd2bec4, 0x3fd2bec5):       # the k = 0 / 
                         for lo in (0, 0x80000000, 0xffffffff, 0x12345678)]))
 bad = sum(struct.pack("<d", L.rngn_host_log1p_neg(-float(u), fused)) != struct.pack("<d", math.log1p(-float(u)))
           for u in np.concatenate(us))
-print("mismatches", bad)
-sys.exit(1 if bad else 0)
+v = r.random(400000) * 3.66
+xs = np.concatenate([-0.5 * v * v, -r.random(20000) * 1e-12, -r.random(1000) * 2.0 ** -53, -r.random(1000) * 2.0 ** -60, [-0.0, -6.7]])
+bad_exp = sum(L.rngn_host_exp_neg(float(x), fused) != math.exp(float(x)) for x in xs)
+print("log1p mismatches", bad, "exp mismatches", bad_exp)
+sys.exit(1 if bad or bad_exp else 0)
 """
 
 
 @pytest.mark.parametrize("fused", [1, 0])
-def test_log1p_is_glibcs_in_both_builds(tmp_path, fused):
-    """rngn_log1p_neg against this machine's libm on 435 000 arguments of the ziggurat tail's domain (random, tiny,
-    |f| < 2^-20, the branch boundary): bit-identical - the -mfma build as the process normally resolves it, the plain
-    build with the FMA capability masked (GLIBC_TUNABLES), each detected by the probe the product uses."""
-    from dfd_starter_b200.noise_sources import libm_log1p_fused
-    if not fused and libm_log1p_fused() == 0:
+def test_log1p_and_exp_are_glibcs_in_both_builds(tmp_path, fused):
+    """rngn_log1p_neg / rngn_exp_neg against this machine's libm: 435 000 arguments of the ziggurat tail's domain
+    (random, tiny, |f| < 2^-20, the branch boundary) and 420 000 of the wedge test's (-v^2/2, tiny): bit-identical -
+    the -mfma builds as the process normally resolves them, the plain builds with the FMA capability masked
+    (GLIBC_TUNABLES), each detected by the probe the product uses."""
+    from dfd_starter_b200.noise_sources import libm_fused
+    if not fused and libm_fused() == 0:
         pytest.skip("this CPU already runs the plain build (covered by fused=... of the other case)")
     _build(str(tmp_path))
     env = dict(os.environ)
     if not fused:
         env["GLIBC_TUNABLES"] = "glibc.cpu.hwcaps=-FMA,-AVX2"
-    elif libm_log1p_fused() == 0:
+    elif libm_fused() == 0:
         pytest.skip("no FMA on this CPU")
     p = subprocess.run([sys.executable, "-c", _LOG1P_CHECK, os.path.join(str(tmp_path), "librngcore.so"), str(fused), ROOT],
                        env=env, capture_output=True, text=True)
