@@ -19,25 +19,31 @@
 // 257-wide rows of weight_ih are not 16-byte aligned: rows r = 8q + c form class c, whose rows are 8*257 elements apart -
 // a legal TMA stride - so an M tile is a class (gate row of lane q = 8q + c); the reward column is added in the epilogue.
 // fp16 operands (10-bit mantissa, the precision of tf32), fp32 accumulate; BN folds, biases, LSTM cell, policy head fp32.
+#include <type_traits>
 #include "impala_tail.cuh"
 
 namespace {
 
 constexpr int IT_WORKERS = 384, IT_THREADS = IT_WORKERS + 32, IT_GROUPS = IT_WORKERS / 128;   // worker warps come in groups of four TMEM lane quarters
-// shared memory map (bytes from the 1024-aligned base)
-constexpr int IT_A = 0, IT_A_BYTES = 49152;                  // ring of 3 im2col buffers [128 pixels x 64 k] fp16
-constexpr int IT_B = IT_A + IT_A_BYTES, IT_B_BYTES = 20480;   // weights of a layer: up to 5 boxes of [32 x 64]; two buffers
+// shared memory map (bytes from the 1024-aligned base).  Operand maps are PLANES: plane j holds channels 8j .. 8j + 7 of
+// every position of the zero-bordered (W + 2) x (W + 2) map, 16 bytes per position, positions in row-major order - the
+// UMMA no-swizzle K-major layout with the POSITION as the row: a core matrix is 8 consecutive positions (128 contiguous
+// bytes), the next 8-row group follows at +128 (SBO), the next 8 channels are one plane further (LBO).  A filter tap
+// (dy, dx) is then nothing but the descriptor's start address moved by (dy * (W + 2) + dx) positions: no im2col copy.
+constexpr int IT_M0 = 0, IT_M0_BYTES = 49152;                 // operand map buffer 0
+constexpr int IT_B = IT_M0 + IT_M0_BYTES, IT_B_BYTES = 20480; // weights of a layer: up to 5 boxes of [32 x 64]; two buffers
 constexpr int IT_XH_BYTES = 38400;                            // one operand map (34*34*16*2 = 36 992 is the largest)
-constexpr int IT_XHA = IT_B + 2 * IT_B_BYTES, IT_XHB = IT_XHA + IT_XH_BYTES;
-constexpr int IT_BAND = IT_XHB + IT_XH_BYTES, IT_BAND_BYTES = 36864;   // 9 rows x 64 x 16 (or 32 x 32) fp32
+constexpr int IT_M1 = IT_B + 2 * IT_B_BYTES, IT_M2 = IT_M1 + IT_XH_BYTES;   // buffers 1, 2; the 66 x 66 frame map (69 696 B) spans both
+constexpr int IT_BAND = IT_M2 + IT_XH_BYTES, IT_BAND_BYTES = 36864;   // 9 conv rows x (C / 4) x W float4 (fp32)
 constexpr int IT_FCIN = IT_BAND + IT_BAND_BYTES;              // fp16 [2][2048]: BN'd trunk outputs of the two members
-constexpr int IT_PAR = IT_FCIN + 8192, IT_PAR_WORDS = 160;    // two buffers of: sN[32] tN[32] bias[32] offs[40]
+constexpr int IT_PAR = IT_FCIN + 8192, IT_PAR_WORDS = 96;     // two buffers of: sN[32] tN[32] bias[32]
 constexpr int IT_SMEM = IT_PAR + 2 * IT_PAR_WORDS * 4 + 1024;
 constexpr int IT_XT = IT_BAND;                                // dense tail: x tiles (impala_tail.cuh) in the band buffer
+static_assert(IT_M2 + IT_XH_BYTES >= 131072 + 2 * 5120, "the dense tail's tile ring and core / h0 tiles live below the band buffer");
 // tensor memory columns of the trunk
-constexpr uint32_t TC_R = 0, TC_Y = 128, TC_P = 256;          // residual stream | block-internal map | stage-conv band
-// barriers: the tail's (impala_tail.cuh; TB_MMA doubles as "layer / band done" in the trunk), then the im2col pipeline's
-enum { IB_MMA = TB_MMA, IB_AFULL = TB_COUNT, IB_AEMPTY = IB_AFULL + 3, IB_COUNT = IB_AEMPTY + 3 };
+constexpr uint32_t TC_R = 0, TC_Y = 160, TC_P = 320;          // residual stream (<= 144) | block-internal map | stage-conv band (<= 96)
+// barriers: the tail's (impala_tail.cuh; TB_MMA doubles as "layer / band done" in the trunk), then "operands ready"
+enum { IB_MMA = TB_MMA, IB_GO = TB_COUNT, IB_COUNT = IB_GO + 1 };
 
 __device__ __forceinline__ void it_wsync() { asm volatile("bar.sync 1, %0;" ::"n"(IT_WORKERS) : "memory"); }
 __device__ __forceinline__ void it_tmem_st16(uint32_t taddr, const float* v) {
@@ -55,17 +61,22 @@ struct ItCtx {
     __device__ __forceinline__ float par(int p) const { return perturb1(theta[p], sg, row[p]); }
 };
 
-// Everything a layer needs that is not its input map: weights -> B operand [cout rows x K] fp16, K-major 128-byte swizzle,
-// k = tap * cinp + c (one 64-wide box per im2col pass); conv bias; byte offsets of the 16-byte chunks of a pixel's 3x3 window
-// in the zero-bordered channel-last input map (Wp = padded width); input-side BN of the NEXT convolution folded to scale /
-// shift (applied by THIS layer's epilogue).  par: sN[32] tN[32] bias[32] offs[40].
-__device__ __noinline__ void it_prep_layer(const ItCtx& c, const ConvP& p, int cinp, int Wp, uint8_t* Bs, float* par, const ConvP* nxt) {
+// Everything a layer needs that is not its input map: weights -> B operand [cout rows x K] fp16, K-major 128-byte swizzle
+// in 64-wide boxes.  K order = the order the MMAs walk the map: 16-channel layers k = tap * 16 + c (one MMA per tap);
+// 32-channel layers k = tap * 32 + c (two MMAs per tap: planes 0-1, planes 2-3); the first convolution (3 channels in a
+// single plane) pairs neighbouring taps - the second core matrix of an MMA is the NEXT position of the same plane (LBO =
+// 16 bytes) - so k = (dy * 2 + (dx >> 1)) * 16 + (dx & 1) * 8 + c, K = 96 with zeros for the fourth tap of a row and the
+// five missing channels.  Also: conv bias; input-side BN of the NEXT convolution folded to scale / shift (applied by THIS
+// layer's epilogue).  par: sN[32] tN[32] bias[32].
+template <int CIN>
+__device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uint8_t* Bs, float* par, const ConvP* nxt) {
+    constexpr bool first = CIN == 3;
     const int tid = threadIdx.x;
-    const int k9 = p.cin * 9, n = p.cout * k9;
+    constexpr int k9 = CIN * 9;
+    const int n = p.cout * k9;
     float *sN = par, *tN = par + 32, *bias = par + 64;
-    int* offs = reinterpret_cast<int*>(par + 96);
-    if (cinp != p.cin) {       // first layer: padded channel and K tail are zeros
-        for (int i = tid; i < 16 * 128 / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(Bs)[i] = make_uint4(0, 0, 0, 0);
+    if (first) {       // phantom tap and padded channels are zeros
+        for (int i = tid; i < 2 * 16 * 128 / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(Bs)[i] = make_uint4(0, 0, 0, 0);
         it_wsync();
     }
     // compact code on purpose (the kernel's instruction footprint is what a layer pays for first): 6 weights per round
@@ -82,7 +93,11 @@ __device__ __noinline__ void it_prep_layer(const ItCtx& c, const ConvP& p, int c
             const int t = t0 + u * IT_WORKERS;
             if (t < n) {
                 const int oc = t / k9, rem = t - oc * k9, ci = rem / 9, tap = rem - ci * 9;
-                const int k = tap * cinp + ci;
+                int k = tap * CIN + ci;
+                if (first) {
+                    const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+                    k = (dy * 2 + (dx >> 1)) * 16 + (dx & 1) * 8 + ci;
+                }
                 *reinterpret_cast<__half*>(Bs + (k >> 6) * (p.cout * 128) + oc * 128 + ((((k & 63) >> 3) ^ (oc & 7)) << 4) + (k & 7) * 2) =
                     __float2half_rn(perturb1(a[u], c.sg, e[u]));
             }
@@ -95,51 +110,13 @@ __device__ __noinline__ void it_prep_layer(const ItCtx& c, const ConvP& p, int c
         const float s = c.par(nxt->g + ch) * inv;
         sN[ch] = s;
         tN[ch] = c.par(nxt->be + ch) - c.bn[nxt->bm + ch] * s;
-    } else if (tid >= 64 && tid < 64 + 40) {
-        const int q = tid - 64;
-        if (cinp == 4) {                 // first layer: offs[tap] of the 8-byte pixel
-            const int dy = (q * 11) >> 5, dx = q - 3 * dy;
-            offs[q] = (dy * Wp + dx) * 8;
-        } else {
-            const int cpt = cinp >> 3, tap = q / cpt, part = q - tap * cpt, dy = (tap * 11) >> 5, dx = tap - 3 * dy;
-            offs[q] = ((dy * Wp + dx) * cinp + part * 8) * 2;
-        }
     }
 }
 
-// one im2col unit: output pixels T*128 + r of a W x W map, chunks [q0, q0 + nq) (nq <= 8: one 64-wide K box) of the 3x3
-// window: a 16-byte copy per (pixel, chunk) from the channel-last map into the 128-byte swizzled K-major tile
-__device__ __forceinline__ void it_build(uint32_t Ab, const uint8_t* xh, const int* offs, int lw, int cin, int T, int M, int q0, int nq) {
-    const int t = threadIdx.x, r = t & 127, j0 = t >> 7, p = T * 128 + r;
-    if (p < M) {
-        const int W = 1 << lw, y = p >> lw, x = p & (W - 1);
-        const uint8_t* pb = xh + ((y * (W + 2) + x) * cin) * 2;
-        const uint32_t db = Ab + (uint32_t)(r * 128);
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const int j = j0 + IT_GROUPS * h;
-            if (j < nq) {
-                const uint4 v = *reinterpret_cast<const uint4*>(pb + offs[q0 + j]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(db + (uint32_t)((j ^ (r & 7)) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-            }
-        }
-    }
-}
-// the first convolution: 4 (3 + 1 zero) halves per pixel, K = 36 padded to 48: chunk q = taps 2q, 2q + 1 (taps >= 9 are zeros)
-__device__ __forceinline__ void it_build_first(uint32_t Ab, const uint8_t* xh, const int* offs, int T) {
-    const int t = threadIdx.x, r = t & 127, j0 = t >> 7, p = T * 128 + r, y = p >> 6, x = p & 63;
-    const uint8_t* pb = xh + (y * 66 + x) * 8;
-    const uint32_t db = Ab + (uint32_t)(r * 128);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int j = j0 + IT_GROUPS * h;
-        if (j < 6) {
-            uint2 v0 = make_uint2(0, 0), v1 = make_uint2(0, 0);
-            if (2 * j < 9) v0 = *reinterpret_cast<const uint2*>(pb + offs[2 * j]);
-            if (2 * j + 1 < 9) v1 = *reinterpret_cast<const uint2*>(pb + offs[2 * j + 1]);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(db + (uint32_t)((j ^ (r & 7)) << 4)), "r"(v0.x), "r"(v0.y), "r"(v1.x), "r"(v1.y) : "memory");
-        }
-    }
+__device__ __forceinline__ void it_prep_layer(const ItCtx& c, const ConvP& p, bool first, uint8_t* Bs, float* par, const ConvP* nxt) {
+    if (first) it_prep_layer_t<3>(c, p, Bs, par, nxt);
+    else if (p.cin == 16) it_prep_layer_t<16>(c, p, Bs, par, nxt);
+    else it_prep_layer_t<32>(c, p, Bs, par, nxt);
 }
 
 template <int C>
@@ -148,36 +125,13 @@ __device__ __forceinline__ void it_tmem_ld(uint32_t taddr, float* v) {
     else tmem_ld32(taddr, v);
 }
 
-// passes (one 64-wide K box each) of a layer with `cin` (padded) input channels and the k-steps of pass ps
-__device__ __forceinline__ int it_npass(int cin) { return cin == 4 ? 1 : (cin == 16 ? 3 : 5); }
-__device__ __forceinline__ int it_nchunk(int cin, int ps) { return cin == 4 ? 6 : (cin == 16 ? (ps < 2 ? 8 : 2) : (ps < 4 ? 8 : 4)); }
-
-// worker side of the im2col pipeline (3 buffers): wait until the MMAs that read the buffer have completed (one poller per
-// warp), copy, make the copies visible to the tensor core's proxy, publish.  `ug` = running unit number, the same
-// sequence in the workers and in the MMA warp.
-__device__ __noinline__ int it_build_tile(uint32_t bar0, uint32_t a0, int ug, const uint8_t* xh, const int* offs, int lw, int cin, int T, int M, long long* prof) {
-#define IT_US(slot) do { if (prof != nullptr && blockIdx.x == 7 && threadIdx.x == 0 && ug >= 60 && ug < 62) prof[32 + (ug - 60) * 8 + (slot)] = clock64(); } while (0)
-    const int lane = threadIdx.x & 31;
-    const int np = it_npass(cin);
-#pragma unroll 1
-    for (int ps = 0; ps < np; ++ps) {
-        const int bufi = ug % 3;
-        IT_US(0);
-        if (lane == 0) dr_wait(bar0 + 8u * (uint32_t)(IB_AEMPTY + bufi), (uint32_t)((ug / 3) & 1) ^ 1u);
-        __syncwarp();
-        IT_US(1);
-        const uint32_t Ab = a0 + (uint32_t)bufi * 16384u;
-        if (cin == 4) it_build_first(Ab, xh, offs, T);
-        else it_build(Ab, xh, offs, lw, cin, T, M, ps * 8, it_nchunk(cin, ps));
-        IT_US(2);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        IT_US(3);
-        if (lane == 0) dr_arrive(bar0 + 8u * (uint32_t)(IB_AFULL + bufi));
-        ++ug;
-    }
-    return ug;
-#undef IT_US
+// workers -> MMA warp: everything the next batch of MMAs reads (operand map, weights) is written and visible to the
+// tensor core's proxy, and every TMEM access of the previous epilogue has retired
+__device__ __forceinline__ void it_go(uint32_t bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    it_wsync();
+    if (threadIdx.x == 0) dr_arrive(bar);
 }
 __device__ __forceinline__ void it_layer_wait(uint32_t bar0, uint32_t& mph) {
     if ((threadIdx.x & 31) == 0) dr_wait(bar0 + 8u * (uint32_t)IB_MMA, mph);
@@ -185,35 +139,44 @@ __device__ __forceinline__ void it_layer_wait(uint32_t bar0, uint32_t& mph) {
     mph ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void it_zero_map(uint8_t* xh) {
-    for (int i = threadIdx.x; i < IT_XH_BYTES / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(xh)[i] = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ void it_zero(uint8_t* xh, int bytes) {
+    for (int i = threadIdx.x; i < bytes / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(xh)[i] = make_uint4(0, 0, 0, 0);
+}
+// eight BN'd (optionally ReLU'd) channels of one position -> one 16-byte chunk of a plane
+__device__ __forceinline__ uint4 it_pack8(const float* v, const float* sc, const float* sh, const float* bias, bool relu) {
+    uint32_t o[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float u0 = fmaf(v[2 * g] + (bias ? bias[2 * g] : 0.f), sc[2 * g], sh[2 * g]);
+        float u1 = fmaf(v[2 * g + 1] + (bias ? bias[2 * g + 1] : 0.f), sc[2 * g + 1], sh[2 * g + 1]);
+        if (relu) { u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); }
+        o[g] = dr_pack(u0, u1);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// MMA-warp side of the pipeline: the passes of one output tile; frees each buffer with a commit
-__device__ __noinline__ int it_mma_tile(uint32_t bar0, uint32_t s0, uint32_t tmem, int ug, int li, uint32_t d_col, int cin, int cout, bool accumulate, long long* prof) {
-#define IT_MS(slot) do { if (prof != nullptr && blockIdx.x == 7 && (threadIdx.x & 31) == 0 && ug >= 60 && ug < 62) prof[32 + (ug - 60) * 8 + (slot)] = clock64(); } while (0)
-    const int np = it_npass(cin);
+// MMA-warp side: all MMAs of one 128-position output tile whose first position (relative to the first interior pixel) is
+// q0.  map: shared address of the input map, Wp its padded width, cin its channels (3: the first convolution).
+__device__ __forceinline__ void it_mma_tile(uint32_t map, int Wp, int cin, uint32_t Bb, int cout, int q0, uint32_t d_tmem, bool accumulate) {
     const uint32_t idesc = dr_idesc(cout, 0);
-    const uint32_t Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
+    const uint32_t plane = (uint32_t)(Wp * Wp * 16);
+    if (cin == 3) {
 #pragma unroll 1
-    for (int ps = 0; ps < np; ++ps) {
-        const int bufi = ug % 3;
-        IT_MS(4);
-        dr_wait(bar0 + 8u * (uint32_t)(IB_AFULL + bufi), (uint32_t)((ug / 3) & 1));
-        IT_MS(5);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int nk = cin == 4 ? 3 : it_nchunk(cin, ps) >> 1;
-        const uint64_t adesc = make_desc_sw128(s0 + IT_A + (uint32_t)bufi * 16384u);
-        const uint64_t bdesc = make_desc_sw128(Bb + (uint32_t)(ps * cout * 128));
-#pragma unroll 1
-        for (int ks = 0; ks < nk; ++ks)
-            dr_umma_ss(tmem + d_col, adesc + (uint64_t)(ks * 2), bdesc + (uint64_t)(ks * 2), idesc, ((ps | ks) != 0 || accumulate) ? 1u : 0u);
-        umma_commit_elect(bar0 + 8u * (uint32_t)(IB_AEMPTY + bufi));
-        IT_MS(6);
-        ++ug;
+        for (int j = 0; j < 6; ++j) {                         // (dy, tap pair): taps dx = 2 * (j & 1), + 1
+            const uint32_t a = map + (uint32_t)((q0 + (j >> 1) * Wp + (j & 1) * 2) * 16);
+            dr_umma_ss(d_tmem, make_desc(a, 16, 128), make_desc_sw128(Bb + (uint32_t)((j >> 2) * cout * 128)) + (uint64_t)((j & 3) * 2), idesc,
+                       (j != 0 || accumulate) ? 1u : 0u);
+        }
+        return;
     }
-    return ug;
-#undef IT_MS
+    const int halves = cin >> 4, nj = 9 * halves;             // K = 16 per MMA: two planes
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) {
+        const int tap = halves == 1 ? j : (j >> 1), hf = halves == 1 ? 0 : (j & 1), dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+        const uint32_t a = map + (uint32_t)hf * 2u * plane + (uint32_t)((q0 + dy * Wp + dx) * 16);
+        dr_umma_ss(d_tmem, make_desc(a, plane, 128), make_desc_sw128(Bb + (uint32_t)((j >> 2) * cout * 128)) + (uint64_t)((j & 3) * 2), idesc,
+                   (j != 0 || accumulate) ? 1u : 0u);
+    }
 }
 
 __global__ void __launch_bounds__(IT_THREADS, 1)
@@ -258,11 +221,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) { targs.inst[i] = inst[i]; targs.sgi[i] = sgi[i]; targs.ids[i] = ids[i]; targs.rows[i] = rows[i]; }
 
     if (tid == 0) {
-        for (int s = 0; s < TB_COUNT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(IT_BAR(s)));
-        for (int s = 0; s < 3; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(IT_BAR(IB_AFULL + s)), "r"(IT_WORKERS / 32));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(IT_BAR(IB_AEMPTY + s)));
-        }
+        for (int s = 0; s < IB_COUNT; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(IT_BAR(s)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -276,23 +235,24 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
     const int q4 = warp & 3, wg = warp >> 2;                    // TMEM lane quarter of this warp, its group of four warps
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     uint32_t mph = 0;
-    int ug = 0, li = 0;                  // running im2col unit / layer numbers: identical sequences in the workers and the MMA warp
+    int li = 0;                          // running layer number: the same sequence in the workers and the MMA warp
     stamp();
 
     if (worker) {
         auto Bbuf = [&](int l) { return sm + IT_B + (l & 1) * IT_B_BYTES; };
         auto Pbuf = [&](int l) { return par_s + (l & 1) * IT_PAR_WORDS; };
+        const int r128 = q4 * 32 + lane;                        // this thread's TMEM lane = row of every tile
 
 #pragma unroll 1
         for (int mem = 0; mem < nmem; ++mem) {
             ItCtx c;
             c.theta = theta; c.bn = bnbuf; c.sg = sigma * (float)sgi[mem]; c.row = rows[mem];
-            uint8_t* xa = sm + IT_XHA;
-            uint8_t* xb = sm + IT_XHB;
+            uint8_t* xa = sm + IT_M1;                           // the frame map spans buffers 1 and 2
+            uint8_t* xb = sm + IT_M0;
             it_wsync();
-            // ---- frame / 255 -> BN of the first convolution -> fp16 [66 x 66][4] zero-bordered (impala.py:142) ----
+            // ---- frame / 255 -> BN of the first convolution -> fp16 plane [66 x 66][8] (3 channels + 5 zeros), zero border ----
             float* fpar = reinterpret_cast<float*>(band);        // scale / shift of the three input channels
-            it_zero_map(xa);
+            it_zero(xa, 2 * IT_XH_BYTES);
             if (tid < 3) {
                 const ConvP& p0 = L.feat[0];
                 const float inv = 1.0f / sqrtf(bnbuf[p0.bv + tid] + 1e-5f);
@@ -300,7 +260,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 fpar[tid] = s;
                 fpar[4 + tid] = c.par(p0.be + tid) - bnbuf[p0.bm + tid] * s;
             }
-            it_prep_layer(c, L.feat[0], 4, 66, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
+            it_prep_layer(c, L.feat[0], true, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
             it_wsync();
             {
                 const float* fr = frame + (int64_t)inst[mem] * 12288;
@@ -316,102 +276,99 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                     const int p = min(tid + u * IT_WORKERS, 4095);
                     const uint32_t lo = dr_pack(fmaf(f[3 * u] / 255.0f, fpar[0], fpar[4]), fmaf(f[3 * u + 1] / 255.0f, fpar[1], fpar[5]));
                     const uint32_t hi = dr_pack(fmaf(f[3 * u + 2] / 255.0f, fpar[2], fpar[6]), 0.f);
-                    *reinterpret_cast<uint2*>(xa + (((p >> 6) + 1) * 66 + (p & 63) + 1) * 8) = make_uint2(lo, hi);
+                    *reinterpret_cast<uint4*>(xa + (((p >> 6) + 1) * 66 + (p & 63) + 1) * 16) = make_uint4(lo, hi, 0u, 0u);
                 }
             }
-            it_wsync();
             if (mem == 0) stamp();
-#pragma unroll 1
-            for (int s = 0; s < 3; ++s) {
+            auto stage = [&](auto Cc, const int s) {
+                constexpr int C = decltype(Cc)::value, C4 = C >> 2;
                 // =========== stage convolution (BN on the input, no ReLU) + max-pool 3x3 / 2 pad 1 ===========
-                const ConvP& fp = L.feat[s];
-                const int lwc = 6 - s, Wc = 1 << lwc, C = fp.cout, cinp = s == 0 ? 4 : fp.cin;
-                const int lwo = lwc - 1, Wo = 1 << lwo;
+                const int Wc = 64 >> s, Wpc = Wc + 2;
+                const int Wo = Wc >> 1, Wpo = Wo + 2, planeo = Wpo * Wpo * 16;
                 const float* par = Pbuf(li);
                 const float *sN = par, *tN = par + 32, *bias = par + 64;
-                const int* offs = reinterpret_cast<const int*>(par + 96);
-                it_zero_map(xb);                                   // becomes the pooled operand map (new geometry)
-                const int tiles_band = (8 * Wc) >> 7;           // 4, 2, 1 tiles of 128 conv pixels per band of 8 rows
-                const int npool = 4 * Wo;                       // pooled pixels per band: 128, 64, 32
+                it_zero(xb, IT_XH_BYTES);                          // becomes the pooled operand map (new geometry)
+                const int ntb = (8 * Wpc + 127) >> 7;           // 5, 3, 2 tiles per band of 8 conv rows
+                const int ntR = (Wo * Wpo - 2 + 127) >> 7;      // tiles of the residual stream: 9, 3, 1
                 const ConvP& pa0 = L.res[0][s][0];
+                float4* band4 = reinterpret_cast<float4*>(band);
 #pragma unroll 1
                 for (int b = 0; b < Wc / 8; ++b) {
-                    if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && s == 0 && b == 3) prof[48] = clock64();
-#pragma unroll 1
-                    for (int tl = 0; tl < tiles_band; ++tl) ug = it_build_tile(bar0, s0 + IT_A, ug, xa, offs, lwc, cinp, b * tiles_band + tl, Wc * Wc, prof);
-                    auto bst = [&](int i) { if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && s == 0 && b == 3) prof[48 + i] = clock64(); };
-                    bst(1);
+                    it_go(IT_BAR(IB_GO));                        // band b's MMAs may start (TC_P is free, map / weights visible)
                     if (b == 0)                                 // the first block convolution's weights, under this layer's MMAs
-                        it_prep_layer(c, pa0, pa0.cin, Wo + 2, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);
+                        it_prep_layer(c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);
                     it_layer_wait(bar0, mph);
-                    bst(2);
-                    // band epilogue: conv rows 8b .. 8b + 7 (+ bias) -> circular band [row % 9][x][c] fp32
+                    // band epilogue: conv rows 8b .. 8b + 7 (+ bias) -> circular band [row % 9][c / 4][x] float4
 #pragma unroll 1
-                    for (int tg = wg; tg < tiles_band; tg += IT_GROUPS) {
-                        const int p = (b * tiles_band + tg) * 128 + q4 * 32 + lane, y = p >> lwc, x = p & (Wc - 1);
-                        float* dst = band + ((y % 9) * Wc + x) * C;
+                    for (int tg = wg; tg < ntb; tg += IT_GROUPS) {
+                        const int ql = tg * 128 + r128, yl = ql / Wpc, x = ql - yl * Wpc;
                         float v[32];
                         if (C == 16) it_tmem_ld<16>(tmem + lane_sel + TC_P + (uint32_t)(tg * 16), v);
                         else it_tmem_ld<32>(tmem + lane_sel + TC_P + (uint32_t)(tg * 32), v);
+                        if (yl < 8 && x < Wc) {
+                            float4* dst = band4 + (((8 * b + yl) % 9) * C4) * Wc + x;
 #pragma unroll
-                        for (int ch = 0; ch < 32; ch += 4)
-                            if (ch < C)
-                                *reinterpret_cast<float4*>(dst + ch) = make_float4(v[ch] + bias[ch], v[ch + 1] + bias[ch + 1], v[ch + 2] + bias[ch + 2], v[ch + 3] + bias[ch + 3]);
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            for (int g = 0; g < 8; ++g)
+                                if (g < C4)
+                                    dst[g * Wc] = make_float4(v[4 * g] + bias[4 * g], v[4 * g + 1] + bias[4 * g + 1], v[4 * g + 2] + bias[4 * g + 2],
+                                                              v[4 * g + 3] + bias[4 * g + 3]);
+                        }
                     }
-                    bst(3);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     it_wsync();
-                    bst(4);
-                    // pool: pooled pixel P = b * npool + i lives in lane P % 128 of residual tile P / 128
-                    const int l0 = (b * npool) & 127;
-                    if (tid >= l0 && tid < l0 + npool) {
-                        const int Pp = b * npool + (tid - l0), py = Pp >> lwo, px = Pp & (Wo - 1);
-                        float m[32];
+                    // pool: pooled rows 4b .. 4b + 3 = positions [4b * Wpo, (4b + 4) * Wpo) of the new geometry; position q
+                    // lives in lane q % 128 of residual tile q / 128
+                    {
+                        const int qlo = 4 * b * Wpo, tile = (qlo >> 7) + (tid >> 7), q = tile * 128 + (tid & 127);
+                        const bool in_range = q >= qlo && q < qlo + 4 * Wpo;
+                        if (tile < ntR && __any_sync(0xffffffffu, in_range)) {
+                            const int py = q / Wpo, px = q - py * Wpo;
+                            const bool valid = in_range && px < Wo;
+                            float m[32];
+                            const uint32_t rt = tmem + lane_sel + TC_R + (uint32_t)(tile * C);
+                            if (C == 16) it_tmem_ld<16>(rt, m);           // lanes outside this band keep what they hold
+                            else it_tmem_ld<32>(rt, m);
+                            if (valid) {
 #pragma unroll
-                        for (int ch = 0; ch < 32; ++ch) m[ch] = -INFINITY;
-                        for (int dy = -1; dy <= 1; ++dy) {
-                            const int yy = 2 * py + dy;
-                            if (yy < 0 || yy >= Wc) continue;
-                            for (int dx = -1; dx <= 1; ++dx) {
-                                const int xx = 2 * px + dx;
-                                if (xx < 0 || xx >= Wc) continue;
-                                const float4* src = reinterpret_cast<const float4*>(band + ((yy % 9) * Wc + xx) * C);
+                                for (int ch = 0; ch < 32; ++ch) m[ch] = -INFINITY;
+                                for (int dy = -1; dy <= 1; ++dy) {
+                                    const int yy = 2 * py + dy;
+                                    if (yy < 0 || yy >= Wc) continue;
+                                    for (int dx = -1; dx <= 1; ++dx) {
+                                        const int xx = 2 * px + dx;
+                                        if (xx < 0 || xx >= Wc) continue;
+                                        const float4* src = band4 + ((yy % 9) * C4) * Wc + xx;
 #pragma unroll
-                                for (int g = 0; g < 8; ++g) {
-                                    if (g * 4 < C) {
-                                        const float4 f = src[g];
-                                        m[4 * g] = fmaxf(m[4 * g], f.x); m[4 * g + 1] = fmaxf(m[4 * g + 1], f.y);
-                                        m[4 * g + 2] = fmaxf(m[4 * g + 2], f.z); m[4 * g + 3] = fmaxf(m[4 * g + 3], f.w);
+                                        for (int g = 0; g < 8; ++g) {
+                                            if (g < C4) {
+                                                const float4 f = src[g * Wc];
+                                                m[4 * g] = fmaxf(m[4 * g], f.x); m[4 * g + 1] = fmaxf(m[4 * g + 1], f.y);
+                                                m[4 * g + 2] = fmaxf(m[4 * g + 2], f.z); m[4 * g + 3] = fmaxf(m[4 * g + 3], f.w);
+                                            }
+                                        }
                                     }
                                 }
                             }
-                        }
-                        // raw pooled map -> TMEM residual stream; BN + ReLU of the first block convolution -> operand map
-                        const uint32_t rt = tmem + lane_sel + TC_R + (uint32_t)((Pp >> 7) * C);
-                        it_tmem_st16(rt, m);
-                        if (C == 32) it_tmem_st16(rt + 16u, m + 16);
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        uint32_t o[16];
+                            // raw pooled map -> TMEM residual stream; BN + ReLU of the first block convolution -> operand map
+                            it_tmem_st16(rt, m);
+                            if (C == 32) it_tmem_st16(rt + 16u, m + 16);
+                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                            if (valid) {
+                                uint8_t* dst = xb + (q + Wpo + 1) * 16;
 #pragma unroll
-                        for (int g = 0; g < 16; ++g)
-                            o[g] = dr_pack(fmaxf(fmaf(m[2 * g], sN[2 * g], tN[2 * g]), 0.f), fmaxf(fmaf(m[2 * g + 1], sN[2 * g + 1], tN[2 * g + 1]), 0.f));
-                        uint4* dst = reinterpret_cast<uint4*>(xb + (((py + 1) * (Wo + 2) + px + 1) * C) * 2);
-                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                        if (C == 32) { dst[2] = make_uint4(o[8], o[9], o[10], o[11]); dst[3] = make_uint4(o[12], o[13], o[14], o[15]); }
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                                for (int j = 0; j < 4; ++j)
+                                    if (8 * j < C) *reinterpret_cast<uint4*>(dst + j * planeo) = it_pack8(m + 8 * j, sN + 8 * j, tN + 8 * j, nullptr, true);
+                            }
+                        }
                     }
-                    bst(5);
-                    it_wsync();
-                    bst(6);
                 }
                 ++li;
                 { uint8_t* t_ = xa; xa = xb; xb = t_; }            // xa: operand map of the first block convolution
-                it_zero_map(xb);                                       // old-geometry map: becomes the block-internal operand map
                 it_wsync();
+                it_zero(xb, IT_XH_BYTES);                              // old-geometry map: becomes the block-internal operand map
                 if (mem == 0) stamp();
                 // =========== two residual blocks: x += conv_b(relu(BN_b(conv_a(relu(BN_a(x)))))) ===========
-                const int lw = lwo, W = Wo, M = W * W, ntile = (M + 127) >> 7;
+                const int W = Wo, Wp = Wpo, plane = planeo, ntile = ntR;
 #pragma unroll 1
                 for (int blk = 0; blk < 2; ++blk) {
                     const ConvP& pb = L.res[blk][s][1];
@@ -421,58 +378,39 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                     {
                         const float* pr = Pbuf(li);
                         const float *sA = pr, *tA = pr + 32, *bA = pr + 64;
-                        const int* offs_a = reinterpret_cast<const int*>(pr + 96);
-                        auto fine = [&](int i) { if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && blk == 0) prof[16 + 4 * s + i] = clock64(); };
-                        fine(0);
-#pragma unroll 1
-                        for (int T = 0; T < ntile; ++T) ug = it_build_tile(bar0, s0 + IT_A, ug, xa, offs_a, lw, C, T, M, prof);
-                        fine(1);
-                        it_prep_layer(c, pb, pb.cin, W + 2, Bbuf(li + 1), Pbuf(li + 1), nxt);     // conv b's weights, under conv a's MMAs
-                        fine(2);
+                        it_go(IT_BAR(IB_GO));
+                        it_prep_layer(c, pb, false, Bbuf(li + 1), Pbuf(li + 1), nxt);     // conv b's weights, under conv a's MMAs
                         it_layer_wait(bar0, mph);
-                        fine(3);
 #pragma unroll 1
                         for (int T = wg; T < ntile; T += IT_GROUPS) {
-                            const int p = T * 128 + q4 * 32 + lane;
+                            const int q = T * 128 + r128, y = q / Wp, x = q - y * Wp;
                             float v[32];
                             if (C == 16) it_tmem_ld<16>(tmem + lane_sel + TC_Y + (uint32_t)(T * 16), v);
                             else it_tmem_ld<32>(tmem + lane_sel + TC_Y + (uint32_t)(T * 32), v);
-                            if (p < M) {
-                                const int y = p >> lw, x = p & (W - 1);
-                                uint4* dst = reinterpret_cast<uint4*>(xb + (((y + 1) * (W + 2) + x + 1) * C) * 2);
-                                uint32_t o[16];
+                            if (y < W && x < W) {
+                                uint8_t* dst = xb + (q + Wp + 1) * 16;
 #pragma unroll
-                                for (int g = 0; g < 16; ++g)
-                                    if (2 * g < C)
-                                        o[g] = dr_pack(fmaxf(fmaf(v[2 * g] + bA[2 * g], sA[2 * g], tA[2 * g]), 0.f),
-                                                       fmaxf(fmaf(v[2 * g + 1] + bA[2 * g + 1], sA[2 * g + 1], tA[2 * g + 1]), 0.f));
-                                dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                                dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                                if (C == 32) { dst[2] = make_uint4(o[8], o[9], o[10], o[11]); dst[3] = make_uint4(o[12], o[13], o[14], o[15]); }
+                                for (int j = 0; j < 4; ++j)
+                                    if (8 * j < C) *reinterpret_cast<uint4*>(dst + j * plane) = it_pack8(v + 8 * j, sA + 8 * j, tA + 8 * j, bA + 8 * j, true);
                             }
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         }
                         ++li;
-                        it_wsync();
                     }
                     // ---- conv b accumulates ONTO the residual stream in TMEM; epilogue: x += bias, next operand map -> xa ----
                     {
                         const float* pr = Pbuf(li);
                         const float *sB = pr, *tB = pr + 32, *bB = pr + 64;
-                        const int* offs_b = reinterpret_cast<const int*>(pr + 96);
                         const bool relu_next = blk == 0;             // next consumer: a block convolution (BN + ReLU) or a stage convolution (BN only)
-#pragma unroll 1
-                        for (int T = 0; T < ntile; ++T) ug = it_build_tile(bar0, s0 + IT_A, ug, xb, offs_b, lw, C, T, M, prof);
+                        it_go(IT_BAR(IB_GO));
                         if (nxt != nullptr) {                        // the next layer's weights, under conv b's MMAs
                             const bool nxt_stage = blk == 1;
-                            it_prep_layer(c, *nxt, nxt->cin, W + 2, Bbuf(li + 1), Pbuf(li + 1),
-                                          nxt_stage ? &L.res[0][s + 1][0] : &L.res[1][s][1]);
+                            it_prep_layer(c, *nxt, false, Bbuf(li + 1), Pbuf(li + 1), nxt_stage ? &L.res[0][s + 1][0] : &L.res[1][s][1]);
                         }
                         it_layer_wait(bar0, mph);
                         float* fscr = band;                          // relu(x) of the last layer, [c * 64 + pixel]
 #pragma unroll 1
                         for (int T = wg; T < ntile; T += IT_GROUPS) {
-                            const int p = T * 128 + q4 * 32 + lane;
+                            const int q = T * 128 + r128, y = q / Wp, x = q - y * Wp;
                             float v[32];
                             const uint32_t rt = tmem + lane_sel + TC_R + (uint32_t)(T * C);
                             if (C == 16) it_tmem_ld<16>(rt, v);
@@ -485,31 +423,22 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                                 if (C == 32) it_tmem_st16(rt + 16u, v + 16);
                                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                             }
-                            if (p < M) {
+                            if (y < W && x < W) {
                                 if (!last) {
-                                    const int y = p >> lw, x = p & (W - 1);
-                                    uint4* dst = reinterpret_cast<uint4*>(xa + (((y + 1) * (W + 2) + x + 1) * C) * 2);
-                                    uint32_t o[16];
+                                    uint8_t* dst = xa + (q + Wp + 1) * 16;
 #pragma unroll
-                                    for (int g = 0; g < 16; ++g)
-                                        if (2 * g < C) {
-                                            float u0 = fmaf(v[2 * g], sB[2 * g], tB[2 * g]), u1 = fmaf(v[2 * g + 1], sB[2 * g + 1], tB[2 * g + 1]);
-                                            if (relu_next) { u0 = fmaxf(u0, 0.f); u1 = fmaxf(u1, 0.f); }
-                                            o[g] = dr_pack(u0, u1);
-                                        }
-                                    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                                    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                                    if (C == 32) { dst[2] = make_uint4(o[8], o[9], o[10], o[11]); dst[3] = make_uint4(o[12], o[13], o[14], o[15]); }
+                                    for (int j = 0; j < 4; ++j)
+                                        if (8 * j < C) *reinterpret_cast<uint4*>(dst + j * plane) = it_pack8(v + 8 * j, sB + 8 * j, tB + 8 * j, nullptr, relu_next);
                                 } else {
 #pragma unroll
-                                    for (int ch = 0; ch < 32; ++ch) fscr[ch * 64 + p] = fmaxf(v[ch], 0.f);
+                                    for (int ch = 0; ch < 32; ++ch) fscr[ch * 64 + y * 8 + x] = fmaxf(v[ch], 0.f);
                                 }
                             }
-                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         }
                         ++li;
-                        it_wsync();
                         if (last) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            it_wsync();
                             // relu -> flatten (C, H, W) -> BN1d(2048), exactly perturbed gamma / beta (impala.py:153-155)
                             constexpr int NK = (2048 + IT_WORKERS - 1) / IT_WORKERS;
                             float gt[NK], ge[NK], bt[NK], be[NK], vm[NK], vv[NK];
@@ -532,7 +461,10 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                     }
                     if (mem == 0) stamp();
                 }
-            }
+            };
+            stage(std::integral_constant<int, 16>(), 0);
+            stage(std::integral_constant<int, 32>(), 1);
+            stage(std::integral_constant<int, 32>(), 2);
         }
         // ======================================= dense tail =======================================
         stamp_i = 11;
@@ -541,30 +473,44 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
         stamp();
     } else {
         // =============================== MMA issue warp of the trunk ===============================
-        // mirrors the workers' sequence of im2col units: waits for a buffer, issues its k-steps, frees it with a commit;
-        // a second commit at the end of every layer (stage convolutions: every band) tells the workers the accumulator is ready
+        // mirrors the workers' sequence of layers / bands: waits until the operands are ready, issues every tile of the
+        // batch (a filter tap = a start address), and commits: the commit tells the workers the accumulators are ready
+        uint32_t gph = 0;
+        auto go_wait = [&]() {
+            dr_wait(IT_BAR(IB_GO), gph);
+            gph ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        };
 #pragma unroll 1
         for (int mem = 0; mem < nmem; ++mem) {
+            uint32_t xa = s0 + IT_M1, xb = s0 + IT_M0;
 #pragma unroll 1
             for (int s = 0; s < 3; ++s) {
-                const int Wc = 64 >> s, C = s == 0 ? 16 : 32, cinp = s == 0 ? 4 : (s == 1 ? 16 : 32);
-                const int tiles_band = (8 * Wc) >> 7;
+                const int Wc = 64 >> s, Wpc = Wc + 2, C = s == 0 ? 16 : 32, cin = s == 0 ? 3 : (s == 1 ? 16 : 32);
+                const int ntb = (8 * Wpc + 127) >> 7;
 #pragma unroll 1
                 for (int b = 0; b < Wc / 8; ++b) {
+                    go_wait();
+                    const uint32_t Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
 #pragma unroll 1
-                    for (int tl = 0; tl < tiles_band; ++tl) ug = it_mma_tile(bar0, s0, tmem, ug, li, TC_P + (uint32_t)(tl * C), cinp, C, false, prof);
+                    for (int tl = 0; tl < ntb; ++tl) it_mma_tile(xa, Wpc, cin, Bb, C, 8 * b * Wpc + tl * 128, tmem + TC_P + (uint32_t)(tl * C), false);
                     umma_commit_elect(IT_BAR(IB_MMA));
                 }
                 ++li;
-                const int W = Wc >> 1, M = W * W, ntile = (M + 127) >> 7;
+                { const uint32_t t_ = xa; xa = xb; xb = t_; }
+                const int W = Wc >> 1, Wp = W + 2, ntile = (W * Wp - 2 + 127) >> 7;
 #pragma unroll 1
                 for (int blk = 0; blk < 2; ++blk) {
+                    go_wait();
+                    uint32_t Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
 #pragma unroll 1
-                    for (int T = 0; T < ntile; ++T) ug = it_mma_tile(bar0, s0, tmem, ug, li, TC_Y + (uint32_t)(T * C), C, C, false, prof);
+                    for (int T = 0; T < ntile; ++T) it_mma_tile(xa, Wp, C, Bb, C, T * 128, tmem + TC_Y + (uint32_t)(T * C), false);
                     umma_commit_elect(IT_BAR(IB_MMA));
                     ++li;
+                    go_wait();
+                    Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
 #pragma unroll 1
-                    for (int T = 0; T < ntile; ++T) ug = it_mma_tile(bar0, s0, tmem, ug, li, TC_R + (uint32_t)(T * C), C, C, true, prof);
+                    for (int T = 0; T < ntile; ++T) it_mma_tile(xb, Wp, C, Bb, C, T * 128, tmem + TC_R + (uint32_t)(T * C), true);
                     umma_commit_elect(IT_BAR(IB_MMA));
                     ++li;
                 }
