@@ -30,7 +30,7 @@ constexpr int IT_WORKERS = 384, IT_THREADS = IT_WORKERS + 32, IT_GROUPS = IT_WOR
 // UMMA no-swizzle K-major layout with the POSITION as the row: a core matrix is 8 consecutive positions (128 contiguous
 // bytes), the next 8-row group follows at +128 (SBO), the next 8 channels are one plane further (LBO).  A filter tap
 // (dy, dx) is then nothing but the descriptor's start address moved by (dy * (W + 2) + dx) positions: no im2col copy.
-constexpr int IT_M0 = 0, IT_M0_BYTES = 49152;                 // operand map buffer 0
+constexpr int IT_M0 = 0, IT_M0_BYTES = 38912;                 // operand map buffer 0 (the B operands behind it need 1024-byte aligned swizzle atoms)
 constexpr int IT_B = IT_M0 + IT_M0_BYTES, IT_B_BYTES = 20480; // weights of a layer: up to 5 boxes of [32 x 64]; two buffers
 constexpr int IT_XH_BYTES = 38400;                            // one operand map (34*34*16*2 = 36 992 is the largest)
 constexpr int IT_M1 = IT_B + 2 * IT_B_BYTES, IT_M2 = IT_M1 + IT_XH_BYTES;   // buffers 1, 2; the 66 x 66 frame map (69 696 B) spans both
@@ -38,12 +38,15 @@ constexpr int IT_BAND = IT_M2 + IT_XH_BYTES, IT_BAND_BYTES = 36864;   // 9 conv 
 constexpr int IT_FCIN = IT_BAND + IT_BAND_BYTES;              // fp16 [2][2048]: BN'd trunk outputs of the two members
 constexpr int IT_PAR = IT_FCIN + 8192, IT_PAR_WORDS = 96;     // two buffers of: sN[32] tN[32] bias[32]
 constexpr int IT_SMEM = IT_PAR + 2 * IT_PAR_WORDS * 4 + 1024;
+static_assert(IT_SMEM <= 232448, "shared memory");
+static_assert(IT_B % 1024 == 0 && IT_B_BYTES % 1024 == 0 && IT_BAND % 1024 == 0, "swizzle atoms");
 constexpr int IT_XT = IT_BAND;                                // dense tail: x tiles (impala_tail.cuh) in the band buffer
 static_assert(IT_M2 + IT_XH_BYTES >= 131072 + 2 * 5120, "the dense tail's tile ring and core / h0 tiles live below the band buffer");
 // tensor memory columns of the trunk
-constexpr uint32_t TC_R = 0, TC_Y = 160, TC_P = 320;          // residual stream (<= 144) | block-internal map | stage-conv band (<= 96)
+constexpr uint32_t TC_R = 0, TC_Y = 160, TC_P = 320, TC_PW = 96;   // residual stream (<= 144) | block-internal map | two stage-conv band accumulators (<= 96 each)
 // barriers: the tail's (impala_tail.cuh; TB_MMA doubles as "layer / band done" in the trunk), then "operands ready"
-enum { IB_MMA = TB_MMA, IB_GO = TB_COUNT, IB_COUNT = IB_GO + 1 };
+// IB_PD + i: band accumulator i holds a finished band; IB_PF + i: the workers have read it (the MMA warp runs a band ahead)
+enum { IB_MMA = TB_MMA, IB_GO = TB_COUNT, IB_PD = IB_GO + 1, IB_PF = IB_PD + 2, IB_COUNT = IB_PF + 2 };
 
 __device__ __forceinline__ void it_wsync() { asm volatile("bar.sync 1, %0;" ::"n"(IT_WORKERS) : "memory"); }
 __device__ __forceinline__ void it_tmem_st16(uint32_t taddr, const float* v) {
@@ -73,33 +76,44 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
     constexpr bool first = CIN == 3;
     const int tid = threadIdx.x;
     constexpr int k9 = CIN * 9;
-    const int n = p.cout * k9;
     float *sN = par, *tN = par + 32, *bias = par + 64;
-    if (first) {       // phantom tap and padded channels are zeros
+    if (first) {
+        // phantom tap and padded channels are zeros; 432 weights: one per thread and round, generic index arithmetic
         for (int i = tid; i < 2 * 16 * 128 / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(Bs)[i] = make_uint4(0, 0, 0, 0);
         it_wsync();
-    }
-    // compact code on purpose (the kernel's instruction footprint is what a layer pays for first): 6 weights per round
+        const int n = p.cout * k9;
 #pragma unroll 1
-    for (int t0 = tid; t0 < n; t0 += 6 * IT_WORKERS) {
-        float a[6], e[6];
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int t = min(t0 + u * IT_WORKERS, n - 1);
-            a[u] = c.theta[p.w + t]; e[u] = c.row[p.w + t];
+        for (int t = tid; t < n; t += IT_WORKERS) {
+            const int oc = t / k9, rem = t - oc * k9, ci = rem / 9, tap = rem - ci * 9;
+            const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+            const int k = (dy * 2 + (dx >> 1)) * 16 + (dx & 1) * 8 + ci;
+            *reinterpret_cast<__half*>(Bs + (k >> 6) * (p.cout * 128) + oc * 128 + ((((k & 63) >> 3) ^ (oc & 7)) << 4) + (k & 7) * 2) =
+                __float2half_rn(c.par(p.w + t));
         }
+    } else {
+        // A lane is an INPUT CHANNEL (the dimension that is contiguous in the K-major operand): the 32 lanes of a warp
+        // write 64 contiguous-but-swizzled bytes per tap - no bank conflicts, no index arithmetic beyond shifts - and read
+        // theta / eps at a stride of 9 floats: the nine loads of an output channel walk the same ten lines, so all but the
+        // first hit L1 (ld.global.nc).  32 / CIN output channels per warp and round.  Measured against (a) coalesced loads
+        // + 2-byte scatter stores (8-way bank conflicts, 30 instructions of index arithmetic per weight, optionally from
+        // an offset table) and (b) a two-pass build through a staging buffer: this form is the fastest of the three; what
+        // bounds all of them is the delivery of 8 bytes of theta / eps per weight from L2 while the other SMs stream
+        // their dense-tail tiles (10 B / cycle / SM observed).
+        constexpr int OPW = 32 / CIN;
+        const int w = tid >> 5, l = tid & 31, ci = l & (CIN - 1), o2 = l / CIN;
+        const int rowb = p.cout * 128;
+#pragma unroll 1
+        for (int oc = w * OPW + o2; oc < p.cout; oc += (IT_WORKERS / 32) * OPW) {
+            const float* wt = c.theta + p.w + oc * k9 + ci * 9;
+            const float* we = c.row + p.w + oc * k9 + ci * 9;
+            float a[9], e[9];
 #pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int t = t0 + u * IT_WORKERS;
-            if (t < n) {
-                const int oc = t / k9, rem = t - oc * k9, ci = rem / 9, tap = rem - ci * 9;
-                int k = tap * CIN + ci;
-                if (first) {
-                    const int dy = (tap * 11) >> 5, dx = tap - 3 * dy;
-                    k = (dy * 2 + (dx >> 1)) * 16 + (dx & 1) * 8 + ci;
-                }
-                *reinterpret_cast<__half*>(Bs + (k >> 6) * (p.cout * 128) + oc * 128 + ((((k & 63) >> 3) ^ (oc & 7)) << 4) + (k & 7) * 2) =
-                    __float2half_rn(perturb1(a[u], c.sg, e[u]));
+            for (int tap = 0; tap < 9; ++tap) { a[tap] = __ldg(wt + tap); e[tap] = __ldg(we + tap); }
+            uint8_t* dst = Bs + oc * 128 + (ci & 7) * 2;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int k = tap * CIN + ci;
+                *reinterpret_cast<__half*>(dst + (k >> 6) * rowb + ((((k & 63) >> 3) ^ (oc & 7)) << 4)) = __float2half_rn(perturb1(a[tap], c.sg, e[tap]));
             }
         }
     }
@@ -155,27 +169,37 @@ __device__ __forceinline__ uint4 it_pack8(const float* v, const float* sc, const
     return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// MMA-warp side: all MMAs of one 128-position output tile whose first position (relative to the first interior pixel) is
-// q0.  map: shared address of the input map, Wp its padded width, cin its channels (3: the first convolution).
-__device__ __forceinline__ void it_mma_tile(uint32_t map, int Wp, int cin, uint32_t Bb, int cout, int q0, uint32_t d_tmem, bool accumulate) {
+// MMA-warp side: all MMAs of a batch of `nt` output tiles of 128 positions (tile T starts at position q0 + 128 T, relative
+// to the first interior pixel; accumulator columns d_tmem + T * cout).  map: shared address of the input map, Wp its
+// padded width, cin its channels (3: the first convolution).  TAPS OUTER, TILES INNER: consecutive MMAs write different
+// accumulators - back-to-back MMAs onto the same small accumulator wait for each other (measured: ~100 cycles each).
+__device__ __forceinline__ void it_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc),
+                 "l"(bdesc), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+// called by ONE lane (which also commits): the inner loop is two adds and the MMA
+__device__ __forceinline__ void it_mma_batch(uint32_t map, int Wp, int cin, uint32_t Bb, int cout, int q0, int nt, uint32_t d_tmem, bool accumulate) {
     const uint32_t idesc = dr_idesc(cout, 0);
     const uint32_t plane = (uint32_t)(Wp * Wp * 16);
-    if (cin == 3) {
-#pragma unroll 1
-        for (int j = 0; j < 6; ++j) {                         // (dy, tap pair): taps dx = 2 * (j & 1), + 1
-            const uint32_t a = map + (uint32_t)((q0 + (j >> 1) * Wp + (j & 1) * 2) * 16);
-            dr_umma_ss(d_tmem, make_desc(a, 16, 128), make_desc_sw128(Bb + (uint32_t)((j >> 2) * cout * 128)) + (uint64_t)((j & 3) * 2), idesc,
-                       (j != 0 || accumulate) ? 1u : 0u);
-        }
-        return;
-    }
-    const int halves = cin >> 4, nj = 9 * halves;             // K = 16 per MMA: two planes
+    const int halves = cin == 3 ? 1 : cin >> 4, nj = cin == 3 ? 6 : 9 * halves;
 #pragma unroll 1
     for (int j = 0; j < nj; ++j) {
-        const int tap = halves == 1 ? j : (j >> 1), hf = halves == 1 ? 0 : (j & 1), dy = (tap * 11) >> 5, dx = tap - 3 * dy;
-        const uint32_t a = map + (uint32_t)hf * 2u * plane + (uint32_t)((q0 + dy * Wp + dx) * 16);
-        dr_umma_ss(d_tmem, make_desc(a, plane, 128), make_desc_sw128(Bb + (uint32_t)((j >> 2) * cout * 128)) + (uint64_t)((j & 3) * 2), idesc,
-                   (j != 0 || accumulate) ? 1u : 0u);
+        uint32_t a, lbo;
+        if (cin == 3) {                                       // (dy, tap pair): taps dx = 2 * (j & 1), + 1; second core matrix = next position
+            a = map + (uint32_t)((q0 + (j >> 1) * Wp + (j & 1) * 2) * 16);
+            lbo = 16;
+        } else {                                              // K = 16 per MMA: two planes
+            const int tap = halves == 1 ? j : (j >> 1), hf = halves == 1 ? 0 : (j & 1), dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+            a = map + (uint32_t)hf * 2u * plane + (uint32_t)((q0 + dy * Wp + dx) * 16);
+            lbo = plane;
+        }
+        const uint64_t bdesc = make_desc_sw128(Bb + (uint32_t)((j >> 2) * cout * 128)) + (uint64_t)((j & 3) * 2);
+        const uint32_t acc = (j != 0 || accumulate) ? 1u : 0u;
+        uint64_t adesc = make_desc(a, lbo, 128);
+        uint32_t d = d_tmem;
+#pragma unroll 1
+        for (int T = 0; T < nt; ++T, adesc += 128, d += (uint32_t)cout) it_umma(d, adesc, bdesc, idesc, acc);     // next tile: 128 positions = 2048 bytes
     }
 }
 
@@ -242,6 +266,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
         auto Bbuf = [&](int l) { return sm + IT_B + (l & 1) * IT_B_BYTES; };
         auto Pbuf = [&](int l) { return par_s + (l & 1) * IT_PAR_WORDS; };
         const int r128 = q4 * 32 + lane;                        // this thread's TMEM lane = row of every tile
+        int gb = 0;                                             // running band number (both roles): accumulator gb & 1, its use number gb >> 1
 
 #pragma unroll 1
         for (int mem = 0; mem < nmem; ++mem) {
@@ -249,6 +274,15 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
             c.theta = theta; c.bn = bnbuf; c.sg = sigma * (float)sgi[mem]; c.row = rows[mem];
             uint8_t* xa = sm + IT_M1;                           // the frame map spans buffers 1 and 2
             uint8_t* xb = sm + IT_M0;
+            // the member's convolution parameters (the first 0.4 MB of its table row) and its frame: into L2 now, so that
+            // the weight builds of the 15 layers find them there
+            if (tid < 8 && (mem == 0 || !shared_row)) {
+                const int span = L.fc_w, part = (span + 7) / 8, lo = tid * part;
+                if (lo < span) l2_prefetch(rows[mem] + lo, (size_t)min(part, span - lo) * 4);
+            } else if (tid == 32) {
+                l2_prefetch(frame + (int64_t)inst[mem] * 12288, 12288 * 4);
+                if (mem == 0 && nmem == 2) l2_prefetch(frame + (int64_t)inst[1] * 12288, 12288 * 4);
+            }
             it_wsync();
             // ---- frame / 255 -> BN of the first convolution -> fp16 plane [66 x 66][8] (3 channels + 5 zeros), zero border ----
             float* fpar = reinterpret_cast<float*>(band);        // scale / shift of the three input channels
@@ -292,19 +326,26 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 const int ntR = (Wo * Wpo - 2 + 127) >> 7;      // tiles of the residual stream: 9, 3, 1
                 const ConvP& pa0 = L.res[0][s][0];
                 float4* band4 = reinterpret_cast<float4*>(band);
+                it_go(IT_BAR(IB_GO));                            // the stage's map and weights are visible: the MMA warp may start its bands
+                it_prep_layer(c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);   // the first block convolution's weights, under the MMAs
 #pragma unroll 1
-                for (int b = 0; b < Wc / 8; ++b) {
-                    it_go(IT_BAR(IB_GO));                        // band b's MMAs may start (TC_P is free, map / weights visible)
-                    if (b == 0)                                 // the first block convolution's weights, under this layer's MMAs
-                        it_prep_layer(c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);
-                    it_layer_wait(bar0, mph);
+                for (int b = 0; b < Wc / 8; ++b, ++gb) {
+                    auto bst = [&](int i) { if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && s == 0 && b == 3) prof[48 + i] = clock64(); };
+                    const uint32_t pbuf = (uint32_t)(gb & 1), tcp = TC_P + pbuf * TC_PW;
+                    bst(0);
+                    it_wsync();                                  // the previous band's pool has read the rows this band overwrites
+                    bst(1);
+                    if (lane == 0) dr_wait(IT_BAR(IB_PD + pbuf), (uint32_t)((gb >> 1) & 1));
+                    __syncwarp();
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    bst(2);
                     // band epilogue: conv rows 8b .. 8b + 7 (+ bias) -> circular band [row % 9][c / 4][x] float4
 #pragma unroll 1
                     for (int tg = wg; tg < ntb; tg += IT_GROUPS) {
                         const int ql = tg * 128 + r128, yl = ql / Wpc, x = ql - yl * Wpc;
                         float v[32];
-                        if (C == 16) it_tmem_ld<16>(tmem + lane_sel + TC_P + (uint32_t)(tg * 16), v);
-                        else it_tmem_ld<32>(tmem + lane_sel + TC_P + (uint32_t)(tg * 32), v);
+                        if (C == 16) it_tmem_ld<16>(tmem + lane_sel + tcp + (uint32_t)(tg * 16), v);
+                        else it_tmem_ld<32>(tmem + lane_sel + tcp + (uint32_t)(tg * 32), v);
                         if (yl < 8 && x < Wc) {
                             float4* dst = band4 + (((8 * b + yl) % 9) * C4) * Wc + x;
 #pragma unroll
@@ -315,7 +356,10 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                         }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    bst(3);
                     it_wsync();
+                    if (tid == 0) dr_arrive(IT_BAR(IB_PF + pbuf));  // the accumulator may be overwritten (band b + 2)
+                    bst(4);
                     // pool: pooled rows 4b .. 4b + 3 = positions [4b * Wpo, (4b + 4) * Wpo) of the new geometry; position q
                     // lives in lane q % 128 of residual tile q / 128
                     {
@@ -361,6 +405,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                             }
                         }
                     }
+                    bst(5);
                 }
                 ++li;
                 { uint8_t* t_ = xa; xa = xb; xb = t_; }            // xa: operand map of the first block convolution
@@ -378,9 +423,14 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                     {
                         const float* pr = Pbuf(li);
                         const float *sA = pr, *tA = pr + 32, *bA = pr + 64;
+                        auto fine = [&](int i) { if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && blk == 0) prof[16 + 5 * s + i] = clock64(); };
+                        fine(0);
                         it_go(IT_BAR(IB_GO));
+                        fine(1);
                         it_prep_layer(c, pb, false, Bbuf(li + 1), Pbuf(li + 1), nxt);     // conv b's weights, under conv a's MMAs
+                        fine(2);
                         it_layer_wait(bar0, mph);
+                        fine(3);
 #pragma unroll 1
                         for (int T = wg; T < ntile; T += IT_GROUPS) {
                             const int q = T * 128 + r128, y = q / Wp, x = q - y * Wp;
@@ -394,6 +444,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                                     if (8 * j < C) *reinterpret_cast<uint4*>(dst + j * plane) = it_pack8(v + 8 * j, sA + 8 * j, tA + 8 * j, bA + 8 * j, true);
                             }
                         }
+                        fine(4);
                         ++li;
                     }
                     // ---- conv b accumulates ONTO the residual stream in TMEM; epilogue: x += bias, next operand map -> xa ----
@@ -476,6 +527,8 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
         // mirrors the workers' sequence of layers / bands: waits until the operands are ready, issues every tile of the
         // batch (a filter tap = a start address), and commits: the commit tells the workers the accumulators are ready
         uint32_t gph = 0;
+        int gb = 0;
+        if (lane == 0) {
         auto go_wait = [&]() {
             dr_wait(IT_BAR(IB_GO), gph);
             gph ^= 1u;
@@ -488,13 +541,19 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
             for (int s = 0; s < 3; ++s) {
                 const int Wc = 64 >> s, Wpc = Wc + 2, C = s == 0 ? 16 : 32, cin = s == 0 ? 3 : (s == 1 ? 16 : 32);
                 const int ntb = (8 * Wpc + 127) >> 7;
-#pragma unroll 1
-                for (int b = 0; b < Wc / 8; ++b) {
-                    go_wait();
+                go_wait();
+                {
                     const uint32_t Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
 #pragma unroll 1
-                    for (int tl = 0; tl < ntb; ++tl) it_mma_tile(xa, Wpc, cin, Bb, C, 8 * b * Wpc + tl * 128, tmem + TC_P + (uint32_t)(tl * C), false);
-                    umma_commit_elect(IT_BAR(IB_MMA));
+                    for (int b = 0; b < Wc / 8; ++b, ++gb) {
+                        const uint32_t pbuf = (uint32_t)(gb & 1);
+                        if (gb >= 2) {                           // the accumulator's previous band has been read
+                            dr_wait(IT_BAR(IB_PF + pbuf), (uint32_t)(((gb >> 1) - 1) & 1));
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        it_mma_batch(xa, Wpc, cin, Bb, C, 8 * b * Wpc, ntb, tmem + TC_P + pbuf * TC_PW, false);
+                        umma_commit(IT_BAR(IB_PD + pbuf));
+                    }
                 }
                 ++li;
                 { const uint32_t t_ = xa; xa = xb; xb = t_; }
@@ -503,18 +562,17 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 for (int blk = 0; blk < 2; ++blk) {
                     go_wait();
                     uint32_t Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
-#pragma unroll 1
-                    for (int T = 0; T < ntile; ++T) it_mma_tile(xa, Wp, C, Bb, C, T * 128, tmem + TC_Y + (uint32_t)(T * C), false);
-                    umma_commit_elect(IT_BAR(IB_MMA));
+                    it_mma_batch(xa, Wp, C, Bb, C, 0, ntile, tmem + TC_Y, false);
+                    umma_commit(IT_BAR(IB_MMA));
                     ++li;
                     go_wait();
                     Bb = s0 + IT_B + (uint32_t)((li & 1) * IT_B_BYTES);
-#pragma unroll 1
-                    for (int T = 0; T < ntile; ++T) it_mma_tile(xb, Wp, C, Bb, C, T * 128, tmem + TC_R + (uint32_t)(T * C), true);
-                    umma_commit_elect(IT_BAR(IB_MMA));
+                    it_mma_batch(xb, Wp, C, Bb, C, 0, ntile, tmem + TC_R, true);
+                    umma_commit(IT_BAR(IB_MMA));
                     ++li;
                 }
             }
+        }
         }
         __syncwarp();
         if (lane == 0) {
@@ -557,14 +615,11 @@ int dfd_impala_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, co
         cudaStreamSynchronize(st);
         long long h[64];
         cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
-        for (int u = 0; u < 2; ++u)
-            fprintf(stderr, "[impala tcgen05 timeline] unit %d: worker wait-empty %lld copy %lld fence %lld | mma: wait-full from %lld to %lld (rel. worker start), issued+commit %lld\n", 60 + u,
-                    h[33 + 8 * u] - h[32 + 8 * u], h[34 + 8 * u] - h[33 + 8 * u], h[35 + 8 * u] - h[34 + 8 * u], h[36 + 8 * u] - h[32 + 8 * u], h[37 + 8 * u] - h[32 + 8 * u], h[38 + 8 * u] - h[37 + 8 * u]);
-        fprintf(stderr, "[impala tcgen05 timeline] stage 0 band 3: builds %lld | wait MMA %lld | band epilogue %lld | sync %lld | pool %lld | sync %lld\n",
-                h[49] - h[48], h[50] - h[49], h[51] - h[50], h[52] - h[51], h[53] - h[52], h[54] - h[53]);
+        fprintf(stderr, "[impala tcgen05 timeline] stage 0 band 3: go %lld | wait MMA %lld | band epilogue %lld | sync %lld | pool %lld\n",
+                h[49] - h[48], h[50] - h[49], h[51] - h[50], h[52] - h[51], h[53] - h[52]);
         for (int s = 0; s < 3; ++s)
-            fprintf(stderr, "[impala tcgen05 timeline] stage %d first block conv a: builds %lld | prep next %lld | wait MMA %lld | (start at %lld after stage conv)\n", s,
-                    h[17 + 4 * s] - h[16 + 4 * s], h[18 + 4 * s] - h[17 + 4 * s], h[19 + 4 * s] - h[18 + 4 * s], h[16 + 4 * s] - h[2 + 3 * s]);
+            fprintf(stderr, "[impala tcgen05 timeline] stage %d first block conv a: go %lld | prep next %lld | wait MMA %lld | epilogue %lld\n", s,
+                    h[17 + 5 * s] - h[16 + 5 * s], h[18 + 5 * s] - h[17 + 5 * s], h[19 + 5 * s] - h[18 + 5 * s], h[20 + 5 * s] - h[19 + 5 * s]);
         fprintf(stderr, "[impala tcgen05 timeline] CTA 7, cycles per phase of its first member: frame %lld | s0 conv+pool %lld res %lld %lld | "
                         "s1 conv+pool %lld res %lld %lld | s2 conv+pool %lld res %lld %lld | all trunks done at %lld | dense tail %lld | total %lld\n",
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7], h[9] - h[8],
