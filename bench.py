@@ -130,13 +130,13 @@ def workload(args):
 def forward_precision(kind, precision, E):
     """--precision -> (tensor path on?, dfd_policy_desc.precision level).  MuJoCo MLPs: tcgen05 tf32 (level 1: accurate
     tanh, level 2: tanh.approx) when asked for, or by default from 32 observations per member; IMPALA: tensor-core
-    convolutions (level 1) unless fp32 is asked for; Atari: tcgen05 convolutions and first Linear with TMA-fed weight tiles
+    convolutions + dense tail on tcgen05 (level 3) unless fp32 is asked for; Atari: tcgen05 convolutions and first Linear with TMA-fed weight tiles
     (level 1) unless fp32 is asked for; Discrete: the exact fp32 kernels only."""
     if kind == "mujoco":
         on = precision in ("tf32", "tf32a") or (precision == "auto" and E >= 32)
         return on, (1 if precision == "tf32" else 2)
     if kind == "impala":
-        return precision != "fp32", 2       # level 2: mma.sync trunk + TMA-fed tcgen05 dense tail
+        return precision != "fp32", 3       # level 3: tcgen05 trunk (a filter tap = a shifted UMMA descriptor) + TMA-fed tcgen05 dense tail
     if kind == "atari":
         return precision != "fp32", 1
     return False, 0
@@ -614,7 +614,7 @@ def run_workload(env, args, w, full=True):
     table = D.SharedNoiseTable(args.table_size, P, TABLE_SEED, device=local)
     policy.bind_table(table)
     if is_impala and use_tc:
-        # the bench calls dfd_impala_forward directly: register the sigma-scaled fp16 table mirror the level-2 dense tail
+        # the bench calls dfd_impala_forward directly: register the sigma-scaled fp16 table mirror the dense tail
         # streams its weight tiles from (ImpalaPolicy.forward_members_impala does this on first use)
         table.device_table.ensure_scaled16(SIGMA, P)
 
@@ -1121,7 +1121,8 @@ def run_workload(env, args, w, full=True):
     if not use_tc:
         dtype = "f32"
     elif w["kind"] == "impala":
-        dtype = ("fp16 operands (10-bit mantissa as tf32), fp32 accumulate: convolutions on mma.sync m16n8k16, dense tail (Linear + LSTM) on "
+        dtype = ("fp16 operands (10-bit mantissa as tf32), fp32 accumulate: convolutions as implicit GEMMs on tcgen05 kind::f16 (operand "
+                 "maps in the UMMA layout, a filter tap = a shifted descriptor), dense tail (Linear + LSTM) on "
                  "tcgen05 kind::f16 with weight tiles by TMA from an fp16 repack of theta and the sigma-scaled fp16 table mirror; "
                  "fp32 BatchNorm folds, LSTM cell and head; f32 estimator")
     elif w["kind"] == "atari":

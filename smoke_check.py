@@ -126,10 +126,10 @@ def _smoke_tensor_paths(O, D):
         e_at = max(e_at, float(np.abs(aout[m] - O.atari_forward(La, thm, bufa, aobs[m])).max()))
     assert e_at <= 2e-3, ("atari tensor-path forward mismatch", e_at)
 
-    # IMPALA, tensor-core convolutions + TMA-fed tcgen05 dense tail (level 2), one antithetic pair
+    # IMPALA, tcgen05 trunk (shifted-descriptor implicit GEMMs) + TMA-fed tcgen05 dense tail (level 3), one antithetic pair
     L = O.impala_layout(15)
     t_imp = D.SharedNoiseTable(2_000_000, L.num_params, 123, device=0)
-    ipol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=2).bind_table(t_imp)
+    ipol = D.ImpalaPolicy((3, 64, 64), 15, seed=124, device=0, precision=3).bind_table(t_imp)
     th, buf = O.synthetic_theta(L, 43), O.synthetic_buffers(L, 44)
     ipol.set_trainable_flat(th)
     ipol.set_buffers(buf)

@@ -58,8 +58,8 @@ def test_precision_flag_maps_to_policy_levels():
     assert bench.forward_precision("mujoco", "auto", 1) == (False, 2)
     assert bench.forward_precision("mujoco", "tf32", 1) == (True, 1)
     assert bench.forward_precision("mujoco", "fp32", 128)[0] is False
-    assert bench.forward_precision("impala", "auto", 1) == (True, 2)
-    assert bench.forward_precision("impala", "fp32", 1) == (False, 2)
+    assert bench.forward_precision("impala", "auto", 1) == (True, 3)
+    assert bench.forward_precision("impala", "fp32", 1) == (False, 3)
     assert bench.forward_precision("atari", "auto", 1) == (True, 1)
     assert bench.forward_precision("atari", "fp32", 1) == (False, 1)
     for prec in ("auto", "fp32", "tf32", "tf32a"):
