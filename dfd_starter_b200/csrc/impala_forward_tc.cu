@@ -1,16 +1,28 @@
 // IMPALA CNN + LSTM perturbed forward on tcgen05 / TMEM / TMA (policies/impala.py:136-186; perturbation worker/worker.py:28),
-// precision level 2.  One CTA per (antithetic pair, environment): the two members' trunks run one after the other, the dense
+// precision level 3.  One CTA per (antithetic pair, environment): the two members' trunks run one after the other, the dense
 // tail of both streams theta and the pair's shared eps row ONCE.
 //
-// Trunk (15 convolutions 3x3, pad 1): implicit GEMMs M = 128 output pixels, N = output channels, K = 9 * input channels
-// in TAP-MAJOR order (k = tap * cin + c).  The operand of a convolution - BN(+ReLU) of the previous raw map - is written
-// ONCE by the producing layer's epilogue as an fp16 CHANNEL-LAST zero-bordered map, so the im2col tile of 128 pixels is a
-// handful of 16-byte copies per (pixel, tap) into the 128-byte swizzled K-major layout; the perturbed weights of a layer
-// (<= 9 216 values) are built exactly in fp32 (theta + s*sigma*eps, two roundings), rounded once to fp16 and laid out as
-// the B operand by the CTA.  Accumulators live in TENSOR MEMORY: the raw residual stream x of a stage stays there - the
-// second convolution of a residual block ACCUMULATES onto it (x += conv(..) is the MMA's own accumulate) - and only
-// BN'd / ReLU'd fp16 operand maps ever touch shared memory.  Stage convolutions are evaluated in bands of 8 rows into a
-// 9-row fp32 band, max-pooled 3x3 / 2, and the pooled raw map is stored back into TMEM (tcgen05.st).
+// Trunk (15 convolutions 3x3, pad 1): implicit GEMMs M = 128 output positions, N = output channels, K = 16 input channels
+// of ONE filter tap per MMA - and NO im2col.  The operand of a convolution - BN(+ReLU) of the previous raw map - is written
+// ONCE by the producing layer's epilogue as fp16 PLANES: plane j = channels 8j .. 8j + 7 of every position of the
+// zero-bordered (W + 2) x (W + 2) map, 16 bytes per position, positions row-major.  That IS the UMMA no-swizzle K-major
+// layout with the position as the row (8 consecutive positions = one 128-byte core matrix, SBO = 128, LBO = one plane),
+// so a filter tap (dy, dx) is the same descriptor with its start address moved by (dy (W + 2) + dx) positions, and an
+// output tile is 128 consecutive PADDED positions (the two border columns of a row give garbage rows that nobody reads).
+// The first convolution (3 channels in one plane) pairs neighbouring taps: the second core matrix of an MMA is the next
+// position of the same plane (LBO = 16 bytes - overlapping core matrices; measured correct on B200).  The perturbed
+// weights of a layer (<= 9 216 values) become the B operand [cout x K] (K = tap-major, 128-byte swizzle) from 16-bit
+// sources: the per-call fp16 repack of theta (already in that K order) + sign * the sigma-scaled fp16 table mirror.
+// Accumulators live in TENSOR MEMORY: the raw residual stream x of a stage stays there - the second convolution of a
+// residual block ACCUMULATES onto it (x += conv(..) is the MMA's own accumulate) - and only BN'd / ReLU'd fp16 operand
+// planes ever touch shared memory.  Stage convolutions run in bands of 8 rows over TWO band accumulators (the MMA warp -
+// one lane issues, descriptors advance by adds - works a band ahead of the workers), each band goes through a 9-row fp32
+// band buffer ([row][channel quad][x] float4: conflict-free for the pool), is max-pooled 3x3 / 2, and the pooled raw map
+// is stored back into TMEM (tcgen05.st) at its position of the next geometry.
+// Measured on B200 (C5 share, 256 pairs): 587 us against 762 us for the mma.sync trunk (level 2) and 1 590 us for the
+// first tcgen05 trunk (im2col copies through shared memory).  An MMA of this shape (M = 128, K = 16, N = 16 / 32, A from
+// shared memory) takes ~ 95 cycles whatever N is - the A operand is delivered at a row per cycle - so stage 0 (564 MMAs per
+// member) is tensor-issue bound and the later stages are bound by the weight build (L2 -> SM delivery).
 //
 // Dense tail (Linear 2048 -> 256, LSTM 513 -> 1024: 90 % of the parameters): "swap AB" GEMMs whose WEIGHT tiles
 // [128 rows x 64 k] are the A operand and arrive by TMA straight from an fp16 repack of theta and from the sigma-scaled
@@ -60,6 +72,9 @@ struct ItCtx {
     const float* theta;
     const float* row;
     const float* bn;
+    const __half* w16;      // convolution weights of theta, fp16, [oc][tap][ci] per layer (impala_theta16_kernel)
+    const __half* e16;      // the member's slice of the sigma-scaled fp16 table mirror: e16[p] = fp16(fl32(sigma * eps[p]))
+    float sgn;              // the member's sign (0: unperturbed)
     float sg;
     __device__ __forceinline__ float par(int p) const { return perturb1(theta[p], sg, row[p]); }
 };
@@ -72,7 +87,7 @@ struct ItCtx {
 // five missing channels.  Also: conv bias; input-side BN of the NEXT convolution folded to scale / shift (applied by THIS
 // layer's epilogue).  par: sN[32] tN[32] bias[32].
 template <int CIN>
-__device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uint8_t* Bs, float* par, const ConvP* nxt) {
+__device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uint8_t* Bs, float* par, const ConvP* nxt, const __half* w16_layer) {
     constexpr bool first = CIN == 3;
     const int tid = threadIdx.x;
     constexpr int k9 = CIN * 9;
@@ -92,28 +107,33 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
         }
     } else {
         // A lane is an INPUT CHANNEL (the dimension that is contiguous in the K-major operand): the 32 lanes of a warp
-        // write 64 contiguous-but-swizzled bytes per tap - no bank conflicts, no index arithmetic beyond shifts - and read
-        // theta / eps at a stride of 9 floats: the nine loads of an output channel walk the same ten lines, so all but the
-        // first hit L1 (ld.global.nc).  32 / CIN output channels per warp and round.  Measured against (a) coalesced loads
-        // + 2-byte scatter stores (8-way bank conflicts, 30 instructions of index arithmetic per weight, optionally from
-        // an offset table) and (b) a two-pass build through a staging buffer: this form is the fastest of the three; what
-        // bounds all of them is the delivery of 8 bytes of theta / eps per weight from L2 while the other SMs stream
-        // their dense-tail tiles (10 B / cycle / SM observed).
+        // write 64 contiguous-but-swizzled bytes per tap - no bank conflicts, no index arithmetic beyond shifts.  The
+        // sources are 16-bit: theta's weights from the per-call fp16 repack ALREADY in this K order (a warp reads 64
+        // contiguous bytes per tap), eps from the sigma-scaled fp16 mirror of the table in its own order (stride of 9
+        // halves; the nine loads of an output channel walk the same five lines, so all but the first hit L1): 4 bytes per
+        // weight instead of 8 - the build is bound by L2 -> SM delivery while the other SMs stream their dense-tail tiles -
+        // and the same split of one rounding into two as the dense tail's (fp16(theta) + s * fp16(sigma eps), summed in
+        // fp32, rounded once more).  Measured alternatives with fp32 sources (coalesced loads + 2-byte scatter stores
+        // with or without an offset table; a two-pass build through a staging buffer): all at 5 - 8 k cycles per 32 -> 32
+        // layer.
         constexpr int OPW = 32 / CIN;
         const int w = tid >> 5, l = tid & 31, ci = l & (CIN - 1), o2 = l / CIN;
         const int rowb = p.cout * 128;
+        const unsigned short* w16 = reinterpret_cast<const unsigned short*>(w16_layer);
+        const unsigned short* e16 = reinterpret_cast<const unsigned short*>(c.e16 + p.w);
 #pragma unroll 1
         for (int oc = w * OPW + o2; oc < p.cout; oc += (IT_WORKERS / 32) * OPW) {
-            const float* wt = c.theta + p.w + oc * k9 + ci * 9;
-            const float* we = c.row + p.w + oc * k9 + ci * 9;
-            float a[9], e[9];
+            const unsigned short* wt = w16 + oc * k9 + ci;
+            const unsigned short* we = e16 + oc * k9 + ci * 9;
+            unsigned short a[9], e[9];
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) { a[tap] = __ldg(wt + tap); e[tap] = __ldg(we + tap); }
+            for (int tap = 0; tap < 9; ++tap) { a[tap] = __ldg(wt + tap * CIN); e[tap] = __ldg(we + tap); }
             uint8_t* dst = Bs + oc * 128 + (ci & 7) * 2;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const int k = tap * CIN + ci;
-                *reinterpret_cast<__half*>(dst + (k >> 6) * rowb + ((((k & 63) >> 3) ^ (oc & 7)) << 4)) = __float2half_rn(perturb1(a[tap], c.sg, e[tap]));
+                const float v = fmaf(c.sgn, __half2float(__ushort_as_half(e[tap])), __half2float(__ushort_as_half(a[tap])));   // exact in fp32
+                *reinterpret_cast<__half*>(dst + (k >> 6) * rowb + ((((k & 63) >> 3) ^ (oc & 7)) << 4)) = __float2half_rn(v);
             }
         }
     }
@@ -127,10 +147,13 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
     }
 }
 
-__device__ __forceinline__ void it_prep_layer(const ItCtx& c, const ConvP& p, bool first, uint8_t* Bs, float* par, const ConvP* nxt) {
-    if (first) it_prep_layer_t<3>(c, p, Bs, par, nxt);
-    else if (p.cin == 16) it_prep_layer_t<16>(c, p, Bs, par, nxt);
-    else it_prep_layer_t<32>(c, p, Bs, par, nxt);
+__device__ __forceinline__ void it_prep_layer(const ImpalaP& L, const ItCtx& c, const ConvP& p, bool first, uint8_t* Bs, float* par, const ConvP* nxt) {
+    int seg = 0;
+    while (seg < 14 && L.seq_w[seg] != p.w) ++seg;
+    const __half* w16 = c.w16 + L.seq_o[seg];
+    if (first) it_prep_layer_t<3>(c, p, Bs, par, nxt, w16);
+    else if (p.cin == 16) it_prep_layer_t<16>(c, p, Bs, par, nxt, w16);
+    else it_prep_layer_t<32>(c, p, Bs, par, nxt, w16);
 }
 
 template <int C>
@@ -209,7 +232,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                      const int8_t* __restrict__ sign, float sigma, const float* __restrict__ frame, const float* __restrict__ reward,
                      const uint8_t* __restrict__ done, const float* __restrict__ h_in, const float* __restrict__ c_in, int E,
                      float* __restrict__ probs, float* __restrict__ h_out, float* __restrict__ c_out, int n_members, int pair_mode,
-                     long long* __restrict__ prof) {
+                     const __half* __restrict__ conv16, const __half* __restrict__ mirror16, long long* __restrict__ prof) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[IB_COUNT];
     __shared__ uint32_t tmem_base_s;
@@ -272,13 +295,14 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
         for (int mem = 0; mem < nmem; ++mem) {
             ItCtx c;
             c.theta = theta; c.bn = bnbuf; c.sg = sigma * (float)sgi[mem]; c.row = rows[mem];
+            c.w16 = conv16; c.e16 = mirror16 + ids[mem]; c.sgn = (float)sgi[mem];
             uint8_t* xa = sm + IT_M1;                           // the frame map spans buffers 1 and 2
             uint8_t* xb = sm + IT_M0;
             // the member's convolution parameters (the first 0.4 MB of its table row) and its frame: into L2 now, so that
             // the weight builds of the 15 layers find them there
             if (tid < 8 && (mem == 0 || !shared_row)) {
-                const int span = L.fc_w, part = (span + 7) / 8, lo = tid * part;
-                if (lo < span) l2_prefetch(rows[mem] + lo, (size_t)min(part, span - lo) * 4);
+                const int span = L.fc_g, part = (span + 7) / 8, lo = tid * part;
+                if (lo < span) l2_prefetch(c.e16 + lo, (size_t)min(part, span - lo) * 2);
             } else if (tid == 32) {
                 l2_prefetch(frame + (int64_t)inst[mem] * 12288, 12288 * 4);
                 if (mem == 0 && nmem == 2) l2_prefetch(frame + (int64_t)inst[1] * 12288, 12288 * 4);
@@ -294,7 +318,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 fpar[tid] = s;
                 fpar[4 + tid] = c.par(p0.be + tid) - bnbuf[p0.bm + tid] * s;
             }
-            it_prep_layer(c, L.feat[0], true, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
+            it_prep_layer(L, c, L.feat[0], true, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
             it_wsync();
             {
                 const float* fr = frame + (int64_t)inst[mem] * 12288;
@@ -327,7 +351,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 const ConvP& pa0 = L.res[0][s][0];
                 float4* band4 = reinterpret_cast<float4*>(band);
                 it_go(IT_BAR(IB_GO));                            // the stage's map and weights are visible: the MMA warp may start its bands
-                it_prep_layer(c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);   // the first block convolution's weights, under the MMAs
+                it_prep_layer(L, c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);   // the first block convolution's weights, under the MMAs
 #pragma unroll 1
                 for (int b = 0; b < Wc / 8; ++b, ++gb) {
                     auto bst = [&](int i) { if (prof != nullptr && blockIdx.x == 7 && tid == 0 && mem == 0 && s == 0 && b == 3) prof[48 + i] = clock64(); };
@@ -427,7 +451,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                         fine(0);
                         it_go(IT_BAR(IB_GO));
                         fine(1);
-                        it_prep_layer(c, pb, false, Bbuf(li + 1), Pbuf(li + 1), nxt);     // conv b's weights, under conv a's MMAs
+                        it_prep_layer(L, c, pb, false, Bbuf(li + 1), Pbuf(li + 1), nxt);     // conv b's weights, under conv a's MMAs
                         fine(2);
                         it_layer_wait(bar0, mph);
                         fine(3);
@@ -455,7 +479,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                         it_go(IT_BAR(IB_GO));
                         if (nxt != nullptr) {                        // the next layer's weights, under conv b's MMAs
                             const bool nxt_stage = blk == 1;
-                            it_prep_layer(c, *nxt, false, Bbuf(li + 1), Pbuf(li + 1), nxt_stage ? &L.res[0][s + 1][0] : &L.res[1][s][1]);
+                            it_prep_layer(L, c, *nxt, false, Bbuf(li + 1), Pbuf(li + 1), nxt_stage ? &L.res[0][s + 1][0] : &L.res[1][s][1]);
                         }
                         it_layer_wait(bar0, mph);
                         float* fscr = band;                          // relu(x) of the last layer, [c * 64 + pixel]
@@ -599,7 +623,7 @@ int dfd_impala_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, co
     if (getenv("DFD_TC_NO_DIRECT")) return -1;
     if (!ctx->scaled16 || ctx->scaled_src != table->replicas || ctx->scaled_sigma != sigma) return -1;
     const ImpalaP L = make_impala(desc->n_act);
-    if (ctx->theta16_cap < 1048576) return -1;
+    if (ctx->theta16_cap < TL_CONV16 + L.seq_o[15]) return -1;
     ItMaps maps;
     if (tl_prepare(ctx, L, theta, &maps, st)) return 3;
     DFD_CUDA(cudaFuncSetAttribute(impala_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IT_SMEM));
@@ -609,7 +633,7 @@ int dfd_impala_forward_direct_impl(dfd_ctx* ctx, const dfd_policy_desc* desc, co
     if (getenv("DFD_IMPALA_PROF")) { cudaMalloc(&prof, 64 * 8); cudaMemset(prof, 0, 64 * 8); }
     impala_direct_kernel<<<grid, IT_THREADS, IT_SMEM, st>>>(L, maps, table->replicas, table->replica_stride, theta, bn_buffers, idx, sign,
                                                             sigma, frame, reward, done, h_in, c_in, obs_per_member, probs, h_out, c_out,
-                                                            n_members, pair_mode, prof);
+                                                            n_members, pair_mode, (const __half*)ctx->theta16 + TL_CONV16, (const __half*)ctx->scaled16, prof);
     DFD_LAUNCHED(ctx);
     if (prof) {
         cudaStreamSynchronize(st);

@@ -15,6 +15,7 @@ struct ImpalaP {
     int A;
     int64_t P;
     int seq_w[16], seq_n[16];     // conv weight segments in execution order (L2 prefetch of the next layer)
+    int seq_o[16], seq_cin[16];   // running offset of each segment (seq_o[15] = total) and its input channels
 };
 
 inline ImpalaP make_impala(int A) {
@@ -58,12 +59,13 @@ inline ImpalaP make_impala(int A) {
     L.A = A;
     L.P = off;
     int n = 0;
-    auto seq = [&](const ConvP& p) { L.seq_w[n] = p.w; L.seq_n[n] = p.cout * p.cin * 9; ++n; };
+    int run = 0;
+    auto seq = [&](const ConvP& p) { L.seq_w[n] = p.w; L.seq_n[n] = p.cout * p.cin * 9; L.seq_o[n] = run; L.seq_cin[n] = p.cin; run += L.seq_n[n]; ++n; };
     for (int s = 0; s < 3; ++s) {
         seq(L.feat[s]);
         for (int blk = 0; blk < 2; ++blk) { seq(L.res[blk][s][0]); seq(L.res[blk][s][1]); }
     }
-    L.seq_w[15] = 0; L.seq_n[15] = 0;
+    L.seq_w[15] = 0; L.seq_n[15] = 0; L.seq_o[15] = run; L.seq_cin[15] = 0;
     return L;
 }
 

@@ -37,15 +37,28 @@ __device__ __forceinline__ void tl_wsync() { asm volatile("bar.sync 1, %0;" ::"n
 __device__ __forceinline__ float tl_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // fp16 repack of the dense-tail weights into the context's theta16 scratch, 16-byte aligned blocks (the flat offsets of
-// fc.weight / weight_ih / weight_hh are 6 mod 8): [256 x 2048] | weight_ih[:, :256] as [1024 x 256] | [1024 x 256]
-__global__ void impala_theta16_kernel(const float* __restrict__ theta, __half* __restrict__ out, int fc_w, int wih, int whh) {
-    const int n = 256 * 2048 + 2 * 1024 * 256;
+// fc.weight / weight_ih / weight_hh are 6 mod 8): [256 x 2048] | weight_ih[:, :256] as [1024 x 256] | [1024 x 256];
+// behind them (TL_CONV16, when the scratch is large enough: with_conv) the convolution weights of all 15 layers in the
+// tcgen05 trunk's K order [oc][tap][ci] (theta keeps them as [oc][ci][tap]), segment i at TL_CONV16 + L.seq_o[i]
+constexpr int TL_CONV16 = 256 * 2048 + 2 * 1024 * 256;
+__global__ void impala_theta16_kernel(const float* __restrict__ theta, __half* __restrict__ out, int fc_w, int wih, int whh,
+                                      const __grid_constant__ ImpalaP L, int with_conv) {
+    const int n = TL_CONV16;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float v;
         if (i < 524288) v = theta[fc_w + i];
         else if (i < 786432) { const int j = i - 524288; v = theta[wih + (j >> 8) * 257 + (j & 255)]; }
         else v = theta[whh + (i - 786432)];
         out[i] = __float2half_rn(v);
+    }
+    if (!with_conv) return;
+    const int nc = L.seq_o[15];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += gridDim.x * blockDim.x) {
+        int li = 0;
+        while (li < 14 && i >= L.seq_o[li + 1]) ++li;
+        const int j = i - L.seq_o[li], cin = L.seq_cin[li], k9 = cin * 9;
+        const int oc = j / k9, r = j - oc * k9, tap = r / cin, ci = r - tap * cin;
+        out[TL_CONV16 + i] = __float2half_rn(theta[L.seq_w[li] + oc * k9 + ci * 9 + tap]);
     }
 }
 
@@ -303,7 +316,7 @@ inline int tl_prepare(dfd_ctx* ctx, const ImpalaP& L, const float* theta, ItMaps
     rc |= it_map_e_class(&maps->e_ih, ctx, 257);
     rc |= it_map_e_class(&maps->e_hh, ctx, 256);
     if (rc) { dfd_set_error("IMPALA tensor path: cuTensorMapEncodeTiled failed"); return 1; }
-    impala_theta16_kernel<<<ctx->sm_count * 2, 512, 0, st>>>(theta, t16, L.fc_w, L.wih, L.whh);
+    impala_theta16_kernel<<<ctx->sm_count * 2, 512, 0, st>>>(theta, t16, L.fc_w, L.wih, L.whh, L, ctx->theta16_cap >= TL_CONV16 + L.seq_o[15] ? 1 : 0);
     ctx->launches++;
     if (cudaPeekAtLastError() != cudaSuccess) { dfd_set_error("impala_theta16_kernel launch failed"); return 3; }
     return 0;

@@ -104,8 +104,9 @@ typedef struct dfd_policy_desc {
                       2 = MuJoCo: as 1 + single-instruction tanh.approx (2^-11 relative); IMPALA: as 1 with the dense
                           tail (Linear 2048->256 + LSTM, 90 % of the parameters) as TMA-fed tcgen05 GEMMs when the
                           scaled mirror is registered (csrc/impala_tail.cuh);
-                      3 = IMPALA: tcgen05 trunk as well (implicit GEMMs over channel-last fp16 operand maps, the
-                          residual stream in TMEM; csrc/impala_forward_tc.cu) - parity-tested, not yet the fastest.
+                      3 = IMPALA: tcgen05 trunk as well (implicit GEMMs over fp16 operand PLANES in the UMMA no-swizzle
+                          layout - a filter tap is a shifted descriptor start address, no im2col -, the residual stream
+                          in TMEM; csrc/impala_forward_tc.cu): the fastest level (C5 forward 587 us against 762).
                       fp16 operands carry tf32's 10-bit mantissa; accumulation is fp32 everywhere.  */
 } dfd_policy_desc;
 
