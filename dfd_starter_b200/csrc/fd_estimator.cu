@@ -171,8 +171,15 @@ __global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const flo
                                                                     int n_returns, int R_pairs, const float* __restrict__ dist,
                                                                     int64_t dist_stride, int64_t P, double* __restrict__ out,
                                                                     const __half* __restrict__ mirror, int64_t mstride, double inv_sigma) {
-    __shared__ __align__(16) float d_s[DOTE_CHUNK];
+    // d_e chunk in two planes: floats [8v, 8v+4) of vector v in plane 0, [8v+4, 8v+8) in plane 1 (64 bytes further than half
+    // the chunk, so the planes start 16 banks apart): a lane of the fp16 path reads ONE float4 from each plane for its 8
+    // table entries and consecutive lanes read consecutive float4 (in column order a lane's two float4 are 32 bytes apart
+    // from its neighbour's: two-way bank conflicts on every read, 47 % of the kernel's shared-memory wavefronts in
+    // prof_dots_c5); the fp32 path (float4 per lane) alternates planes lane by lane and stays conflict-free
+    constexpr int DS_P1 = DOTE_CHUNK / 2 + 16;
+    __shared__ __align__(16) float d_s[DOTE_CHUNK + 16];
     __shared__ double sh[DOT_THREADS / 32];
+    auto ds_at = [](int c) { return ((c >> 2) & 1) * DS_P1 + (c >> 3) * 4 + (c & 3); };
     const int e = blockIdx.y;
     const int RB = R_pairs > 0 ? R_pairs : n_returns;
     const int64_t c0 = (int64_t)blockIdx.x * DOTE_CHUNK;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const flo
             for (int k = 0; k < 4 && c + k < nc; ++k) t[k] = de[c + k];
             v = make_float4(t[0], t[1], t[2], t[3]);
         }
-        *reinterpret_cast<float4*>(d_s + c) = v;
+        *reinterpret_cast<float4*>(d_s + ds_at(c)) = v;
         dd += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
     }
     dd = warp_sum(dd);
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const flo
                     if (c < nc8) {
                         const float2 e0 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].x)), e1 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].y));
                         const float2 e2 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].z)), e3 = __half22float2(*reinterpret_cast<const __half2*>(&x[u].w));
-                        const float4 ya = *reinterpret_cast<const float4*>(d_s + c), yb = *reinterpret_cast<const float4*>(d_s + c + 4);
+                        const float4 ya = *reinterpret_cast<const float4*>(d_s + (c >> 1)), yb = *reinterpret_cast<const float4*>(d_s + DS_P1 + (c >> 1));
                         float s = e0.x * ya.x;
                         s = fmaf(e0.y, ya.y, s); s = fmaf(e1.x, ya.z, s); s = fmaf(e1.y, ya.w, s);
                         s = fmaf(e2.x, yb.x, s); s = fmaf(e2.y, yb.y, s); s = fmaf(e3.x, yb.z, s); s = fmaf(e3.y, yb.w, s);
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const flo
                     }
                 }
             }
-            for (int c = nc8 + lane; c < nc; c += 32) acc += (double)__half2float(a16[c]) * (double)d_s[c];
+            for (int c = nc8 + lane; c < nc; c += 32) acc += (double)__half2float(a16[c]) * (double)d_s[ds_at(c)];
             acc *= inv_sigma;
         } else {
             const float* a = table_row_ptr(replicas, stride, id) + c0;
@@ -268,14 +275,14 @@ __global__ void __launch_bounds__(DOT_THREADS, 4) fd_dots_epoch_kernel(const flo
                 for (int u = 0; u < 8; ++u) {
                     const int c = 4 * (lane + 32 * (u + 8 * half));
                     if (c < nc4) {
-                        const float4 yv = *reinterpret_cast<const float4*>(d_s + c);
+                        const float4 yv = *reinterpret_cast<const float4*>(d_s + ds_at(c));
                         float s = x[u].x * yv.x;
                         s = fmaf(x[u].y, yv.y, s); s = fmaf(x[u].z, yv.z, s); s = fmaf(x[u].w, yv.w, s);
                         acc += (double)s;
                     }
                 }
             }
-            for (int c = nc4 + lane; c < nc; c += 32) acc += (double)a[c] * (double)d_s[c];
+            for (int c = nc4 + lane; c < nc; c += 32) acc += (double)a[c] * (double)d_s[ds_at(c)];
         }
         acc = warp_sum(acc);
         if (lane == 0) {

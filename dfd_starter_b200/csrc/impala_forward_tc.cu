@@ -48,8 +48,8 @@ constexpr int IT_XH_BYTES = 38400;                            // one operand map
 constexpr int IT_M1 = IT_B + 2 * IT_B_BYTES, IT_M2 = IT_M1 + IT_XH_BYTES;   // buffers 1, 2; the 66 x 66 frame map (69 696 B) spans both
 constexpr int IT_BAND = IT_M2 + IT_XH_BYTES, IT_BAND_BYTES = 36864;   // 9 conv rows x (C / 4) x W float4 (fp32)
 constexpr int IT_FCIN = IT_BAND + IT_BAND_BYTES;              // fp16 [2][2048]: BN'd trunk outputs of the two members
-constexpr int IT_PAR = IT_FCIN + 8192, IT_PAR_WORDS = 96;     // two buffers of: sN[32] tN[32] bias[32]
-constexpr int IT_SMEM = IT_PAR + 2 * IT_PAR_WORDS * 4 + 1024;
+constexpr int IT_PAR = IT_FCIN + 8192, IT_PAR_WORDS = 96;     // per layer (15, execution order): sN[32] tN[32] bias[32]
+constexpr int IT_SMEM = IT_PAR + 15 * IT_PAR_WORDS * 4 + 1024;
 static_assert(IT_SMEM <= 232448, "shared memory");
 static_assert(IT_B % 1024 == 0 && IT_B_BYTES % 1024 == 0 && IT_BAND % 1024 == 0, "swizzle atoms");
 constexpr int IT_XT = IT_BAND;                                // dense tail: x tiles (impala_tail.cuh) in the band buffer
@@ -91,7 +91,6 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
     constexpr bool first = CIN == 3;
     const int tid = threadIdx.x;
     constexpr int k9 = CIN * 9;
-    float *sN = par, *tN = par + 32, *bias = par + 64;
     if (first) {
         // phantom tap and padded channels are zeros; 432 weights: one per thread and round, generic index arithmetic
         for (int i = tid; i < 2 * 16 * 128 / 16; i += IT_WORKERS) reinterpret_cast<uint4*>(Bs)[i] = make_uint4(0, 0, 0, 0);
@@ -137,13 +136,35 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
             }
         }
     }
-    if (tid < p.cout) bias[tid] = c.par(p.b + tid);
-    else if (nxt != nullptr && tid >= 32 && tid < 32 + nxt->cin) {
-        const int ch = tid - 32;
-        const float inv = 1.0f / sqrtf(c.bn[nxt->bv + ch] + 1e-5f);
-        const float s = c.par(nxt->g + ch) * inv;
-        sN[ch] = s;
-        tN[ch] = c.par(nxt->be + ch) - c.bn[nxt->bm + ch] * s;
+}
+
+// layer li of the trunk in execution order: per stage the stage convolution, then the two residual blocks (a, b each)
+__device__ __forceinline__ const ConvP& it_layer(const ImpalaP& L, int li) {
+    const int s = li / 5, r = li - 5 * s;
+    return r == 0 ? L.feat[s] : L.res[(r - 1) >> 1][s][(r - 1) & 1];
+}
+// Everything a layer's epilogue needs besides the accumulator, for ALL 15 layers of a member at once (one round of loads
+// in flight instead of a dependent chain per layer): par[li] = sN[32] tN[32] bias[32] - the layer's own conv bias and the
+// input-side BN of the NEXT convolution folded to scale / shift (applied by THIS layer's epilogue), exactly perturbed.
+__device__ __noinline__ void it_prep_params(const ImpalaP& L, const ItCtx& c, float* par_all) {
+#pragma unroll 1
+    for (int i = threadIdx.x; i < 15 * 64; i += IT_WORKERS) {
+        const int li = i >> 6, ch = i & 31;
+        float* par = par_all + li * IT_PAR_WORDS;
+        if (i & 32) {
+            if (li < 14) {
+                const ConvP& nx = it_layer(L, li + 1);
+                if (ch < nx.cin) {
+                    const float inv = 1.0f / sqrtf(c.bn[nx.bv + ch] + 1e-5f);
+                    const float s = c.par(nx.g + ch) * inv;
+                    par[ch] = s;
+                    par[32 + ch] = c.par(nx.be + ch) - c.bn[nx.bm + ch] * s;
+                }
+            }
+        } else {
+            const ConvP& p = it_layer(L, li);
+            if (ch < p.cout) par[64 + ch] = c.par(p.b + ch);
+        }
     }
 }
 
@@ -287,7 +308,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
 
     if (worker) {
         auto Bbuf = [&](int l) { return sm + IT_B + (l & 1) * IT_B_BYTES; };
-        auto Pbuf = [&](int l) { return par_s + (l & 1) * IT_PAR_WORDS; };
+        auto Pbuf = [&](int l) { return par_s + (l % 15) * IT_PAR_WORDS; };
         const int r128 = q4 * 32 + lane;                        // this thread's TMEM lane = row of every tile
         int gb = 0;                                             // running band number (both roles): accumulator gb & 1, its use number gb >> 1
 
@@ -318,6 +339,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 fpar[tid] = s;
                 fpar[4 + tid] = c.par(p0.be + tid) - bnbuf[p0.bm + tid] * s;
             }
+            it_prep_params(L, c, par_s);
             it_prep_layer(L, c, L.feat[0], true, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
             it_wsync();
             {
