@@ -55,7 +55,7 @@ for ll in ("launches_c2.csv", "launches_c3.csv", "launches_c4.csv", "launches_c5
         for k, v in seq:
             f.write("%s,%.0f\n" % (k, v))
     # the last full step = last 6..8 launches starting at a forward kernel
-    last = [i for i, (k, v) in enumerate(seq) if "forward" in k][-1]
+    last = [i for i, (k, v) in enumerate(seq) if "forward" in k or "impala_direct" in k][-1]
     step = seq[last:]
     tot = sum(v for k, v in step)
     lines.append("## %s — one step, per-launch device time (cold cache, serialised: compare SHARES)\n" % ll)
