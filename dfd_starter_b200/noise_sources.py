@@ -129,6 +129,18 @@ def device_normal_rows(ctx, streams, rows_per_stream, n_params, out=None, row_st
         streams = np.array([[int(s) & m64, int(s) >> 64, int(i) & m64, int(i) >> 64] for s, i in streams], dtype=np.uint64)
     streams = np.ascontiguousarray(streams.reshape(-1, 4))
     n = streams.shape[0]
+    if n > 65535:                     # one launch serves up to 65 535 streams (grid.y): split, rows land in the same buffers
+        assert out is not None and not want_f64, "more than 65 535 streams: pass the output buffer"
+        marks = []
+        for lo in range(0, n, 65535):
+            hi = min(lo + 65535, n)
+            dr = (np.arange(lo, hi) if dest_row is None else np.asarray(dest_row)[lo * int(rows_per_stream):hi * int(rows_per_stream)])
+            if rows_per_stream != 1 and dest_row is None:
+                dr = np.arange(lo * int(rows_per_stream), hi * int(rows_per_stream))
+            _, _, m, status = device_normal_rows(ctx, streams[lo:hi], rows_per_stream, n_params, out=out, row_stride=row_stride,
+                                                 theta=theta, sigma=sigma, dest_row=dr, force_serial=force_serial, margin=margin)
+            marks.append(m)
+        return out, None, RowMarks(np.concatenate([m.words for m in marks]), np.concatenate([m._states for m in marks])), status
     n_rows = n * int(rows_per_stream)
     row_stride = int(row_stride or n_params)
     fused = libm_fused()

@@ -128,3 +128,24 @@ def test_long_stream_and_throughput(D):
     assert (status & 7) == 0
     assert np.array_equal(_bits(out.cpu().numpy()), _bits(ref.astype(np.float32)))
     print("\nrng rows: %d normals, device %.3f ms (incl. host round trips), numpy %.1f ms" % (n_rows * P, e0.elapsed_time(e1), t_np * 1e3))
+
+
+def test_more_streams_than_one_launch_serves(D):
+    """70 000 return keys in one decode (grid.y of a launch is 65 535): split into launches by the host wrapper, rows and
+    end states still numpy's."""
+    from dfd_starter_b200.noise_sources import device_normal_rows
+    ctx = get_context(0)
+    n, P = 70_000, 5
+    base = np.random.default_rng(4)
+    s0, inc = _state(base)
+    streams = [(s0 + 977 * j, inc) for j in range(n)]                 # arbitrary distinct states of one sequence
+    out = torch.zeros(n * 8, dtype=torch.float32, device=ctx.device)
+    out, _, marks, status = device_normal_rows(ctx, streams, 1, P, out=out, row_stride=8)
+    assert (status & 7) == 0
+    got = out.cpu().numpy().reshape(n, 8)
+    g = np.random.default_rng(0)
+    for j in (0, 1, 65534, 65535, 65536, n - 1):
+        g.bit_generator.state = {"bit_generator": "PCG64", "state": {"state": streams[j][0] % (1 << 128), "inc": inc}, "has_uint32": 0, "uinteger": 0}
+        ref = g.standard_normal(P)
+        assert np.array_equal(_bits(got[j, :P]), _bits(ref.astype(np.float32))), j
+        assert marks.state(j, 1) == _state(g)[0]
