@@ -19,6 +19,7 @@
 //                       (= the key of the next row).
 // All integer work and IEEE double arithmetic; HBM traffic is the rows written once (4 bytes per normal) plus 18 bytes
 // of chunk records per 32 words.
+#include <type_traits>
 #include "common.cuh"
 #include "rng_normal_core.h"
 
@@ -88,17 +89,28 @@ __device__ __forceinline__ rngn_u128 jump_to_chunk(rngn_u128 s, rngn_u128 inc, i
     return s;
 }
 
+// state before the first word of this thread's chunk (chunk blockIdx.x * RNG_BLOCK + threadIdx.x of the stream): one
+// thread jumps to the CTA's first chunk (one multiply-multiply-add per set bit of the block number: up to ~20 of them,
+// a fifth of a thread's work if every thread did it), the others add their own seven bits.  Contains a __syncthreads.
+__device__ __forceinline__ rngn_u128 chunk_state(rngn_u128 st, rngn_u128 inc) {
+    __shared__ rngn_u128 base_s;
+    if (threadIdx.x == 0) base_s = jump_to_chunk(st, inc, (int64_t)blockIdx.x * RNG_BLOCK);
+    __syncthreads();
+    return jump_to_chunk(base_s, inc, (int64_t)threadIdx.x);
+}
+
 __global__ void __launch_bounds__(RNG_BLOCK) rng_table_kernel(RngArgs a) {
     __shared__ uint64_t sm[768];
     rngn_tables t;
     load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.y;
     const int64_t c = (int64_t)blockIdx.x * RNG_BLOCK + threadIdx.x;
-    if (c >= a.n_chunks) return;
     rngn_u128 st, inc;
     stream_state(a.streams, s, st, inc);
+    const rngn_u128 sc = chunk_state(st, inc);
+    if (c >= a.n_chunks) return;
     unsigned status = 0;
-    a.rec[(int64_t)s * a.n_chunks + c] = rngn_table_chunk(jump_to_chunk(st, inc, c), inc, t, &status);
+    a.rec[(int64_t)s * a.n_chunks + c] = rngn_table_chunk(sc, inc, t, &status);
     if (status) atomicOr(a.status, status);
 }
 
@@ -228,15 +240,25 @@ struct EmitArgs {
     uint64_t* row_state;       // nullable: n_streams x (rows_per_stream + 1) x {lo, hi}
 };
 
+// F64 = the caller also wants the raw fp64 normals: staged as doubles, transformed when they leave.  Otherwise the sink
+// finishes a normal on the spot - fp32(eps), or fp32(fp64(theta[col]) + sigma * eps) with theta read through L1 (a lane
+// walks consecutive columns) - and stages 4 bytes: 22 KB of shared memory per CTA instead of 39, twice the resident warps
+// for a loop that is one long dependent chain per thread.
+template <bool F64>
 struct StageSink {
-    double* stage;
+    typename std::conditional<F64, double, float>::type* stage;
     int64_t g0;                // first normal of this CTA
     int64_t next_row_end;      // index of the next normal that ends a row
     int64_t n_params;
+    int64_t col;               // column of the next normal
+    const float* theta;
+    double sigma;
     int64_t* row_words;
     uint64_t* row_state;
     __device__ __forceinline__ void operator()(int64_t g, double v, int64_t words_after, rngn_u128 st) {
-        stage[g - g0] = v;
+        if (F64) stage[g - g0] = v;
+        else stage[g - g0] = __double2float_rn(theta ? __dadd_rn((double)__ldg(theta + col), __dmul_rn(sigma, v)) : v);
+        ++col;
         if (g == next_row_end) {
             const int64_t r = (g + 1) / n_params;
             row_words[r] = words_after;
@@ -245,14 +267,17 @@ struct StageSink {
                 row_state[2 * r + 1] = st.hi;
             }
             next_row_end += n_params;
+            col = 0;
         }
     }
 };
 
+template <bool F64>
 __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs o) {
+    typedef typename std::conditional<F64, double, float>::type stage_t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* sm = reinterpret_cast<uint64_t*>(smem_raw);
-    double* stage = reinterpret_cast<double*>(sm + 768);             // RNG_BLOCK * RNGN_CHUNK doubles
+    stage_t* stage = reinterpret_cast<stage_t*>(sm + 768);           // RNG_BLOCK * RNGN_CHUNK values
     rngn_tables t;
     load_tables(sm, t, a.libm_fused);
     const int s = blockIdx.y;
@@ -263,6 +288,9 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
     int tot;
     const int pre = block_exclusive_scan(k, &tot);
     if (g0 >= a.n_draws) return;                                     // uniform per CTA
+    rngn_u128 st, inc;
+    stream_state(a.streams, s, st, inc);
+    const rngn_u128 sc = chunk_state(st, inc);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         o.row_words[(int64_t)s * (a.rows_per_stream + 1)] = 0;
         if (o.row_state) {
@@ -273,18 +301,20 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
     if (c < a.n_chunks && k > 0) {
         int e = a.entry[at];
         if (e == 255) e = a.entry_big[at];
-        rngn_u128 st, inc;
-        stream_state(a.streams, s, st, inc);
         const int64_t first_g = g0 + pre;
-        StageSink sink;
+        StageSink<F64> sink;
         sink.stage = stage;
         sink.g0 = g0;
         sink.n_params = a.n_params;
-        sink.next_row_end = (first_g / a.n_params + 1) * a.n_params - 1;
+        const int64_t row0 = first_g / a.n_params;
+        sink.next_row_end = (row0 + 1) * a.n_params - 1;
+        sink.col = first_g - row0 * a.n_params;
+        sink.theta = o.theta;
+        sink.sigma = o.sigma;
         sink.row_words = o.row_words + (int64_t)s * (a.rows_per_stream + 1);
         sink.row_state = o.row_state ? o.row_state + 2 * (int64_t)s * (a.rows_per_stream + 1) : nullptr;
         unsigned status = 0;
-        rngn_emit_chunk(jump_to_chunk(st, inc, c), inc, t, c, e, first_g, a.n_draws, &status, sink);
+        rngn_emit_chunk(sc, inc, t, c, e, first_g, a.n_draws, &status, sink);
         // status bits were already reported by the table / resolve kernels for the same attempts
     }
     __syncthreads();
@@ -296,13 +326,17 @@ __global__ void __launch_bounds__(RNG_BLOCK) rng_emit_kernel(RngArgs a, EmitArgs
     for (int64_t i = threadIdx.x; i < n_here; i += RNG_BLOCK) {
         const int64_t r_launch = (int64_t)s * a.rows_per_stream + row;
         const int64_t r_out = o.dest_row ? o.dest_row[r_launch] : r_launch;
-        const double eps = stage[i];
-        if (o.rows_out_f64) o.rows_out_f64[r_out * o.row_stride + col] = eps;
-        if (o.rows_out) {
-            // worker.py:28 with fp64 noise: flat (fp32 -> fp64) + sigma * eps, two roundings, then the fp32 cast of
-            // set_trainable_flat; the learner's decode is the plain cast
-            const double v = o.theta ? __dadd_rn((double)o.theta[col], __dmul_rn(o.sigma, eps)) : eps;
-            o.rows_out[r_out * o.row_stride + col] = __double2float_rn(v);
+        if (F64) {
+            const double eps = (double)stage[i];
+            if (o.rows_out_f64) o.rows_out_f64[r_out * o.row_stride + col] = eps;
+            if (o.rows_out) {
+                // worker.py:28 with fp64 noise: flat (fp32 -> fp64) + sigma * eps, two roundings, then the fp32 cast of
+                // set_trainable_flat; the learner's decode is the plain cast
+                const double v = o.theta ? __dadd_rn((double)o.theta[col], __dmul_rn(o.sigma, eps)) : eps;
+                o.rows_out[r_out * o.row_stride + col] = __double2float_rn(v);
+            }
+        } else {
+            o.rows_out[r_out * o.row_stride + col] = (float)stage[i];
         }
         col += RNG_BLOCK;
         while (col >= a.n_params) {
@@ -426,13 +460,18 @@ extern "C" int dfd_rng_normal_rows(dfd_ctx* ctx, const uint64_t* streams, int n_
     DFD_LAUNCHED(ctx);
     rng_scan_kernel<<<n_streams, 1024, 0, st>>>(a);
     DFD_LAUNCHED(ctx);
-    const size_t smem = 768 * sizeof(uint64_t) + (size_t)RNG_BLOCK * RNGN_CHUNK * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DFD_CUDA(cudaFuncSetAttribute(rng_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    if (rows_out_f64) {
+        const size_t smem = 768 * sizeof(uint64_t) + (size_t)RNG_BLOCK * RNGN_CHUNK * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            DFD_CUDA(cudaFuncSetAttribute(rng_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        rng_emit_kernel<true><<<grid, RNG_BLOCK, smem, st>>>(a, o);
+    } else {
+        const size_t smem = 768 * sizeof(uint64_t) + (size_t)RNG_BLOCK * RNGN_CHUNK * sizeof(float);
+        rng_emit_kernel<false><<<grid, RNG_BLOCK, smem, st>>>(a, o);
     }
-    rng_emit_kernel<<<grid, RNG_BLOCK, smem, st>>>(a, o);
     DFD_LAUNCHED(ctx);
     return 0;
 }
