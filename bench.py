@@ -18,6 +18,11 @@ e2e     : the same step through the reference-facing objects (Worker.evaluate ->
           copied out every step.
 Weak scaling: every rank evaluates the workload's full per-GPU population (no data-path
 collective in the forward; one parameter-sized allreduce in the estimator).
+Beside the headline (default run, one GPU) the same JSON line carries: `workloads` (C3 / C4 / C5 at the same N),
+`operating_points` (C2 at E = 1, E = 16, exact fp32) and `noise_sources.rng` - the reference drivers' DEFAULT noise
+source (RNGNoiseSource: numpy PCG64 + ziggurat) drawn on the device bit-identically to numpy: rows/s at the C2 / C3 row
+shapes next to numpy's rate on this host, and the reference-style worker -> learner step with the rows drawn on the
+device vs on the host.
 """
 import argparse
 import json
