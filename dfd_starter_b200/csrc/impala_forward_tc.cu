@@ -20,9 +20,9 @@
 // band buffer ([row][channel quad][x] float4: conflict-free for the pool), is max-pooled 3x3 / 2, and the pooled raw map
 // is stored back into TMEM (tcgen05.st) at its position of the next geometry.
 // Measured on B200 (C5 share, 256 pairs): 587 us against 762 us for the mma.sync trunk (level 2) and 1 590 us for the
-// first tcgen05 trunk (im2col copies through shared memory).  An MMA of this shape (M = 128, K = 16, N = 16 / 32, A from
-// shared memory) takes ~ 95 cycles whatever N is - the A operand is delivered at a row per cycle - so stage 0 (564 MMAs per
-// member) is tensor-issue bound and the later stages are bound by the weight build (L2 -> SM delivery).
+// first tcgen05 trunk (im2col copies through shared memory).  An MMA of M = 128, K = 16 costs 63 cycles for EVERY N <= 128
+// (scripts/probe_umma.cu; 78 in this kernel) - the pipe's floor is max(64, N / 2) - so stage 0 (564 MMAs per member, N = 16)
+// is tensor-issue bound and the later stages wait for the weight build.
 //
 // Dense tail (Linear 2048 -> 256, LSTM 513 -> 1024: 90 % of the parameters): "swap AB" GEMMs whose WEIGHT tiles
 // [128 rows x 64 k] are the A operand and arrive by TMA straight from an fp16 repack of theta and from the sigma-scaled
@@ -242,7 +242,7 @@ __device__ __forceinline__ void it_mma_batch(uint32_t map, int Wp, int cin, uint
         const uint32_t acc = (j != 0 || accumulate) ? 1u : 0u;
         uint64_t adesc = make_desc(a, lbo, 128);
         uint32_t d = d_tmem;
-#pragma unroll 1
+#pragma unroll 3
         for (int T = 0; T < nt; ++T, adesc += 128, d += (uint32_t)cout) it_umma(d, adesc, bdesc, idesc, acc);     // next tile: 128 positions = 2048 bytes
     }
 }
