@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | ((uint
 // mode 0: A = planes (no swizzle, LBO = plane, SBO = 128), start shifted per MMA like a filter tap
 // mode 1: A = 128-byte swizzled K-major tile          mode 2: A in tensor memory
 // same_acc: every MMA accumulates onto accumulator 0; else round-robin over n_acc accumulators
-__global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_mma, int same_acc, long long* cycles) {
+__global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_mma, int same_acc, int tf32, long long* cycles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_s;
@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_mma
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_s, s0 = smem_u32(smem);
     if (tid == 0) {
-        const uint32_t idesc = idesc_f16(N);
+        // kind::tf32: K = 8 per MMA (format fields 2 / 2), same descriptors (contents are zeros)
+        const uint32_t idesc = tf32 ? ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : idesc_f16(N);
         const uint32_t a_base = s0, b_base = s0 + 65536;          // A: 64 KB region, B: [N <= 256 rows x 64 k] swizzled (32 KB)
         const int n_acc = same_acc ? 1 : (448 / N > 8 ? 8 : 448 / N);
         // eight (accumulator, A descriptor, B descriptor) triples prepared up front: the timed loop is eight MMAs and a
@@ -65,7 +66,15 @@ __global__ void __launch_bounds__(128, 1) umma_kernel(int mode, int N, int n_mma
                               : desc_sw128(a_base + (uint32_t)((u & 3) * 16384)) + (uint64_t)(((u >> 2) & 1) * 2);
         }
         const long long t0 = clock64();
-        if (mode == 2) {
+        if (mode == 2 && tf32) {
+#pragma unroll 1
+            for (int i = 0; i < n_mma; i += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(dd[u]),
+                                 "r"(tmem + 448u), "l"(bd[u]), "r"(idesc), "r"(1u) : "memory");
+            }
+        } else if (mode == 2) {
 #pragma unroll 1
             for (int i = 0; i < n_mma; i += 8) {
 #pragma unroll
@@ -113,7 +122,7 @@ int main() {
             for (int same = 0; same < 2; ++same) {
                 printf("grid %3d  %-42s %s:", grid, names[mode], same ? "same accumulator " : "round-robin accs ");
                 for (int N = 16; N <= 256; N *= 2) {
-                    umma_kernel<<<grid, 128, smem>>>(mode, N, n_mma, same, d_cyc);
+                    umma_kernel<<<grid, 128, smem>>>(mode, N, n_mma, same, 0, d_cyc);
                     CK(cudaDeviceSynchronize());
                     long long h[2 * 256];
                     CK(cudaMemcpy(h, d_cyc, sizeof(long long) * 2 * grid, cudaMemcpyDeviceToHost));
@@ -123,6 +132,17 @@ int main() {
                 }
                 printf("\n");
             }
+    printf("kind::tf32 (K = 8 per MMA), A in TMEM, %d SMs:", sms);
+    for (int N = 16; N <= 256; N *= 2) {
+        umma_kernel<<<sms, 128, smem>>>(2, N, n_mma, 0, 1, d_cyc);
+        CK(cudaDeviceSynchronize());
+        long long h[2 * 256];
+        CK(cudaMemcpy(h, d_cyc, sizeof(long long) * 2 * sms, cudaMemcpyDeviceToHost));
+        double b = 0;
+        for (int i = 0; i < sms; ++i) b += h[2 * i + 1];
+        printf("  N=%3d %5.1f", N, b / sms / n_mma);
+    }
+    printf("\n");
     cudaFree(d_cyc);
     return 0;
 }
