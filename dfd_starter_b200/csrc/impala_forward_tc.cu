@@ -339,7 +339,6 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 fpar[tid] = s;
                 fpar[4 + tid] = c.par(p0.be + tid) - bnbuf[p0.bm + tid] * s;
             }
-            it_prep_params(L, c, par_s);
             it_prep_layer(L, c, L.feat[0], true, Bbuf(li), Pbuf(li), &L.res[0][0][0]);
             it_wsync();
             {
@@ -354,8 +353,8 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
 #pragma unroll
                 for (int u = 0; u < NF; ++u) {
                     const int p = min(tid + u * IT_WORKERS, 4095);
-                    const uint32_t lo = dr_pack(fmaf(f[3 * u] / 255.0f, fpar[0], fpar[4]), fmaf(f[3 * u + 1] / 255.0f, fpar[1], fpar[5]));
-                    const uint32_t hi = dr_pack(fmaf(f[3 * u + 2] / 255.0f, fpar[2], fpar[6]), 0.f);
+                    const uint32_t lo = dr_pack(fmaf(f[3 * u] * (1.0f / 255.0f), fpar[0], fpar[4]), fmaf(f[3 * u + 1] * (1.0f / 255.0f), fpar[1], fpar[5]));
+                    const uint32_t hi = dr_pack(fmaf(f[3 * u + 2] * (1.0f / 255.0f), fpar[2], fpar[6]), 0.f);
                     *reinterpret_cast<uint4*>(xa + (((p >> 6) + 1) * 66 + (p & 63) + 1) * 16) = make_uint4(lo, hi, 0u, 0u);
                 }
             }
@@ -373,6 +372,7 @@ impala_direct_kernel(const __grid_constant__ ImpalaP L, const __grid_constant__ 
                 const ConvP& pa0 = L.res[0][s][0];
                 float4* band4 = reinterpret_cast<float4*>(band);
                 it_go(IT_BAR(IB_GO));                            // the stage's map and weights are visible: the MMA warp may start its bands
+                if (s == 0) it_prep_params(L, c, par_s);        // all 15 layers' folded parameters, under the first bands' MMAs (first used by the band epilogue)
                 it_prep_layer(L, c, pa0, false, Bbuf(li + 1), Pbuf(li + 1), &L.res[0][s][1]);   // the first block convolution's weights, under the MMAs
 #pragma unroll 1
                 for (int b = 0; b < Wc / 8; ++b, ++gb) {
