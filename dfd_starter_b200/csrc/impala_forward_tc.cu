@@ -115,24 +115,30 @@ __device__ __noinline__ void it_prep_layer_t(const ItCtx& c, const ConvP& p, uin
         // fp32, rounded once more).  Measured alternatives with fp32 sources (coalesced loads + 2-byte scatter stores
         // with or without an offset table; a two-pass build through a staging buffer): all at 5 - 8 k cycles per 32 -> 32
         // layer.
-        constexpr int OPW = 32 / CIN;
-        const int w = tid >> 5, l = tid & 31, ci = l & (CIN - 1), o2 = l / CIN;
+        // A lane is a PAIR of input channels: theta's two halves are one 32-bit load, the two results leave as one 32-bit
+        // store (half as many shared-memory store instructions and no 2-byte ones: the build tracked the number of
+        // sub-word memory instructions in every variant measured), eps stays two 2-byte loads at a stride of 9 halves.
+        constexpr int LPO = CIN / 2, OPW = 32 / LPO;                  // lanes per output channel, output channels per warp and round
+        const int w = tid >> 5, l = tid & 31, ci = 2 * (l & (LPO - 1)), o2 = l / LPO;
         const int rowb = p.cout * 128;
         const unsigned short* w16 = reinterpret_cast<const unsigned short*>(w16_layer);
         const unsigned short* e16 = reinterpret_cast<const unsigned short*>(c.e16 + p.w);
 #pragma unroll 1
         for (int oc = w * OPW + o2; oc < p.cout; oc += (IT_WORKERS / 32) * OPW) {
-            const unsigned short* wt = w16 + oc * k9 + ci;
+            const uint32_t* wt = reinterpret_cast<const uint32_t*>(w16 + oc * k9 + ci);      // [oc][tap][ci]: 4-byte aligned (ci even, CIN even)
             const unsigned short* we = e16 + oc * k9 + ci * 9;
-            unsigned short a[9], e[9];
+            uint32_t a[9];
+            unsigned short e0[9], e1[9];
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) { a[tap] = __ldg(wt + tap * CIN); e[tap] = __ldg(we + tap); }
+            for (int tap = 0; tap < 9; ++tap) { a[tap] = __ldg(wt + tap * (CIN / 2)); e0[tap] = __ldg(we + tap); e1[tap] = __ldg(we + 9 + tap); }
             uint8_t* dst = Bs + oc * 128 + (ci & 7) * 2;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
                 const int k = tap * CIN + ci;
-                const float v = fmaf(c.sgn, __half2float(__ushort_as_half(e[tap])), __half2float(__ushort_as_half(a[tap])));   // exact in fp32
-                *reinterpret_cast<__half*>(dst + (k >> 6) * rowb + ((((k & 63) >> 3) ^ (oc & 7)) << 4)) = __float2half_rn(v);
+                const float2 th = __half22float2(*reinterpret_cast<const __half2*>(&a[tap]));
+                const float v0 = fmaf(c.sgn, __half2float(__ushort_as_half(e0[tap])), th.x);                     // exact in fp32
+                const float v1 = fmaf(c.sgn, __half2float(__ushort_as_half(e1[tap])), th.y);
+                *reinterpret_cast<uint32_t*>(dst + (k >> 6) * rowb + ((((k & 63) >> 3) ^ (oc & 7)) << 4)) = dr_pack(v0, v1);
             }
         }
     }
