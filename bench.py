@@ -1269,10 +1269,10 @@ def rng_noise_source_point(ctx, full=True, rows_only=False):
     wl = WORKLOADS["C2"]
     n, E = 2 * wl["pairs"], wl["E"]
     steps = {}
-    for mode in ("device", "host"):
+    for mode in ("device", "device_arrays", "host"):
         policy = D.MujocoPolicy(wl["n_in"], wl["n_act"], seed=TABLE_SEED, h1=wl["h1"], h2=wl["h2"], device=ctx.device_index, precision=0)
         P = policy.num_params
-        src = D.RNGNoiseSource(P, TABLE_SEED, device=(mode == "device"))
+        src = D.RNGNoiseSource(P, TABLE_SEED, device=(mode != "host"))
         agent = D.SyntheticAgent(policy, E, seed=1)
 
         class Omega(object):
@@ -1281,7 +1281,7 @@ def rng_noise_source_point(ctx, full=True, rows_only=False):
         opt.coef = np.sqrt(P)
         learner = D.FiniteDifferences(policy, opt, Omega(), src, noise_std=SIGMA, batch_size=n, max_delayed_return=3)
         worker = D.Worker(policy, agent, src, None, sigma=SIGMA, eval_prob=0.0, random_seed=TABLE_SEED)
-        n_steps = 5 if mode == "device" else 2
+        n_steps = 5 if mode != "host" else 2
         import contextlib
         import io
         for k in range(1 + n_steps):
@@ -1291,13 +1291,14 @@ def rng_noise_source_point(ctx, full=True, rows_only=False):
             worker.epoch = learner.epoch
             rets = worker.collect_returns(n)
             with contextlib.redirect_stdout(io.StringIO()):
-                learner.step([r for r in rets if not r.is_eval], 0.0, 0.0, 0.0)
+                learner.step(rets.non_eval() if mode == "device_arrays" else [r for r in rets if not r.is_eval], 0.0, 0.0, 0.0)
         torch.cuda.synchronize()
         steps[mode] = (time.perf_counter() - t0) / n_steps * 1e3
     out["worker_learner_step_C2"] = {"members": n, "obs_per_member": E, "ms_per_step_rows_on_device": steps["device"],
+                                     "ms_per_step_rows_on_device_batch_as_arrays": steps["device_arrays"],
                                      "ms_per_step_rows_on_host": steps["host"],
                                      "env_steps_per_s_rows_on_device": n * E / steps["device"] * 1e3,
-                                     "note": "per-return FDReturn objects as in the reference loop; exact fp32 forward"}
+                                     "note": "per-return FDReturn objects as in the reference loop (rows_on_device / rows_on_host) or the Worker's ReturnBatch handed to the learner untouched (batch_as_arrays); exact fp32 forward"}
     return out
 
 

@@ -164,6 +164,11 @@ class FiniteDifferences(object):
         if soa is not None:                      # untouched ReturnBatch from the batched Worker: arrays as they are
             return self.step_arrays(soa[0], soa[1], soa[2], soa[3], policy_reward)
         if self.table is None:
+            keys = getattr(batch, "keys", None)
+            if keys is not None and getattr(batch, "_records", 0) is None:
+                # untouched ReturnBatch of a keyed noise source (the batched Worker's): arrays and keys as they are
+                return self._step_keyed_arrays(np.asarray(batch.epoch, dtype=np.int64), np.asarray(batch.reward, dtype=np.float64),
+                                               list(keys), policy_reward)
             return self._step_host_noise(batch, policy_reward)
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
@@ -173,31 +178,35 @@ class FiniteDifferences(object):
         return self.step_arrays(epochs, idx, sign, rewards, policy_reward)
 
     def _step_host_noise(self, batch, policy_reward):
-        """Noise sources without a device table: `decode` every ACCEPTED return on the host, in batch order like
-        finite_differences.py:87 (too-old returns are rejected before they are decoded, :82-85), stage the fp32 vectors
-        as a RowTable and run the ordinary device step over it."""
-        from .noise_sources import RowTable
+        """Noise sources without a device table, per-record form (finite_differences.py:80-112 over a list of FDReturn)."""
         batch = list(batch)
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
+        return self._step_keyed_arrays(epochs, rewards, [r.encoded_noise for r in batch], policy_reward)
+
+    def _step_keyed_arrays(self, epochs, rewards, keys, policy_reward):
+        """Noise sources without a device table: the vector of every ACCEPTED return is recovered from its key, in batch
+        order like finite_differences.py:87 (too-old returns are rejected before they are decoded, :82-85) - redrawn on
+        the device for RNGNoiseSource (bit-identical to decode(), csrc/rng_normal.cu; the source's generator ends where the
+        last decode() would have left it), decoded on the host otherwise -, staged as a RowTable, and the ordinary device
+        step runs over it."""
+        from .noise_sources import RowTable
+        n = len(keys)
         ok = np.array([(e == self.epoch) or (e in self._dist_epoch) for e in epochs], dtype=bool)
         if not ok.any():
-            return self.step_arrays(epochs, np.zeros(len(batch), np.int64), np.ones(len(batch), np.int8), rewards, policy_reward)
+            return self.step_arrays(epochs, np.zeros(n, np.int64), np.ones(n, np.int8), rewards, policy_reward)
+        good = [keys[j] for j in np.nonzero(ok)[0]]
         if getattr(self.noise_source, "device_rows", False):
-            # RNGNoiseSource: the accepted returns' vectors are redrawn from their keys ON THE DEVICE, bit-identical to
-            # decode() (csrc/rng_normal.cu), straight into the row table; the source's generator ends where the last
-            # decode() would have left it
-            rt = RowTable(self.ctx, shape=(int(ok.sum()), self.P))
-            self.noise_source.decode_rows(self.ctx, [r.encoded_noise for r, k in zip(batch, ok) if k], rt.raw, rt.Ps)
+            rt = RowTable(self.ctx, shape=(len(good), self.P))
+            self.noise_source.decode_rows(self.ctx, good, rt.raw, rt.Ps)
             rt.build()
         else:
-            rt = RowTable(self.ctx, np.stack([np.asarray(self.noise_source.decode(r.encoded_noise), dtype=np.float32)
-                                              for r, k in zip(batch, ok) if k]))
-        idx = np.zeros(len(batch), dtype=np.int64)
+            rt = RowTable(self.ctx, np.stack([np.asarray(self.noise_source.decode(k), dtype=np.float32) for k in good]))
+        idx = np.zeros(n, dtype=np.int64)
         idx[ok] = rt.idx
         self.table = rt
         try:
-            return self.step_arrays(epochs, idx, np.ones(len(batch), dtype=np.int8), rewards, policy_reward)
+            return self.step_arrays(epochs, idx, np.ones(n, dtype=np.int8), rewards, policy_reward)
         finally:
             self.table = None
 

@@ -149,3 +149,38 @@ def test_more_streams_than_one_launch_serves(D):
         ref = g.standard_normal(P)
         assert np.array_equal(_bits(got[j, :P]), _bits(ref.astype(np.float32))), j
         assert marks.state(j, 1) == _state(g)[0]
+
+
+def test_learner_takes_keyed_batches_as_arrays(D):
+    """FiniteDifferences.step on the batched Worker's untouched ReturnBatch (keys + arrays, no per-return objects) = the
+    per-record form of the reference loop: same gradient bits, same theta, same generator state afterwards."""
+    import contextlib
+    import io
+    P = D.MujocoPolicy(17, 6, seed=124, device=0).num_params
+
+    class Omega(object):
+        omega, min_omega, max_omega = 0.3, 0.0, 1.0
+
+    def run(as_arrays):
+        torch.manual_seed(124)
+        pol = D.MujocoPolicy(17, 6, seed=124, device=0)
+        src = D.RNGNoiseSource(P, 77)
+        opt = D.DSGD([torch.nn.Parameter(torch.zeros(1))], lr=0.01)
+        opt.coef = np.sqrt(P)
+        fd = D.FiniteDifferences(pol, opt, Omega(), src, noise_std=0.02, batch_size=40, max_delayed_return=3)
+        w = D.Worker(pol, D.SyntheticAgent(pol, 4, seed=1), src, None, sigma=0.02, eval_prob=0.2, random_seed=5)
+        grads = []
+        for _ in range(3):
+            w.epoch = fd.epoch
+            rets = w.collect_returns(40)
+            batch = rets.non_eval() if as_arrays else [r for r in rets if not r.is_eval]
+            with contextlib.redirect_stdout(io.StringIO()):
+                fd.step(batch, 0.0, 0.0, 0.0)
+            grads.append(np.array(fd.gradient_memory, copy=True))
+        return grads, pol.get_trainable_flat(), _state(src.rng)
+
+    ga, ta, sa = run(True)
+    gr, tr, sr = run(False)
+    for a, b in zip(ga, gr):
+        assert np.array_equal(_bits(a.astype(np.float32)), _bits(b.astype(np.float32)))
+    assert np.array_equal(_bits(ta), _bits(tr)) and sa == sr
