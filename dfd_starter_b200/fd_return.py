@@ -106,7 +106,7 @@ class ReturnBatch(object):
             return None if x is None else [x[j] for j in w]
         wk = self.wire_keys
         return ReturnBatch(self.epoch[w], self.idx[w], self.sign[w], self.reward[w], self.entropy[w], self.timesteps[w],
-                           self.is_eval[w], states=self.states, keys=pick(self.keys),
+                           self.is_eval[w], states=self.states, keys=self.keys.take(w) if hasattr(self.keys, "take") else pick(self.keys),
                            novelty=None if self.novelty is None else self.novelty[w], eval_states=pick(self.eval_states),
                            obs_stats_updates=pick(self.obs_stats_updates),
                            wire_keys=None if wk is None else (lambda j, w=w, wk=wk: wk(int(w[j]))))

@@ -168,7 +168,7 @@ class FiniteDifferences(object):
             if keys is not None and getattr(batch, "_records", 0) is None:
                 # untouched ReturnBatch of a keyed noise source (the batched Worker's): arrays and keys as they are
                 return self._step_keyed_arrays(np.asarray(batch.epoch, dtype=np.int64), np.asarray(batch.reward, dtype=np.float64),
-                                               list(keys), policy_reward)
+                                               keys, policy_reward)
             return self._step_host_noise(batch, policy_reward)
         epochs = np.fromiter((int(r.epoch) for r in batch), dtype=np.int64, count=len(batch))
         rewards = np.fromiter((float(r.reward) for r in batch), dtype=np.float64, count=len(batch))
@@ -195,7 +195,7 @@ class FiniteDifferences(object):
         ok = np.array([(e == self.epoch) or (e in self._dist_epoch) for e in epochs], dtype=bool)
         if not ok.any():
             return self.step_arrays(epochs, np.zeros(n, np.int64), np.ones(n, np.int8), rewards, policy_reward)
-        good = [keys[j] for j in np.nonzero(ok)[0]]
+        good = keys.take(np.nonzero(ok)[0]) if hasattr(keys, "take") else [keys[j] for j in np.nonzero(ok)[0]]
         if getattr(self.noise_source, "device_rows", False):
             rt = RowTable(self.ctx, shape=(len(good), self.P))
             self.noise_source.decode_rows(self.ctx, good, rt.raw, rt.Ps)

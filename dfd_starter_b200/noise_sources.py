@@ -188,6 +188,36 @@ class RowMarks(object):
         return self.words[i]
 
 
+class LazyKeys(object):
+    """The `encoded_noise` keys of a batch drawn on the device, held as arrays: streams uint64 [n, 4] = {state_lo, state_hi,
+    inc_lo, inc_hi} of every member, is_key False for members without a draw (eval members: key "0", worker.py:34).
+    Behaves like the list of key strings the reference carries (len, indexing, iteration) and formats a key only when
+    somebody asks for it; the learner takes `streams` as they are (no 128-bit decimal round trip per return)."""
+
+    def __init__(self, streams, is_key):
+        self.streams = np.ascontiguousarray(streams, dtype=np.uint64).reshape(-1, 4)
+        self.is_key = np.asarray(is_key, dtype=bool)
+
+    def __len__(self):
+        return len(self.is_key)
+
+    def __getitem__(self, j):
+        if isinstance(j, slice):
+            return [self[i] for i in range(*j.indices(len(self)))]
+        j = int(j)
+        if not self.is_key[j]:
+            return "0"
+        a = self.streams[j]
+        return "{},{}".format(int(a[0]) | (int(a[1]) << 64), int(a[2]) | (int(a[3]) << 64))
+
+    def __iter__(self):
+        return (self[j] for j in range(len(self)))
+
+    def take(self, which):
+        w = np.asarray(which)
+        return LazyKeys(self.streams[w], self.is_key[w])
+
+
 class RNGNoiseSource(object):
     """utils/noise_sources.py:4-20 restated for numpy >= 2 (the reference reads `rng.__getstate__()['state']`, which
     newer numpy no longer lays out that way; the PCG64 words themselves are the same).  The key is the generator's
@@ -223,21 +253,31 @@ class RNGNoiseSource(object):
         return self.rng.standard_normal(size=self.n_params)
 
     # ---- batched device forms ------------------------------------------------
-    def sample_rows(self, ctx, n, out, row_stride, dest_row=None, theta=None, sigma=0.0):
+    def sample_rows(self, ctx, n, out, row_stride, dest_row=None, theta=None, sigma=0.0, as_streams=False):
         """n successive `sample()` calls: returns their keys; row j goes to row dest_row[j] of `out` (fp32 device
         buffer, row_stride apart) as fp32(eps) or, with theta, as fp32(fp64(theta) + sigma * eps) (worker.py:28)."""
         s0, inc = self._state()
         _, _, marks, _ = device_normal_rows(ctx, [(s0, inc)], n, self.n_params, out=out, row_stride=row_stride, theta=theta,
                                             sigma=sigma, dest_row=dest_row)
-        keys = ["{},{}".format(marks.state(0, r), inc) for r in range(n)]
         self._set_state(marks.state(0, n), inc)
-        return keys
+        if as_streams:              # [n, 4] uint64: the keys as numbers (LazyKeys formats them on demand)
+            m64 = (1 << 64) - 1
+            out4 = np.empty((n, 4), dtype=np.uint64)
+            out4[:, :2] = marks._states[0, :n]
+            out4[:, 2], out4[:, 3] = inc & m64, inc >> 64
+            return out4
+        return ["{},{}".format(marks.state(0, r), inc) for r in range(n)]
 
     def decode_rows(self, ctx, keys, out, row_stride):
         """`decode(key)` for every key, in order: row j of `out` = fp32(noise_j)."""
-        streams = [tuple(int(v) for v in str(k).split(",")) for k in keys]
+        if hasattr(keys, "streams"):            # LazyKeys: the numbers themselves
+            streams = keys.streams
+            last_inc = int(streams[-1, 2]) | (int(streams[-1, 3]) << 64)
+        else:
+            streams = [tuple(int(v) for v in str(k).split(",")) for k in keys]
+            last_inc = streams[-1][1]
         _, _, marks, _ = device_normal_rows(ctx, streams, 1, self.n_params, out=out, row_stride=row_stride)
-        self._set_state(marks.state(len(streams) - 1, 1), streams[-1][1])    # where the last decode() leaves the generator
+        self._set_state(marks.state(len(streams) - 1, 1), last_inc)    # where the last decode() leaves the generator
 
 
 class SimpleNoiseSource(object):

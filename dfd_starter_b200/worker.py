@@ -109,12 +109,12 @@ class Worker(object):
         train = np.nonzero(~is_eval)[0]
         rt = RowTable(ctx, shape=(n, P))
         rows = rt.raw[:n * rt.Ps].view(n, rt.Ps)
-        keys = ["0"] * n
+        from .noise_sources import LazyKeys
+        streams = np.zeros((n, 4), dtype=np.uint64)
         if len(train):
-            drawn = self.noise_source.sample_rows(ctx, len(train), rt.raw, rt.Ps, dest_row=train, theta=theta,
-                                                  sigma=float(self.sigma))
-            for j, k in zip(train, drawn):
-                keys[j] = k
+            streams[train] = self.noise_source.sample_rows(ctx, len(train), rt.raw, rt.Ps, dest_row=train, theta=theta,
+                                                           sigma=float(self.sigma), as_streams=True)
+        keys = LazyKeys(streams, ~is_eval)        # "state,inc" strings on demand; eval members: "0"
         if is_eval.any():
             rows[torch.from_numpy(np.nonzero(is_eval)[0]).to(ctx.device), :P] = theta
         rt.build()
