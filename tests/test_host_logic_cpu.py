@@ -276,3 +276,28 @@ def test_exchange_mode_is_validated_without_a_gpu():
     src = inspect.getsource(F.FiniteDifferences.__init__)
     assert 'exchange_mode not in ("fd_return", "general")' in src
     assert src.index("exchange_mode not in") < src.index("get_context(")
+
+
+def test_lazy_keys_behave_like_the_key_strings():
+    """Batches drawn on the device carry their RNGNoiseSource keys as numbers (noise_sources.LazyKeys): the strings the
+    reference puts in FDReturn.encoded_noise (utils/noise_sources.py:11: "state,inc"; worker.py:34: "0" for eval members)
+    appear on demand, through ReturnBatch.key / iteration / select / concat alike."""
+    import numpy as np
+    from dfd_starter_b200.noise_sources import LazyKeys
+    from dfd_starter_b200.fd_return import ReturnBatch
+    rng = np.random.default_rng(3)
+    states = [int.from_bytes(rng.bytes(16), "little") for _ in range(5)]
+    inc = int.from_bytes(rng.bytes(16), "little") | 1
+    m64 = (1 << 64) - 1
+    streams = np.array([[s & m64, s >> 64, inc & m64, inc >> 64] for s in states], dtype=np.uint64)
+    is_eval = np.array([False, True, False, False, True])
+    keys = LazyKeys(streams, ~is_eval)
+    want = ["0" if e else "{},{}".format(s, inc) for s, e in zip(states, is_eval)]
+    assert list(keys) == want and len(keys) == 5 and keys[2] == want[2] and keys[1:3] == want[1:3]
+    rb = ReturnBatch(np.full(5, 7), np.arange(5), np.ones(5, np.int8), np.arange(5.0), np.zeros(5), np.ones(5), is_eval, keys=keys)
+    assert [rb.key(j) for j in range(5)] == want
+    ne = rb.non_eval()
+    assert isinstance(ne.keys, LazyKeys) and [r.encoded_noise for r in ne] == [w for w, e in zip(want, is_eval) if not e]
+    both = ReturnBatch.concat([ne, rb])
+    assert [both.key(j) for j in range(len(both))] == [w for w, e in zip(want, is_eval) if not e] + want
+    assert rb.soa is None                      # keyed batches never take the table-index path
